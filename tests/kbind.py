@@ -1,0 +1,268 @@
+"""ctypes bindings used by the tests only: the oracle restatement (oracle/libkalign_oracle.so)
+and the real reference behind oracle/_ref/libref_harness.so.  Never imported by the product."""
+import ctypes as C
+import os
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_SO = os.path.join(ROOT, "oracle", "libkalign_oracle.so")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libkalign_ref.so")
+REFH_SO = os.path.join(ROOT, "oracle", "_ref", "libref_harness.so")
+
+f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+
+NEGF = -np.finfo(np.float32).max
+
+
+class KoJob(C.Structure):
+    _fields_ = [("kind", C.c_int),
+                ("seq1", C.c_void_p), ("seq2", C.c_void_p),
+                ("prof1", C.c_void_p), ("prof2", C.c_void_p),
+                ("len_a", C.c_int), ("len_b", C.c_int), ("sip", C.c_int),
+                ("subm", C.c_void_p),
+                ("gpo", C.c_float), ("gpe", C.c_float), ("tgpe", C.c_float),
+                ("soff", C.c_float),
+                ("bonus", C.c_void_p)]
+
+
+class KoStats(C.Structure):
+    _fields_ = [("cells", C.c_double), ("margin_sum", C.c_float), ("margin_count", C.c_int),
+                ("top_score", C.c_float), ("n_boxes", C.c_int)]
+
+
+_oracle = None
+_refh = None
+_ref = None
+
+
+def have_oracle():
+    return os.path.exists(ORACLE_SO)
+
+
+def have_ref():
+    return os.path.exists(REFH_SO) and os.path.exists(REF_SO)
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        lib = C.CDLL(ORACLE_SO)
+        lib.ko_align.argtypes = [C.POINTER(KoJob), i32p, C.POINTER(KoStats)]
+        lib.ko_align.restype = C.c_int
+        lib.ko_bpm_block.argtypes = [u8p, u8p, C.c_int, C.c_int]
+        lib.ko_bpm_block.restype = C.c_int
+        lib.ko_pair_distance.argtypes = [u8p, C.c_int, u8p, C.c_int]
+        lib.ko_pair_distance.restype = C.c_float
+        lib.ko_make_profile.argtypes = [u8p, C.c_int, f32p, C.c_float, C.c_float, C.c_float, C.c_float, f32p]
+        lib.ko_make_profile.restype = None
+        lib.ko_set_gap_penalties.argtypes = [f32p, C.c_int, C.c_int]
+        lib.ko_set_gap_penalties.restype = None
+        lib.ko_update.argtypes = [f32p, f32p, f32p, i32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float]
+        lib.ko_update.restype = None
+        lib.ko_code_path.argtypes = [i32p, C.c_int, C.c_int, C.c_int]
+        lib.ko_code_path.restype = None
+        lib.ko_posmap_from_path.argtypes = [i32p, C.c_int, i32p]
+        lib.ko_posmap_from_path.restype = None
+        _oracle = lib
+    return _oracle
+
+
+def ref():
+    """The unmodified reference library (internal symbols are exported)."""
+    global _ref
+    if _ref is None:
+        lib = C.CDLL(REF_SO, mode=C.RTLD_GLOBAL)
+        lib.bpm_block.argtypes = [u8p, u8p, C.c_int, C.c_int]
+        lib.bpm_block.restype = C.c_int
+        _ref = lib
+    return _ref
+
+
+def refh():
+    global _refh
+    if _refh is None:
+        ref()
+        lib = C.CDLL(REFH_SO)
+        lib.refh_pair_align.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_int, C.c_int, C.c_int,
+                                        f32p, C.c_float, C.c_float, C.c_float, C.c_float,
+                                        C.c_void_p, C.c_int,
+                                        i32p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int)]
+        lib.refh_pair_align.restype = C.c_int
+        lib.refh_code_path.argtypes = [i32p, C.c_int, C.c_int, C.c_int]
+        lib.refh_make_profile.argtypes = [u8p, C.c_int, f32p, C.c_float, C.c_float, C.c_float, C.c_float, f32p]
+        lib.refh_set_gap_penalties.argtypes = [f32p, C.c_int, C.c_int]
+        lib.refh_update.argtypes = [f32p, f32p, f32p, i32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float]
+        lib.refh_run_pipeline.argtypes = [C.POINTER(C.c_char_p), i32p, C.c_int, C.c_int, C.c_int,
+                                          C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_int]
+        lib.refh_run_pipeline.restype = C.c_void_p
+        for name in ("refh_numseq", "refh_biotype", "refh_alnlen"):
+            getattr(lib, name).argtypes = [C.c_void_p]
+            getattr(lib, name).restype = C.c_int
+        lib.refh_times.argtypes = [C.c_void_p, np.ctypeslib.ndpointer(dtype=np.float64)]
+        lib.refh_times.restype = None
+        lib.refh_get_order.argtypes = [C.c_void_p, i32p, i32p]
+        lib.refh_get_order.restype = None
+        lib.refh_get_codes.argtypes = [C.c_void_p, C.c_int, u8p]
+        lib.refh_get_codes.restype = None
+        lib.refh_get_tasks.argtypes = [C.c_void_p, i32p]
+        lib.refh_get_tasks.restype = C.c_int
+        lib.refh_get_task_confidence.argtypes = [C.c_void_p, f32p]
+        lib.refh_get_task_confidence.restype = None
+        lib.refh_get_seq_distances.argtypes = [C.c_void_p, f32p]
+        lib.refh_get_seq_distances.restype = None
+        lib.refh_get_params.argtypes = [C.c_void_p, f32p, f32p]
+        lib.refh_get_params.restype = None
+        lib.refh_get_anchor_ids.argtypes = [C.c_void_p, i32p]
+        lib.refh_get_anchor_ids.restype = C.c_int
+        lib.refh_get_posmap.argtypes = [C.c_void_p, C.c_int, C.c_int, i32p]
+        lib.refh_get_posmap.restype = C.c_int
+        lib.refh_get_gaps.argtypes = [C.c_void_p, C.c_int, i32p]
+        lib.refh_get_gaps.restype = None
+        lib.refh_get_aligned.argtypes = [C.c_void_p, C.c_char_p]
+        lib.refh_get_aligned.restype = C.c_int
+        lib.refh_distance_matrix.argtypes = [C.POINTER(C.c_char_p), i32p, C.c_int, f32p, i32p, C.POINTER(C.c_int)]
+        lib.refh_distance_matrix.restype = C.c_int
+        lib.refh_free.argtypes = [C.c_void_p]
+        lib.refh_free.restype = None
+        lib.refh_time_public_api.argtypes = [C.POINTER(C.c_char_p), i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]
+        lib.refh_time_public_api.restype = C.c_double
+        _refh = lib
+    return _refh
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def oracle_align(kind, len_a, len_b, subm, gpo, gpe, tgpe, soff=0.0, seq1=None, seq2=None,
+                 prof1=None, prof2=None, sip=0, bonus=None):
+    """returns (raw path [len_a+2], stats dict)"""
+    job = KoJob()
+    job.kind = kind
+    job.seq1 = _ptr(seq1); job.seq2 = _ptr(seq2)
+    job.prof1 = _ptr(prof1); job.prof2 = _ptr(prof2)
+    job.len_a = len_a; job.len_b = len_b; job.sip = sip
+    job.subm = _ptr(subm)
+    job.gpo = gpo; job.gpe = gpe; job.tgpe = tgpe; job.soff = soff
+    job.bonus = _ptr(bonus)
+    path = np.full(len_a + 2, -7, dtype=np.int32)
+    st = KoStats()
+    rc = oracle().ko_align(C.byref(job), path, C.byref(st))
+    assert rc == 0
+    return path, dict(cells=st.cells, margin_sum=st.margin_sum, margin_count=st.margin_count,
+                      top_score=st.top_score, n_boxes=st.n_boxes)
+
+
+def ref_align(kind, len_a, len_b, subm, gpo, gpe, tgpe, soff=0.0, seq1=None, seq2=None,
+              prof1=None, prof2=None, sip=0, bonus=None, score_only=False):
+    path = np.full(len_a + 2, -7, dtype=np.int32)
+    score = C.c_float(0); ms = C.c_float(0); mc = C.c_int(0)
+    rc = refh().refh_pair_align(kind, _ptr(seq1), _ptr(seq2), _ptr(prof1), _ptr(prof2),
+                                len_a, len_b, sip, np.ascontiguousarray(subm, dtype=np.float32),
+                                gpo, gpe, tgpe, soff, _ptr(bonus), int(score_only),
+                                path, C.byref(score), C.byref(ms), C.byref(mc))
+    assert rc == 0
+    return path, dict(score=score.value, margin_sum=ms.value, margin_count=mc.value)
+
+
+class RefRun:
+    """One run of the reference pipeline with access to its intermediate state."""
+
+    def __init__(self, seqs, n_threads=1, type_=8, gpo=-1.0, gpe=-1.0, tgpe=-1.0,
+                 consistency=0, weight=2.0, stop_after=0):
+        lib = refh()
+        n = len(seqs)
+        arr = (C.c_char_p * n)(*[s.encode() if isinstance(s, str) else s for s in seqs])
+        lens = np.array([len(s) for s in seqs], dtype=np.int32)
+        self._h = lib.refh_run_pipeline(arr, lens, n, n_threads, type_, gpo, gpe, tgpe,
+                                        consistency, weight, stop_after)
+        if not self._h:
+            raise RuntimeError("reference pipeline failed")
+        self.lib = lib
+        self.n = lib.refh_numseq(self._h)
+        self.rank = np.zeros(self.n, dtype=np.int32)
+        self.lens = np.zeros(self.n, dtype=np.int32)
+        lib.refh_get_order(self._h, self.rank, self.lens)
+
+    def times(self):
+        t = np.zeros(4, dtype=np.float64)
+        self.lib.refh_times(self._h, t)
+        return dict(dist_tree=t[0], anchor=t[1], tree_aln=t[2], total=t[3])
+
+    def codes(self, i):
+        out = np.zeros(int(self.lens[i]), dtype=np.uint8)
+        self.lib.refh_get_codes(self._h, i, out)
+        return out
+
+    def tasks(self):
+        out = np.zeros(3 * (self.n - 1), dtype=np.int32)
+        nt = self.lib.refh_get_tasks(self._h, out)
+        return out.reshape(-1, 3)[:nt].copy()
+
+    def task_confidence(self):
+        out = np.zeros(self.n - 1, dtype=np.float32)
+        self.lib.refh_get_task_confidence(self._h, out)
+        return out
+
+    def seq_distances(self):
+        out = np.zeros(self.n, dtype=np.float32)
+        self.lib.refh_get_seq_distances(self._h, out)
+        return out
+
+    def params(self):
+        subm = np.zeros(23 * 23, dtype=np.float32)
+        gp = np.zeros(4, dtype=np.float32)
+        self.lib.refh_get_params(self._h, subm, gp)
+        return subm.reshape(23, 23), gp
+
+    def biotype(self):
+        return self.lib.refh_biotype(self._h)
+
+    def anchor_ids(self):
+        out = np.zeros(64, dtype=np.int32)
+        k = self.lib.refh_get_anchor_ids(self._h, out)
+        return out[:k].copy()
+
+    def posmap(self, i, k):
+        out = np.zeros(int(self.lens[i]), dtype=np.int32)
+        assert self.lib.refh_get_posmap(self._h, i, k, out) == 0
+        return out
+
+    def gaps(self, i):
+        out = np.zeros(int(self.lens[i]) + 1, dtype=np.int32)
+        self.lib.refh_get_gaps(self._h, i, out)
+        return out
+
+    def aligned(self):
+        L = self.lib.refh_alnlen(self._h)
+        buf = C.create_string_buffer(self.n * (L + 1))
+        self.lib.refh_get_aligned(self._h, buf)
+        raw = buf.raw
+        return [raw[i * (L + 1): i * (L + 1) + L].decode() for i in range(self.n)]
+
+    def close(self):
+        if self._h:
+            self.lib.refh_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def ref_distance_matrix(seqs):
+    lib = refh()
+    n = len(seqs)
+    arr = (C.c_char_p * n)(*[s.encode() for s in seqs])
+    lens = np.array([len(s) for s in seqs], dtype=np.int32)
+    na = min(32, n)
+    dm = np.zeros(n * na, dtype=np.float32)
+    anchors = np.zeros(na, dtype=np.int32)
+    nout = C.c_int(0)
+    assert lib.refh_distance_matrix(arr, lens, n, dm, anchors, C.byref(nout)) == 0
+    return dm.reshape(n, na), anchors
