@@ -1,0 +1,138 @@
+/*
+ * kalign_b200.h -- C ABI of the B200-native kalign alignment hot path.
+ *
+ * Plain pointers and sizes only.  All entry points return KB200_OK (0) or KB200_FAIL (1), the
+ * reference's own convention (lib/src/tldevel.h:29-30); diagnostics go to stderr.  There is NO
+ * CPU fallback: without a usable CUDA device every compute entry point fails.
+ *
+ * The three "seam" entry points sit at exactly the granularity at which the reference's run
+ * wrapper (lib/src/aln_wrap.c:133-261) calls into its hot path:
+ *
+ *   kb200_distances      <->  d_estimation()              lib/src/sequence_distance.c:37
+ *                              (called from build_tree_kmeans, lib/src/bisectingKmeans.c:205,294)
+ *   kb200_anchor_posmaps <->  anchor_consistency_build()  lib/src/anchor_consistency.c:200
+ *                              (the serial N x K pairwise_align_map loop, :246-267)
+ *   kb200_align_tree     <->  create_msa_tree()           lib/src/aln_run.c:43
+ *                              (recursive_aln / do_align / aln_runner, the aln_task scheduler)
+ *
+ * kb200_pair_align_batch exposes the batched Hirschberg engine itself (aln_runner,
+ * lib/src/aln_controller.c:21) and kb200_kalign / kb200_msa_run mirror the public
+ * kalign() / kalign_run_seeded() of lib/include/kalign/kalign.h:45,51 on plain arrays.
+ *
+ * Index space: like the reference after msa_sort_len_name (lib/src/msa_sort.c:14) all per-sequence
+ * arrays below are in the caller's order; "seqs" is the concatenation of the internal residue
+ * codes (uint8, lib/src/alphabet.c) with offs[i] the start of sequence i.
+ */
+#ifndef KALIGN_B200_H
+#define KALIGN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KB200_OK 0
+#define KB200_FAIL 1
+
+/* same numeric values as lib/include/kalign/kalign.h:18-26 */
+#define KB200_TYPE_DNA 0
+#define KB200_TYPE_DNA_INTERNAL 1
+#define KB200_TYPE_RNA 2
+#define KB200_TYPE_PROTEIN 3
+#define KB200_TYPE_PROTEIN_DIVERGENT 4
+#define KB200_TYPE_PROTEIN_PFASUM43 5
+#define KB200_TYPE_PROTEIN_PFASUM60 6
+#define KB200_TYPE_PROTEIN_PFASUM_AUTO 7
+#define KB200_TYPE_UNDEFINED 8
+
+#define KB200_KIND_SS 0   /* sequence x sequence   (lib/src/aln_seqseq.c)         */
+#define KB200_KIND_SP 1   /* profile(rows) x seq   (lib/src/aln_seqprofile.c)     */
+#define KB200_KIND_PP 2   /* profile x profile     (lib/src/aln_profileprofile.c) */
+
+typedef struct kb200_ctx kb200_ctx;
+
+/* scoring parameters: struct aln_param of lib/src/aln_param.h:24-39, flattened */
+typedef struct kb200_params {
+        float subm[23 * 23];      /* row-major substitution matrix */
+        float gpo, gpe, tgpe;
+        float vsm_amax;           /* variable scoring matrix amax (aln_param.c:96) */
+        int   nalpha;             /* 5 (nucleotide codes) or 23 (protein codes) */
+} kb200_params;
+
+/* one pairwise job for kb200_pair_align_batch (HOST pointers) */
+typedef struct kb200_pair {
+        int kind;                 /* KB200_KIND_* */
+        const uint8_t* seq_rows;  /* SS: row residues */
+        const uint8_t* seq_cols;  /* SS, SP: column residues */
+        const float* prof_rows;   /* SP, PP: (len_a+2)*64 floats, gap terms [27..29] already set */
+        const float* prof_cols;   /* PP: (len_b+2)*64 floats */
+        int len_a;                /* DP rows */
+        int len_b;                /* DP cols */
+        int sip;                  /* SP: sequences in the row profile (aln_seqprofile.c:18) */
+        float soff;               /* SS: subm_offset (aln_seqseq.c:38) */
+        const float* bonus;       /* optional dense len_a*len_b consistency bonus, or NULL */
+        int* path_out;            /* raw path, len_a+2 ints (aln_controller.c:200-201) */
+        float* score_out;         /* optional: top-level meet-up score */
+} kb200_pair;
+
+/* statistics of the last engine call on a context */
+typedef struct kb200_stats {
+        double dp_cells;          /* sum over all sweeps of rows * (endb-startb)   */
+        double dp_seconds;        /* device time of the DP rounds (CUDA events) */
+        double sweep_seconds;     /* device time of the sweep kernels only */
+        long long n_boxes;        /* Hirschberg boxes processed */
+        long long n_launches;     /* kernels launched by the call */
+        double bpm_seconds;       /* device time of the bpm kernel */
+        double bpm_pairs;
+        double h2d_bytes, d2h_bytes;
+} kb200_stats;
+
+int  kb200_device_count(void);
+int  kb200_ctx_create(int device, kb200_ctx** out);
+void kb200_ctx_destroy(kb200_ctx* ctx);
+int  kb200_get_stats(kb200_ctx* ctx, kb200_stats* out);
+const char* kb200_version(void);
+
+/* default scoring parameters of aln_param_init (lib/src/aln_param.c:17-109).
+   biotype: 0 protein, 1 nucleotide (msa_struct.h:19-20); negative gpo/gpe/tgpe keep defaults. */
+int kb200_params_init(kb200_params* p, int biotype, int type, float gpo, float gpe, float tgpe);
+
+/* Batched Hirschberg alignments; every job is independent (aln_runner, aln_controller.c:21). */
+int kb200_pair_align_batch(kb200_ctx* ctx, const kb200_params* prm,
+                           const kb200_pair* jobs, int njobs);
+
+/* dm[r*ncols + c] = calc_distance(seq rows[r], seq cols[c]) + length term
+   (sequence_distance.c:117-123,153-162).  Codes must be < 13. */
+int kb200_distances(kb200_ctx* ctx, const uint8_t* seqs, const int64_t* offs, const int* lens,
+                    int nseq, const int* rows, int nrows, const int* cols, int ncols, float* dm);
+
+/* posmaps: concatenated over i of K maps of len_i ints: map (i,k) starts at
+   K*offs[i] + k*lens[i]  (anchor_consistency.c:246-267). Only pairs p in [pair_begin,pair_end)
+   of the flattened (i*K+k) list are computed (multi-GPU shard); others are left untouched. */
+int kb200_anchor_posmaps(kb200_ctx* ctx, const kb200_params* prm,
+                         const uint8_t* seqs, const int64_t* offs, const int* lens, int nseq,
+                         const int* anchor_ids, int K,
+                         long long pair_begin, long long pair_end, int* posmaps);
+
+/* Progressive alignment over a guide tree (create_msa_tree, aln_run.c:43).
+   tasks_abc: ntasks x 3 (a, b, c) sorted by c (task.c:151-161); seq_distances: nseq floats
+   (bisectingKmeans.c:247-256) or NULL; posmaps/K/weight: consistency table or NULL/0.
+   gaps_out: concatenated gaps[] of every sequence (len_i+1 ints each, at offs[i]+i). */
+int kb200_align_tree(kb200_ctx* ctx, const kb200_params* prm,
+                     const uint8_t* seqs, const int64_t* offs, const int* lens, int nseq,
+                     const int* tasks_abc, int ntasks, const float* seq_distances,
+                     const int* posmaps, int K, float weight,
+                     int* gaps_out);
+
+/* kalign() of lib/include/kalign/kalign.h:45 on the GPU: same arguments, same ownership
+   (rows and the array are malloc'd; caller frees).  consistency_anchors = 0 reproduces
+   kalign()/kalign_run(); 5 with weight 2.0 reproduces the CLI default mode. */
+int kb200_kalign(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_threads, int type,
+                 float gpo, float gpe, float tgpe, int consistency_anchors, float consistency_weight,
+                 char*** aligned, int* out_aln_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,155 @@
+"""ctypes binding of the product C-ABI (include/kalign_b200.h -> kalign_b200/libkalign_b200.so).
+
+The extension is the ONLY implementation: if it is missing or no CUDA device is usable every call
+raises -- there is no CPU fallback."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(HERE, "libkalign_b200.so")
+
+KIND_SS, KIND_SP, KIND_PP = 0, 1, 2
+
+f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+i64p = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+
+
+class Params(C.Structure):
+    _fields_ = [("subm", C.c_float * (23 * 23)),
+                ("gpo", C.c_float), ("gpe", C.c_float), ("tgpe", C.c_float),
+                ("vsm_amax", C.c_float), ("nalpha", C.c_int)]
+
+
+class Pair(C.Structure):
+    _fields_ = [("kind", C.c_int),
+                ("seq_rows", C.c_void_p), ("seq_cols", C.c_void_p),
+                ("prof_rows", C.c_void_p), ("prof_cols", C.c_void_p),
+                ("len_a", C.c_int), ("len_b", C.c_int), ("sip", C.c_int), ("soff", C.c_float),
+                ("bonus", C.c_void_p), ("path_out", C.c_void_p), ("score_out", C.c_void_p)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("dp_cells", C.c_double), ("dp_seconds", C.c_double), ("sweep_seconds", C.c_double),
+                ("n_boxes", C.c_longlong), ("n_launches", C.c_longlong),
+                ("bpm_seconds", C.c_double), ("bpm_pairs", C.c_double),
+                ("h2d_bytes", C.c_double), ("d2h_bytes", C.c_double)]
+
+
+# every symbol include/kalign_b200.h declares
+EXPORTS = ["kb200_device_count", "kb200_ctx_create", "kb200_ctx_destroy", "kb200_get_stats",
+           "kb200_version", "kb200_params_init", "kb200_pair_align_batch", "kb200_distances",
+           "kb200_anchor_posmaps", "kb200_align_tree", "kb200_kalign"]
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise RuntimeError("kalign_b200: %s is missing (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                           "there is no CPU fallback" % SO_PATH)
+    lib = C.CDLL(SO_PATH)
+    lib.kb200_device_count.restype = C.c_int
+    lib.kb200_version.restype = C.c_char_p
+    lib.kb200_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.kb200_ctx_create.restype = C.c_int
+    lib.kb200_ctx_destroy.argtypes = [C.c_void_p]
+    lib.kb200_ctx_destroy.restype = None
+    lib.kb200_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+    lib.kb200_get_stats.restype = C.c_int
+    lib.kb200_params_init.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.c_float, C.c_float, C.c_float]
+    lib.kb200_params_init.restype = C.c_int
+    lib.kb200_pair_align_batch.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Pair), C.c_int]
+    lib.kb200_pair_align_batch.restype = C.c_int
+    lib.kb200_distances.argtypes = [C.c_void_p, u8p, i64p, i32p, C.c_int, i32p, C.c_int, i32p, C.c_int, f32p]
+    lib.kb200_distances.restype = C.c_int
+    lib.kb200_anchor_posmaps.argtypes = [C.c_void_p, C.POINTER(Params), u8p, i64p, i32p, C.c_int,
+                                         i32p, C.c_int, C.c_longlong, C.c_longlong, i32p]
+    lib.kb200_anchor_posmaps.restype = C.c_int
+    lib.kb200_align_tree.argtypes = [C.c_void_p, C.POINTER(Params), u8p, i64p, i32p, C.c_int,
+                                     i32p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float, i32p]
+    lib.kb200_align_tree.restype = C.c_int
+    lib.kb200_kalign.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), i32p, C.c_int, C.c_int, C.c_int,
+                                 C.c_float, C.c_float, C.c_float, C.c_int, C.c_float,
+                                 C.POINTER(C.POINTER(C.c_char_p)), C.POINTER(C.c_int)]
+    lib.kb200_kalign.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def make_params(biotype, type_=8, gpo=-1.0, gpe=-1.0, tgpe=-1.0):
+    p = Params()
+    if load().kb200_params_init(C.byref(p), biotype, type_, gpo, gpe, tgpe) != 0:
+        raise RuntimeError("kb200_params_init failed")
+    return p
+
+
+def params_from(subm, gpo, gpe, tgpe, nalpha=23, vsm_amax=0.0):
+    p = Params()
+    flat = np.ascontiguousarray(subm, dtype=np.float32).reshape(-1)
+    for i in range(23 * 23):
+        p.subm[i] = float(flat[i])
+    p.gpo, p.gpe, p.tgpe = float(gpo), float(gpe), float(tgpe)
+    p.nalpha = nalpha
+    p.vsm_amax = vsm_amax
+    return p
+
+
+class Context:
+    def __init__(self, device=0):
+        self.lib = load()
+        h = C.c_void_p()
+        if self.lib.kb200_ctx_create(device, C.byref(h)) != 0:
+            raise RuntimeError("kalign_b200: no usable CUDA device %d (no CPU fallback)" % device)
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.lib.kb200_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def stats(self):
+        s = Stats()
+        self.lib.kb200_get_stats(self.h, C.byref(s))
+        return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+    def pair_align_batch(self, prm, jobs):
+        """jobs: list of dicts(kind, len_a, len_b, seq_rows, seq_cols, prof_rows, prof_cols, sip, soff, bonus).
+        returns (list of raw paths, np.array of top scores)"""
+        n = len(jobs)
+        arr = (Pair * n)()
+        paths, keep = [], []
+        scores = np.zeros(n, dtype=np.float32)
+        for i, j in enumerate(jobs):
+            p = arr[i]
+            p.kind = j["kind"]
+            for name in ("seq_rows", "seq_cols", "prof_rows", "prof_cols", "bonus"):
+                a = j.get(name)
+                if a is not None:
+                    a = np.ascontiguousarray(a)
+                    keep.append(a)
+                    setattr(p, name, a.ctypes.data)
+            p.len_a = j["len_a"]
+            p.len_b = j["len_b"]
+            p.sip = j.get("sip", 0)
+            p.soff = j.get("soff", 0.0)
+            path = np.full(j["len_a"] + 2, -7, dtype=np.int32)
+            paths.append(path)
+            p.path_out = path.ctypes.data
+            p.score_out = scores.ctypes.data + 4 * i
+        rc = self.lib.kb200_pair_align_batch(self.h, C.byref(prm), arr, n)
+        if rc != 0:
+            raise RuntimeError("kb200_pair_align_batch failed")
+        return paths, scores

@@ -1,0 +1,116 @@
+// kb_common.cuh -- shared device/host structures of the B200 Hirschberg engine.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <float.h>
+#include <vector>
+
+#include "../../include/kalign_b200.h"
+
+#define KB_NEGF (-FLT_MAX)
+
+#define KB_CUDA(call)                                                                          \
+        do {                                                                                   \
+                cudaError_t e__ = (call);                                                      \
+                if (e__ != cudaSuccess) {                                                      \
+                        fprintf(stderr, "[kalign_b200] CUDA error %s at %s:%d: %s\n",         \
+                                cudaGetErrorName(e__), __FILE__, __LINE__, cudaGetErrorString(e__)); \
+                        return KB200_FAIL;                                                     \
+                }                                                                              \
+        } while (0)
+
+#define KB_RUN(call)                                                                           \
+        do {                                                                                   \
+                if ((call) != KB200_OK) {                                                      \
+                        fprintf(stderr, "[kalign_b200] failure at %s:%d\n", __FILE__, __LINE__); \
+                        return KB200_FAIL;                                                     \
+                }                                                                              \
+        } while (0)
+
+// One pairwise alignment ("struct aln_mem" of lib/src/aln_struct.h:16-59, device-resident).
+struct KbJob {
+        const uint8_t* seq_r;   // SS: row residues
+        const uint8_t* seq_c;   // SS, SP: column residues
+        const float* prof_r;    // SP, PP: row profile  (len_a+2)*64
+        const float* prof_c;    // PP: column profile   (len_b+2)*64
+        int len_a;              // DP rows
+        int len_b;              // DP cols
+        int kind;               // KB200_KIND_*
+        int nalpha;             // PP: residues that can have non-zero counts (5 / 23)
+        float o, e, t;          // SS: -gpo,-gpe,-tgpe; SP: -(gpo*sip), -(gpe*sip), -(tgpe*sip)
+        float nsoff;            // SS: -subm_offset
+        int* path;              // raw path, len_a+2
+        float4* rowF;           // final forward rows of the job's boxes, (len_a+len_b+2) entries
+        float4* rowB;           // final backward rows
+        const float* bonus;     // dense bonus (flat i*len_b + j) or nullptr
+        const int* bkey;        // sparse bonus: sorted flat keys (i*len_b + j) ...
+        const float* bval;      // ... and values; nb entries
+        int nb;
+        float* score;           // optional: top-level meet-up score
+};
+
+// One Hirschberg box = one (forward sweep, backward sweep, meet-up) triple
+// (aln_runner / aln_continue, lib/src/aln_controller.c:21,194).
+struct __align__(16) KbBox {
+        int job;
+        int sa, ea, sb, eb;
+        float f0a, f0ga, f0gb;  // injected forward boundary state  (m->f[0])
+        float b0a, b0ga, b0gb;  // injected backward boundary state (m->b[0])
+        int depth;
+};
+
+// growable device buffer
+struct KbDevBuf {
+        void* p = nullptr;
+        size_t cap = 0;
+        int ensure(size_t bytes)
+        {
+                if (bytes <= cap) {
+                        return KB200_OK;
+                }
+                if (p) {
+                        cudaFree(p);
+                        p = nullptr;
+                        cap = 0;
+                }
+                size_t want = bytes + bytes / 8 + 256;
+                cudaError_t e = cudaMalloc(&p, want);
+                if (e != cudaSuccess) {
+                        fprintf(stderr, "[kalign_b200] cudaMalloc(%zu) failed: %s\n", want, cudaGetErrorString(e));
+                        return KB200_FAIL;
+                }
+                cap = want;
+                return KB200_OK;
+        }
+        void release()
+        {
+                if (p) {
+                        cudaFree(p);
+                }
+                p = nullptr;
+                cap = 0;
+        }
+        template <typename T> T* as() const { return (T*)p; }
+};
+
+struct kb200_ctx {
+        int device = 0;
+        int sm_count = 148;
+        cudaStream_t stream = nullptr;
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+        kb200_stats stats;
+        // engine scratch
+        KbDevBuf d_jobs, d_boxA, d_boxB, d_counters, d_rows, d_tbl;
+        // staging for the host-pointer entry points
+        KbDevBuf d_stage0, d_stage1, d_stage2, d_stage3, d_stage4, d_stage5;
+};
+
+// DP engine (kb_dp.cu): run all jobs (device-resident descriptors are built from `jobs`, whose
+// pointers are device pointers; rowF/rowB are assigned here).  subm: 23*23 floats (host).
+int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>& jobs);
+
+// bpm (kb_bpm.cu)
+int kb_bpm_pairs(kb200_ctx* ctx, const uint8_t* d_seqs, const int64_t* d_offs, const int* d_lens,
+                 const int* d_rows, int nrows, const int* d_cols, int ncols, float* d_dm);
