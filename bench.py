@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py -- DP cells/s of the kalign alignment hot path on B200 (BASELINE.json metric).
+
+A "step" is one pass of the DP stages of a multiple alignment -- the anchor-consistency batch
+(N x K seq-seq Hirschberg alignments) plus the progressive alignment over the guide tree
+(kb200_msa_align == anchor_consistency_build + create_msa_tree of the reference,
+lib/src/aln_wrap.c:208-226) -- on one batch of synthetic sequences (kalign_b200/synth.py).
+
+  value : DP cells / device-timed span of the step with the sequences already resident in HBM
+          (CUDA events on the engine's stream; max over ranks for N>1)
+  e2e   : DP cells / wall time of the public call kb200_kalign (host strings in, aligned host
+          strings out: encode, H2D, distances, guide tree, DP stages, D2H, finalise)
+  roofline : the sweep kernel (kb_sweep_kernel), algorithmic bytes (25 B per ss/sp
+          cell, 128 B per pp cell, +4 B per cell that reads a consistency bonus) / its device time,
+          against MEASURED_PEAKS.json's HBM copy bandwidth
+  cpu_baseline : the unmodified reference (oracle/_ref) on a bounded sample of the same workload
+  --impl reference : the reference's own DP stages (anchor_consistency_build + create_msa_tree
+          timed inside its unmodified kalign_run_seeded call sequence, all host threads)
+
+Cells are counted once by the GPU engine (paths are bit-identical, so the box recursion and the
+cell count are identical for both arms)."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+from kalign_b200 import synth  # noqa: E402
+
+METRIC = "dp_cells_per_sec"
+UNIT = "cells/s"
+
+# workload name -> (synth config, kalign type, consistency anchors, label)
+WORKLOADS = {
+    "C2": ("C2", 8, 5, "1000 protein x ~400 aa, default mode (consistency K=5)"),
+    "C3": ("C3", 2, 5, "10000 16S-like RNA x ~1500 nt, --type rna, default mode (consistency K=5)"),
+    "C4": ("C4", 8, 0, "100000 protein x ~300 aa, --fast"),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)", d
+    return 6650.0, "fallback (B200_PROFILING.md)", {}
+
+
+class ClockSampler:
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append(line.strip())
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for name, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def algorithmic_bytes(st):
+    return 25.0 * (st["cells_ss"] + st["cells_sp"]) + 128.0 * st["cells_pp"] + 4.0 * st["cells_bonus"]
+
+
+def delta(a, b):
+    return {k: b[k] - a[k] for k in b}
+
+
+def ref_sample(wl, n_sample, n_threads):
+    """the unmodified reference on a bounded sample of the workload; returns timings"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import kbind
+    cfg, type_, K, _ = WORKLOADS[wl]
+    seqs = synth.config(cfg, n=n_sample)
+    run = kbind.RefRun(seqs, n_threads=n_threads, type_=type_, consistency=K, weight=2.0)
+    t = run.times()
+    rows = run.aligned()
+    run.close()
+    return seqs, t, rows
+
+
+def count_cells_gpu(seqs, type_, K):
+    from kalign_b200 import _lib
+    ctx = _lib.Context(int(os.environ.get("LOCAL_RANK", "0")))
+    m = _lib.Msa(ctx, seqs, n_threads=max(1, (os.cpu_count() or 2) - 1), type_=type_, consistency=K, weight=2.0)
+    s0 = ctx.stats()
+    m.align()
+    s1 = ctx.stats()
+    rows = m.result()
+    m.close()
+    ctx.close()
+    return s1["dp_cells"] - s0["dp_cells"], rows
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("KB200_WORKLOAD", "C3"), choices=sorted(WORKLOADS))
+    ap.add_argument("--n", type=int, default=None, help="override the number of sequences")
+    ap.add_argument("--ref-sample", type=int, default=None, help="sequences in the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg, type_, K, label = WORKLOADS[args.workload]
+    host_threads = max(1, (os.cpu_count() or 2))
+    default_sample = {"C2": 400, "C3": 160, "C4": 4000}[args.workload]
+    n_sample = args.ref_sample or default_sample
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        # bounded sample of the same workload, every step re-runs it
+        times = []
+        seqs = None
+        for it in range(args.warmup + args.steps):
+            seqs, t, rows = ref_sample(args.workload, n_sample, host_threads)
+            if it >= args.warmup:
+                times.append(t["anchor"] + t["tree_aln"])
+        cells, gpu_rows = count_cells_gpu(seqs, type_, K)
+        identical = (gpu_rows == rows)
+        T = float(np.mean(times)) if times else float("nan")
+        v = cells / T
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * T, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "%s sample: first %d sequences of %s" % (args.workload, n_sample, label),
+                           "timed": "anchor_consistency_build + create_msa_tree inside the reference's own call sequence"},
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": host_threads, "kind": "reference",
+                                 "sample": "%d sequences of %s, %d OpenMP threads (the anchor phase is serial in the reference)" % (n_sample, args.workload, host_threads)},
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "cells_per_step": cells, "cells_counted_by": "gpu engine, untimed (bit-identical paths)",
+                "msa_identical_to_gpu": identical}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    from kalign_b200 import _lib
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = _lib.Context(local_rank)
+    seqs = synth.config(cfg, n=args.n)
+    nseq = len(seqs)
+    # N>1: weak scaling -- every rank aligns its own family of the same shape (independent
+    # objects, no data-path collective); value = cells of all ranks / max time over ranks
+    if world > 1:
+        N, L, alphabet, seed, sub, indel = synth.CONFIGS[cfg]
+        seqs = synth.family(args.n or N, L, alphabet, seed + 1000 * rank, sub, indel, indel)
+    t0 = time.perf_counter()
+    m = _lib.Msa(ctx, seqs, n_threads=host_threads, type_=type_, consistency=K, weight=2.0)
+    t_create = time.perf_counter() - t0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        m.align()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    s0 = ctx.stats()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        m.align()
+    barrier()
+    w1 = time.perf_counter()
+    s1 = ctx.stats()
+    clocks = sampler.stop()
+    d = delta(s0, s1)
+    t_dev = d["align_seconds"]
+    cells = d["dp_cells"]
+    if world > 1:
+        tt = torch.tensor([t_dev, cells], dtype=torch.float64, device="cuda")
+        tmax = tt.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = tt.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        t_dev = float(tmax[0])
+        cells = float(tsum[1])
+    value = cells / t_dev
+    # ---- e2e through the public call, host buffers in / out
+    e2e = None
+    if rank == 0 or world > 1:
+        e_times = []
+        se0 = ctx.stats()
+        n_e2e = max(1, min(2, args.steps))
+        for it in range(1 + n_e2e):
+            if it == 1:
+                se0 = ctx.stats()
+            a = time.perf_counter()
+            rows = ctx.kalign(seqs, n_threads=host_threads, type_=type_, consistency=K, weight=2.0)
+            b = time.perf_counter()
+            if it >= 1:
+                e_times.append(b - a)
+        se1 = ctx.stats()
+        de = delta(se0, se1)
+        te = float(np.mean(e_times))
+        e_cells = de["dp_cells"] / n_e2e
+        if world > 1:
+            tt = torch.tensor([te, e_cells], dtype=torch.float64, device="cuda")
+            tmax = tt.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            tsum = tt.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+            te, e_cells = float(tmax[0]), float(tsum[1])
+        e2e = {"value": e_cells / te, "unit": UNIT, "seconds_per_call": te,
+               "h2d_bytes_per_step": de["h2d_bytes"] / n_e2e, "d2h_bytes_per_step": de["d2h_bytes"] / n_e2e,
+               "includes": "encode, H2D, bpm distances, host guide tree, DP stages, D2H, finalise"}
+        ok = all(r.replace("-", "") == s for r, s in zip(rows, seqs))
+        e2e["residues_preserved"] = bool(ok)
+    peak, peak_src, _ = peaks()
+    abytes = algorithmic_bytes(d)
+    ach = abytes / d["sweep_seconds"] / 1e9 if d["sweep_seconds"] > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "kb_sweep_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_step": abytes / max(1, args.steps),
+                "kernel_seconds_per_step": d["sweep_seconds"] / max(1, args.steps),
+                "kernel_share_of_step": d["sweep_seconds"] / d["align_seconds"] if d["align_seconds"] > 0 else None,
+                "cells_per_sec_in_kernel": d["dp_cells"] / d["sweep_seconds"] if d["sweep_seconds"] > 0 else None}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / max(1, args.steps), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%s: %s" % (args.workload, label), "nseq_per_gpu": len(seqs),
+                       "l2": "inputs larger than L2 (row buffers + work lists are GBs; no flush needed)",
+                       "step": "kb200_msa_align = anchor batch + progressive alignment, sequences resident in HBM"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(d["n_launches"]),
+            "roofline": roofline,
+            "cells_per_step": cells / max(1, args.steps),
+            "cells_by_kind": {"ss": d["cells_ss"], "sp": d["cells_sp"], "pp": d["cells_pp"], "with_bonus": d["cells_bonus"]},
+            "wall_s_timed_region": w1 - w0, "create_seconds": t_create,
+            "dp_round_seconds_per_step": d["dp_seconds"] / max(1, args.steps)}
+    # ---- CPU baseline beside it (rank 0, N=1 only)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            sseqs, t, ref_rows = ref_sample(args.workload, n_sample, host_threads)
+            scells, gpu_rows = count_cells_gpu(sseqs, type_, K)
+            T = t["anchor"] + t["tree_aln"]
+            line["cpu_baseline"] = {"value": scells / T, "unit": UNIT, "cores": host_threads, "kind": "reference",
+                                    "sample": "first %d sequences of %s; anchor_consistency_build %.2fs (serial in the reference) + create_msa_tree %.2fs on %d threads" % (n_sample, args.workload, t["anchor"], t["tree_aln"], host_threads),
+                                    "msa_identical_to_gpu": gpu_rows == ref_rows}
+        except Exception as e:  # noqa: BLE001
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": host_threads, "kind": "reference",
+                                    "sample": "failed: %r" % (e,)}
+    m.close()
+    ctx.close()
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -86,6 +86,9 @@ typedef struct kb200_stats {
         double bpm_seconds;       /* device time of the bpm kernel */
         double bpm_pairs;
         double h2d_bytes, d2h_bytes;
+        double cells_ss, cells_sp, cells_pp;   /* dp_cells split by kernel kind */
+        double cells_bonus;       /* cells that also read the consistency bonus */
+        double align_seconds;     /* device-timed span of kb200_msa_align calls (CUDA events) */
 } kb200_stats;
 
 int  kb200_device_count(void);
@@ -131,6 +134,23 @@ int kb200_align_tree(kb200_ctx* ctx, const kb200_params* prm,
 int kb200_kalign(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_threads, int type,
                  float gpo, float gpe, float tgpe, int consistency_anchors, float consistency_weight,
                  char*** aligned, int* out_aln_len);
+
+/* The same pipeline in stages, so that the DP stages can be run (and timed) on sequences that
+   are already resident in HBM:
+     kb200_msa_create : everything of kalign_run_seeded that precedes the DP stages
+                        (aln_wrap.c:144-205: check, sort, encode, upload, distances, guide tree,
+                         parameters, anchor selection)
+     kb200_msa_align  : anchor_consistency_build + create_msa_tree (aln_wrap.c:208-226), repeatable
+     kb200_msa_result : finalise_alignment + msa_sort_rank + kalign_msa_to_arr (aln_wrap.c:240-242)
+   The input strings must stay alive until kb200_msa_free. */
+typedef struct kb200_msa kb200_msa;
+int  kb200_msa_create(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_threads, int type,
+                      float gpo, float gpe, float tgpe, int consistency_anchors, float consistency_weight,
+                      kb200_msa** out);
+int  kb200_msa_align(kb200_msa* m);
+int  kb200_msa_result(kb200_msa* m, char*** aligned, int* out_aln_len);
+int  kb200_msa_info(kb200_msa* m, int* numseq, int* biotype, int* n_anchors);
+void kb200_msa_free(kb200_msa* m);
 
 #ifdef __cplusplus
 }

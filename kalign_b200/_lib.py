@@ -36,13 +36,16 @@ class Stats(C.Structure):
     _fields_ = [("dp_cells", C.c_double), ("dp_seconds", C.c_double), ("sweep_seconds", C.c_double),
                 ("n_boxes", C.c_longlong), ("n_launches", C.c_longlong),
                 ("bpm_seconds", C.c_double), ("bpm_pairs", C.c_double),
-                ("h2d_bytes", C.c_double), ("d2h_bytes", C.c_double)]
+                ("h2d_bytes", C.c_double), ("d2h_bytes", C.c_double),
+                ("cells_ss", C.c_double), ("cells_sp", C.c_double), ("cells_pp", C.c_double),
+                ("cells_bonus", C.c_double), ("align_seconds", C.c_double)]
 
 
 # every symbol include/kalign_b200.h declares
 EXPORTS = ["kb200_device_count", "kb200_ctx_create", "kb200_ctx_destroy", "kb200_get_stats",
            "kb200_version", "kb200_params_init", "kb200_pair_align_batch", "kb200_distances",
-           "kb200_anchor_posmaps", "kb200_align_tree", "kb200_kalign"]
+           "kb200_anchor_posmaps", "kb200_align_tree", "kb200_kalign",
+           "kb200_msa_create", "kb200_msa_align", "kb200_msa_result", "kb200_msa_info", "kb200_msa_free"]
 
 _lib = None
 
@@ -77,8 +80,19 @@ def load():
     lib.kb200_align_tree.restype = C.c_int
     lib.kb200_kalign.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), i32p, C.c_int, C.c_int, C.c_int,
                                  C.c_float, C.c_float, C.c_float, C.c_int, C.c_float,
-                                 C.POINTER(C.POINTER(C.c_char_p)), C.POINTER(C.c_int)]
+                                 C.POINTER(C.POINTER(C.c_void_p)), C.POINTER(C.c_int)]
     lib.kb200_kalign.restype = C.c_int
+    lib.kb200_msa_create.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), i32p, C.c_int, C.c_int, C.c_int,
+                                     C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.POINTER(C.c_void_p)]
+    lib.kb200_msa_create.restype = C.c_int
+    lib.kb200_msa_align.argtypes = [C.c_void_p]
+    lib.kb200_msa_align.restype = C.c_int
+    lib.kb200_msa_result.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_void_p)), C.POINTER(C.c_int)]
+    lib.kb200_msa_result.restype = C.c_int
+    lib.kb200_msa_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.kb200_msa_info.restype = C.c_int
+    lib.kb200_msa_free.argtypes = [C.c_void_p]
+    lib.kb200_msa_free.restype = None
     _lib = lib
     return lib
 
@@ -153,3 +167,129 @@ class Context:
         if rc != 0:
             raise RuntimeError("kb200_pair_align_batch failed")
         return paths, scores
+
+
+def pack(seqs_codes):
+    """list of uint8 arrays -> (concatenated codes, offs int64, lens int32)"""
+    lens = np.array([len(s) for s in seqs_codes], dtype=np.int32)
+    offs = np.zeros(len(seqs_codes), dtype=np.int64)
+    if len(seqs_codes) > 1:
+        offs[1:] = np.cumsum(lens[:-1], dtype=np.int64)
+    flat = np.concatenate([np.asarray(s, dtype=np.uint8) for s in seqs_codes]) if len(seqs_codes) else np.zeros(0, np.uint8)
+    return np.ascontiguousarray(flat), offs, lens
+
+
+def _distances(self, flat, offs, lens, rows, cols):
+    rows = np.ascontiguousarray(rows, dtype=np.int32)
+    cols = np.ascontiguousarray(cols, dtype=np.int32)
+    dm = np.zeros(len(rows) * len(cols), dtype=np.float32)
+    if self.lib.kb200_distances(self.h, flat, offs, lens, len(lens), rows, len(rows), cols, len(cols), dm) != 0:
+        raise RuntimeError("kb200_distances failed")
+    return dm.reshape(len(rows), len(cols))
+
+
+def _anchor_posmaps(self, prm, flat, offs, lens, anchor_ids, begin=0, end=None, out=None):
+    anchor_ids = np.ascontiguousarray(anchor_ids, dtype=np.int32)
+    K = len(anchor_ids)
+    n = len(lens)
+    if end is None:
+        end = n * K
+    if out is None:
+        out = np.full(int(lens.sum()) * K, -9, dtype=np.int32)
+    if self.lib.kb200_anchor_posmaps(self.h, C.byref(prm), flat, offs, lens, n, anchor_ids, K, begin, end, out) != 0:
+        raise RuntimeError("kb200_anchor_posmaps failed")
+    return out
+
+
+def posmap_view(posmaps, offs, lens, K, i, k):
+    o = K * int(offs[i]) + k * int(lens[i])
+    return posmaps[o:o + int(lens[i])]
+
+
+def _align_tree(self, prm, flat, offs, lens, tasks, seq_distances=None, posmaps=None, K=0, weight=2.0):
+    tasks = np.ascontiguousarray(tasks, dtype=np.int32).reshape(-1)
+    n = len(lens)
+    gaps = np.zeros(int(lens.sum()) + n, dtype=np.int32)
+    sd = None if seq_distances is None else np.ascontiguousarray(seq_distances, dtype=np.float32)
+    pm = None if posmaps is None else np.ascontiguousarray(posmaps, dtype=np.int32)
+    rc = self.lib.kb200_align_tree(self.h, C.byref(prm), flat, offs, lens, n, tasks, len(tasks) // 3,
+                                   None if sd is None else sd.ctypes.data,
+                                   None if pm is None else pm.ctypes.data, K, weight, gaps)
+    if rc != 0:
+        raise RuntimeError("kb200_align_tree failed")
+    return [gaps[int(offs[i]) + i: int(offs[i]) + i + int(lens[i]) + 1] for i in range(n)]
+
+
+def _kalign(self, seqs, n_threads=1, type_=8, gpo=-1.0, gpe=-1.0, tgpe=-1.0, consistency=0, weight=2.0):
+    n = len(seqs)
+    keep = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
+    arr = (C.c_char_p * n)(*keep)
+    lens = np.array([len(s) for s in keep], dtype=np.int32)
+    out = C.POINTER(C.c_void_p)()
+    alen = C.c_int(0)
+    rc = self.lib.kb200_kalign(self.h, arr, lens, n, n_threads, type_, gpo, gpe, tgpe, consistency, weight,
+                               C.byref(out), C.byref(alen))
+    if rc != 0:
+        raise RuntimeError("kb200_kalign failed")
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    nrows = int((lens > 0).sum())
+    rows = []
+    for i in range(nrows):
+        rows.append(C.string_at(out[i], alen.value).decode())
+        libc.free(out[i])
+    libc.free(C.cast(out, C.c_void_p))
+    return rows
+
+
+Context.distances = _distances
+Context.anchor_posmaps = _anchor_posmaps
+Context.align_tree = _align_tree
+Context.kalign = _kalign
+
+
+class Msa:
+    """staged pipeline (kb200_msa_*): create -> align (repeatable, device-resident inputs) -> result"""
+
+    def __init__(self, ctx, seqs, n_threads=1, type_=8, gpo=-1.0, gpe=-1.0, tgpe=-1.0, consistency=0, weight=2.0):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        n = len(seqs)
+        self._keep = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
+        self._arr = (C.c_char_p * n)(*self._keep)
+        self._lens = np.array([len(s) for s in self._keep], dtype=np.int32)
+        h = C.c_void_p()
+        if self.lib.kb200_msa_create(ctx.h, self._arr, self._lens, n, n_threads, type_, gpo, gpe, tgpe,
+                                     consistency, weight, C.byref(h)) != 0:
+            raise RuntimeError("kb200_msa_create failed")
+        self.h = h
+        self.nrows = int((self._lens > 0).sum())
+
+    def align(self):
+        if self.lib.kb200_msa_align(self.h) != 0:
+            raise RuntimeError("kb200_msa_align failed")
+
+    def result(self):
+        out = C.POINTER(C.c_void_p)()
+        alen = C.c_int(0)
+        if self.lib.kb200_msa_result(self.h, C.byref(out), C.byref(alen)) != 0:
+            raise RuntimeError("kb200_msa_result failed")
+        libc = C.CDLL(None)
+        libc.free.argtypes = [C.c_void_p]
+        rows = []
+        for i in range(self.nrows):
+            rows.append(C.string_at(out[i], alen.value).decode())
+            libc.free(out[i])
+        libc.free(C.cast(out, C.c_void_p))
+        return rows
+
+    def close(self):
+        if self.h:
+            self.lib.kb200_msa_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

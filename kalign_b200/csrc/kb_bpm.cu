@@ -25,11 +25,13 @@ kb_bpm_kernel(const uint8_t* __restrict__ seqs, const int64_t* __restrict__ offs
               const int* __restrict__ rows, const int nrows, const int* __restrict__ cols, const int ncols,
               float* __restrict__ dm)
 {
+        // ncols > 0: rectangular rows x cols matrix, pair = r*ncols + c  -> (rows[r], cols[c])
+        // ncols == 0: explicit pair list of nrows pairs             -> (rows[p], cols[p])
         __shared__ unsigned long long s_peq[(BPM_THREADS / LP) * 13 * LP];
         const int tid = threadIdx.x;
         const int grp = tid / LP;
         const int b = tid % LP;
-        const long long npairs = (long long)nrows * (long long)ncols;
+        const long long npairs = (ncols > 0) ? (long long)nrows * (long long)ncols : (long long)nrows;
         const long long pair = (long long)blockIdx.x * (BPM_THREADS / LP) + grp;
         const bool live = pair < npairs;
         unsigned long long* peq = s_peq + grp * 13 * LP;
@@ -37,9 +39,14 @@ kb_bpm_kernel(const uint8_t* __restrict__ seqs, const int64_t* __restrict__ offs
         const uint8_t* pt = seqs;
         int n = 0, m = 0, l1 = 0, l2 = 0;
         if (live) {
-                const int r = (int)(pair / ncols);
-                const int c = (int)(pair % ncols);
-                const int s1 = rows[r], s2 = cols[c];
+                int s1, s2;
+                if (ncols > 0) {
+                        s1 = rows[(int)(pair / ncols)];
+                        s2 = cols[(int)(pair % ncols)];
+                } else {
+                        s1 = rows[pair];
+                        s2 = cols[pair];
+                }
                 l1 = lens[s1];
                 l2 = lens[s2];
                 // calc_distance (sequence_distance.c:153-162): longer is the text; on equal
@@ -140,7 +147,7 @@ template <int LP>
 int launch(kb200_ctx* ctx, const uint8_t* d_seqs, const int64_t* d_offs, const int* d_lens,
            const int* d_rows, int nrows, const int* d_cols, int ncols, float* d_dm)
 {
-        const long long npairs = (long long)nrows * (long long)ncols;
+        const long long npairs = (ncols > 0) ? (long long)nrows * (long long)ncols : (long long)nrows;
         const int per = BPM_THREADS / LP;
         const long long grid = (npairs + per - 1) / per;
         if (grid > 0x7fffffffLL) {
@@ -158,7 +165,7 @@ int launch(kb200_ctx* ctx, const uint8_t* d_seqs, const int64_t* d_offs, const i
 int kb_bpm_pairs_words(kb200_ctx* ctx, int max_words, const uint8_t* d_seqs, const int64_t* d_offs, const int* d_lens,
                        const int* d_rows, int nrows, const int* d_cols, int ncols, float* d_dm)
 {
-        if (nrows <= 0 || ncols <= 0) {
+        if (nrows <= 0 || ncols < 0) {
                 return KB200_OK;
         }
         KB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -176,7 +183,7 @@ int kb_bpm_pairs_words(kb200_ctx* ctx, int max_words, const uint8_t* d_seqs, con
         float ms = 0.0f;
         cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
         ctx->stats.bpm_seconds += 1e-3 * (double)ms;
-        ctx->stats.bpm_pairs += (double)nrows * (double)ncols;
+        ctx->stats.bpm_pairs += (ncols > 0) ? (double)nrows * (double)ncols : (double)nrows;
         ctx->stats.n_launches += 1;
         return KB200_OK;
 }

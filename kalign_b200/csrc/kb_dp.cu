@@ -411,7 +411,11 @@ kb_meetup_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes
                         m.max2 = kmax(lose, w2);
                 }
                 if (lane == 0) {
-                        atomicAdd(cells, (unsigned long long)(ea - sa) * (unsigned long long)(eb - sb));
+                        const unsigned long long nc = (unsigned long long)(ea - sa) * (unsigned long long)(eb - sb);
+                        atomicAdd(cells + J.kind, nc);
+                        if (J.bonus) {
+                                atomicAdd(cells + 3, nc);
+                        }
                         if (bx.depth == 0 && J.score) {
                                 *J.score = m.max;
                         }
@@ -548,7 +552,7 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
                 KbBox* nxt = ctx->d_boxB.as<KbBox>();
                 unsigned int* d_cursor = ctx->d_counters.as<unsigned int>();
                 unsigned int* d_next = d_cursor + 1;
-                unsigned long long* d_cells = (unsigned long long*)(d_cursor + 2);
+                unsigned long long* d_cells = (unsigned long long*)(d_cursor + 2);   // [ss, sp, pp, bonus]
                 float sweep_ms = 0.0f;
                 KB_CUDA(cudaEventRecord(ctx->ev0, st));
                 while (count > 0) {
@@ -579,14 +583,18 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
                         std::swap(cur, nxt);
                 }
                 KB_CUDA(cudaEventRecord(ctx->ev1, st));
-                unsigned long long cells = 0;
-                KB_CUDA(cudaMemcpyAsync(&cells, d_cells, sizeof(cells), cudaMemcpyDeviceToHost, st));
+                unsigned long long cells[4] = {0, 0, 0, 0};
+                KB_CUDA(cudaMemcpyAsync(cells, d_cells, sizeof(cells), cudaMemcpyDeviceToHost, st));
                 KB_CUDA(cudaStreamSynchronize(st));
                 float ms = 0.0f;
                 cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
                 ctx->stats.dp_seconds += 1e-3 * (double)ms;
                 ctx->stats.sweep_seconds += 1e-3 * (double)sweep_ms;
-                ctx->stats.dp_cells += (double)cells;
+                ctx->stats.dp_cells += (double)cells[0] + (double)cells[1] + (double)cells[2];
+                ctx->stats.cells_ss += (double)cells[0];
+                ctx->stats.cells_sp += (double)cells[1];
+                ctx->stats.cells_pp += (double)cells[2];
+                ctx->stats.cells_bonus += (double)cells[3];
         }
         return KB200_OK;
 }

@@ -1,0 +1,251 @@
+// kb_host.cu -- host orchestration of the distance matrix and the anchor-consistency batch.
+//
+//   kb200_distances      <-> d_estimation             lib/src/sequence_distance.c:37
+//   kb200_anchor_posmaps <-> anchor_consistency_build lib/src/anchor_consistency.c:200
+//                            (pairwise_align_map :19, the serial N x K loop :246-267)
+#include "kb_host.cuh"
+
+#include <string.h>
+#include <algorithm>
+
+int KbSeqs::upload(kb200_ctx* ctx, const uint8_t* seqs, const int64_t* offs, const int* lens, int nseq)
+{
+        h_seqs = seqs;
+        h_offs = offs;
+        h_lens = lens;
+        n = nseq;
+        total = 0;
+        for (int i = 0; i < nseq; i++) {
+                total = std::max<int64_t>(total, offs[i] + lens[i]);
+        }
+        KB_RUN(d_seqs.ensure((size_t)total + 16));
+        KB_RUN(d_offs.ensure(sizeof(int64_t) * (size_t)nseq));
+        KB_RUN(d_lens.ensure(sizeof(int) * (size_t)nseq));
+        KB_CUDA(cudaMemcpyAsync(d_seqs.p, seqs, (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
+        KB_CUDA(cudaMemcpyAsync(d_offs.p, offs, sizeof(int64_t) * (size_t)nseq, cudaMemcpyHostToDevice, ctx->stream));
+        KB_CUDA(cudaMemcpyAsync(d_lens.p, lens, sizeof(int) * (size_t)nseq, cudaMemcpyHostToDevice, ctx->stream));
+        KB_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->stats.h2d_bytes += (double)total + 12.0 * nseq;
+        return KB200_OK;
+}
+
+float* KbArena::alloc_floats(size_t n)
+{
+        size_t bytes = (n * sizeof(float) + 255) & ~(size_t)255;
+        if (chunks.empty() || used + bytes > cap) {
+                size_t want = std::max(chunk_bytes, bytes);
+                void* p = nullptr;
+                if (cudaMalloc(&p, want) != cudaSuccess) {
+                        fprintf(stderr, "[kalign_b200] arena: cudaMalloc(%zu) failed\n", want);
+                        cudaGetLastError();
+                        return nullptr;
+                }
+                chunks.push_back(p);
+                cap = want;
+                used = 0;
+        }
+        float* r = (float*)((char*)chunks.back() + used);
+        used += bytes;
+        total_bytes += (double)bytes;
+        return r;
+}
+
+void KbArena::release()
+{
+        for (void* p : chunks) {
+                cudaFree(p);
+        }
+        chunks.clear();
+        used = cap = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+
+int kb_distances_dev(kb200_ctx* ctx, KbSeqs& S, const int* rows, int nrows, const int* cols, int ncols,
+                     int explicit_pairs, float* dm_host)
+{
+        if (nrows <= 0) {
+                return KB200_OK;
+        }
+        const size_t ncol_items = explicit_pairs ? (size_t)nrows : (size_t)ncols;
+        const size_t npairs = explicit_pairs ? (size_t)nrows : (size_t)nrows * (size_t)ncols;
+        if (npairs == 0) {
+                return KB200_OK;
+        }
+        // longest pattern any pair can have: min(longest row, longest col), capped at 1024
+        int maxr = 0, maxc = 0;
+        for (int i = 0; i < nrows; i++) {
+                maxr = std::max(maxr, S.h_lens[rows[i]]);
+        }
+        for (size_t i = 0; i < ncol_items; i++) {
+                maxc = std::max(maxc, S.h_lens[cols[i]]);
+        }
+        int m = std::min(std::min(maxr, maxc), 1024);
+        if (explicit_pairs) {
+                m = 0;
+                for (int i = 0; i < nrows; i++) {
+                        m = std::max(m, std::min(S.h_lens[rows[i]], S.h_lens[cols[i]]));
+                }
+                m = std::min(m, 1024);
+        }
+        const int words = std::max(1, (m + 63) / 64);
+        KB_RUN(ctx->d_stage4.ensure(sizeof(int) * ((size_t)nrows + ncol_items)));
+        KB_RUN(ctx->d_stage5.ensure(sizeof(float) * npairs));
+        int* d_rows = ctx->d_stage4.as<int>();
+        int* d_cols = d_rows + nrows;
+        KB_CUDA(cudaMemcpyAsync(d_rows, rows, sizeof(int) * (size_t)nrows, cudaMemcpyHostToDevice, ctx->stream));
+        KB_CUDA(cudaMemcpyAsync(d_cols, cols, sizeof(int) * ncol_items, cudaMemcpyHostToDevice, ctx->stream));
+        KB_RUN(kb_bpm_pairs_words(ctx, words, S.d_seqs.as<uint8_t>(), S.d_offs.as<int64_t>(), S.d_lens.as<int>(),
+                                  d_rows, nrows, d_cols, explicit_pairs ? 0 : ncols, ctx->d_stage5.as<float>()));
+        KB_CUDA(cudaMemcpyAsync(dm_host, ctx->d_stage5.p, sizeof(float) * npairs, cudaMemcpyDeviceToHost, ctx->stream));
+        KB_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->stats.d2h_bytes += (double)(sizeof(float) * npairs);
+        return KB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+
+int kb_anchor_posmaps_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S, const int* anchor_ids, int K,
+                          long long pair_begin, long long pair_end, int* posmaps)
+{
+        const int N = S.n;
+        if (pair_begin < 0) pair_begin = 0;
+        if (pair_end > (long long)N * K) pair_end = (long long)N * K;
+        if (pair_end <= pair_begin) {
+                return KB200_OK;
+        }
+        cudaStream_t st = ctx->stream;
+        auto map_off = [&](long long p) -> size_t {
+                const int i = (int)(p / K), k = (int)(p % K);
+                return (size_t)K * (size_t)S.h_offs[i] + (size_t)k * (size_t)S.h_lens[i];
+        };
+        const size_t out_begin = map_off(pair_begin);
+        size_t out_end;
+        {
+                const long long last = pair_end - 1;
+                out_end = map_off(last) + (size_t)S.h_lens[(int)(last / K)];
+        }
+        const size_t out_n = out_end - out_begin;
+        // sizes
+        size_t n_raw = 0, n_coded = 0, n_scr = 0;
+        std::vector<KbJob> jobs;
+        std::vector<KbPathJob> pjobs;
+        jobs.reserve((size_t)(pair_end - pair_begin));
+        pjobs.reserve((size_t)(pair_end - pair_begin));
+        for (long long p = pair_begin; p < pair_end; p++) {
+                const int i = (int)(p / K), k = (int)(p % K);
+                const int ak = anchor_ids[k];
+                if (i == ak) {
+                        continue;
+                }
+                const int li = S.h_lens[i], lj = S.h_lens[ak];
+                const int rows = (li <= lj) ? li : lj;      // anchor_consistency.c:47-63
+                n_raw += (size_t)rows + 2;
+                n_coded += (size_t)li + (size_t)lj + 2;
+                n_scr += (size_t)li + 2;
+        }
+        KB_RUN(ctx->d_stage0.ensure(sizeof(int) * (n_raw + 8)));
+        KB_RUN(ctx->d_stage1.ensure(sizeof(int) * (n_coded + 8)));
+        KB_RUN(ctx->d_stage2.ensure(sizeof(int) * (n_scr + 8)));
+        KB_RUN(ctx->d_stage3.ensure(sizeof(int) * (out_n + 8)));
+        int* d_raw = ctx->d_stage0.as<int>();
+        int* d_coded = ctx->d_stage1.as<int>();
+        int* d_scr = ctx->d_stage2.as<int>();
+        int* d_out = ctx->d_stage3.as<int>();
+        size_t o_raw = 0, o_coded = 0, o_scr = 0;
+        for (long long p = pair_begin; p < pair_end; p++) {
+                const int i = (int)(p / K), k = (int)(p % K);
+                const int ak = anchor_ids[k];
+                if (i == ak) {
+                        continue;
+                }
+                const int li = S.h_lens[i], lj = S.h_lens[ak];
+                const bool swapped = !(li <= lj);
+                KbJob j;
+                memset(&j, 0, sizeof(j));
+                j.kind = KB200_KIND_SS;
+                j.nalpha = prm->nalpha;
+                if (!swapped) {
+                        j.seq_r = S.dseq(i); j.len_a = li;
+                        j.seq_c = S.dseq(ak); j.len_b = lj;
+                } else {
+                        j.seq_r = S.dseq(ak); j.len_a = lj;
+                        j.seq_c = S.dseq(i); j.len_b = li;
+                }
+                // pairwise_align_map runs with the UNSCALED ap and subm_offset = 0
+                j.o = -prm->gpo; j.e = -prm->gpe; j.t = -prm->tgpe; j.nsoff = -0.0f;
+                j.path = d_raw + o_raw;
+                jobs.push_back(j);
+                KbPathJob pj;
+                pj.raw = d_raw + o_raw;
+                pj.coded = d_coded + o_coded;
+                pj.scratch = d_scr + o_scr;
+                pj.posmap = d_out + (map_off(p) - out_begin);
+                pj.len_a = li;
+                pj.len_b = lj;
+                pj.mirror = swapped ? 1 : 0;
+                pjobs.push_back(pj);
+                o_raw += (size_t)j.len_a + 2;
+                o_coded += (size_t)li + (size_t)lj + 2;
+                o_scr += (size_t)li + 2;
+        }
+        if (!jobs.empty()) {
+                KB_CUDA(cudaMemsetAsync(d_raw, 0xFF, sizeof(int) * n_raw, st));
+                KB_RUN(kb_run_hirschberg(ctx, prm->subm, jobs));
+                KB_RUN(ctx->d_stage4.ensure(sizeof(KbPathJob) * pjobs.size()));
+                KB_CUDA(cudaMemcpyAsync(ctx->d_stage4.p, pjobs.data(), sizeof(KbPathJob) * pjobs.size(), cudaMemcpyHostToDevice, st));
+                KB_RUN(kb_code_paths(ctx, ctx->d_stage4.as<KbPathJob>(), (int)pjobs.size()));
+        }
+        KB_CUDA(cudaMemcpyAsync(posmaps + out_begin, d_out, sizeof(int) * out_n, cudaMemcpyDeviceToHost, st));
+        KB_CUDA(cudaStreamSynchronize(st));
+        ctx->stats.d2h_bytes += (double)(sizeof(int) * out_n);
+        // identity maps for the anchors themselves (anchor_consistency.c:252-258)
+        for (long long p = pair_begin; p < pair_end; p++) {
+                const int i = (int)(p / K), k = (int)(p % K);
+                if (i == anchor_ids[k]) {
+                        int* m = posmaps + map_off(p);
+                        for (int q = 0; q < S.h_lens[i]; q++) {
+                                m[q] = q;
+                        }
+                }
+        }
+        return KB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int kb200_distances(kb200_ctx* ctx, const uint8_t* seqs, const int64_t* offs, const int* lens,
+                    int nseq, const int* rows, int nrows, const int* cols, int ncols, float* dm)
+{
+        if (!ctx || !seqs || !offs || !lens || !rows || !cols || !dm || nseq <= 0) {
+                return KB200_FAIL;
+        }
+        KB_CUDA(cudaSetDevice(ctx->device));
+        KbSeqs S;
+        int rc = S.upload(ctx, seqs, offs, lens, nseq);
+        if (rc == KB200_OK) {
+                rc = kb_distances_dev(ctx, S, rows, nrows, cols, ncols, 0, dm);
+        }
+        S.release();
+        return rc;
+}
+
+int kb200_anchor_posmaps(kb200_ctx* ctx, const kb200_params* prm,
+                         const uint8_t* seqs, const int64_t* offs, const int* lens, int nseq,
+                         const int* anchor_ids, int K, long long pair_begin, long long pair_end, int* posmaps)
+{
+        if (!ctx || !prm || !seqs || !offs || !lens || !anchor_ids || !posmaps || nseq <= 0 || K <= 0) {
+                return KB200_FAIL;
+        }
+        KB_CUDA(cudaSetDevice(ctx->device));
+        KbSeqs S;
+        int rc = S.upload(ctx, seqs, offs, lens, nseq);
+        if (rc == KB200_OK) {
+                rc = kb_anchor_posmaps_dev(ctx, prm, S, anchor_ids, K, pair_begin, pair_end, posmaps);
+        }
+        S.release();
+        return rc;
+}
+
+} // extern "C"

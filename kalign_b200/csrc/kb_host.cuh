@@ -1,0 +1,47 @@
+// kb_host.cuh -- internal host-side interfaces shared by the C-ABI entry points.
+#pragma once
+#include "kb_common.cuh"
+#include "kb_profile.cuh"
+
+#include <vector>
+
+// sequences resident on the device (codes concatenated) + the host view they were uploaded from
+struct KbSeqs {
+        const uint8_t* h_seqs = nullptr;
+        const int64_t* h_offs = nullptr;
+        const int* h_lens = nullptr;
+        int n = 0;
+        int64_t total = 0;
+        KbDevBuf d_seqs, d_offs, d_lens;
+        int upload(kb200_ctx* ctx, const uint8_t* seqs, const int64_t* offs, const int* lens, int nseq);
+        void release()
+        {
+                d_seqs.release();
+                d_offs.release();
+                d_lens.release();
+        }
+        const uint8_t* dseq(int i) const { return d_seqs.as<uint8_t>() + h_offs[i]; }
+};
+
+// chunked bump arena for device-resident profiles (never freed before the call ends)
+struct KbArena {
+        std::vector<void*> chunks;
+        size_t chunk_bytes = (size_t)1 << 30;
+        size_t used = 0;      // in the last chunk
+        size_t cap = 0;       // of the last chunk
+        double total_bytes = 0;
+        float* alloc_floats(size_t n);
+        void release();
+};
+
+// d_estimation replacement on device-resident sequences.
+// explicit == 0: rows x cols rectangle; explicit == 1: nrows pairs (rows[p], cols[p]).
+int kb_distances_dev(kb200_ctx* ctx, KbSeqs& S, const int* rows, int nrows, const int* cols, int ncols,
+                     int explicit_pairs, float* dm_host);
+
+int kb_anchor_posmaps_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S, const int* anchor_ids, int K,
+                          long long pair_begin, long long pair_end, int* posmaps_host);
+
+int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
+                      const int* tasks_abc, int ntasks, const float* seq_distances,
+                      const int* posmaps, int K, float weight, int n_threads, int* gaps_out);

@@ -1,0 +1,818 @@
+// kb_msa.cu -- the kalign() / kalign_run_seeded() call sequence on plain arrays, with the three
+// hot-path seams running on the GPU.
+//
+// Host-side mirror of (behaviour cited, nothing copied):
+//   kalign / kalign_run_seeded          lib/src/aln_wrap.c:110,133
+//   kalign_arr_to_msa / detect_alphabet lib/src/msa_op.c:440,142
+//   kalign_essential_input_check        lib/src/msa_check.c:66
+//   msa_sort_len_name / msa_sort_rank   lib/src/msa_sort.c:14,25
+//   create_alphabet (+ merge/clean)     lib/src/alphabet.c:66-437
+//   pick_anchor / select_seqs           lib/src/pick_anchor.c:17,33
+//   build_tree_kmeans / bisecting_kmeans / split2 / upgma / label_internal / create_tasks
+//                                       lib/src/bisectingKmeans.c:177,273,766,974,1067,1084
+//   edist_256 (AVX lane order)          lib/src/euclidean_dist.c:161-206
+//   select_anchors                      lib/src/anchor_consistency.c:124-198
+//   finalise_alignment                  lib/src/msa_op.c:546
+// The guide tree is still host code (SURVEY.md section 8f-1 "next"); its two distance-matrix
+// calls (d_estimation pair=0 / pair=1) run on the GPU as two batched bpm launches.
+#include "kb_host.cuh"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+// ---- alphabets (alphabet.c) ------------------------------------------------------------------
+enum { ALPHA_DNA = 5, ALPHA_RED = 13, ALPHA_AMB = 23 };
+
+struct Alphabet {
+        int8_t to_internal[128];
+        int L;
+};
+
+void merge2(Alphabet& a, int x, int y)
+{
+        const int8_t m = std::min(a.to_internal[x], a.to_internal[y]);
+        a.to_internal[x] = m;
+        a.to_internal[y] = m;
+}
+
+// compress the codes that are in use to 0..L-1 in increasing order and mirror to lower case
+// (clean_and_set_to_extern, alphabet.c:393-437)
+void finish(Alphabet& a)
+{
+        int8_t trans[32];
+        for (int i = 0; i < 32; i++) trans[i] = -1;
+        for (int i = 64; i < 96; i++) {
+                if (a.to_internal[i] != -1) trans[a.to_internal[i]] = 1;
+        }
+        int code = 0;
+        for (int i = 0; i < 32; i++) {
+                if (trans[i] == 1) trans[i] = (int8_t)code++;
+        }
+        a.L = code;
+        for (int i = 64; i < 96; i++) {
+                if (a.to_internal[i] != -1) {
+                        a.to_internal[i] = trans[a.to_internal[i]];
+                        a.to_internal[i + 32] = a.to_internal[i];
+                }
+        }
+}
+
+Alphabet make_alphabet(int type)
+{
+        Alphabet a;
+        for (int i = 0; i < 128; i++) a.to_internal[i] = -1;
+        a.L = 0;
+        if (type == ALPHA_AMB) {
+                const char* aa = "ARNDCQEGHILKMFPSTWYVBZX";                       // alphabet.c:179-203
+                for (int i = 0; i < 23; i++) a.to_internal[(int)aa[i]] = (int8_t)i;
+                a.to_internal[(int)'U'] = 22;
+        } else if (type == ALPHA_DNA) {
+                const char* nt = "ACGTUNRYSWKMBDHV";                              // alphabet.c:206-245
+                for (int i = 0; i < 16; i++) a.to_internal[(int)nt[i]] = (int8_t)i;
+                merge2(a, 'U', 'T');
+                const char* amb = "RYSWKMBDHV";
+                for (int i = 0; i < 10; i++) merge2(a, 'N', amb[i]);
+        } else {
+                const char* aa = "ACDEFGHIKLMNPQRSTVWY";                          // alphabet.c:248-302
+                for (int i = 0; i < 20; i++) a.to_internal[(int)aa[i]] = (int8_t)i;
+                a.to_internal[(int)'B'] = 20;
+                a.to_internal[(int)'Z'] = 21;
+                a.to_internal[(int)'X'] = 22;
+                merge2(a, 'L', 'M'); merge2(a, 'I', 'V'); merge2(a, 'K', 'R'); merge2(a, 'E', 'Q');
+                merge2(a, 'A', 'S'); merge2(a, 'A', 'T'); merge2(a, 'S', 'T'); merge2(a, 'N', 'D');
+                merge2(a, 'F', 'Y'); merge2(a, 'B', 'N'); merge2(a, 'B', 'D'); merge2(a, 'Z', 'E');
+                merge2(a, 'Z', 'Q');
+                a.to_internal[(int)'U'] = a.to_internal[(int)'C'];
+        }
+        finish(a);
+        return a;
+}
+
+// ---- sequences -------------------------------------------------------------------------------
+struct Seq {
+        const char* seq;
+        std::string name;
+        int len;
+        int rank;
+};
+
+int cmp_len_name(const void* a, const void* b)       // msa_sort.c:62-81
+{
+        const Seq* one = *(Seq* const*)a;
+        const Seq* two = *(Seq* const*)b;
+        if (one->len > two->len) return -1;
+        if (one->len == two->len) {
+                return strncmp(one->name.c_str(), two->name.c_str(), 256) < 0 ? -1 : 1;
+        }
+        return 1;
+}
+
+struct LenId {
+        int len;
+        int id;
+};
+
+int cmp_len_only(const void* a, const void* b)       // pick_anchor.c:74-84 (never returns 0)
+{
+        const LenId* one = *(LenId* const*)a;
+        const LenId* two = *(LenId* const*)b;
+        return (one->len > two->len) ? -1 : 1;
+}
+
+// ---- guide tree ------------------------------------------------------------------------------
+struct Node {
+        int left = -1, right = -1;
+        int id = -1;
+};
+
+struct Cluster {
+        std::vector<int> samples;
+        int root = -1;          // node index of the UPGMA sub-tree (filled later)
+        int placeholder = -1;   // node slot that stands for this cluster in the k-means tree
+};
+
+struct TreeBuilder {
+        std::vector<Node> nodes;
+        std::vector<Cluster> clusters;
+        const float* dm = nullptr;      // N x stride
+        int stride = 0;
+        int num_anchors = 0;
+        int N = 0;
+};
+
+inline int cmp_floats(float a, float b)               // bisectingKmeans.c:63-73
+{
+        const float epsilon = 1e-6;
+        if (fabsf(a - b) < epsilon) return 0;
+        return (a > b) ? 1 : -1;
+}
+
+// edist_256: 8 lanes accumulate (a-b)^2 over chunks of 8, then the AVX horizontal sum order
+// ((l0+l4)+(l1+l5)) + ((l2+l6)+(l3+l7)), then sqrtf  (euclidean_dist.c:161-206)
+inline float edist8(const float* a, const float* b, int len)
+{
+        float r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < len; i += 8) {
+                for (int l = 0; l < 8; l++) {
+                        const float t = a[i + l] - b[i + l];
+                        const float t2 = t * t;
+                        r[l] = r[l] + t2;
+                }
+        }
+        const float s0 = r[0] + r[4], s1 = r[1] + r[5], s2 = r[2] + r[6], s3 = r[3] + r[7];
+        const float d = (s0 + s1) + (s2 + s3);
+        return sqrtf(d);
+}
+
+struct Split {
+        std::vector<int> sl, sr;
+        float score = FLT_MAX;
+};
+
+// split2, bisectingKmeans.c:766-971
+void split2(const TreeBuilder& B, const std::vector<int>& samples, int seed_pick, Split& res)
+{
+        const int na = B.num_anchors;
+        const int num_var = ((na + 7) / 8) * 8;
+        const int ns = (int)samples.size();
+        std::vector<float> w(num_var, 0.0f), wl(num_var, 0.0f), wr(num_var, 0.0f), cl(num_var, 0.0f), cr(num_var, 0.0f);
+        res.sl.resize(ns);
+        res.sr.resize(ns);
+        for (int i = 0; i < ns; i++) {
+                const float* row = B.dm + (size_t)samples[i] * B.stride;
+                for (int j = 0; j < na; j++) w[j] += row[j];
+        }
+        for (int j = 0; j < na; j++) w[j] /= (float)ns;
+        {
+                const float* row = B.dm + (size_t)samples[seed_pick] * B.stride;
+                for (int j = 0; j < na; j++) cl[j] = row[j];
+        }
+        for (int j = 0; j < na; j++) cr[j] = w[j] - (cl[j] - w[j]);
+        float* pcl = cl.data(); float* pcr = cr.data(); float* pwl = wl.data(); float* pwr = wr.data();
+        int num_l = 0, num_r = 0;
+        float score = 0.0f;
+        for (int stop = 0; stop < 500; stop++) {
+                num_l = 0; num_r = 0;
+                for (int i = 0; i < na; i++) { pwr[i] = 0.0f; pwl[i] = 0.0f; }
+                score = 0.0f;
+                for (int i = 0; i < ns; i++) {
+                        const int s = samples[i];
+                        const float* row = B.dm + (size_t)s * B.stride;
+                        const float dl = edist8(row, pcl, na);
+                        const float dr = edist8(row, pcr, na);
+                        score += (dl < dr) ? dl : dr;
+                        const int r = cmp_floats(dr, dl);
+                        float* wsel;
+                        if (r == -1) { wsel = pwr; res.sr[num_r++] = s; }
+                        else if (r == 1) { wsel = pwl; res.sl[num_l++] = s; }
+                        else if (i & 1) { wsel = pwr; res.sr[num_r++] = s; }
+                        else { wsel = pwl; res.sl[num_l++] = s; }
+                        for (int j = 0; j < na; j++) wsel[j] += row[j];
+                }
+                if (num_l == 0 || num_r == 0) {
+                        score = 0.0f;
+                        num_l = 0; num_r = 0;
+                        for (int i = 0; i < ns / 2; i++) res.sl[num_l++] = samples[i];
+                        for (int i = ns / 2; i < ns; i++) res.sr[num_r++] = samples[i];
+                        break;
+                }
+                for (int j = 0; j < na; j++) {
+                        pwl[j] /= (float)num_l;
+                        pwr[j] /= (float)num_r;
+                }
+                int changed = 0;
+                for (int j = 0; j < na; j++) {
+                        if (cmp_floats(pwl[j], pcl[j]) != 0) { changed = 1; break; }
+                        if (cmp_floats(pwr[j], pcr[j]) != 0) { changed = 1; break; }
+                }
+                if (!changed) break;
+                std::swap(pcl, pwl);
+                std::swap(pcr, pwr);
+        }
+        res.sl.resize(num_l);
+        res.sr.resize(num_r);
+        res.score = score;
+}
+
+// bisecting_kmeans, bisectingKmeans.c:273-406.  Returns the node index of the sub-tree; leaf
+// clusters (< 50 samples) are recorded and resolved by UPGMA after one batched distance launch.
+int bisect(TreeBuilder& B, std::vector<int>& samples)
+{
+        const int ns = (int)samples.size();
+        if (ns < 50) {
+                int slot;
+#ifdef _OPENMP
+#pragma omp critical(kb_tree_nodes)
+#endif
+                {
+                        slot = (int)B.nodes.size();
+                        B.nodes.push_back(Node());
+                        Cluster c;
+                        c.samples.swap(samples);
+                        c.placeholder = slot;
+                        B.clusters.push_back(std::move(c));
+                }
+                return slot;
+        }
+        const int tries = std::min(40, ns);
+        const int step = ns / tries;
+        Split best;
+        bool have_best = false;
+        for (int i = 0; i < tries; i += 4) {
+                Split res[4];
+#ifdef _OPENMP
+#pragma omp taskloop if (ns > 2000) default(shared) grainsize(1)
+#endif
+                for (int j = 0; j < 4; j++) {
+                        split2(B, samples, (i + j) * step, res[j]);
+                }
+                int change = 0;
+                for (int j = 0; j < 4; j++) {
+                        if (!have_best) {
+                                best = std::move(res[j]);
+                                have_best = true;
+                                change++;
+                        } else if (best.score > res[j].score) {
+                                std::swap(best, res[j]);
+                                change++;
+                        }
+                }
+                if (!change) break;
+        }
+        std::vector<int>().swap(samples);
+        int l = -1, r = -1;
+#ifdef _OPENMP
+#pragma omp task shared(B, best, l) if (ns > 2000)
+#endif
+        l = bisect(B, best.sl);
+#ifdef _OPENMP
+#pragma omp task shared(B, best, r) if (ns > 2000)
+#endif
+        r = bisect(B, best.sr);
+#ifdef _OPENMP
+#pragma omp taskwait
+#endif
+        int slot;
+#ifdef _OPENMP
+#pragma omp critical(kb_tree_nodes)
+#endif
+        {
+                slot = (int)B.nodes.size();
+                Node n;
+                n.left = l; n.right = r;
+                B.nodes.push_back(n);
+        }
+        return slot;
+}
+
+// upgma, bisectingKmeans.c:974-1053.  dm: n x n (modified in place).  Returns sub-tree root.
+int upgma(TreeBuilder& B, float* dm, const std::vector<int>& samples)
+{
+        const int n = (int)samples.size();
+        std::vector<int> as(n), tree(n);
+        for (int i = 0; i < n; i++) {
+                as[i] = i + 1;
+                Node nd;
+                nd.id = samples[i];
+                tree[i] = (int)B.nodes.size();
+                B.nodes.push_back(nd);
+        }
+        int node_a = 0, node_b = 0;
+        for (int cnode = n; cnode != 2 * n - 1; cnode++) {
+                float mn = FLT_MAX;
+                for (int i = 0; i < n - 1; i++) {
+                        if (!as[i]) continue;
+                        for (int j = i + 1; j < n; j++) {
+                                if (as[j] && dm[i * n + j] < mn) {
+                                        mn = dm[i * n + j];
+                                        node_a = i;
+                                        node_b = j;
+                                }
+                        }
+                }
+                Node nd;
+                nd.left = tree[node_a];
+                nd.right = tree[node_b];
+                tree[node_a] = (int)B.nodes.size();
+                B.nodes.push_back(nd);
+                tree[node_b] = -1;
+                as[node_a] = cnode + 1;
+                as[node_b] = 0;
+                for (int j = n; j--;) {
+                        if (j != node_b) {
+                                dm[node_a * n + j] = (dm[node_a * n + j] + dm[node_b * n + j]) * 0.5F + 0.001F;
+                        }
+                }
+                dm[node_a * n + node_a] = 0.0F;
+                for (int j = n; j--;) {
+                        dm[j * n + node_a] = dm[node_a * n + j];
+                }
+        }
+        return tree[node_a];
+}
+
+// label_internal (post-order labels) + create_tasks, then sorted by c == post-order of internals
+void emit_tasks(const TreeBuilder& B, int root, int N, std::vector<int>& abc)
+{
+        // iterative post-order
+        std::vector<int> label(B.nodes.size(), -1);
+        std::vector<std::pair<int, int>> stack;
+        int next = N;
+        stack.emplace_back(root, 0);
+        while (!stack.empty()) {
+                auto& top = stack.back();
+                const Node& nd = B.nodes[(size_t)top.first];
+                if (nd.left < 0 && nd.right < 0) {
+                        label[(size_t)top.first] = nd.id;
+                        stack.pop_back();
+                        continue;
+                }
+                if (top.second == 0) {
+                        top.second = 1;
+                        stack.emplace_back(nd.left, 0);
+                } else if (top.second == 1) {
+                        top.second = 2;
+                        stack.emplace_back(nd.right, 0);
+                } else {
+                        const int me = top.first;
+                        label[(size_t)me] = next++;
+                        abc.push_back(label[(size_t)nd.left]);
+                        abc.push_back(label[(size_t)nd.right]);
+                        abc.push_back(label[(size_t)me]);
+                        stack.pop_back();
+                }
+        }
+}
+
+// select_anchors, anchor_consistency.c:124-198
+void select_anchors(const float* sd, int N, int K, std::vector<int>& ids)
+{
+        ids.assign((size_t)K, 0);
+        std::vector<float> min_dist((size_t)N);
+        float sum = 0.0f;
+        for (int i = 0; i < N; i++) sum += sd[i];
+        const float mean = sum / (float)N;
+        float best_diff = FLT_MAX;
+        int best_idx = 0;
+        for (int i = 0; i < N; i++) {
+                float diff = sd[i] - mean;
+                if (diff < 0) diff = -diff;
+                if (diff < best_diff) { best_diff = diff; best_idx = i; }
+        }
+        ids[0] = best_idx;
+        for (int i = 0; i < N; i++) {
+                float d = sd[i] - sd[ids[0]];
+                if (d < 0) d = -d;
+                min_dist[(size_t)i] = d;
+        }
+        for (int k = 1; k < K; k++) {
+                float best_min = -1.0f;
+                int bi = 0;
+                for (int i = 0; i < N; i++) {
+                        bool skip = false;
+                        for (int j = 0; j < k; j++) {
+                                if (ids[(size_t)j] == i) { skip = true; break; }
+                        }
+                        if (skip) continue;
+                        if (min_dist[(size_t)i] > best_min) { best_min = min_dist[(size_t)i]; bi = i; }
+                }
+                ids[(size_t)k] = bi;
+                for (int i = 0; i < N; i++) {
+                        float d = sd[i] - sd[bi];
+                        if (d < 0) d = -d;
+                        if (d < min_dist[(size_t)i]) min_dist[(size_t)i] = d;
+                }
+        }
+}
+
+} // namespace
+
+// Guide tree on device-resident tree-alphabet sequences: tasks (a,b,c) sorted by c and
+// msa->seq_distances (build_tree_kmeans, bisectingKmeans.c:177-271).
+int kb_build_tree(kb200_ctx* ctx, KbSeqs& S, int n_threads, std::vector<int>& abc, std::vector<float>& seq_distances)
+{
+        const int N = S.n;
+        TreeBuilder B;
+        B.N = N;
+        // pick_anchor / select_seqs (pick_anchor.c:17-72)
+        const int num_anchor = std::min(32, N);
+        std::vector<int> anchors((size_t)num_anchor);
+        {
+                std::vector<LenId> items((size_t)N);
+                std::vector<LenId*> ptrs((size_t)N);
+                for (int i = 0; i < N; i++) {
+                        items[(size_t)i].id = i;
+                        items[(size_t)i].len = S.h_lens[i];
+                        ptrs[(size_t)i] = &items[(size_t)i];
+                }
+                qsort(ptrs.data(), (size_t)N, sizeof(LenId*), cmp_len_only);
+                const int stride = N / num_anchor;
+                for (int i = 0; i < num_anchor; i++) anchors[(size_t)i] = ptrs[(size_t)(i * stride)]->id;
+        }
+        // d_estimation(pair = 0): N x num_anchor, rows padded to a multiple of 8 with zeros
+        const int stride = ((num_anchor + 7) / 8) * 8;
+        std::vector<float> dm((size_t)N * stride, 0.0f);
+        {
+                std::vector<int> rows((size_t)N);
+                for (int i = 0; i < N; i++) rows[(size_t)i] = i;
+                std::vector<float> tmp((size_t)N * num_anchor);
+                KB_RUN(kb_distances_dev(ctx, S, rows.data(), N, anchors.data(), num_anchor, 0, tmp.data()));
+                for (int i = 0; i < N; i++) {
+                        memcpy(dm.data() + (size_t)i * stride, tmp.data() + (size_t)i * num_anchor, sizeof(float) * (size_t)num_anchor);
+                }
+        }
+        B.dm = dm.data();
+        B.stride = stride;
+        B.num_anchors = num_anchor;
+        B.nodes.reserve((size_t)2 * N + 64);
+        std::vector<int> samples((size_t)N);
+        for (int i = 0; i < N; i++) samples[(size_t)i] = i;
+        int root = -1;
+#ifdef _OPENMP
+#pragma omp parallel num_threads(n_threads > 0 ? n_threads : 1)
+#pragma omp single
+#endif
+        root = bisect(B, samples);
+        // leaf clusters: one batched launch for every i<j pair of every cluster.
+        // d_estimation(pair=1) leaves dm[i][j] (i<j) = calc_distance(seq_j, seq_i)
+        // (sequence_distance.c:53-81: the later (j,i) iteration overwrites both entries).
+        {
+                size_t npairs = 0;
+                for (const Cluster& c : B.clusters) {
+                        const size_t n = c.samples.size();
+                        npairs += n * (n - 1) / 2;
+                }
+                std::vector<int> pa(npairs), pb(npairs);
+                size_t e = 0;
+                for (const Cluster& c : B.clusters) {
+                        const int n = (int)c.samples.size();
+                        for (int i = 0; i < n; i++) {
+                                for (int j = i + 1; j < n; j++) {
+                                        pa[e] = c.samples[(size_t)j];
+                                        pb[e] = c.samples[(size_t)i];
+                                        e++;
+                                }
+                        }
+                }
+                std::vector<float> pd(npairs);
+                if (npairs) {
+                        KB_RUN(kb_distances_dev(ctx, S, pa.data(), (int)npairs, pb.data(), 0, 1, pd.data()));
+                }
+                e = 0;
+                // clusters were recorded in completion order; the result is order independent
+                std::vector<int> cluster_root(B.clusters.size());
+                for (size_t ci = 0; ci < B.clusters.size(); ci++) {
+                        const Cluster& c = B.clusters[ci];
+                        const int n = (int)c.samples.size();
+                        std::vector<float> cdm((size_t)n * n, 0.0f);
+                        for (int i = 0; i < n; i++) {
+                                for (int j = i + 1; j < n; j++) {
+                                        cdm[(size_t)i * n + j] = pd[e];
+                                        cdm[(size_t)j * n + i] = pd[e];
+                                        e++;
+                                }
+                        }
+                        cluster_root[ci] = upgma(B, cdm.data(), c.samples);
+                }
+                // splice the UPGMA sub-trees in place of the placeholders
+                for (size_t ci = 0; ci < B.clusters.size(); ci++) {
+                        B.nodes[(size_t)B.clusters[ci].placeholder] = B.nodes[(size_t)cluster_root[ci]];
+                }
+        }
+        abc.clear();
+        abc.reserve((size_t)3 * (N - 1));
+        emit_tasks(B, root, N, abc);
+        if ((int)abc.size() != 3 * (N - 1)) {
+                fprintf(stderr, "[kalign_b200] guide tree: %zu tasks for %d sequences\n", abc.size() / 3, N);
+                return KB200_FAIL;
+        }
+        seq_distances.resize((size_t)N);
+        for (int i = 0; i < N; i++) {
+                float sum = 0.0f;
+                for (int j = 0; j < num_anchor; j++) sum += dm[(size_t)i * stride + j];
+                const float mean_dist = sum / (float)num_anchor;
+                const float seq_len = (float)S.h_lens[i];
+                seq_distances[(size_t)i] = (seq_len > 0.0f) ? mean_dist / seq_len : 0.0f;
+        }
+        return KB200_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// staged pipeline object: create (encode, sort, upload, distances, guide tree) -> align (the DP
+// stages on device-resident sequences: anchor batch + progressive alignment) -> result.
+struct kb200_msa {
+        kb200_ctx* ctx = nullptr;
+        int n_threads = 1;
+        int biotype = 2;
+        int N = 0;
+        std::vector<Seq> store;
+        std::vector<Seq*> order;
+        std::vector<int64_t> offs;
+        std::vector<int> lens;
+        std::vector<uint8_t> codes;
+        int64_t total = 0;
+        KbSeqs S;
+        std::vector<int> abc;
+        std::vector<float> seq_distances;
+        std::vector<int> posmaps;
+        std::vector<int> gaps;
+        std::vector<int> anchor_ids;
+        kb200_params prm;
+        int K = 0;
+        float weight = 2.0f;
+        bool aligned = false;
+        double t_create = 0, t_tree = 0;
+};
+
+static void encode_seqs(kb200_msa* M, int alpha)
+{
+        const Alphabet a = make_alphabet(alpha);
+        bool warned = false;
+        for (int i = 0; i < M->N; i++) {
+                const char* s = M->order[(size_t)i]->seq;
+                uint8_t* d = M->codes.data() + M->offs[(size_t)i];
+                for (int j = 0; j < M->lens[(size_t)i]; j++) {
+                        const int ch = (int)(unsigned char)s[j];
+                        const int8_t t = (ch < 128) ? a.to_internal[ch] : (int8_t)-1;
+                        if (t == -1) {
+                                if (!warned) {
+                                        fprintf(stderr, "[kalign_b200] warning: character '%c' does not match the alphabet (coded as 0)\n", s[j]);
+                                        warned = true;
+                                }
+                                d[j] = 0;
+                        } else {
+                                d[j] = (uint8_t)t;
+                        }
+                }
+        }
+}
+
+extern "C" {
+
+void kb200_msa_free(kb200_msa* M)
+{
+        if (!M) return;
+        if (M->ctx) cudaSetDevice(M->ctx->device);
+        M->S.release();
+        delete M;
+}
+
+// everything of kalign_run_seeded (aln_wrap.c:133-205) that precedes the DP stages
+int kb200_msa_create(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_threads, int type,
+                     float gpo, float gpe, float tgpe, int consistency_anchors, float consistency_weight,
+                     kb200_msa** out)
+{
+        if (!ctx || !seq || !len || !out) {
+                return KB200_FAIL;
+        }
+        *out = nullptr;
+        if (n_threads < 1) n_threads = 1;
+        KB_CUDA(cudaSetDevice(ctx->device));
+        // ---- kalign_arr_to_msa: letter frequencies, alphabet detection (msa_op.c:440-520,142-215)
+        int letter_freq[128];
+        memset(letter_freq, 0, sizeof(letter_freq));
+        for (int i = 0; i < numseq; i++) {
+                for (int j = 0; j < len[i]; j++) {
+                        const int ch = (int)(unsigned char)seq[i][j];
+                        if (ch < 128) letter_freq[ch]++;
+                }
+        }
+        int biotype = 2;
+        {
+                double DNA[128], protein[128];
+                const char* DNA_letters = "acgtunACGTUN";
+                const char* protein_letters = "acdefghiklmnpqrstvwyACDEFGHIKLMNPQRSTVWY";
+                for (int i = 0; i < 128; i++) {
+                        DNA[i] = log(0.0001 * 1.0 / 116.0);
+                        protein[i] = log(0.0001 * 1.0 / 88.0);
+                }
+                for (int i = 0; i < 12; i++) DNA[(int)DNA_letters[i]] = log(0.9999 * 1.0 / 12.0);
+                for (int i = 0; i < 40; i++) protein[(int)protein_letters[i]] = log(0.9999 * 1.0 / 40.0);
+                double dna_prob = 0.0, prot_prob = 0.0;
+                for (int i = 0; i < 128; i++) {
+                        if (letter_freq[i]) {
+                                dna_prob += DNA[i] * (double)letter_freq[i];
+                                prot_prob += protein[i] * (double)letter_freq[i];
+                        }
+                }
+                if (dna_prob > prot_prob) biotype = 1;
+                else if (prot_prob > dna_prob) biotype = 0;
+        }
+        if (biotype == 2) {
+                fprintf(stderr, "[kalign_b200] Unable to determine what alphabet to use.\n");
+                return KB200_FAIL;
+        }
+        // ---- kalign_essential_input_check: ranks, drop empty sequences (msa_check.c:66-139)
+        if (numseq <= 1) {
+                fprintf(stderr, "[kalign_b200] only %d sequences found.\n", numseq);
+                return KB200_FAIL;
+        }
+        kb200_msa* M = new kb200_msa();
+        M->ctx = ctx;
+        M->n_threads = n_threads;
+        M->biotype = biotype;
+        M->weight = consistency_weight;
+        M->store.resize((size_t)numseq);
+        M->order.reserve((size_t)numseq);
+        for (int i = 0; i < numseq; i++) {
+                Seq& s = M->store[(size_t)i];
+                s.seq = seq[i];
+                s.len = len[i];
+                s.rank = i;
+                s.name = "s" + std::to_string(i);
+                if (len[i] > 0) M->order.push_back(&s);
+        }
+        const int N = (int)M->order.size();
+        M->N = N;
+        if (N <= 1) {
+                fprintf(stderr, "[kalign_b200] only %d sequences found.\n", N);
+                delete M;
+                return KB200_FAIL;
+        }
+        // ---- msa_sort_len_name (same libc qsort, same comparator semantics)
+        qsort(M->order.data(), (size_t)N, sizeof(Seq*), cmp_len_name);
+        M->offs.resize((size_t)N);
+        M->lens.resize((size_t)N);
+        int64_t total = 0;
+        for (int i = 0; i < N; i++) {
+                M->offs[(size_t)i] = total;
+                M->lens[(size_t)i] = M->order[(size_t)i]->len;
+                total += M->order[(size_t)i]->len;
+        }
+        M->total = total;
+        M->codes.resize((size_t)total + 16);
+        M->gaps.assign((size_t)total + (size_t)N, 0);
+        encode_seqs(M, biotype == 1 ? ALPHA_DNA : ALPHA_RED);
+        int rc = M->S.upload(ctx, M->codes.data(), M->offs.data(), M->lens.data(), N);
+        if (rc == KB200_OK) rc = kb_build_tree(ctx, M->S, n_threads, M->abc, M->seq_distances);
+        if (rc == KB200_OK && biotype == 0) {
+                encode_seqs(M, ALPHA_AMB);
+                rc = M->S.upload(ctx, M->codes.data(), M->offs.data(), M->lens.data(), N);
+        }
+        if (rc == KB200_OK) {
+                // resolve_pfasum_auto, aln_wrap.c:31-68
+                if (type == KB200_TYPE_PROTEIN_PFASUM_AUTO) {
+                        if (biotype != 0) {
+                                type = KB200_TYPE_PROTEIN_PFASUM43;
+                        } else {
+                                int mn = M->lens[0], mxl = M->lens[0];
+                                for (int i = 1; i < N; i++) { mn = std::min(mn, M->lens[(size_t)i]); mxl = std::max(mxl, M->lens[(size_t)i]); }
+                                const float ratio = (mn > 0) ? (float)mxl / (float)mn : 1.0f;
+                                type = (ratio < 1.5f) ? KB200_TYPE_PROTEIN_PFASUM43 : KB200_TYPE_PROTEIN_PFASUM60;
+                        }
+                }
+                rc = kb200_params_init(&M->prm, biotype, type, gpo, gpe, tgpe);
+        }
+        if (rc == KB200_OK && consistency_anchors > 0 && N >= 3) {
+                M->K = std::min(consistency_anchors, N);
+                select_anchors(M->seq_distances.data(), N, M->K, M->anchor_ids);
+                M->posmaps.assign((size_t)total * (size_t)M->K, -1);
+        }
+        if (rc != KB200_OK) {
+                kb200_msa_free(M);
+                return KB200_FAIL;
+        }
+        *out = M;
+        return KB200_OK;
+}
+
+// the DP stages (anchor_consistency_build + create_msa_tree) on device-resident sequences;
+// may be called repeatedly (bench), every call recomputes everything.
+int kb200_msa_align(kb200_msa* M)
+{
+        if (!M) return KB200_FAIL;
+        kb200_ctx* ctx = M->ctx;
+        KB_CUDA(cudaSetDevice(ctx->device));
+        cudaEvent_t e0, e1;
+        KB_CUDA(cudaEventCreate(&e0));
+        KB_CUDA(cudaEventCreate(&e1));
+        KB_CUDA(cudaEventRecord(e0, ctx->stream));
+        if (M->K > 0) {
+                KB_RUN(kb_anchor_posmaps_dev(ctx, &M->prm, M->S, M->anchor_ids.data(), M->K, 0, (long long)M->N * M->K, M->posmaps.data()));
+        }
+        KB_RUN(kb_align_tree_dev(ctx, &M->prm, M->S, M->abc.data(), M->N - 1, M->seq_distances.data(),
+                                 M->K > 0 ? M->posmaps.data() : nullptr, M->K, M->weight, M->n_threads, M->gaps.data()));
+        KB_CUDA(cudaEventRecord(e1, ctx->stream));
+        KB_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        ctx->stats.align_seconds += 1e-3 * (double)ms;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        M->aligned = true;
+        return KB200_OK;
+}
+
+// finalise_alignment (msa_op.c:546-598) + msa_sort_rank + kalign_msa_to_arr (msa_op.c:377)
+int kb200_msa_result(kb200_msa* M, char*** aligned, int* out_aln_len)
+{
+        if (!M || !M->aligned || !aligned || !out_aln_len) return KB200_FAIL;
+        const int N = M->N;
+        int aln_len = M->lens[0];
+        {
+                const int* g = M->gaps.data() + M->offs[0] + 0;
+                for (int j = 0; j <= M->lens[0]; j++) aln_len += g[j];
+        }
+        std::vector<int> by_rank((size_t)N);
+        for (int i = 0; i < N; i++) by_rank[(size_t)i] = i;
+        std::sort(by_rank.begin(), by_rank.end(), [&](int x, int y) { return M->order[(size_t)x]->rank < M->order[(size_t)y]->rank; });
+        char** out = (char**)malloc(sizeof(char*) * (size_t)N);
+        if (!out) return KB200_FAIL;
+        for (int r = 0; r < N; r++) {
+                const int i = by_rank[(size_t)r];
+                const int* g = M->gaps.data() + M->offs[(size_t)i] + i;
+                char* row = (char*)malloc((size_t)aln_len + 1);
+                if (!row) return KB200_FAIL;
+                int f = 0;
+                const char* s = M->order[(size_t)i]->seq;
+                const int li = M->lens[(size_t)i];
+                for (int j = 0; j < li; j++) {
+                        for (int c = 0; c < g[j] && f < aln_len; c++) row[f++] = '-';
+                        if (f < aln_len) row[f++] = s[j];
+                }
+                for (int c = 0; c < g[li] && f < aln_len; c++) row[f++] = '-';
+                while (f < aln_len) row[f++] = '-';
+                row[aln_len] = 0;
+                out[r] = row;
+        }
+        *aligned = out;
+        *out_aln_len = aln_len;
+        return KB200_OK;
+}
+
+int kb200_msa_info(kb200_msa* M, int* numseq, int* biotype, int* n_anchors)
+{
+        if (!M) return KB200_FAIL;
+        if (numseq) *numseq = M->N;
+        if (biotype) *biotype = M->biotype;
+        if (n_anchors) *n_anchors = M->K;
+        return KB200_OK;
+}
+
+int kb200_kalign(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_threads, int type,
+                 float gpo, float gpe, float tgpe, int consistency_anchors, float consistency_weight,
+                 char*** aligned, int* out_aln_len)
+{
+        if (!aligned || !out_aln_len) {
+                return KB200_FAIL;
+        }
+        kb200_msa* M = nullptr;
+        KB_RUN(kb200_msa_create(ctx, seq, len, numseq, n_threads, type, gpo, gpe, tgpe,
+                                consistency_anchors, consistency_weight, &M));
+        int rc = kb200_msa_align(M);
+        if (rc == KB200_OK) rc = kb200_msa_result(M, aligned, out_aln_len);
+        kb200_msa_free(M);
+        return rc;
+}
+
+} // extern "C"

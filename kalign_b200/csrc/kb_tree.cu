@@ -1,0 +1,547 @@
+// kb_tree.cu -- progressive alignment over the guide tree, one batched launch sequence per level.
+//
+// Replaces the aln_task scheduler and do_align:
+//   create_msa_tree / recursive_aln   lib/src/aln_run.c:43,81   (post-order OpenMP task recursion)
+//   do_align                          lib/src/aln_run.c:213-441
+//   compute_subm_offset               lib/src/aln_run.c:166-203
+//   make_seq / update_gaps            lib/src/weave_alignment.c:41,96
+//   anchor_consistency_get_bonus_profile / get_node_anchor_positions
+//                                     lib/src/anchor_consistency.c:469,352
+//
+// All tasks whose children are finished (same "level": 1 + max level of the children) are
+// mutually independent (aln_run.c:95-109).  Per level: leaf profiles / gap-penalty rescale
+// (streaming kernels) -> one batched Hirschberg run over every task of the level -> path coding
+// on device -> profile merge on device -> the coded paths come back to the host for the gap
+// weaving bookkeeping (msa->gaps, sip, nsip, plen).  Profiles never leave the device.
+#include "kb_host.cuh"
+
+#include <string.h>
+#include <algorithm>
+#include <utility>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+__global__ void kb_scatter_kernel(float* __restrict__ dst, const long long* __restrict__ idx,
+                                  const float* __restrict__ val, const long long n)
+{
+        const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        if (i < n) {
+                dst[idx[i]] = val[i];
+        }
+}
+
+struct Tree {
+        int N = 0;
+        const KbSeqs* S = nullptr;
+        std::vector<int> nsip, plen, level;
+        std::vector<std::vector<int>> sip;
+        std::vector<float*> prof;
+        std::vector<std::vector<int>> gaps;   // per sequence, len+1
+        const int* posmaps = nullptr;
+        int K = 0;
+        float weight = 0.0f;
+};
+
+// get_node_anchor_positions, anchor_consistency.c:352-467
+void node_anchor_positions(const Tree& T, int node, int dp_len, int k,
+                           std::vector<int>& positions, std::vector<float>& conf,
+                           std::vector<int>& col2u, std::vector<int>& best, std::vector<int>& agree, std::vector<int>& total)
+{
+        const KbSeqs& S = *T.S;
+        positions.assign((size_t)dp_len, -1);
+        conf.assign((size_t)dp_len, 0.0f);
+        if (T.nsip[node] == 1) {
+                const int* map = T.posmaps + (size_t)T.K * (size_t)S.h_offs[node] + (size_t)k * (size_t)S.h_lens[node];
+                const int seq_len = S.h_lens[node];
+                for (int i = 0; i < dp_len && i < seq_len; i++) {
+                        positions[i] = map[i];
+                        conf[i] = (map[i] >= 0) ? 1.0f : 0.0f;
+                }
+                return;
+        }
+        col2u.assign((size_t)dp_len + 1, -1);
+        best.assign((size_t)dp_len, -1);
+        agree.assign((size_t)dp_len, 0);
+        total.assign((size_t)dp_len, 0);
+        for (int si : T.sip[node]) {
+                const int* map = T.posmaps + (size_t)T.K * (size_t)S.h_offs[si] + (size_t)k * (size_t)S.h_lens[si];
+                const int seq_len = S.h_lens[si];
+                const std::vector<int>& g = T.gaps[si];
+                int col = 0;
+                for (int p = 0; p <= seq_len && col < dp_len; p++) {
+                        for (int q = 0; q < g[p] && col < dp_len; q++) {
+                                col2u[col++] = -1;
+                        }
+                        if (p < seq_len && col < dp_len) {
+                                col2u[col++] = p;
+                        }
+                }
+                while (col < dp_len) {
+                        col2u[col++] = -1;
+                }
+                for (int c = 0; c < dp_len; c++) {
+                        const int ugp = col2u[c];
+                        if (ugp < 0 || ugp >= seq_len) continue;
+                        const int apos = map[ugp];
+                        if (apos < 0) continue;
+                        total[c]++;
+                        if (best[c] < 0) {
+                                best[c] = apos;
+                                agree[c] = 1;
+                        } else if (apos == best[c]) {
+                                agree[c]++;
+                        }
+                }
+        }
+        for (int c = 0; c < dp_len; c++) {
+                if (total[c] > 0 && agree[c] > 0) {
+                        positions[c] = best[c];
+                        conf[c] = (float)agree[c] / (float)total[c];
+                }
+        }
+}
+
+// anchor_consistency_get_bonus_profile, anchor_consistency.c:469-561, as a sorted sparse list of
+// (flat index i*len_b + bj, value); contributions to one cell are summed in anchor order k.
+void build_bonus(const Tree& T, int node_a, int len_a, int node_b, int len_b,
+                 std::vector<std::pair<long long, float>>& out)
+{
+        out.clear();
+        const int K = T.K;
+        const float paw = T.weight / (float)K;
+        std::vector<int> apos_a, apos_b, col2u, best, agree, total, inv_b;
+        std::vector<float> conf_a, conf_b, inv_conf_b;
+        std::vector<std::pair<long long, float>> ent;
+        for (int k = 0; k < K; k++) {
+                node_anchor_positions(T, node_a, len_a, k, apos_a, conf_a, col2u, best, agree, total);
+                node_anchor_positions(T, node_b, len_b, k, apos_b, conf_b, col2u, best, agree, total);
+                int anchor_len = 0;
+                for (int i = 0; i < len_a; i++) {
+                        if (apos_a[i] >= anchor_len) anchor_len = apos_a[i] + 1;
+                }
+                for (int j = 0; j < len_b; j++) {
+                        if (apos_b[j] >= anchor_len) anchor_len = apos_b[j] + 1;
+                }
+                if (anchor_len == 0) continue;
+                inv_b.assign((size_t)anchor_len, -1);
+                inv_conf_b.assign((size_t)anchor_len, 0.0f);
+                for (int j = 0; j < len_b; j++) {
+                        if (apos_b[j] >= 0 && apos_b[j] < anchor_len) {
+                                inv_b[apos_b[j]] = j;
+                                inv_conf_b[apos_b[j]] = conf_b[j];
+                        }
+                }
+                for (int i = 0; i < len_a; i++) {
+                        const int ak = apos_a[i];
+                        if (ak >= 0 && ak < anchor_len) {
+                                const int bj = inv_b[ak];
+                                if (bj >= 0) {
+                                        const float v = paw * conf_a[i] * inv_conf_b[ak];
+                                        ent.emplace_back((long long)i * (long long)len_b + (long long)bj, v);
+                                }
+                        }
+                }
+        }
+        std::stable_sort(ent.begin(), ent.end(),
+                         [](const std::pair<long long, float>& x, const std::pair<long long, float>& y) { return x.first < y.first; });
+        for (size_t i = 0; i < ent.size();) {
+                float v = 0.0f;
+                size_t j = i;
+                while (j < ent.size() && ent[j].first == ent[i].first) {
+                        v += ent[j].second;
+                        j++;
+                }
+                out.emplace_back(ent[i].first, v);
+                i = j;
+        }
+}
+
+// make_seq + update_gaps, weave_alignment.c:41-112
+void weave(Tree& T, int a, int b, const int* path)
+{
+        const int alnlen = path[0];
+        std::vector<int> gap_a((size_t)alnlen + 1, 0), gap_b((size_t)alnlen + 1, 0);
+        int posa = 0, posb = 0;
+        for (int c = 1; path[c] != 3; c++) {
+                const int p = path[c];
+                if (!p) {
+                        posa++; posb++;
+                } else if (p & 1) {
+                        gap_a[posa] += 1; posb++;
+                } else if (p & 2) {
+                        gap_b[posb] += 1; posa++;
+                }
+        }
+        auto upd = [&](int si, const std::vector<int>& ng) {
+                std::vector<int>& gis = T.gaps[si];
+                const int old_len = T.S->h_lens[si];
+                int rel = 0;
+                for (int i = 0; i <= old_len; i++) {
+                        int add = 0;
+                        for (int j = rel; j <= rel + gis[i]; j++) {
+                                add += ng[j];
+                        }
+                        rel += gis[i] + 1;
+                        gis[i] += add;
+                }
+        };
+        for (int si : T.sip[a]) upd(si, gap_a);
+        for (int si : T.sip[b]) upd(si, gap_b);
+}
+
+} // namespace
+
+int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
+                      const int* tasks_abc, int ntasks, const float* seq_distances,
+                      const int* posmaps, int K, float weight, int n_threads, int* gaps_out)
+{
+        const int N = S.n;
+        if (ntasks != N - 1 || N < 2) {
+                fprintf(stderr, "[kalign_b200] align_tree: need exactly N-1 tasks (N=%d, ntasks=%d)\n", N, ntasks);
+                return KB200_FAIL;
+        }
+        cudaStream_t st = ctx->stream;
+        const int NP = 2 * N - 1;
+        Tree T;
+        T.N = N; T.S = &S;
+        T.nsip.assign(NP, 0); T.plen.assign(NP, 0); T.level.assign(NP, 0);
+        T.sip.resize(NP); T.prof.assign(NP, nullptr);
+        T.gaps.resize(N);
+        T.posmaps = (K > 0 && N >= 3) ? posmaps : nullptr;     // anchor_consistency_build: N<3 -> no table
+        T.K = std::min(K, N); T.weight = weight;
+        for (int i = 0; i < N; i++) {
+                T.nsip[i] = 1;
+                T.sip[i].assign(1, i);
+                T.plen[i] = 0;
+                T.gaps[i].assign((size_t)S.h_lens[i] + 1, 0);
+        }
+        int maxlevel = 0;
+        for (int t = 0; t < ntasks; t++) {
+                const int a = tasks_abc[3 * t], b = tasks_abc[3 * t + 1], c = tasks_abc[3 * t + 2];
+                if (a < 0 || b < 0 || c < N || a >= NP || b >= NP || c >= NP) {
+                        return KB200_FAIL;
+                }
+                T.level[c] = 1 + std::max(T.level[a], T.level[b]);
+                maxlevel = std::max(maxlevel, T.level[c]);
+        }
+        std::vector<std::vector<int>> by_level((size_t)maxlevel + 1);
+        for (int t = 0; t < ntasks; t++) {
+                by_level[(size_t)T.level[tasks_abc[3 * t + 2]]].push_back(t);
+        }
+        KbArena arena;
+        KbDevBuf d_subm, d_leaf, d_gapset, d_prefix, d_raw, d_coded, d_scr, d_pjobs, d_mjobs, d_src, d_bonus, d_bidx, d_bval;
+        int rc = KB200_OK;
+        auto cleanup = [&]() {
+                arena.release();
+                KbDevBuf* bufs[] = {&d_subm, &d_leaf, &d_gapset, &d_prefix, &d_raw, &d_coded, &d_scr, &d_pjobs, &d_mjobs, &d_src, &d_bonus, &d_bidx, &d_bval};
+                for (KbDevBuf* b : bufs) b->release();
+        };
+#define TR(x) do { if ((x) != KB200_OK) { fprintf(stderr, "[kalign_b200] align_tree failure at %s:%d\n", __FILE__, __LINE__); cleanup(); return KB200_FAIL; } } while (0)
+#define TC(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { fprintf(stderr, "[kalign_b200] CUDA error %s at %s:%d\n", cudaGetErrorString(e__), __FILE__, __LINE__); cleanup(); return KB200_FAIL; } } while (0)
+        TR(d_subm.ensure(sizeof(float) * 23 * 23));
+        TC(cudaMemcpyAsync(d_subm.p, prm->subm, sizeof(float) * 23 * 23, cudaMemcpyHostToDevice, st));
+
+        std::vector<std::vector<std::pair<long long, float>>> bonus_lists;
+        for (int L = 1; L <= maxlevel; L++) {
+                const std::vector<int>& tl = by_level[(size_t)L];
+                const int nt = (int)tl.size();
+                if (nt == 0) continue;
+                // ---- per task: scoring offset, operand lengths ----
+                std::vector<float> soff((size_t)nt, 0.0f);
+                std::vector<int> la((size_t)nt), lb((size_t)nt);
+                for (int q = 0; q < nt; q++) {
+                        const int a = tasks_abc[3 * tl[q]], b = tasks_abc[3 * tl[q] + 1];
+                        la[q] = (T.nsip[a] == 1) ? S.h_lens[a] : T.plen[a];
+                        lb[q] = (T.nsip[b] == 1) ? S.h_lens[b] : T.plen[b];
+                        // compute_subm_offset, aln_run.c:166-203
+                        const float amax = prm->vsm_amax;
+                        if (amax > 0.0f && seq_distances) {
+                                float sum = 0.0f;
+                                int count = 0;
+                                for (int si : T.sip[a]) { sum += seq_distances[si]; count++; }
+                                for (int si : T.sip[b]) { sum += seq_distances[si]; count++; }
+                                if (count) {
+                                        const float avg = sum / (float)count;
+                                        float off = amax - avg;
+                                        if (off < 0.0f) off = 0.0f;
+                                        soff[q] = off;
+                                }
+                        }
+                }
+                // ---- leaf profiles (make_profile_n with THIS task's offset) and gap rescale ----
+                std::vector<KbLeafProfile> leaves;
+                std::vector<long long> leaf_prefix;
+                std::vector<KbGapSet> gsets;
+                std::vector<long long> gs_prefix;
+                long long leaf_cols = 0, gs_cols = 0;
+                for (int q = 0; q < nt; q++) {
+                        const int a = tasks_abc[3 * tl[q]], b = tasks_abc[3 * tl[q] + 1];
+                        const int nodes[2] = {a, b};
+                        const int other[2] = {b, a};
+                        for (int s = 0; s < 2; s++) {
+                                const int nd = nodes[s];
+                                if (T.nsip[nd] == 1) {
+                                        const int len = S.h_lens[nd];
+                                        float* p = arena.alloc_floats((size_t)(len + 2) * 64);
+                                        if (!p) { cleanup(); return KB200_FAIL; }
+                                        T.prof[nd] = p;
+                                        KbLeafProfile lp;
+                                        lp.seq = S.dseq(nd); lp.prof = p; lp.len = len;
+                                        lp.nsoff = -soff[q];
+                                        lp.ngpo = -prm->gpo; lp.ngpe = -prm->gpe; lp.ntgpe = -prm->tgpe;
+                                        leaves.push_back(lp);
+                                        leaf_prefix.push_back(leaf_cols);
+                                        leaf_cols += len + 2;
+                                } else {
+                                        KbGapSet gs;
+                                        gs.prof = T.prof[nd]; gs.len = T.plen[nd]; gs.nsip = T.nsip[other[s]];
+                                        gsets.push_back(gs);
+                                        gs_prefix.push_back(gs_cols);
+                                        gs_cols += T.plen[nd] + 2;
+                                }
+                        }
+                }
+                TR(d_leaf.ensure(sizeof(KbLeafProfile) * leaves.size() + 16));
+                TR(d_gapset.ensure(sizeof(KbGapSet) * gsets.size() + 16));
+                TR(d_prefix.ensure(sizeof(long long) * (leaves.size() + gsets.size() + (size_t)nt) + 64));
+                long long* d_pref_leaf = d_prefix.as<long long>();
+                long long* d_pref_gs = d_pref_leaf + leaves.size();
+                long long* d_pref_mg = d_pref_gs + gsets.size();
+                if (!leaves.empty()) {
+                        TC(cudaMemcpyAsync(d_leaf.p, leaves.data(), sizeof(KbLeafProfile) * leaves.size(), cudaMemcpyHostToDevice, st));
+                        TC(cudaMemcpyAsync(d_pref_leaf, leaf_prefix.data(), sizeof(long long) * leaves.size(), cudaMemcpyHostToDevice, st));
+                        TR(kb_make_profiles(ctx, d_leaf.as<KbLeafProfile>(), (int)leaves.size(), d_pref_leaf, leaf_cols, d_subm.as<float>()));
+                }
+                if (!gsets.empty()) {
+                        TC(cudaMemcpyAsync(d_gapset.p, gsets.data(), sizeof(KbGapSet) * gsets.size(), cudaMemcpyHostToDevice, st));
+                        TC(cudaMemcpyAsync(d_pref_gs, gs_prefix.data(), sizeof(long long) * gsets.size(), cudaMemcpyHostToDevice, st));
+                        TR(kb_set_gap_penalties(ctx, d_gapset.as<KbGapSet>(), (int)gsets.size(), d_pref_gs, gs_cols));
+                }
+                TC(cudaStreamSynchronize(st));   // host vectors above go out of scope per level
+
+                // ---- jobs ----
+                std::vector<KbJob> jobs((size_t)nt);
+                std::vector<KbPathJob> pjobs((size_t)nt);
+                std::vector<char> mirror((size_t)nt, 0);
+                std::vector<int> rown((size_t)nt), coln((size_t)nt), rlen((size_t)nt), clen((size_t)nt);
+                size_t n_raw = 0, n_coded = 0, n_scr = 0;
+                for (int q = 0; q < nt; q++) {
+                        const int a = tasks_abc[3 * tl[q]], b = tasks_abc[3 * tl[q] + 1];
+                        const bool leaf_a = T.nsip[a] == 1, leaf_b = T.nsip[b] == 1;
+                        KbJob j;
+                        memset(&j, 0, sizeof(j));
+                        j.nalpha = prm->nalpha;
+                        // kernel choice and orientation, aln_run.c:297-388
+                        if (leaf_a && leaf_b) {
+                                j.kind = KB200_KIND_SS;
+                                if (la[q] < lb[q]) { rown[q] = a; coln[q] = b; } else { rown[q] = b; coln[q] = a; mirror[q] = 1; }
+                                j.seq_r = S.dseq(rown[q]); j.seq_c = S.dseq(coln[q]);
+                                j.o = -prm->gpo; j.e = -prm->gpe; j.t = -prm->tgpe;
+                                j.nsoff = -soff[q];
+                        } else if (leaf_a) {
+                                j.kind = KB200_KIND_SP;
+                                rown[q] = b; coln[q] = a; mirror[q] = 1;
+                                j.prof_r = T.prof[b]; j.seq_c = S.dseq(a);
+                                const float sipf = (float)T.nsip[b];
+                                j.o = -(prm->gpo * sipf); j.e = -(prm->gpe * sipf); j.t = -(prm->tgpe * sipf);
+                        } else if (leaf_b) {
+                                j.kind = KB200_KIND_SP;
+                                rown[q] = a; coln[q] = b;
+                                j.prof_r = T.prof[a]; j.seq_c = S.dseq(b);
+                                const float sipf = (float)T.nsip[a];
+                                j.o = -(prm->gpo * sipf); j.e = -(prm->gpe * sipf); j.t = -(prm->tgpe * sipf);
+                        } else {
+                                j.kind = KB200_KIND_PP;
+                                if (la[q] < lb[q]) { rown[q] = a; coln[q] = b; } else { rown[q] = b; coln[q] = a; mirror[q] = 1; }
+                                j.prof_r = T.prof[rown[q]]; j.prof_c = T.prof[coln[q]];
+                        }
+                        rlen[q] = mirror[q] ? lb[q] : la[q];
+                        clen[q] = mirror[q] ? la[q] : lb[q];
+                        j.len_a = rlen[q];
+                        j.len_b = clen[q];
+                        jobs[(size_t)q] = j;
+                        n_raw += (size_t)rlen[q] + 2;
+                        n_coded += (size_t)la[q] + (size_t)lb[q] + 2;
+                        n_scr += (size_t)la[q] + 2;
+                }
+                // ---- consistency bonus (default mode), dense on device ----
+                if (T.posmaps) {
+                        bonus_lists.assign((size_t)nt, {});
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads > 0 ? n_threads : 1)
+#endif
+                        for (int q = 0; q < nt; q++) {
+                                build_bonus(T, rown[q], rlen[q], coln[q], clen[q], bonus_lists[(size_t)q]);
+                        }
+                        size_t dense = 0, nent = 0;
+                        for (int q = 0; q < nt; q++) {
+                                dense += (size_t)rlen[q] * (size_t)clen[q];
+                                nent += bonus_lists[(size_t)q].size();
+                        }
+                        TR(d_bonus.ensure(sizeof(float) * (dense + 16)));
+                        TR(d_bidx.ensure(sizeof(long long) * (nent + 16)));
+                        TR(d_bval.ensure(sizeof(float) * (nent + 16)));
+                        std::vector<long long> hidx(nent);
+                        std::vector<float> hval(nent);
+                        size_t off = 0, e = 0;
+                        for (int q = 0; q < nt; q++) {
+                                jobs[(size_t)q].bonus = d_bonus.as<float>() + off;
+                                for (const auto& pr : bonus_lists[(size_t)q]) {
+                                        hidx[e] = (long long)off + pr.first;
+                                        hval[e] = pr.second;
+                                        e++;
+                                }
+                                off += (size_t)rlen[q] * (size_t)clen[q];
+                        }
+                        TC(cudaMemsetAsync(d_bonus.p, 0, sizeof(float) * dense, st));
+                        if (nent) {
+                                TC(cudaMemcpyAsync(d_bidx.p, hidx.data(), sizeof(long long) * nent, cudaMemcpyHostToDevice, st));
+                                TC(cudaMemcpyAsync(d_bval.p, hval.data(), sizeof(float) * nent, cudaMemcpyHostToDevice, st));
+                                kb_scatter_kernel<<<(unsigned)((nent + 255) / 256), 256, 0, st>>>(d_bonus.as<float>(), d_bidx.as<long long>(), d_bval.as<float>(), (long long)nent);
+                                TC(cudaGetLastError());
+                                ctx->stats.n_launches++;
+                        }
+                        TC(cudaStreamSynchronize(st));
+                        ctx->stats.h2d_bytes += 12.0 * (double)nent;
+                }
+                TR(d_raw.ensure(sizeof(int) * (n_raw + 16)));
+                TR(d_coded.ensure(sizeof(int) * (n_coded + 16)));
+                TR(d_scr.ensure(sizeof(int) * (n_scr + 16)));
+                {
+                        size_t o_raw = 0, o_coded = 0, o_scr = 0;
+                        for (int q = 0; q < nt; q++) {
+                                jobs[(size_t)q].path = d_raw.as<int>() + o_raw;
+                                KbPathJob pj;
+                                pj.raw = d_raw.as<int>() + o_raw;
+                                pj.coded = d_coded.as<int>() + o_coded;
+                                pj.scratch = d_scr.as<int>() + o_scr;
+                                pj.posmap = nullptr;
+                                pj.len_a = la[q]; pj.len_b = lb[q];
+                                pj.mirror = mirror[q];
+                                pjobs[(size_t)q] = pj;
+                                o_raw += (size_t)rlen[q] + 2;
+                                o_coded += (size_t)la[q] + (size_t)lb[q] + 2;
+                                o_scr += (size_t)la[q] + 2;
+                        }
+                }
+                TC(cudaMemsetAsync(d_raw.p, 0xFF, sizeof(int) * n_raw, st));
+                TR(kb_run_hirschberg(ctx, prm->subm, jobs));
+                TR(d_pjobs.ensure(sizeof(KbPathJob) * (size_t)nt));
+                TC(cudaMemcpyAsync(d_pjobs.p, pjobs.data(), sizeof(KbPathJob) * (size_t)nt, cudaMemcpyHostToDevice, st));
+                TR(kb_code_paths(ctx, d_pjobs.as<KbPathJob>(), nt));
+                std::vector<int> hcoded(n_coded);
+                TC(cudaMemcpyAsync(hcoded.data(), d_coded.p, sizeof(int) * n_coded, cudaMemcpyDeviceToHost, st));
+                TC(cudaStreamSynchronize(st));
+                ctx->stats.d2h_bytes += (double)(sizeof(int) * n_coded);
+                // ---- merge profiles on device (update_n), skipped for the root task ----
+                std::vector<KbMergeJob> mjobs;
+                std::vector<long long> mprefix;
+                std::vector<size_t> coded_off((size_t)nt);
+                long long mcols = 0;
+                size_t nsrc = 0;
+                {
+                        size_t o = 0;
+                        for (int q = 0; q < nt; q++) {
+                                coded_off[(size_t)q] = o;
+                                o += (size_t)la[q] + (size_t)lb[q] + 2;
+                        }
+                }
+                for (int q = 0; q < nt; q++) {
+                        if (tl[q] == ntasks - 1) continue;
+                        nsrc += (size_t)hcoded[coded_off[(size_t)q]] + 2;
+                }
+                TR(d_src.ensure(sizeof(int2) * (nsrc + 16)));
+                {
+                        size_t osrc = 0;
+                        for (int q = 0; q < nt; q++) {
+                                const int t = tl[q];
+                                const int a = tasks_abc[3 * t], b = tasks_abc[3 * t + 1], c = tasks_abc[3 * t + 2];
+                                const int alnlen = hcoded[coded_off[(size_t)q]];
+                                if (t != ntasks - 1) {
+                                        float* np = arena.alloc_floats((size_t)(alnlen + 2) * 64);
+                                        if (!np) { cleanup(); return KB200_FAIL; }
+                                        T.prof[c] = np;
+                                        KbMergeJob m;
+                                        m.pa = T.prof[a]; m.pb = T.prof[b]; m.newp = np;
+                                        m.path = d_coded.as<int>() + coded_off[(size_t)q];
+                                        m.src = d_src.as<int2>() + osrc;
+                                        m.alnlen = alnlen;
+                                        m.sipa = T.nsip[a]; m.sipb = T.nsip[b];
+                                        m.gpo = prm->gpo; m.gpe = prm->gpe; m.tgpe = prm->tgpe;
+                                        mjobs.push_back(m);
+                                        mprefix.push_back(mcols);
+                                        mcols += alnlen + 2;
+                                        osrc += (size_t)alnlen + 2;
+                                }
+                        }
+                }
+                if (!mjobs.empty()) {
+                        TR(d_mjobs.ensure(sizeof(KbMergeJob) * mjobs.size()));
+                        TC(cudaMemcpyAsync(d_mjobs.p, mjobs.data(), sizeof(KbMergeJob) * mjobs.size(), cudaMemcpyHostToDevice, st));
+                        TC(cudaMemcpyAsync(d_pref_mg, mprefix.data(), sizeof(long long) * mprefix.size(), cudaMemcpyHostToDevice, st));
+                        TR(kb_merge_index(ctx, d_mjobs.as<KbMergeJob>(), (int)mjobs.size()));
+                        TR(kb_merge_profiles(ctx, d_mjobs.as<KbMergeJob>(), (int)mjobs.size(), d_pref_mg, mcols));
+                }
+                // ---- host bookkeeping while the merge kernels run: gaps, sip, nsip, plen ----
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads > 0 ? n_threads : 1)
+#endif
+                for (int q = 0; q < nt; q++) {
+                        const int t = tl[q];
+                        weave(T, tasks_abc[3 * t], tasks_abc[3 * t + 1], hcoded.data() + coded_off[(size_t)q]);
+                }
+                for (int q = 0; q < nt; q++) {
+                        const int t = tl[q];
+                        const int a = tasks_abc[3 * t], b = tasks_abc[3 * t + 1], c = tasks_abc[3 * t + 2];
+                        T.plen[c] = hcoded[coded_off[(size_t)q]];
+                        T.nsip[c] = T.nsip[a] + T.nsip[b];
+                        std::vector<int>& sc = T.sip[c];
+                        sc.clear();
+                        sc.reserve((size_t)T.nsip[c]);
+                        for (int j = T.nsip[a]; j--;) sc.push_back(T.sip[a][(size_t)j]);     // aln_run.c:428-436
+                        for (int j = T.nsip[b]; j--;) sc.push_back(T.sip[b][(size_t)j]);
+                        if (!T.posmaps) {
+                                std::vector<int>().swap(T.sip[a]);   // children are dead; keep memory bounded
+                                std::vector<int>().swap(T.sip[b]);
+                        } else {
+                                std::vector<int>().swap(T.sip[a]);
+                                std::vector<int>().swap(T.sip[b]);
+                        }
+                }
+                TC(cudaStreamSynchronize(st));
+        }
+        for (int i = 0; i < N; i++) {
+                memcpy(gaps_out + S.h_offs[i] + i, T.gaps[i].data(), sizeof(int) * ((size_t)S.h_lens[i] + 1));
+        }
+        cleanup();
+        (void)rc;
+        return KB200_OK;
+#undef TR
+#undef TC
+}
+
+extern "C" int kb200_align_tree(kb200_ctx* ctx, const kb200_params* prm,
+                                const uint8_t* seqs, const int64_t* offs, const int* lens, int nseq,
+                                const int* tasks_abc, int ntasks, const float* seq_distances,
+                                const int* posmaps, int K, float weight, int* gaps_out)
+{
+        if (!ctx || !prm || !seqs || !offs || !lens || !tasks_abc || !gaps_out || nseq < 2) {
+                return KB200_FAIL;
+        }
+        KB_CUDA(cudaSetDevice(ctx->device));
+        KbSeqs S;
+        int rc = S.upload(ctx, seqs, offs, lens, nseq);
+        if (rc == KB200_OK) {
+                int nthr = 1;
+#ifdef _OPENMP
+                nthr = omp_get_max_threads();
+#endif
+                rc = kb_align_tree_dev(ctx, prm, S, tasks_abc, ntasks, seq_distances, posmaps, K, weight, nthr, gaps_out);
+        }
+        S.release();
+        return rc;
+}
