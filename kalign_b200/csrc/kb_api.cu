@@ -55,6 +55,7 @@ void kb200_ctx_destroy(kb200_ctx* ctx)
         }
         cudaSetDevice(ctx->device);
         KbDevBuf* bufs[] = {&ctx->d_jobs, &ctx->d_boxA, &ctx->d_boxB, &ctx->d_counters, &ctx->d_rows, &ctx->d_tbl,
+                            &ctx->d_units, &ctx->d_prog, &ctx->d_pack, &ctx->d_ppidx,
                             &ctx->d_stage0, &ctx->d_stage1, &ctx->d_stage2, &ctx->d_stage3, &ctx->d_stage4, &ctx->d_stage5};
         for (KbDevBuf* b : bufs) {
                 b->release();

@@ -44,6 +44,7 @@ struct KbJob {
         int* path;              // raw path, len_a+2
         float4* rowF;           // final forward rows of the job's boxes, (len_a+len_b+2) entries
         float4* rowB;           // final backward rows
+        const float* cpack;     // PP: packed column records (len_b+2), built by the engine
         const float* bonus;     // dense bonus (flat i*len_b + j) or nullptr
         const int* bkey;        // sparse bonus: sorted flat keys (i*len_b + j) ...
         const float* bval;      // ... and values; nb entries
@@ -102,7 +103,7 @@ struct kb200_ctx {
         cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
         kb200_stats stats;
         // engine scratch
-        KbDevBuf d_jobs, d_boxA, d_boxB, d_counters, d_rows, d_tbl;
+        KbDevBuf d_jobs, d_boxA, d_boxB, d_counters, d_rows, d_tbl, d_units, d_prog, d_pack, d_ppidx;
         // staging for the host-pointer entry points
         KbDevBuf d_stage0, d_stage1, d_stage2, d_stage3, d_stage4, d_stage5;
 };

@@ -12,49 +12,91 @@
 // (v,u)->(enda-1-v, endb-u).  Cell recurrence, operands and operation order are exactly the
 // reference's (x-y is evaluated as x+(-y); compiled with -fmad=false so every multiply and add is
 // rounded separately; max is evaluated with fmaxf, value-identical to the reference's
-// (a>b?a:b) because no NaN can occur and the sign of a zero never reaches a comparison).
+// (a>b?a:b) because no NaN can occur and the sign of a zero never reaches a comparison; the
+// profile-profile dot product runs densely over the alphabet, adding exact zeros for the residues
+// the reference's sparse list skips -- value-identical for the same reason).
 //
-// Parallel shape: one warp sweeps one (box, direction).  Lane l owns K consecutive rows of a strip
-// of 32*K rows and walks the columns with a skew of one column per lane (anti-diagonal wavefront);
-// the in-diagonal hand-off of the row above is a warp shuffle; the row that leaves a strip
-// (H/E/F = a/ga/gb) is streamed through a per-job row buffer in global memory (float4 per column)
-// and read back by the next strip / the meet-up kernel.  Boxes of one Hirschberg depth of ALL jobs
-// of a batch are processed by one sweep launch and one meet-up launch (level-synchronous
-// work-list); the meet-up emits the child boxes of aln_continue into the next work-list.
+// Parallel shape.  The rows of a (box, direction) sweep are cut into STRIPS of 32*K rows; a strip
+// is swept by one warp: lane l owns K consecutive rows and walks the columns with a skew of one
+// column per lane (anti-diagonal wavefront); the in-diagonal hand-off of the row above is a warp
+// shuffle.  The row that leaves a strip (H/E/F = a/ga/gb, one float4 per column) is streamed
+// through the job's row buffer in global memory; the NEXT strip of the same sweep -- run
+// concurrently by another warp, possibly on another SM -- consumes it a few columns behind
+// (progress flags, release/acquire through __threadfence), so one big box is spread over many SMs
+// (pipelined multi-CTA wavefront) while a batch of many boxes simply fills the machine with
+// independent strips.  Work units (box, direction, strip) are handed out in order by an atomic
+// cursor to a persistent grid: a strip only ever waits for a unit that was handed out earlier.
+// All boxes of one Hirschberg depth of ALL jobs of a batch form one round: plan -> sweep ->
+// meet-up (which emits the child boxes of aln_continue into the next round's work-list).
 #include "kb_common.cuh"
 
 #include <algorithm>
+#include <stdlib.h>
 
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int WARPS_PER_CTA = 4;
 constexpr int TBL_STRIDE = 32;
+constexpr int PUBLISH_EVERY = 16;    // columns between progress publications
+
+// kernel variants
+enum { V_SS = 0, V_SP = 1, V_PP5 = 2, V_PP23 = 3 };
+constexpr int PACK5 = 8;             // packed column record, 5-letter alphabets: s0..s4, [27],[28],[29]
+constexpr int PACK23 = 28;           // 23-letter: s0..s22, [27],[28],[29], pad, pad
+
+template <int V> struct VTraits;
+template <> struct VTraits<V_SS> { static constexpr int NA = 0; };
+template <> struct VTraits<V_SP> { static constexpr int NA = 0; };
+template <> struct VTraits<V_PP5> { static constexpr int NA = 5; };
+template <> struct VTraits<V_PP23> { static constexpr int NA = 23; };
 
 struct Trip {
         float a, ga, gb;
+};
+
+struct KbUnit {
+        int item;    // box * 2 + direction
+        int strip;
 };
 
 __device__ __forceinline__ float kmax(float a, float b) { return fmaxf(a, b); }
 
 enum { MODE_FIRST = 0, MODE_MID = 1, MODE_LAST = 2 };
 
+// rows per strip of a job in a round: "wide" rounds (few big boxes) use thin strips so that one
+// box spreads over many warps; otherwise thick strips amortise the per-step overhead.
+__device__ __host__ __forceinline__ int rows_per_strip(int kind, int nalpha, int thin)
+{
+        if (thin) {
+                return 32;
+        }
+        if (kind == KB200_KIND_PP && nalpha > 5) {
+                return 64;
+        }
+        return 128;
+}
+
 // ---------------------------------------------------------------------------------------------
-// per-strip row context
-template <int KIND, int K> struct RowCtx {
-        // SS: table row offsets; SP/PP: profile column pointers and gap terms
-        int rbase[K];           // SS: residue * TBL_STRIDE
-        const float* prow[K];   // SP/PP: profile column of the row
-        float RO[K], RE[K], RT[K], ROp[K];
-        int irow[K];            // absolute DP row index (bonus)
+template <int V, int K> struct RowCtx {
+        int rbase[K];                                   // SS
+        const float* prow[K];                           // SP
+        float cnt[K][VTraits<V>::NA > 0 ? VTraits<V>::NA : 1];   // PP: residue counts of the row
+        float RO[K], RE[K], RT[K], ROp[K];              // SP, PP
+        int irow[K];
 };
 
-template <int KIND, int K, bool TAIL, int MODE, bool BONUS>
-__device__ __forceinline__ void cells(const KbJob& J, const RowCtx<KIND, K>& rc, unsigned vmask,
-                                      bool first_term, bool last_term,
-                                      // column context
-                                      int cres, const float* __restrict__ q, float CO, float CE, float COp, int jcol,
-                                      const float* __restrict__ s_tbl,
+template <int V> struct ColCtx {
+        int cres;                                       // SS, SP
+        float qs[VTraits<V>::NA > 0 ? VTraits<V>::NA : 1];       // PP: scores of the column
+        float CO, CE, COp;
+        int jcol;
+};
+
+template <int V, int K, bool TAIL, int MODE, bool BONUS>
+__device__ __forceinline__ void cells(const KbJob& J, const RowCtx<V, K>& rc, const unsigned vmask,
+                                      const bool first_term, const bool last_term,
+                                      const ColCtx<V>& cc, const float* __restrict__ s_tbl,
                                       float (&sA)[K], float (&sGA)[K], float (&sGB)[K],
                                       Trip d, Trip& u /* in: up at column u; out: bottom row */)
 {
@@ -62,7 +104,7 @@ __device__ __forceinline__ void cells(const KbJob& J, const RowCtx<KIND, K>& rc,
         for (int k = 0; k < K; k++) {
                 const float oA = sA[k], oGA = sGA[k], oGB = sGB[k];
                 float RO, RE, RT, ROp;
-                if constexpr (KIND == KB200_KIND_SS) {
+                if constexpr (V == V_SS) {
                         RO = J.o; RE = J.e; RT = J.t; ROp = J.o;
                 } else {
                         RO = rc.RO[k]; RE = rc.RE[k]; RT = rc.RT[k]; ROp = rc.ROp[k];
@@ -73,25 +115,23 @@ __device__ __forceinline__ void cells(const KbJob& J, const RowCtx<KIND, K>& rc,
                         ga = KB_NEGF;
                         gb = first_term ? (kmax(u.gb, u.a) + RT) : kmax(u.gb + RE, u.a + RO);
                 } else {
-                        a = kmax(kmax(d.a, d.ga + COp), d.gb + ROp);
-                        if constexpr (KIND == KB200_KIND_SS) {
-                                const float x = s_tbl[rc.rbase[k] + cres] + J.nsoff;
+                        a = kmax(kmax(d.a, d.ga + cc.COp), d.gb + ROp);
+                        if constexpr (V == V_SS) {
+                                const float x = s_tbl[rc.rbase[k] + cc.cres] + J.nsoff;
                                 a = a + x;
-                        } else if constexpr (KIND == KB200_KIND_SP) {
-                                a = a + __ldg(rc.prow[k] + 32 + cres);
+                        } else if constexpr (V == V_SP) {
+                                a = a + __ldg(rc.prow[k] + 32 + cc.cres);
                         } else {
-                                const float* __restrict__ p = rc.prow[k];
-                                for (int c = J.nalpha - 1; c >= 0; c--) {
-                                        const float pr = __ldg(p + c);
-                                        const float prod = __fmul_rn(pr, __ldg(q + 32 + c));
-                                        a = __fadd_rn(a, prod);
+#pragma unroll
+                                for (int c = VTraits<V>::NA - 1; c >= 0; c--) {
+                                        a = __fadd_rn(a, __fmul_rn(rc.cnt[k][c], cc.qs[c]));
                                 }
                         }
                         if constexpr (BONUS) {
-                                a = a + __ldg(J.bonus + (size_t)rc.irow[k] * (size_t)J.len_b + (size_t)jcol);
+                                a = a + __ldg(J.bonus + (size_t)rc.irow[k] * (size_t)J.len_b + (size_t)cc.jcol);
                         }
                         if constexpr (MODE == MODE_MID) {
-                                ga = kmax(oGA + CE, oA + CO);
+                                ga = kmax(oGA + cc.CE, oA + cc.CO);
                                 gb = kmax(u.gb + RE, u.a + RO);
                         } else {
                                 ga = KB_NEGF;
@@ -109,17 +149,27 @@ __device__ __forceinline__ void cells(const KbJob& J, const RowCtx<KIND, K>& rc,
         }
 }
 
+__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p)
+{
+        return *((const volatile unsigned*)p);
+}
+
 // One strip of 32*K rows starting at logical row `row0` of the sweep.
-template <int KIND, int K, bool TAIL, bool BONUS>
+//   prev_prog : progress flag of the strip above (nullptr for strip 0: the init row is generated)
+//   my_prog   : progress flag this strip publishes (nullptr when nobody consumes it)
+template <int V, int K, bool TAIL, bool BONUS>
 __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const int eb,
                             const int r0, const int r1, const int row0,
                             const bool first_term, const bool last_term,
                             const Trip in, float4* __restrict__ rowbuf,
+                            const unsigned* __restrict__ prev_prog, unsigned* __restrict__ my_prog,
                             const float* __restrict__ s_tbl, const int lane)
 {
+        constexpr int NA = VTraits<V>::NA;
+        constexpr int PW4 = (V == V_PP5) ? (PACK5 / 4) : (PACK23 / 4);
         const int C = eb - sb;
         const int R = r1 - r0;
-        RowCtx<KIND, K> rc;
+        RowCtx<V, K> rc;
         unsigned vmask = 0;
 #pragma unroll
         for (int k = 0; k < K; k++) {
@@ -133,12 +183,12 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                 }
                 int i = bwd ? (r1 - 1 - g) : (r0 + g);
                 if (R == 0) {
-                        i = r0;      // never used for arithmetic that survives (pass-through rows)
+                        i = r0;      // pass-through rows: values never survive
                         if (i >= J.len_a) i = J.len_a - 1;
                         if (i < 0) i = 0;
                 }
                 rc.irow[k] = i;
-                if constexpr (KIND == KB200_KIND_SS) {
+                if constexpr (V == V_SS) {
                         rc.rbase[k] = (int)J.seq_r[i] * TBL_STRIDE;
                 } else {
                         const float* p = J.prof_r + ((size_t)(i + 1) << 6);
@@ -148,6 +198,12 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                         rc.RE[k] = __ldg(p + 28);
                         rc.RT[k] = __ldg(p + 29);
                         rc.ROp[k] = __ldg(pp + 27);
+                        if constexpr (NA > 0) {
+#pragma unroll
+                                for (int c = 0; c < NA; c++) {
+                                        rc.cnt[k][c] = __ldg(p + c);
+                                }
+                        }
                 }
         }
         float sA[K], sGA[K], sGB[K];
@@ -157,12 +213,16 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
         }
         Trip d = {KB_NEGF, KB_NEGF, KB_NEGF};
         Trip bot = {KB_NEGF, KB_NEGF, KB_NEGF};
-        // init-row generator (strip 0, lane 0 only): previous column's (a, ga)
-        float genA = in.a, genGA = in.ga;
-        float prevCO = 0.0f;   // PP: [27] of the column visited one step earlier
-        const bool gen = (row0 == 0);
+        float genA = in.a, genGA = in.ga;   // init-row generator (strip 0, lane 0)
+        float prevCO = 0.0f;                // PP: [27] of the column visited one step earlier
+        const bool gen = (prev_prog == nullptr);
+        unsigned avail = gen ? 0x7fffffffu : 0u;   // columns of the row above known to be written
         float4 pre = make_float4(0.f, 0.f, 0.f, 0.f);
         if (!gen && lane == 0) {
+                while (avail < 1u) {
+                        avail = ld_volatile_u32(prev_prog);
+                }
+                __threadfence();
                 pre = __ldcg(rowbuf);
         }
         const int steps = C + 32;
@@ -175,24 +235,35 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                 const bool act = (u >= 0) && (u <= C);
                 if (act) {
                         // ---- column context ----
+                        ColCtx<V> cc;
                         const int j = bwd ? (eb - u) : (sb + u);        // state column
                         const int r = bwd ? j : (j - 1);                // residue / profile index
-                        int cres = 0;
-                        const float* q = nullptr;
-                        float CO, CE, CT, COp;
-                        if constexpr (KIND == KB200_KIND_PP) {
-                                // profile column of state column j: r+1; for u==0 this is the
-                                // boundary column visited "before" u==1 (only its [27] is used)
-                                q = J.prof_c + ((size_t)(r + 1) << 6);
-                                CO = __ldg(q + 27);
-                                CE = __ldg(q + 28);
-                                CT = first_term ? __ldg(q + 29) : 0.0f;
-                                COp = prevCO;
-                                prevCO = CO;
+                        cc.jcol = j;
+                        cc.cres = 0;
+                        float CT;
+                        if constexpr (NA > 0) {
+                                // packed record of profile column r+1 (for u==0 the boundary column
+                                // visited "before" u==1: only its [27] is used)
+                                const float4* __restrict__ rec = reinterpret_cast<const float4*>(J.cpack) + (size_t)(r + 1) * PW4;
+                                float buf[PW4 * 4];
+#pragma unroll
+                                for (int w = 0; w < PW4; w++) {
+                                        const float4 v = __ldg(rec + w);
+                                        buf[4 * w] = v.x; buf[4 * w + 1] = v.y; buf[4 * w + 2] = v.z; buf[4 * w + 3] = v.w;
+                                }
+#pragma unroll
+                                for (int c = 0; c < NA; c++) {
+                                        cc.qs[c] = buf[c];
+                                }
+                                cc.CO = buf[NA];
+                                cc.CE = buf[NA + 1];
+                                CT = buf[NA + 2];
+                                cc.COp = prevCO;
+                                prevCO = cc.CO;
                         } else {
-                                CO = J.o; CE = J.e; CT = J.t; COp = J.o;
+                                cc.CO = J.o; cc.CE = J.e; CT = J.t; cc.COp = J.o;
                                 if (u >= 1) {
-                                        cres = (int)__ldg(J.seq_c + r);
+                                        cc.cres = (int)__ldg(J.seq_c + r);
                                 }
                         }
                         // ---- lane 0: take the row above from the source ----
@@ -205,7 +276,7 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                                                 if (first_term) {
                                                         nga = kmax(genGA, genA) + CT;
                                                 } else {
-                                                        nga = kmax(genGA + CE, genA + CO);
+                                                        nga = kmax(genGA + cc.CE, genA + cc.CO);
                                                 }
                                                 up.a = KB_NEGF; up.ga = nga; up.gb = KB_NEGF;
                                                 genA = KB_NEGF; genGA = nga;
@@ -215,20 +286,24 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                                 } else {
                                         up.a = pre.x; up.ga = pre.y; up.gb = pre.z;
                                         if (u < C) {
+                                                const unsigned need = (unsigned)(u + 2);   // column u+1 written
+                                                if (avail < need) {
+                                                        do {
+                                                                avail = ld_volatile_u32(prev_prog);
+                                                        } while (avail < need);
+                                                        __threadfence();
+                                                }
                                                 pre = __ldcg(rowbuf + u + 1);
                                         }
                                 }
                         }
                         const Trip got = up;
                         if (u == 0) {
-                                cells<KIND, K, TAIL, MODE_FIRST, BONUS>(J, rc, vmask, first_term, last_term, cres, q, CO, CE, COp, j,
-                                                                        s_tbl, sA, sGA, sGB, d, up);
+                                cells<V, K, TAIL, MODE_FIRST, BONUS>(J, rc, vmask, first_term, last_term, cc, s_tbl, sA, sGA, sGB, d, up);
                         } else if (u < C) {
-                                cells<KIND, K, TAIL, MODE_MID, BONUS>(J, rc, vmask, first_term, last_term, cres, q, CO, CE, COp, j,
-                                                                      s_tbl, sA, sGA, sGB, d, up);
+                                cells<V, K, TAIL, MODE_MID, BONUS>(J, rc, vmask, first_term, last_term, cc, s_tbl, sA, sGA, sGB, d, up);
                         } else {
-                                cells<KIND, K, TAIL, MODE_LAST, BONUS>(J, rc, vmask, first_term, last_term, cres, q, CO, CE, COp, j,
-                                                                       s_tbl, sA, sGA, sGB, d, up);
+                                cells<V, K, TAIL, MODE_LAST, BONUS>(J, rc, vmask, first_term, last_term, cc, s_tbl, sA, sGA, sGB, d, up);
                         }
                         d = got;
                         bot = up;
@@ -237,14 +312,19 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                         const int uo = t - 31;
                         if (uo >= 0 && uo <= C) {
                                 rowbuf[uo] = make_float4(bot.a, bot.ga, bot.gb, 0.0f);
+                                if (my_prog && (((uo + 1) % PUBLISH_EVERY) == 0 || uo == C)) {
+                                        __threadfence();
+                                        *((volatile unsigned*)my_prog) = (unsigned)(uo + 1);
+                                }
                         }
                 }
         }
         __syncwarp();
 }
 
-template <int KIND, bool BONUS>
-__device__ void sweep_box(const KbJob& J, const KbBox& bx, const int bwd, const float* __restrict__ s_tbl, const int lane)
+template <int V, bool BONUS>
+__device__ void sweep_unit(const KbJob& J, const KbBox& bx, const int bwd, const int strip, const int thin,
+                           unsigned* __restrict__ prog_self, const float* __restrict__ s_tbl, const int lane)
 {
         const int mid = (bx.ea - bx.sa) / 2 + bx.sa;
         const int r0 = bwd ? mid : bx.sa;
@@ -260,25 +340,30 @@ __device__ void sweep_box(const KbJob& J, const KbBox& bx, const int bwd, const 
         } else {
                 in.a = bx.f0a; in.ga = bx.f0ga; in.gb = bx.f0gb;
         }
-        int row0 = 0;
-        do {
-                const int rem = R - row0;
-                if (rem >= 128) {
-                        sweep_strip<KIND, 4, false, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, s_tbl, lane);
-                        row0 += 128;
-                } else if (rem > 32) {
-                        sweep_strip<KIND, 4, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, s_tbl, lane);
-                        row0 += 128;
-                } else {
-                        sweep_strip<KIND, 1, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, s_tbl, lane);
-                        row0 += 32;
-                }
-        } while (row0 < R);
+        const int rps = rows_per_strip(J.kind, J.nalpha, thin);
+        const int nstr = (R + rps - 1) / rps > 0 ? (R + rps - 1) / rps : 1;
+        const int row0 = strip * rps;
+        const unsigned* prev = (strip > 0) ? (prog_self - 1) : nullptr;
+        unsigned* mine = (strip + 1 < nstr) ? prog_self : nullptr;
+        const int rem = R - row0;
+        if (rps == 32) {
+                sweep_strip<V, 1, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, lane);
+        } else if constexpr (V == V_PP23) {
+                if (rem >= 64) sweep_strip<V, 2, false, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, lane);
+                else if (rem > 32) sweep_strip<V, 2, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, lane);
+                else sweep_strip<V, 1, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, lane);
+        } else {
+                if (rem >= 128) sweep_strip<V, 4, false, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, lane);
+                else if (rem > 32) sweep_strip<V, 4, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, lane);
+                else sweep_strip<V, 1, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, lane);
+        }
 }
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-kb_sweep_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes, const int nboxes,
-                unsigned int* __restrict__ cursor, const float* __restrict__ tbl)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
+kb_sweep_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes,
+                const KbUnit* __restrict__ units, const unsigned* __restrict__ nunits_p,
+                unsigned int* __restrict__ cursor, unsigned* __restrict__ prog,
+                const float* __restrict__ tbl, const int thin)
 {
         __shared__ float s_tbl[23 * TBL_STRIDE];
         for (int i = threadIdx.x; i < 23 * TBL_STRIDE; i += blockDim.x) {
@@ -286,29 +371,105 @@ kb_sweep_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes,
         }
         __syncthreads();
         const int lane = threadIdx.x & 31;
-        const unsigned total = 2u * (unsigned)nboxes;
+        const unsigned total = *nunits_p;
         while (true) {
-                unsigned item = 0;
+                unsigned unit = 0;
                 if (lane == 0) {
-                        item = atomicAdd(cursor, 1u);
+                        unit = atomicAdd(cursor, 1u);
                 }
-                item = __shfl_sync(FULL, item, 0);
-                if (item >= total) {
+                unit = __shfl_sync(FULL, unit, 0);
+                if (unit >= total) {
                         break;
                 }
-                const KbBox bx = boxes[item >> 1];
-                const int bwd = (int)(item & 1u);
+                const KbUnit un = units[unit];
+                const KbBox bx = boxes[un.item >> 1];
+                const int bwd = un.item & 1;
                 const KbJob J = jobs[bx.job];
                 const bool bonus = (J.bonus != nullptr);
+                unsigned* ps = prog + unit;
                 if (J.kind == KB200_KIND_SS) {
-                        if (bonus) sweep_box<KB200_KIND_SS, true>(J, bx, bwd, s_tbl, lane);
-                        else sweep_box<KB200_KIND_SS, false>(J, bx, bwd, s_tbl, lane);
+                        if (bonus) sweep_unit<V_SS, true>(J, bx, bwd, un.strip, thin, ps, s_tbl, lane);
+                        else sweep_unit<V_SS, false>(J, bx, bwd, un.strip, thin, ps, s_tbl, lane);
                 } else if (J.kind == KB200_KIND_SP) {
-                        if (bonus) sweep_box<KB200_KIND_SP, true>(J, bx, bwd, s_tbl, lane);
-                        else sweep_box<KB200_KIND_SP, false>(J, bx, bwd, s_tbl, lane);
+                        if (bonus) sweep_unit<V_SP, true>(J, bx, bwd, un.strip, thin, ps, s_tbl, lane);
+                        else sweep_unit<V_SP, false>(J, bx, bwd, un.strip, thin, ps, s_tbl, lane);
+                } else if (J.nalpha <= 5) {
+                        if (bonus) sweep_unit<V_PP5, true>(J, bx, bwd, un.strip, thin, ps, s_tbl, lane);
+                        else sweep_unit<V_PP5, false>(J, bx, bwd, un.strip, thin, ps, s_tbl, lane);
                 } else {
-                        if (bonus) sweep_box<KB200_KIND_PP, true>(J, bx, bwd, s_tbl, lane);
-                        else sweep_box<KB200_KIND_PP, false>(J, bx, bwd, s_tbl, lane);
+                        if (bonus) sweep_unit<V_PP23, true>(J, bx, bwd, un.strip, thin, ps, s_tbl, lane);
+                        else sweep_unit<V_PP23, false>(J, bx, bwd, un.strip, thin, ps, s_tbl, lane);
+                }
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
+// plan: cut every (box, direction) into strips, reserve a contiguous, ordered unit range
+__global__ void kb_plan_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes, const int nboxes,
+                               const int thin, KbUnit* __restrict__ units, unsigned* __restrict__ prog,
+                               unsigned* __restrict__ nunits)
+{
+        const int lane = threadIdx.x & 31;
+        const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        int nstr = 0;
+        if (item < 2LL * nboxes) {
+                const KbBox bx = boxes[item >> 1];
+                const int bwd = (int)(item & 1);
+                const int mid = (bx.ea - bx.sa) / 2 + bx.sa;
+                const int R = bwd ? (bx.ea - mid) : (mid - bx.sa);
+                const int rps = rows_per_strip(jobs[bx.job].kind, jobs[bx.job].nalpha, thin);
+                nstr = (R + rps - 1) / rps;
+                if (nstr < 1) nstr = 1;
+        }
+        // warp-inclusive scan of nstr
+        int incl = nstr;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += v;
+        }
+        const int warp_total = __shfl_sync(FULL, incl, 31);
+        unsigned base = 0;
+        if (lane == 31 && warp_total > 0) {
+                base = atomicAdd(nunits, (unsigned)warp_total);
+        }
+        base = __shfl_sync(FULL, base, 31);
+        const unsigned mine = base + (unsigned)(incl - nstr);
+        for (int s = 0; s < nstr; s++) {
+                KbUnit un;
+                un.item = (int)item;
+                un.strip = s;
+                units[mine + s] = un;
+                prog[mine + s] = 0u;
+        }
+}
+
+// PP jobs: pack the column profile into compact records (scores of the alphabet, [27],[28],[29])
+__global__ void kb_pack_kernel(const KbJob* __restrict__ jobs, const int* __restrict__ pp_jobs, const int npp,
+                               const long long* __restrict__ col_prefix, const long long total_cols)
+{
+        const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        const long long nth = (long long)gridDim.x * blockDim.x;
+        for (long long gc = gid; gc < total_cols; gc += nth) {
+                int lo = 0, hi = npp - 1;
+                while (lo < hi) {
+                        const int mid = (lo + hi + 1) >> 1;
+                        if (col_prefix[mid] <= gc) lo = mid; else hi = mid - 1;
+                }
+                const KbJob& J = jobs[pp_jobs[lo]];
+                const int col = (int)(gc - col_prefix[lo]);
+                const float* q = J.prof_c + ((size_t)col << 6);
+                const int na = (J.nalpha <= 5) ? 5 : 23;
+                const int pw = (J.nalpha <= 5) ? PACK5 : PACK23;
+                float* out = const_cast<float*>(J.cpack) + (size_t)col * pw;
+                for (int c = 0; c < na; c++) {
+                        out[c] = q[32 + c];
+                }
+                out[na] = q[27];
+                out[na + 1] = q[28];
+                out[na + 2] = q[29];
+                for (int c = na + 3; c < pw; c++) {
+                        out[c] = 0.0f;
                 }
         }
 }
@@ -491,28 +652,51 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
                 return KB200_OK;
         }
         cudaStream_t st = ctx->stream;
-        // row buffers
+        // row buffers, packed column records
         size_t total_cols = 0;
         size_t box_cap = 0;
+        size_t unit_cap = 0;
+        size_t pack_floats = 0;
+        std::vector<int> pp_jobs;
+        std::vector<long long> pp_prefix;
+        long long pp_cols = 0;
         for (int i = 0; i < n; i++) {
                 total_cols += (size_t)(jobs[i].len_a + jobs[i].len_b + 2);
                 box_cap += (size_t)std::max(1, jobs[i].len_a);
+                // every box contributes <= ceil(rows/32) + 2 units, rows of same-depth boxes are disjoint
+                unit_cap += (size_t)jobs[i].len_a / 32 + 2 * (size_t)std::max(1, jobs[i].len_a) + 4;
+                if (jobs[i].kind == KB200_KIND_PP) {
+                        const int pw = (jobs[i].nalpha <= 5) ? PACK5 : PACK23;
+                        pp_jobs.push_back(i);
+                        pp_prefix.push_back(pp_cols);
+                        pp_cols += jobs[i].len_b + 2;
+                        pack_floats += (size_t)(jobs[i].len_b + 2) * pw;
+                }
         }
         KB_RUN(ctx->d_rows.ensure(2 * total_cols * sizeof(float4)));
+        KB_RUN(ctx->d_pack.ensure(pack_floats * sizeof(float) + 64));
         {
                 float4* base = ctx->d_rows.as<float4>();
-                size_t off = 0;
+                float* pbase = ctx->d_pack.as<float>();
+                size_t off = 0, poff = 0;
                 for (int i = 0; i < n; i++) {
                         const size_t w = (size_t)(jobs[i].len_a + jobs[i].len_b + 2);
                         jobs[i].rowF = base + off;
                         jobs[i].rowB = base + total_cols + off;
                         off += w;
+                        if (jobs[i].kind == KB200_KIND_PP) {
+                                const int pw = (jobs[i].nalpha <= 5) ? PACK5 : PACK23;
+                                jobs[i].cpack = pbase + poff;
+                                poff += (size_t)(jobs[i].len_b + 2) * pw;
+                        }
                 }
         }
         KB_RUN(ctx->d_jobs.ensure(sizeof(KbJob) * (size_t)n));
         KB_CUDA(cudaMemcpyAsync(ctx->d_jobs.p, jobs.data(), sizeof(KbJob) * (size_t)n, cudaMemcpyHostToDevice, st));
         KB_RUN(ctx->d_boxA.ensure(sizeof(KbBox) * box_cap));
         KB_RUN(ctx->d_boxB.ensure(sizeof(KbBox) * box_cap));
+        KB_RUN(ctx->d_units.ensure(sizeof(KbUnit) * unit_cap));
+        KB_RUN(ctx->d_prog.ensure(sizeof(unsigned) * unit_cap));
         KB_RUN(ctx->d_counters.ensure(64));
         KB_RUN(ctx->d_tbl.ensure(sizeof(float) * 23 * TBL_STRIDE));
         {
@@ -525,76 +709,105 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
                 KB_CUDA(cudaMemcpyAsync(ctx->d_tbl.p, tbl.data(), sizeof(float) * tbl.size(), cudaMemcpyHostToDevice, st));
                 KB_CUDA(cudaStreamSynchronize(st));   // tbl is a stack-lifetime vector
         }
-        {
-                std::vector<KbBox> init;
-                init.reserve(n);
-                for (int i = 0; i < n; i++) {
-                        if (jobs[i].len_a <= 0 || jobs[i].len_b <= 0) {
-                                continue;
-                        }
-                        KbBox b;
-                        b.job = i; b.sa = 0; b.ea = jobs[i].len_a; b.sb = 0; b.eb = jobs[i].len_b;
-                        b.f0a = 0.0F; b.f0ga = KB_NEGF; b.f0gb = KB_NEGF;
-                        b.b0a = 0.0F; b.b0ga = KB_NEGF; b.b0gb = KB_NEGF;
-                        b.depth = 0;
-                        init.push_back(b);
-                }
-                if (init.empty()) {
-                        return KB200_OK;
-                }
-                KB_CUDA(cudaMemcpyAsync(ctx->d_boxA.p, init.data(), sizeof(KbBox) * init.size(), cudaMemcpyHostToDevice, st));
+        if (!pp_jobs.empty()) {
+                KB_RUN(ctx->d_ppidx.ensure(sizeof(int) * pp_jobs.size() + sizeof(long long) * pp_jobs.size() + 64));
+                long long* d_pref = ctx->d_ppidx.as<long long>();
+                int* d_idx = (int*)(d_pref + pp_jobs.size());
+                KB_CUDA(cudaMemcpyAsync(d_pref, pp_prefix.data(), sizeof(long long) * pp_jobs.size(), cudaMemcpyHostToDevice, st));
+                KB_CUDA(cudaMemcpyAsync(d_idx, pp_jobs.data(), sizeof(int) * pp_jobs.size(), cudaMemcpyHostToDevice, st));
+                const int grid = (int)std::min<long long>((pp_cols + 255) / 256, (long long)ctx->sm_count * 16);
+                kb_pack_kernel<<<grid, 256, 0, st>>>(ctx->d_jobs.as<KbJob>(), d_idx, (int)pp_jobs.size(), d_pref, pp_cols);
+                KB_CUDA(cudaGetLastError());
                 KB_CUDA(cudaStreamSynchronize(st));
-                box_cap = std::max(box_cap, init.size());
-                // counters layout: [0] sweep cursor (u32), [1] next count (u32), [2..3] cells (u64)
-                KB_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 64, st));
-                unsigned count = (unsigned)init.size();
-                KbBox* cur = ctx->d_boxA.as<KbBox>();
-                KbBox* nxt = ctx->d_boxB.as<KbBox>();
-                unsigned int* d_cursor = ctx->d_counters.as<unsigned int>();
-                unsigned int* d_next = d_cursor + 1;
-                unsigned long long* d_cells = (unsigned long long*)(d_cursor + 2);   // [ss, sp, pp, bonus]
-                float sweep_ms = 0.0f;
-                KB_CUDA(cudaEventRecord(ctx->ev0, st));
-                while (count > 0) {
-                        KB_CUDA(cudaMemsetAsync(d_cursor, 0, 8, st));
-                        const unsigned items = 2u * count;
-                        int grid = (int)std::min<unsigned>((items + WARPS_PER_CTA - 1) / WARPS_PER_CTA,
-                                                           (unsigned)(ctx->sm_count * 12));
-                        KB_CUDA(cudaEventRecord(ctx->ev2, st));
-                        kb_sweep_kernel<<<grid, WARPS_PER_CTA * 32, 0, st>>>(ctx->d_jobs.as<KbJob>(), cur, (int)count, d_cursor,
-                                                                            ctx->d_tbl.as<float>());
-                        KB_CUDA(cudaEventRecord(ctx->ev3, st));
-                        int mgrid = (int)std::min<unsigned>((count + 3) / 4, (unsigned)(ctx->sm_count * 16));
-                        kb_meetup_kernel<<<mgrid, 128, 0, st>>>(ctx->d_jobs.as<KbJob>(), cur, (int)count, nxt, d_next, d_cells);
-                        KB_CUDA(cudaGetLastError());
-                        unsigned next_count = 0;
-                        KB_CUDA(cudaMemcpyAsync(&next_count, d_next, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-                        KB_CUDA(cudaStreamSynchronize(st));
-                        float ms = 0.0f;
-                        cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3);
-                        sweep_ms += ms;
-                        ctx->stats.n_boxes += count;
-                        ctx->stats.n_launches += 2;
-                        if ((size_t)next_count > box_cap) {
-                                fprintf(stderr, "[kalign_b200] box list overflow (%u > %zu)\n", next_count, box_cap);
-                                return KB200_FAIL;
-                        }
-                        count = next_count;
-                        std::swap(cur, nxt);
-                }
-                KB_CUDA(cudaEventRecord(ctx->ev1, st));
-                unsigned long long cells[4] = {0, 0, 0, 0};
-                KB_CUDA(cudaMemcpyAsync(cells, d_cells, sizeof(cells), cudaMemcpyDeviceToHost, st));
-                KB_CUDA(cudaStreamSynchronize(st));
-                float ms = 0.0f;
-                cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-                ctx->stats.dp_seconds += 1e-3 * (double)ms;
-                ctx->stats.sweep_seconds += 1e-3 * (double)sweep_ms;
-                ctx->stats.dp_cells += (double)cells[0] + (double)cells[1] + (double)cells[2];
-                ctx->stats.cells_ss += (double)cells[0];
-                ctx->stats.cells_sp += (double)cells[1];
-                ctx->stats.cells_pp += (double)cells[2];
-                ctx->stats.cells_bonus += (double)cells[3];
+                ctx->stats.n_launches += 1;
         }
+        std::vector<KbBox> init;
+        init.reserve(n);
+        size_t rows_total = 0;
+        for (int i = 0; i < n; i++) {
+                if (jobs[i].len_a <= 0 || jobs[i].len_b <= 0) {
+                        continue;
+                }
+                KbBox b;
+                b.job = i; b.sa = 0; b.ea = jobs[i].len_a; b.sb = 0; b.eb = jobs[i].len_b;
+                b.f0a = 0.0F; b.f0ga = KB_NEGF; b.f0gb = KB_NEGF;
+                b.b0a = 0.0F; b.b0ga = KB_NEGF; b.b0gb = KB_NEGF;
+                b.depth = 0;
+                init.push_back(b);
+                rows_total += (size_t)jobs[i].len_a;
+        }
+        if (init.empty()) {
+                return KB200_OK;
+        }
+        KB_CUDA(cudaMemcpyAsync(ctx->d_boxA.p, init.data(), sizeof(KbBox) * init.size(), cudaMemcpyHostToDevice, st));
+        KB_CUDA(cudaStreamSynchronize(st));
+        // counters: [0] sweep cursor, [1] next box count, [2] unit count, [4..11] cells (u64 x4)
+        KB_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 64, st));
+        unsigned count = (unsigned)init.size();
+        KbBox* cur = ctx->d_boxA.as<KbBox>();
+        KbBox* nxt = ctx->d_boxB.as<KbBox>();
+        unsigned int* d_cursor = ctx->d_counters.as<unsigned int>();
+        unsigned int* d_next = d_cursor + 1;
+        unsigned int* d_nunits = d_cursor + 2;
+        unsigned long long* d_cells = (unsigned long long*)(d_cursor + 4);   // [ss, sp, pp, bonus]
+        float sweep_ms = 0.0f;
+        const bool trace = getenv("KB200_TRACE") != nullptr;
+        int round = 0;
+        // resident warps of the persistent sweep grid
+        const int sweep_ctas = ctx->sm_count * 4;
+        const size_t resident_warps = (size_t)sweep_ctas * WARPS_PER_CTA;
+        KB_CUDA(cudaEventRecord(ctx->ev0, st));
+        while (count > 0) {
+                KB_CUDA(cudaMemsetAsync(d_cursor, 0, 12, st));
+                // thin strips when thick ones could not occupy the machine: the rows still alive
+                // at this depth are at most rows_total, spread over `count` boxes
+                const size_t thick_units = rows_total / 128 + 2 * (size_t)count;
+                const int thin = (thick_units < 2 * resident_warps) ? 1 : 0;
+                const unsigned items = 2u * count;
+                kb_plan_kernel<<<(items + 127) / 128, 128, 0, st>>>(ctx->d_jobs.as<KbJob>(), cur, (int)count, thin,
+                                                                     ctx->d_units.as<KbUnit>(), ctx->d_prog.as<unsigned>(), d_nunits);
+                KB_CUDA(cudaEventRecord(ctx->ev2, st));
+                kb_sweep_kernel<<<sweep_ctas, WARPS_PER_CTA * 32, 0, st>>>(ctx->d_jobs.as<KbJob>(), cur, ctx->d_units.as<KbUnit>(),
+                                                                            d_nunits, d_cursor, ctx->d_prog.as<unsigned>(),
+                                                                            ctx->d_tbl.as<float>(), thin);
+                KB_CUDA(cudaEventRecord(ctx->ev3, st));
+                int mgrid = (int)std::min<unsigned>((count + 3) / 4, (unsigned)(ctx->sm_count * 16));
+                kb_meetup_kernel<<<mgrid, 128, 0, st>>>(ctx->d_jobs.as<KbJob>(), cur, (int)count, nxt, d_next, d_cells);
+                KB_CUDA(cudaGetLastError());
+                unsigned host_counts[3] = {0, 0, 0};
+                KB_CUDA(cudaMemcpyAsync(host_counts, d_cursor, sizeof(host_counts), cudaMemcpyDeviceToHost, st));
+                KB_CUDA(cudaStreamSynchronize(st));
+                const unsigned next_count = host_counts[1];
+                float ms = 0.0f;
+                cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3);
+                sweep_ms += ms;
+                if (trace) {
+                        fprintf(stderr, "[kb200 trace] jobs=%d round=%d boxes=%u units=%u thin=%d sweep_ms=%.3f\n", n, round, count,
+                                host_counts[2], thin, ms);
+                }
+                round++;
+                ctx->stats.n_boxes += count;
+                ctx->stats.n_launches += 3;
+                if ((size_t)next_count > box_cap || (size_t)host_counts[2] > unit_cap) {
+                        fprintf(stderr, "[kalign_b200] work-list overflow (boxes %u > %zu or units %u > %zu)\n", next_count, box_cap,
+                                host_counts[2], unit_cap);
+                        return KB200_FAIL;
+                }
+                count = next_count;
+                std::swap(cur, nxt);
+        }
+        KB_CUDA(cudaEventRecord(ctx->ev1, st));
+        unsigned long long cells[4] = {0, 0, 0, 0};
+        KB_CUDA(cudaMemcpyAsync(cells, d_cells, sizeof(cells), cudaMemcpyDeviceToHost, st));
+        KB_CUDA(cudaStreamSynchronize(st));
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        ctx->stats.dp_seconds += 1e-3 * (double)ms;
+        ctx->stats.sweep_seconds += 1e-3 * (double)sweep_ms;
+        ctx->stats.dp_cells += (double)cells[0] + (double)cells[1] + (double)cells[2];
+        ctx->stats.cells_ss += (double)cells[0];
+        ctx->stats.cells_sp += (double)cells[1];
+        ctx->stats.cells_pp += (double)cells[2];
+        ctx->stats.cells_bonus += (double)cells[3];
         return KB200_OK;
 }

@@ -16,6 +16,7 @@
 #include "kb_host.cuh"
 
 #include <string.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <utility>
 
@@ -250,6 +251,9 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                 const std::vector<int>& tl = by_level[(size_t)L];
                 const int nt = (int)tl.size();
                 if (nt == 0) continue;
+                if (getenv("KB200_TRACE")) {
+                        fprintf(stderr, "[kb200 trace] tree level %d: %d tasks\n", L, nt);
+                }
                 // ---- per task: scoring offset, operand lengths ----
                 std::vector<float> soff((size_t)nt, 0.0f);
                 std::vector<int> la((size_t)nt), lb((size_t)nt);
