@@ -89,6 +89,8 @@ typedef struct kb200_stats {
         double cells_ss, cells_sp, cells_pp;   /* dp_cells split by kernel kind */
         double cells_bonus;       /* cells that also read the consistency bonus */
         double align_seconds;     /* device-timed span of kb200_msa_align calls (CUDA events) */
+        double small_seconds;     /* device time of the small-box kernel */
+        double small_ss, small_sp, small_pp;   /* cells handled by the small-box kernel (subset of cells_*) */
 } kb200_stats;
 
 int  kb200_device_count(void);

@@ -38,7 +38,8 @@ class Stats(C.Structure):
                 ("bpm_seconds", C.c_double), ("bpm_pairs", C.c_double),
                 ("h2d_bytes", C.c_double), ("d2h_bytes", C.c_double),
                 ("cells_ss", C.c_double), ("cells_sp", C.c_double), ("cells_pp", C.c_double),
-                ("cells_bonus", C.c_double), ("align_seconds", C.c_double)]
+                ("cells_bonus", C.c_double), ("align_seconds", C.c_double), ("small_seconds", C.c_double),
+                ("small_ss", C.c_double), ("small_sp", C.c_double), ("small_pp", C.c_double)]
 
 
 # every symbol include/kalign_b200.h declares

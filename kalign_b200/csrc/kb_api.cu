@@ -55,11 +55,17 @@ void kb200_ctx_destroy(kb200_ctx* ctx)
         }
         cudaSetDevice(ctx->device);
         KbDevBuf* bufs[] = {&ctx->d_jobs, &ctx->d_boxA, &ctx->d_boxB, &ctx->d_counters, &ctx->d_rows, &ctx->d_tbl,
-                            &ctx->d_units, &ctx->d_prog, &ctx->d_pack, &ctx->d_ppidx,
+                            &ctx->d_units, &ctx->d_prog, &ctx->d_pack, &ctx->d_ppidx, &ctx->d_boxS,
                             &ctx->d_stage0, &ctx->d_stage1, &ctx->d_stage2, &ctx->d_stage3, &ctx->d_stage4, &ctx->d_stage5};
         for (KbDevBuf* b : bufs) {
                 b->release();
         }
+        KbDevBuf* tbufs[] = {&ctx->t_subm, &ctx->t_leaf, &ctx->t_gapset, &ctx->t_prefix, &ctx->t_raw, &ctx->t_coded, &ctx->t_scr,
+                             &ctx->t_pjobs, &ctx->t_mjobs, &ctx->t_src, &ctx->t_bonus, &ctx->t_bidx, &ctx->t_bval};
+        for (KbDevBuf* b : tbufs) {
+                b->release();
+        }
+        ctx->arena.release();
         if (ctx->ev0) cudaEventDestroy(ctx->ev0);
         if (ctx->ev1) cudaEventDestroy(ctx->ev1);
         if (ctx->ev2) cudaEventDestroy(ctx->ev2);

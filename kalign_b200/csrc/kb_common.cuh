@@ -96,6 +96,18 @@ struct KbDevBuf {
         template <typename T> T* as() const { return (T*)p; }
 };
 
+// chunked bump arena for device-resident profiles; chunks are kept across calls (reset())
+struct KbArena {
+        std::vector<void*> chunks;
+        std::vector<size_t> caps;
+        size_t chunk_bytes = (size_t)1 << 30;
+        size_t cur = 0;       // chunk being filled
+        size_t used = 0;      // bytes used in chunk `cur`
+        float* alloc_floats(size_t n);
+        void reset() { cur = 0; used = 0; }
+        void release();
+};
+
 struct kb200_ctx {
         int device = 0;
         int sm_count = 148;
@@ -103,9 +115,12 @@ struct kb200_ctx {
         cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
         kb200_stats stats;
         // engine scratch
-        KbDevBuf d_jobs, d_boxA, d_boxB, d_counters, d_rows, d_tbl, d_units, d_prog, d_pack, d_ppidx;
+        KbDevBuf d_jobs, d_boxA, d_boxB, d_boxS, d_counters, d_rows, d_tbl, d_units, d_prog, d_pack, d_ppidx;
         // staging for the host-pointer entry points
         KbDevBuf d_stage0, d_stage1, d_stage2, d_stage3, d_stage4, d_stage5;
+        // progressive alignment (kb_tree.cu)
+        KbDevBuf t_subm, t_leaf, t_gapset, t_prefix, t_raw, t_coded, t_scr, t_pjobs, t_mjobs, t_src, t_bonus, t_bidx, t_bval;
+        KbArena arena;
 };
 
 // DP engine (kb_dp.cu): run all jobs (device-resident descriptors are built from `jobs`, whose

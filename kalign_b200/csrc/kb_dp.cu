@@ -507,6 +507,7 @@ __device__ __forceinline__ void put_child(KbBox* __restrict__ next, int slot, in
 __global__ void __launch_bounds__(128)
 kb_meetup_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes, const int nboxes,
                  KbBox* __restrict__ next, unsigned int* __restrict__ next_count,
+                 KbBox* __restrict__ small, unsigned int* __restrict__ small_count,
                  unsigned long long* __restrict__ cells)
 {
         const int lane = threadIdx.x & 31;
@@ -625,18 +626,279 @@ kb_meetup_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes
                                 }
                                 const bool hasL = (lsa < lea) && (lsb < leb);
                                 const bool hasR = (rsa < rea) && (rsb < reb);
-                                const int nchild = (hasL ? 1 : 0) + (hasR ? 1 : 0);
-                                if (nchild) {
-                                        unsigned slot = atomicAdd(next_count, (unsigned)nchild);
-                                        if (hasL) {
+                                const bool smL = hasL && small && ((lea - lsa) <= 16) && ((leb - lsb) <= 48);
+                                const bool smR = hasR && small && ((rea - rsa) <= 16) && ((reb - rsb) <= 48);
+                                const int nbig = ((hasL && !smL) ? 1 : 0) + ((hasR && !smR) ? 1 : 0);
+                                const int nsml = (smL ? 1 : 0) + (smR ? 1 : 0);
+                                if (nbig) {
+                                        unsigned slot = atomicAdd(next_count, (unsigned)nbig);
+                                        if (hasL && !smL) {
                                                 put_child(next, (int)slot, bx.job, bx.depth + 1, lsa, lea, lsb, leb, fin, lb0);
                                                 slot++;
                                         }
-                                        if (hasR) {
+                                        if (hasR && !smR) {
                                                 put_child(next, (int)slot, bx.job, bx.depth + 1, rsa, rea, rsb, reb, rf0, bin);
                                         }
                                 }
+                                if (nsml) {
+                                        unsigned slot = atomicAdd(small_count, (unsigned)nsml);
+                                        if (smL) {
+                                                put_child(small, (int)slot, bx.job, bx.depth + 1, lsa, lea, lsb, leb, fin, lb0);
+                                                slot++;
+                                        }
+                                        if (smR) {
+                                                put_child(small, (int)slot, bx.job, bx.depth + 1, rsa, rea, rsb, reb, rf0, bin);
+                                        }
+                                }
                         }
+                }
+        }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// small boxes: one THREAD finishes the whole remaining Hirschberg recursion of a box with few rows
+// and columns (serial sweeps exactly as the reference runs them, explicit DFS stack), so the deep
+// recursion levels -- millions of boxes of a handful of cells -- cost one launch instead of one
+// round each.  Arithmetic is the same cell recurrence in the same order.
+constexpr int SMALL_ROWS = 16;
+constexpr int SMALL_COLS = 48;
+constexpr int SMALL_STACK = 12;
+
+__device__ __forceinline__ bool is_small(int sa, int ea, int sb, int eb)
+{
+        return (ea - sa) <= SMALL_ROWS && (eb - sb) <= SMALL_COLS;
+}
+
+struct SBox {
+        int sa, ea, sb, eb;
+        Trip f0, b0;
+};
+
+template <int V>
+__device__ void small_sweep(const KbJob& J, const int bwd, const int r0, const int r1, const int sb, const int eb,
+                            const Trip in, Trip* __restrict__ S, const float* __restrict__ s_tbl)
+{
+        constexpr int NA = VTraits<V>::NA;
+        constexpr int PW = (V == V_PP5) ? PACK5 : PACK23;
+        const int C = eb - sb;
+        const int R = r1 - r0;
+        const bool first_term = bwd ? (eb == J.len_b) : (sb == 0);
+        const bool last_term = bwd ? (sb == 0) : (eb == J.len_b);
+        S[0] = in;
+        for (int u = 1; u < C; u++) {
+                float CO, CE, CT;
+                if constexpr (NA > 0) {
+                        const int j = bwd ? (eb - u) : (sb + u);
+                        const int r = bwd ? j : (j - 1);
+                        const float* rec = J.cpack + (size_t)(r + 1) * PW;
+                        CO = __ldg(rec + NA); CE = __ldg(rec + NA + 1); CT = __ldg(rec + NA + 2);
+                } else {
+                        CO = J.o; CE = J.e; CT = J.t;
+                }
+                Trip t;
+                t.a = KB_NEGF;
+                t.gb = KB_NEGF;
+                t.ga = first_term ? (kmax(S[u - 1].ga, S[u - 1].a) + CT) : kmax(S[u - 1].ga + CE, S[u - 1].a + CO);
+                S[u] = t;
+        }
+        S[C].a = KB_NEGF; S[C].ga = KB_NEGF; S[C].gb = KB_NEGF;
+        for (int v = 0; v < R; v++) {
+                const int i = bwd ? (r1 - 1 - v) : (r0 + v);
+                float RO, RE, RT, ROp;
+                int rbase = 0;
+                const float* prow = nullptr;
+                if constexpr (V == V_SS) {
+                        RO = J.o; RE = J.e; RT = J.t; ROp = J.o;
+                        rbase = (int)J.seq_r[i] * TBL_STRIDE;
+                } else {
+                        prow = J.prof_r + ((size_t)(i + 1) << 6);
+                        const float* pp = bwd ? (prow + 64) : (prow - 64);
+                        RO = __ldg(prow + 27); RE = __ldg(prow + 28); RT = __ldg(prow + 29); ROp = __ldg(pp + 27);
+                }
+                float pa = S[0].a, pga = S[0].ga, pgb = S[0].gb;
+                float xa = KB_NEGF, xga = KB_NEGF;
+                S[0].a = KB_NEGF;
+                S[0].ga = KB_NEGF;
+                S[0].gb = first_term ? (kmax(pgb, pa) + RT) : kmax(pgb + RE, pa + RO);
+                float COp;
+                if constexpr (NA > 0) {
+                        const int r = bwd ? eb : (sb - 1);
+                        COp = __ldg(J.cpack + (size_t)(r + 1) * PW + NA);
+                } else {
+                        COp = J.o;
+                }
+                for (int u = 1; u <= C; u++) {
+                        const int j = bwd ? (eb - u) : (sb + u);
+                        const int r = bwd ? j : (j - 1);
+                        float CO, CE;
+                        const float ca = S[u].a;
+                        float a = kmax(kmax(pa, pga + COp), pgb + ROp);
+                        if constexpr (V == V_SS) {
+                                CO = J.o; CE = J.e;
+                                const float x = s_tbl[rbase + (int)__ldg(J.seq_c + r)] + J.nsoff;
+                                a = a + x;
+                        } else if constexpr (V == V_SP) {
+                                CO = J.o; CE = J.e;
+                                a = a + __ldg(prow + 32 + (int)__ldg(J.seq_c + r));
+                        } else {
+                                const float* rec = J.cpack + (size_t)(r + 1) * PW;
+                                CO = __ldg(rec + NA); CE = __ldg(rec + NA + 1);
+#pragma unroll
+                                for (int c = NA - 1; c >= 0; c--) {
+                                        a = __fadd_rn(a, __fmul_rn(__ldg(prow + c), __ldg(rec + c)));
+                                }
+                        }
+                        if (J.bonus) {
+                                a = a + __ldg(J.bonus + (size_t)i * (size_t)J.len_b + (size_t)j);
+                        }
+                        S[u].a = a;
+                        pga = S[u].ga;
+                        S[u].ga = (u < C) ? kmax(xga + CE, xa + CO) : KB_NEGF;
+                        pgb = S[u].gb;
+                        if (u == C && last_term) {
+                                S[u].gb = kmax(pgb, ca) + RT;
+                        } else {
+                                S[u].gb = kmax(pgb + RE, ca + RO);
+                        }
+                        pa = ca;
+                        xa = a;
+                        xga = S[u].ga;
+                        COp = CO;
+                }
+        }
+}
+
+template <int V>
+__device__ void small_box_run(const KbJob& J, const KbBox& root, const float* __restrict__ s_tbl,
+                              unsigned long long& ncells)
+{
+        Trip F[SMALL_COLS + 1], B[SMALL_COLS + 1];
+        SBox stack[SMALL_STACK];
+        int sp = 0;
+        {
+                SBox b;
+                b.sa = root.sa; b.ea = root.ea; b.sb = root.sb; b.eb = root.eb;
+                b.f0.a = root.f0a; b.f0.ga = root.f0ga; b.f0.gb = root.f0gb;
+                b.b0.a = root.b0a; b.b0.ga = root.b0ga; b.b0.gb = root.b0gb;
+                stack[sp++] = b;
+        }
+        int* __restrict__ path = J.path;
+        const Trip KA = {0.0F, KB_NEGF, KB_NEGF};
+        const Trip KGA = {KB_NEGF, 0.0F, KB_NEGF};
+        const Trip KGB = {KB_NEGF, KB_NEGF, 0.0F};
+        while (sp > 0) {
+                const SBox bx = stack[--sp];
+                const int sa = bx.sa, ea = bx.ea, sb = bx.sb, eb = bx.eb;
+                const int mid = (ea - sa) / 2 + sa;
+                small_sweep<V>(J, 0, sa, mid, sb, eb, bx.f0, F, s_tbl);
+                small_sweep<V>(J, 1, mid, ea, sb, eb, bx.b0, B, s_tbl);
+                ncells += (unsigned long long)(ea - sa) * (unsigned long long)(eb - sb);
+                // meet-up
+                const float middle = (float)(eb - sb) / 2.0F + (float)sb;
+                float x2, x3, x5, x6, x6last, x7;
+                if constexpr (V == V_SS) {
+                        x2 = x3 = x5 = x7 = J.o;
+                        x6 = (sb == 0) ? J.t : J.e;
+                        x6last = (eb == J.len_b) ? J.t : J.e;
+                } else {
+                        const float* P = J.prof_r + ((size_t)(mid + 1) << 6);
+                        x3 = P[27];
+                        x7 = P[-37];
+                        x6 = (sb == 0) ? P[29] : P[28];
+                        x6last = (eb == J.len_b) ? P[29] : P[28];
+                        x2 = x5 = J.o;
+                }
+                Best m;
+                m.max = KB_NEGF; m.max2 = KB_NEGF; m.key = 0x7fffffff;
+                for (int i = sb; i <= eb; i++) {
+                        const Trip f = F[i - sb];
+                        const Trip b = B[eb - i];
+                        float sub = fabsf(middle - (float)i);
+                        sub = __fdiv_rn(sub, 1000.0F);
+                        const int kb = (i - sb) * 8;
+                        if (i < eb) {
+                                if constexpr (V == V_PP5 || V == V_PP23) {
+                                        x2 = J.prof_c[((size_t)(i + 1) << 6) + 27];
+                                        x5 = J.prof_c[((size_t)i << 6) + 27];
+                                }
+                                offer(m, f.a + b.a - sub, kb + 1);
+                                offer(m, f.a + b.ga + x2 - sub, kb + 2);
+                                offer(m, f.a + b.gb + x3 - sub, kb + 3);
+                                offer(m, f.ga + b.a + x5 - sub, kb + 5);
+                                offer(m, f.gb + b.gb + x6 - sub, kb + 6);
+                                offer(m, f.gb + b.a + x7 - sub, kb + 7);
+                        } else {
+                                offer(m, f.a + b.gb + x3 - sub, kb + 3);
+                                offer(m, f.gb + b.gb + x6last - sub, kb + 6);
+                        }
+                }
+                if (m.key == 0x7fffffff) {
+                        continue;
+                }
+                const int c = sb + (m.key >> 3);
+                const int t = m.key & 7;
+                SBox L, Rr;
+                L.sa = sa; L.sb = sb; L.f0 = bx.f0;
+                Rr.ea = ea; Rr.eb = eb; Rr.b0 = bx.b0;
+                switch (t) {
+                case 1:
+                        path[mid] = c; path[mid + 1] = c + 1;
+                        L.ea = mid - 1; L.eb = c - 1; L.b0 = KA;
+                        Rr.sa = mid + 1; Rr.sb = c + 1; Rr.f0 = KA;
+                        break;
+                case 2:
+                        path[mid] = c;
+                        L.ea = mid - 1; L.eb = c - 1; L.b0 = KA;
+                        Rr.sa = mid; Rr.sb = c + 1; Rr.f0 = KGA;
+                        break;
+                case 3:
+                        path[mid] = c;
+                        L.ea = mid - 1; L.eb = c - 1; L.b0 = KA;
+                        Rr.sa = mid + 1; Rr.sb = c; Rr.f0 = KGB;
+                        break;
+                case 5:
+                        path[mid + 1] = c + 1;
+                        L.ea = mid; L.eb = c - 1; L.b0 = KGA;
+                        Rr.sa = mid + 1; Rr.sb = c + 1; Rr.f0 = KA;
+                        break;
+                case 6:
+                        L.ea = mid - 1; L.eb = c; L.b0 = KGB;
+                        Rr.sa = mid + 1; Rr.sb = c; Rr.f0 = KGB;
+                        break;
+                default:
+                        path[mid + 1] = c + 1;
+                        L.ea = mid - 1; L.eb = c; L.b0 = KGB;
+                        Rr.sa = mid + 1; Rr.sb = c + 1; Rr.f0 = KA;
+                        break;
+                }
+                if (Rr.sa < Rr.ea && Rr.sb < Rr.eb && sp < SMALL_STACK) stack[sp++] = Rr;
+                if (L.sa < L.ea && L.sb < L.eb && sp < SMALL_STACK) stack[sp++] = L;
+        }
+}
+
+__global__ void __launch_bounds__(128)
+kb_small_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes, const unsigned* __restrict__ nsmall_p,
+                unsigned long long* __restrict__ cells, const float* __restrict__ tbl)
+{
+        __shared__ float s_tbl[23 * TBL_STRIDE];
+        for (int i = threadIdx.x; i < 23 * TBL_STRIDE; i += blockDim.x) {
+                s_tbl[i] = tbl[i];
+        }
+        __syncthreads();
+        const unsigned n = *nsmall_p;
+        const unsigned nth = gridDim.x * blockDim.x;
+        for (unsigned b = blockIdx.x * blockDim.x + threadIdx.x; b < n; b += nth) {
+                const KbBox bx = boxes[b];
+                const KbJob J = jobs[bx.job];
+                unsigned long long nc = 0;
+                if (J.kind == KB200_KIND_SS) small_box_run<V_SS>(J, bx, s_tbl, nc);
+                else if (J.kind == KB200_KIND_SP) small_box_run<V_SP>(J, bx, s_tbl, nc);
+                else if (J.nalpha <= 5) small_box_run<V_PP5>(J, bx, s_tbl, nc);
+                else small_box_run<V_PP23>(J, bx, s_tbl, nc);
+                atomicAdd(cells + 4 + J.kind, nc);
+                if (J.bonus) {
+                        atomicAdd(cells + 3, nc);
                 }
         }
 }
@@ -695,9 +957,10 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
         KB_CUDA(cudaMemcpyAsync(ctx->d_jobs.p, jobs.data(), sizeof(KbJob) * (size_t)n, cudaMemcpyHostToDevice, st));
         KB_RUN(ctx->d_boxA.ensure(sizeof(KbBox) * box_cap));
         KB_RUN(ctx->d_boxB.ensure(sizeof(KbBox) * box_cap));
+        KB_RUN(ctx->d_boxS.ensure(sizeof(KbBox) * box_cap));
         KB_RUN(ctx->d_units.ensure(sizeof(KbUnit) * unit_cap));
         KB_RUN(ctx->d_prog.ensure(sizeof(unsigned) * unit_cap));
-        KB_RUN(ctx->d_counters.ensure(64));
+        KB_RUN(ctx->d_counters.ensure(128));
         KB_RUN(ctx->d_tbl.ensure(sizeof(float) * 23 * TBL_STRIDE));
         {
                 std::vector<float> tbl(23 * TBL_STRIDE, 0.0f);
@@ -742,7 +1005,7 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
         KB_CUDA(cudaMemcpyAsync(ctx->d_boxA.p, init.data(), sizeof(KbBox) * init.size(), cudaMemcpyHostToDevice, st));
         KB_CUDA(cudaStreamSynchronize(st));
         // counters: [0] sweep cursor, [1] next box count, [2] unit count, [4..11] cells (u64 x4)
-        KB_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 64, st));
+        KB_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 128, st));
         unsigned count = (unsigned)init.size();
         KbBox* cur = ctx->d_boxA.as<KbBox>();
         KbBox* nxt = ctx->d_boxB.as<KbBox>();
@@ -750,6 +1013,9 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
         unsigned int* d_next = d_cursor + 1;
         unsigned int* d_nunits = d_cursor + 2;
         unsigned long long* d_cells = (unsigned long long*)(d_cursor + 4);   // [ss, sp, pp, bonus]
+        unsigned int* d_nsmall = d_cursor + 3;
+        KbBox* d_small = ctx->d_boxS.as<KbBox>();
+        const bool use_small = getenv("KB200_NO_SMALL") == nullptr;
         float sweep_ms = 0.0f;
         const bool trace = getenv("KB200_TRACE") != nullptr;
         int round = 0;
@@ -772,9 +1038,10 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
                                                                             ctx->d_tbl.as<float>(), thin);
                 KB_CUDA(cudaEventRecord(ctx->ev3, st));
                 int mgrid = (int)std::min<unsigned>((count + 3) / 4, (unsigned)(ctx->sm_count * 16));
-                kb_meetup_kernel<<<mgrid, 128, 0, st>>>(ctx->d_jobs.as<KbJob>(), cur, (int)count, nxt, d_next, d_cells);
+                kb_meetup_kernel<<<mgrid, 128, 0, st>>>(ctx->d_jobs.as<KbJob>(), cur, (int)count, nxt, d_next,
+                                                        use_small ? d_small : nullptr, d_nsmall, d_cells);
                 KB_CUDA(cudaGetLastError());
-                unsigned host_counts[3] = {0, 0, 0};
+                unsigned host_counts[4] = {0, 0, 0, 0};
                 KB_CUDA(cudaMemcpyAsync(host_counts, d_cursor, sizeof(host_counts), cudaMemcpyDeviceToHost, st));
                 KB_CUDA(cudaStreamSynchronize(st));
                 const unsigned next_count = host_counts[1];
@@ -788,7 +1055,7 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
                 round++;
                 ctx->stats.n_boxes += count;
                 ctx->stats.n_launches += 3;
-                if ((size_t)next_count > box_cap || (size_t)host_counts[2] > unit_cap) {
+                if ((size_t)next_count > box_cap || (size_t)host_counts[2] > unit_cap || (size_t)host_counts[3] > box_cap) {
                         fprintf(stderr, "[kalign_b200] work-list overflow (boxes %u > %zu or units %u > %zu)\n", next_count, box_cap,
                                 host_counts[2], unit_cap);
                         return KB200_FAIL;
@@ -796,18 +1063,40 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
                 count = next_count;
                 std::swap(cur, nxt);
         }
+        {
+                // every box that became small during the rounds: finish its recursion in one launch
+                KB_CUDA(cudaEventRecord(ctx->ev2, st));
+                kb_small_kernel<<<ctx->sm_count * 8, 128, 0, st>>>(ctx->d_jobs.as<KbJob>(), d_small, d_nsmall, d_cells, ctx->d_tbl.as<float>());
+                KB_CUDA(cudaGetLastError());
+                KB_CUDA(cudaEventRecord(ctx->ev3, st));
+                KB_CUDA(cudaEventSynchronize(ctx->ev3));
+                float sms = 0.0f;
+                cudaEventElapsedTime(&sms, ctx->ev2, ctx->ev3);
+                ctx->stats.small_seconds += 1e-3 * (double)sms;
+                ctx->stats.n_launches += 1;
+                if (trace) {
+                        unsigned ns = 0;
+                        cudaMemcpy(&ns, d_nsmall, sizeof(unsigned), cudaMemcpyDeviceToHost);
+                        fprintf(stderr, "[kb200 trace] jobs=%d small boxes=%u small_ms=%.3f\n", n, ns, sms);
+                }
+        }
         KB_CUDA(cudaEventRecord(ctx->ev1, st));
-        unsigned long long cells[4] = {0, 0, 0, 0};
+        unsigned long long cells[7] = {0, 0, 0, 0, 0, 0, 0};   // sweep ss/sp/pp, bonus, small ss/sp/pp
         KB_CUDA(cudaMemcpyAsync(cells, d_cells, sizeof(cells), cudaMemcpyDeviceToHost, st));
         KB_CUDA(cudaStreamSynchronize(st));
         float ms = 0.0f;
         cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
         ctx->stats.dp_seconds += 1e-3 * (double)ms;
         ctx->stats.sweep_seconds += 1e-3 * (double)sweep_ms;
-        ctx->stats.dp_cells += (double)cells[0] + (double)cells[1] + (double)cells[2];
-        ctx->stats.cells_ss += (double)cells[0];
-        ctx->stats.cells_sp += (double)cells[1];
-        ctx->stats.cells_pp += (double)cells[2];
+        for (int k = 0; k < 3; k++) {
+                ctx->stats.dp_cells += (double)cells[k] + (double)cells[4 + k];
+        }
+        ctx->stats.cells_ss += (double)cells[0] + (double)cells[4];
+        ctx->stats.cells_sp += (double)cells[1] + (double)cells[5];
+        ctx->stats.cells_pp += (double)cells[2] + (double)cells[6];
         ctx->stats.cells_bonus += (double)cells[3];
+        ctx->stats.small_ss += (double)cells[4];
+        ctx->stats.small_sp += (double)cells[5];
+        ctx->stats.small_pp += (double)cells[6];
         return KB200_OK;
 }

@@ -7,6 +7,32 @@
 
 #include <string.h>
 #include <algorithm>
+#include <chrono>
+#include <stdlib.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+int kb_default_threads()
+{
+        int n = 1;
+#ifdef _OPENMP
+        n = omp_get_max_threads();
+#endif
+        FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r");
+        if (f) {
+                char q[64];
+                long long period = 0;
+                if (fscanf(f, "%63s %lld", q, &period) == 2 && period > 0 && strcmp(q, "max") != 0) {
+                        const long long quota = atoll(q);
+                        if (quota > 0) {
+                                n = std::min<long long>(n, std::max<long long>(1, quota / period));
+                        }
+                }
+                fclose(f);
+        }
+        return std::max(1, std::min(n, 16));
+}
 
 int KbSeqs::upload(kb200_ctx* ctx, const uint8_t* seqs, const int64_t* offs, const int* lens, int nseq)
 {
@@ -31,9 +57,19 @@ int KbSeqs::upload(kb200_ctx* ctx, const uint8_t* seqs, const int64_t* offs, con
 
 float* KbArena::alloc_floats(size_t n)
 {
-        size_t bytes = (n * sizeof(float) + 255) & ~(size_t)255;
-        if (chunks.empty() || used + bytes > cap) {
-                size_t want = std::max(chunk_bytes, bytes);
+        const size_t bytes = (n * sizeof(float) + 255) & ~(size_t)255;
+        while (true) {
+                if (cur < chunks.size()) {
+                        if (used + bytes <= caps[cur]) {
+                                float* r = (float*)((char*)chunks[cur] + used);
+                                used += bytes;
+                                return r;
+                        }
+                        cur++;
+                        used = 0;
+                        continue;
+                }
+                const size_t want = std::max(chunk_bytes, bytes);
                 void* p = nullptr;
                 if (cudaMalloc(&p, want) != cudaSuccess) {
                         fprintf(stderr, "[kalign_b200] arena: cudaMalloc(%zu) failed\n", want);
@@ -41,13 +77,8 @@ float* KbArena::alloc_floats(size_t n)
                         return nullptr;
                 }
                 chunks.push_back(p);
-                cap = want;
-                used = 0;
+                caps.push_back(want);
         }
-        float* r = (float*)((char*)chunks.back() + used);
-        used += bytes;
-        total_bytes += (double)bytes;
-        return r;
 }
 
 void KbArena::release()
@@ -56,7 +87,8 @@ void KbArena::release()
                 cudaFree(p);
         }
         chunks.clear();
-        used = cap = 0;
+        caps.clear();
+        cur = used = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -189,15 +221,29 @@ int kb_anchor_posmaps_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S, co
                 o_coded += (size_t)li + (size_t)lj + 2;
                 o_scr += (size_t)li + 2;
         }
+        const auto t0 = std::chrono::steady_clock::now();
+        auto t1 = t0, t2 = t0;
         if (!jobs.empty()) {
                 KB_CUDA(cudaMemsetAsync(d_raw, 0xFF, sizeof(int) * n_raw, st));
                 KB_RUN(kb_run_hirschberg(ctx, prm->subm, jobs));
+                t1 = std::chrono::steady_clock::now();
                 KB_RUN(ctx->d_stage4.ensure(sizeof(KbPathJob) * pjobs.size()));
                 KB_CUDA(cudaMemcpyAsync(ctx->d_stage4.p, pjobs.data(), sizeof(KbPathJob) * pjobs.size(), cudaMemcpyHostToDevice, st));
                 KB_RUN(kb_code_paths(ctx, ctx->d_stage4.as<KbPathJob>(), (int)pjobs.size()));
         }
+        if (getenv("KB200_TRACE")) {
+                KB_CUDA(cudaStreamSynchronize(st));
+                t2 = std::chrono::steady_clock::now();
+        }
         KB_CUDA(cudaMemcpyAsync(posmaps + out_begin, d_out, sizeof(int) * out_n, cudaMemcpyDeviceToHost, st));
         KB_CUDA(cudaStreamSynchronize(st));
+        if (getenv("KB200_TRACE")) {
+                const auto t3 = std::chrono::steady_clock::now();
+                auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+                        return std::chrono::duration<double, std::milli>(b - a).count();
+                };
+                fprintf(stderr, "[kb200 trace] anchor: %zu jobs dp %.2f code_paths %.2f d2h %.2f ms\n", jobs.size(), ms(t0, t1), ms(t1, t2), ms(t2, t3));
+        }
         ctx->stats.d2h_bytes += (double)(sizeof(int) * out_n);
         // identity maps for the anchors themselves (anchor_consistency.c:252-258)
         for (long long p = pair_begin; p < pair_end; p++) {

@@ -23,17 +23,6 @@ struct KbSeqs {
         const uint8_t* dseq(int i) const { return d_seqs.as<uint8_t>() + h_offs[i]; }
 };
 
-// chunked bump arena for device-resident profiles (never freed before the call ends)
-struct KbArena {
-        std::vector<void*> chunks;
-        size_t chunk_bytes = (size_t)1 << 30;
-        size_t used = 0;      // in the last chunk
-        size_t cap = 0;       // of the last chunk
-        double total_bytes = 0;
-        float* alloc_floats(size_t n);
-        void release();
-};
-
 // d_estimation replacement on device-resident sequences.
 // explicit == 0: rows x cols rectangle; explicit == 1: nrows pairs (rows[p], cols[p]).
 int kb_distances_dev(kb200_ctx* ctx, KbSeqs& S, const int* rows, int nrows, const int* cols, int ncols,
@@ -45,3 +34,6 @@ int kb_anchor_posmaps_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S, co
 int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                       const int* tasks_abc, int ntasks, const float* seq_distances,
                       const int* posmaps, int K, float weight, int n_threads, int* gaps_out);
+
+// host threads worth using: min(OpenMP max threads, cgroup CPU quota, 16)
+int kb_default_threads();

@@ -617,6 +617,7 @@ int kb200_msa_create(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_thr
         }
         *out = nullptr;
         if (n_threads < 1) n_threads = 1;
+        n_threads = std::min(n_threads, kb_default_threads());   // never more than the CPU quota
         KB_CUDA(cudaSetDevice(ctx->device));
         // ---- kalign_arr_to_msa: letter frequencies, alphabet detection (msa_op.c:440-520,142-215)
         int letter_freq[128];

@@ -19,6 +19,7 @@
 #include <stdlib.h>
 #include <algorithm>
 #include <utility>
+#include <chrono>
 
 #ifdef _OPENMP
 #include <omp.h>
@@ -47,79 +48,112 @@ struct Tree {
         float weight = 0.0f;
 };
 
-// get_node_anchor_positions, anchor_consistency.c:352-467
-void node_anchor_positions(const Tree& T, int node, int dp_len, int k,
-                           std::vector<int>& positions, std::vector<float>& conf,
-                           std::vector<int>& col2u, std::vector<int>& best, std::vector<int>& agree, std::vector<int>& total)
+// ---- consistency bonus, level-wide ------------------------------------------------------------
+// get_node_anchor_positions (anchor_consistency.c:352-467) for every operand of a tree level and
+// all K anchors at once.  Parallel decomposition (results are order independent per column):
+// work item = (operand node, block of profile columns); inside a block the members are visited
+// in sip[] order, which is all the "first-seen position wins" vote needs (:440-445).
+struct NodePos {
+        int len = 0;
+        std::vector<int> pos;      // K x len, k-major
+        std::vector<float> conf;
+};
+
+struct PosChunk {
+        int slot;                  // index into the level's NodePos array
+        int node;
+        int c0, c1;
+};
+
+// column of residue p of sequence si in its current profile: p + sum_{q<=p} gaps[q]
+void fill_colof(const Tree& T, int si, std::vector<int>& co)
+{
+        const std::vector<int>& g = T.gaps[(size_t)si];
+        const int len = T.S->h_lens[si];
+        co.resize((size_t)len);
+        int col = 0;
+        for (int p = 0; p < len; p++) {
+                col += g[(size_t)p];
+                co[(size_t)p] = col;
+                col++;
+        }
+}
+
+void pos_chunk(const Tree& T, const std::vector<std::vector<int>>& colof, const PosChunk& w, NodePos& out)
 {
         const KbSeqs& S = *T.S;
-        positions.assign((size_t)dp_len, -1);
-        conf.assign((size_t)dp_len, 0.0f);
-        if (T.nsip[node] == 1) {
-                const int* map = T.posmaps + (size_t)T.K * (size_t)S.h_offs[node] + (size_t)k * (size_t)S.h_lens[node];
-                const int seq_len = S.h_lens[node];
-                for (int i = 0; i < dp_len && i < seq_len; i++) {
-                        positions[i] = map[i];
-                        conf[i] = (map[i] >= 0) ? 1.0f : 0.0f;
+        const int K = T.K;
+        const int len = out.len;
+        if (T.nsip[w.node] == 1) {
+                const int seq_len = S.h_lens[w.node];
+                for (int k = 0; k < K; k++) {
+                        const int* map = T.posmaps + (size_t)K * (size_t)S.h_offs[w.node] + (size_t)k * (size_t)seq_len;
+                        for (int i = w.c0; i < w.c1; i++) {
+                                if (i < seq_len) {
+                                        out.pos[(size_t)k * len + i] = map[i];
+                                        out.conf[(size_t)k * len + i] = (map[i] >= 0) ? 1.0f : 0.0f;
+                                } else {
+                                        out.pos[(size_t)k * len + i] = -1;
+                                        out.conf[(size_t)k * len + i] = 0.0f;
+                                }
+                        }
                 }
                 return;
         }
-        col2u.assign((size_t)dp_len + 1, -1);
-        best.assign((size_t)dp_len, -1);
-        agree.assign((size_t)dp_len, 0);
-        total.assign((size_t)dp_len, 0);
-        for (int si : T.sip[node]) {
-                const int* map = T.posmaps + (size_t)T.K * (size_t)S.h_offs[si] + (size_t)k * (size_t)S.h_lens[si];
+        const int W = w.c1 - w.c0;
+        std::vector<int> best((size_t)K * W, -1), agree((size_t)K * W, 0), total((size_t)K * W, 0);
+        for (int si : T.sip[(size_t)w.node]) {
+                const std::vector<int>& co = colof[(size_t)si];
                 const int seq_len = S.h_lens[si];
-                const std::vector<int>& g = T.gaps[si];
-                int col = 0;
-                for (int p = 0; p <= seq_len && col < dp_len; p++) {
-                        for (int q = 0; q < g[p] && col < dp_len; q++) {
-                                col2u[col++] = -1;
-                        }
-                        if (p < seq_len && col < dp_len) {
-                                col2u[col++] = p;
-                        }
-                }
-                while (col < dp_len) {
-                        col2u[col++] = -1;
-                }
-                for (int c = 0; c < dp_len; c++) {
-                        const int ugp = col2u[c];
-                        if (ugp < 0 || ugp >= seq_len) continue;
-                        const int apos = map[ugp];
-                        if (apos < 0) continue;
-                        total[c]++;
-                        if (best[c] < 0) {
-                                best[c] = apos;
-                                agree[c] = 1;
-                        } else if (apos == best[c]) {
-                                agree[c]++;
+                const int* map0 = T.posmaps + (size_t)K * (size_t)S.h_offs[si];
+                int p = (int)(std::lower_bound(co.begin(), co.end(), w.c0) - co.begin());
+                for (; p < seq_len && co[(size_t)p] < w.c1; p++) {
+                        const int c = co[(size_t)p] - w.c0;
+                        for (int k = 0; k < K; k++) {
+                                const int apos = map0[(size_t)k * seq_len + p];
+                                if (apos < 0) continue;
+                                const size_t e = (size_t)k * W + c;
+                                total[e]++;
+                                if (best[e] < 0) {
+                                        best[e] = apos;
+                                        agree[e] = 1;
+                                } else if (apos == best[e]) {
+                                        agree[e]++;
+                                }
                         }
                 }
         }
-        for (int c = 0; c < dp_len; c++) {
-                if (total[c] > 0 && agree[c] > 0) {
-                        positions[c] = best[c];
-                        conf[c] = (float)agree[c] / (float)total[c];
+        for (int k = 0; k < K; k++) {
+                for (int c = 0; c < W; c++) {
+                        const size_t e = (size_t)k * W + c;
+                        const size_t o = (size_t)k * len + (w.c0 + c);
+                        if (total[e] > 0 && agree[e] > 0) {
+                                out.pos[o] = best[e];
+                                out.conf[o] = (float)agree[e] / (float)total[e];
+                        } else {
+                                out.pos[o] = -1;
+                                out.conf[o] = 0.0f;
+                        }
                 }
         }
 }
 
 // anchor_consistency_get_bonus_profile, anchor_consistency.c:469-561, as a sorted sparse list of
 // (flat index i*len_b + bj, value); contributions to one cell are summed in anchor order k.
-void build_bonus(const Tree& T, int node_a, int len_a, int node_b, int len_b,
-                 std::vector<std::pair<long long, float>>& out)
+void combine_bonus(const Tree& T, const NodePos& A, const NodePos& B, std::vector<std::pair<long long, float>>& out)
 {
         out.clear();
         const int K = T.K;
+        const int len_a = A.len, len_b = B.len;
         const float paw = T.weight / (float)K;
-        std::vector<int> apos_a, apos_b, col2u, best, agree, total, inv_b;
-        std::vector<float> conf_a, conf_b, inv_conf_b;
+        std::vector<int> inv_b;
+        std::vector<float> inv_conf_b;
         std::vector<std::pair<long long, float>> ent;
         for (int k = 0; k < K; k++) {
-                node_anchor_positions(T, node_a, len_a, k, apos_a, conf_a, col2u, best, agree, total);
-                node_anchor_positions(T, node_b, len_b, k, apos_b, conf_b, col2u, best, agree, total);
+                const int* apos_a = A.pos.data() + (size_t)k * len_a;
+                const int* apos_b = B.pos.data() + (size_t)k * len_b;
+                const float* conf_a = A.conf.data() + (size_t)k * len_a;
+                const float* conf_b = B.conf.data() + (size_t)k * len_b;
                 int anchor_len = 0;
                 for (int i = 0; i < len_a; i++) {
                         if (apos_a[i] >= anchor_len) anchor_len = apos_a[i] + 1;
@@ -132,16 +166,16 @@ void build_bonus(const Tree& T, int node_a, int len_a, int node_b, int len_b,
                 inv_conf_b.assign((size_t)anchor_len, 0.0f);
                 for (int j = 0; j < len_b; j++) {
                         if (apos_b[j] >= 0 && apos_b[j] < anchor_len) {
-                                inv_b[apos_b[j]] = j;
-                                inv_conf_b[apos_b[j]] = conf_b[j];
+                                inv_b[(size_t)apos_b[j]] = j;
+                                inv_conf_b[(size_t)apos_b[j]] = conf_b[j];
                         }
                 }
                 for (int i = 0; i < len_a; i++) {
                         const int ak = apos_a[i];
                         if (ak >= 0 && ak < anchor_len) {
-                                const int bj = inv_b[ak];
+                                const int bj = inv_b[(size_t)ak];
                                 if (bj >= 0) {
-                                        const float v = paw * conf_a[i] * inv_conf_b[ak];
+                                        const float v = paw * conf_a[i] * inv_conf_b[(size_t)ak];
                                         ent.emplace_back((long long)i * (long long)len_b + (long long)bj, v);
                                 }
                         }
@@ -161,37 +195,132 @@ void build_bonus(const Tree& T, int node_a, int len_a, int node_b, int len_b,
         }
 }
 
-// make_seq + update_gaps, weave_alignment.c:41-112
-void weave(Tree& T, int a, int b, const int* path)
+void level_bonus(Tree& T, int nt, const std::vector<int>& rown, const std::vector<int>& rlen,
+                 const std::vector<int>& coln, const std::vector<int>& clen, int n_threads,
+                 std::vector<std::vector<int>>& colof,
+                 std::vector<std::vector<std::pair<long long, float>>>& lists)
 {
-        const int alnlen = path[0];
-        std::vector<int> gap_a((size_t)alnlen + 1, 0), gap_b((size_t)alnlen + 1, 0);
-        int posa = 0, posb = 0;
-        for (int c = 1; path[c] != 3; c++) {
-                const int p = path[c];
-                if (!p) {
-                        posa++; posb++;
-                } else if (p & 1) {
-                        gap_a[posa] += 1; posb++;
-                } else if (p & 2) {
-                        gap_b[posb] += 1; posa++;
+        const int K = T.K;
+        (void)n_threads;
+        // members of every profile operand of this level
+        std::vector<int> members;
+        for (int q = 0; q < nt; q++) {
+                const int nodes[2] = {rown[(size_t)q], coln[(size_t)q]};
+                for (int s = 0; s < 2; s++) {
+                        if (T.nsip[(size_t)nodes[s]] > 1) {
+                                members.insert(members.end(), T.sip[(size_t)nodes[s]].begin(), T.sip[(size_t)nodes[s]].end());
+                        }
                 }
         }
-        auto upd = [&](int si, const std::vector<int>& ng) {
-                std::vector<int>& gis = T.gaps[si];
-                const int old_len = T.S->h_lens[si];
-                int rel = 0;
-                for (int i = 0; i <= old_len; i++) {
-                        int add = 0;
-                        for (int j = rel; j <= rel + gis[i]; j++) {
-                                add += ng[j];
+        std::vector<NodePos> np((size_t)2 * nt);
+        std::vector<PosChunk> chunks;
+        const int BLK = 512;
+        for (int q = 0; q < nt; q++) {
+                const int nodes[2] = {rown[(size_t)q], coln[(size_t)q]};
+                const int lens2[2] = {rlen[(size_t)q], clen[(size_t)q]};
+                for (int s = 0; s < 2; s++) {
+                        NodePos& P = np[(size_t)2 * q + s];
+                        P.len = lens2[s];
+                        P.pos.resize((size_t)K * P.len);
+                        P.conf.resize((size_t)K * P.len);
+                        for (int c0 = 0; c0 < P.len; c0 += BLK) {
+                                PosChunk w;
+                                w.slot = 2 * q + s; w.node = nodes[s]; w.c0 = c0; w.c1 = std::min(P.len, c0 + BLK);
+                                chunks.push_back(w);
                         }
-                        rel += gis[i] + 1;
-                        gis[i] += add;
                 }
-        };
-        for (int si : T.sip[a]) upd(si, gap_a);
-        for (int si : T.sip[b]) upd(si, gap_b);
+        }
+        lists.assign((size_t)nt, {});
+#ifdef _OPENMP
+#pragma omp parallel num_threads(n_threads > 0 ? n_threads : 1)
+#endif
+        {
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 16)
+#endif
+                for (long long m = 0; m < (long long)members.size(); m++) {
+                        fill_colof(T, members[(size_t)m], colof[(size_t)members[(size_t)m]]);
+                }
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 1)
+#endif
+                for (long long w = 0; w < (long long)chunks.size(); w++) {
+                        pos_chunk(T, colof, chunks[(size_t)w], np[(size_t)chunks[(size_t)w].slot]);
+                }
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 1)
+#endif
+                for (int q = 0; q < nt; q++) {
+                        combine_bonus(T, np[(size_t)2 * q], np[(size_t)2 * q + 1], lists[(size_t)q]);
+                }
+        }
+}
+
+// make_seq + update_gaps, weave_alignment.c:41-112, level-wide: gap vectors per task, then one
+// independent update per member sequence.
+struct WeaveItem {
+        int si;
+        const std::vector<int>* ng;
+};
+
+void level_weave(Tree& T, int nt, const std::vector<int>& tl, const int* tasks_abc, const int* hcoded,
+                 const std::vector<size_t>& coded_off, int n_threads)
+{
+        std::vector<std::vector<int>> gap_a((size_t)nt), gap_b((size_t)nt);
+        std::vector<WeaveItem> items;
+        for (int q = 0; q < nt; q++) {
+                const int* path = hcoded + coded_off[(size_t)q];
+                gap_a[(size_t)q].assign((size_t)path[0] + 1, 0);
+                gap_b[(size_t)q].assign((size_t)path[0] + 1, 0);
+        }
+        for (int q = 0; q < nt; q++) {
+                const int t = tl[(size_t)q];
+                for (int si : T.sip[(size_t)tasks_abc[3 * t]]) items.push_back({si, &gap_a[(size_t)q]});
+                for (int si : T.sip[(size_t)tasks_abc[3 * t + 1]]) items.push_back({si, &gap_b[(size_t)q]});
+        }
+        (void)n_threads;
+#ifdef _OPENMP
+#pragma omp parallel num_threads(n_threads > 0 ? n_threads : 1)
+#endif
+        {
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 1)
+#endif
+                for (int q = 0; q < nt; q++) {
+                        const int* path = hcoded + coded_off[(size_t)q];
+                        std::vector<int>& ga = gap_a[(size_t)q];
+                        std::vector<int>& gb = gap_b[(size_t)q];
+                        int posa = 0, posb = 0;
+                        for (int c = 1; path[c] != 3; c++) {
+                                const int p = path[c];
+                                if (!p) {
+                                        posa++; posb++;
+                                } else if (p & 1) {
+                                        ga[(size_t)posa] += 1; posb++;
+                                } else if (p & 2) {
+                                        gb[(size_t)posb] += 1; posa++;
+                                }
+                        }
+                }
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 8)
+#endif
+                for (long long m = 0; m < (long long)items.size(); m++) {
+                        const WeaveItem& it = items[(size_t)m];
+                        std::vector<int>& gis = T.gaps[(size_t)it.si];
+                        const std::vector<int>& ng = *it.ng;
+                        const int old_len = T.S->h_lens[it.si];
+                        int rel = 0;
+                        for (int i = 0; i <= old_len; i++) {
+                                int add = 0;
+                                for (int j = rel; j <= rel + gis[(size_t)i]; j++) {
+                                        add += ng[(size_t)j];
+                                }
+                                rel += gis[(size_t)i] + 1;
+                                gis[(size_t)i] += add;
+                        }
+                }
+        }
 }
 
 } // namespace
@@ -233,27 +362,31 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
         for (int t = 0; t < ntasks; t++) {
                 by_level[(size_t)T.level[tasks_abc[3 * t + 2]]].push_back(t);
         }
-        KbArena arena;
-        KbDevBuf d_subm, d_leaf, d_gapset, d_prefix, d_raw, d_coded, d_scr, d_pjobs, d_mjobs, d_src, d_bonus, d_bidx, d_bval;
+        // device scratch lives in the context and is reused by later calls
+        KbArena& arena = ctx->arena;
+        arena.reset();
+        KbDevBuf &d_subm = ctx->t_subm, &d_leaf = ctx->t_leaf, &d_gapset = ctx->t_gapset, &d_prefix = ctx->t_prefix,
+                 &d_raw = ctx->t_raw, &d_coded = ctx->t_coded, &d_scr = ctx->t_scr, &d_pjobs = ctx->t_pjobs,
+                 &d_mjobs = ctx->t_mjobs, &d_src = ctx->t_src, &d_bonus = ctx->t_bonus, &d_bidx = ctx->t_bidx, &d_bval = ctx->t_bval;
         int rc = KB200_OK;
-        auto cleanup = [&]() {
-                arena.release();
-                KbDevBuf* bufs[] = {&d_subm, &d_leaf, &d_gapset, &d_prefix, &d_raw, &d_coded, &d_scr, &d_pjobs, &d_mjobs, &d_src, &d_bonus, &d_bidx, &d_bval};
-                for (KbDevBuf* b : bufs) b->release();
-        };
+        auto cleanup = [&]() {};
 #define TR(x) do { if ((x) != KB200_OK) { fprintf(stderr, "[kalign_b200] align_tree failure at %s:%d\n", __FILE__, __LINE__); cleanup(); return KB200_FAIL; } } while (0)
 #define TC(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { fprintf(stderr, "[kalign_b200] CUDA error %s at %s:%d\n", cudaGetErrorString(e__), __FILE__, __LINE__); cleanup(); return KB200_FAIL; } } while (0)
         TR(d_subm.ensure(sizeof(float) * 23 * 23));
         TC(cudaMemcpyAsync(d_subm.p, prm->subm, sizeof(float) * 23 * 23, cudaMemcpyHostToDevice, st));
 
         std::vector<std::vector<std::pair<long long, float>>> bonus_lists;
+        std::vector<std::vector<int>> colof((size_t)N);
         for (int L = 1; L <= maxlevel; L++) {
                 const std::vector<int>& tl = by_level[(size_t)L];
                 const int nt = (int)tl.size();
                 if (nt == 0) continue;
-                if (getenv("KB200_TRACE")) {
-                        fprintf(stderr, "[kb200 trace] tree level %d: %d tasks\n", L, nt);
-                }
+                const bool trace = getenv("KB200_TRACE") != nullptr;
+                auto tnow = []() { return std::chrono::steady_clock::now(); };
+                auto tms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+                        return std::chrono::duration<double, std::milli>(b - a).count();
+                };
+                const auto t_level0 = tnow();
                 // ---- per task: scoring offset, operand lengths ----
                 std::vector<float> soff((size_t)nt, 0.0f);
                 std::vector<int> la((size_t)nt), lb((size_t)nt);
@@ -372,15 +505,10 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                         n_coded += (size_t)la[q] + (size_t)lb[q] + 2;
                         n_scr += (size_t)la[q] + 2;
                 }
+                const auto t_prep = tnow();
                 // ---- consistency bonus (default mode), dense on device ----
                 if (T.posmaps) {
-                        bonus_lists.assign((size_t)nt, {});
-#ifdef _OPENMP
-#pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads > 0 ? n_threads : 1)
-#endif
-                        for (int q = 0; q < nt; q++) {
-                                build_bonus(T, rown[q], rlen[q], coln[q], clen[q], bonus_lists[(size_t)q]);
-                        }
+                        level_bonus(T, nt, rown, rlen, coln, clen, n_threads, colof, bonus_lists);
                         size_t dense = 0, nent = 0;
                         for (int q = 0; q < nt; q++) {
                                 dense += (size_t)rlen[q] * (size_t)clen[q];
@@ -412,6 +540,7 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                         TC(cudaStreamSynchronize(st));
                         ctx->stats.h2d_bytes += 12.0 * (double)nent;
                 }
+                const auto t_bonus = tnow();
                 TR(d_raw.ensure(sizeof(int) * (n_raw + 16)));
                 TR(d_coded.ensure(sizeof(int) * (n_coded + 16)));
                 TR(d_scr.ensure(sizeof(int) * (n_scr + 16)));
@@ -434,6 +563,7 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                 }
                 TC(cudaMemsetAsync(d_raw.p, 0xFF, sizeof(int) * n_raw, st));
                 TR(kb_run_hirschberg(ctx, prm->subm, jobs));
+                const auto t_dp = tnow();
                 TR(d_pjobs.ensure(sizeof(KbPathJob) * (size_t)nt));
                 TC(cudaMemcpyAsync(d_pjobs.p, pjobs.data(), sizeof(KbPathJob) * (size_t)nt, cudaMemcpyHostToDevice, st));
                 TR(kb_code_paths(ctx, d_pjobs.as<KbPathJob>(), nt));
@@ -490,14 +620,9 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                         TR(kb_merge_index(ctx, d_mjobs.as<KbMergeJob>(), (int)mjobs.size()));
                         TR(kb_merge_profiles(ctx, d_mjobs.as<KbMergeJob>(), (int)mjobs.size(), d_pref_mg, mcols));
                 }
+                const auto t_post = tnow();
                 // ---- host bookkeeping while the merge kernels run: gaps, sip, nsip, plen ----
-#ifdef _OPENMP
-#pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads > 0 ? n_threads : 1)
-#endif
-                for (int q = 0; q < nt; q++) {
-                        const int t = tl[q];
-                        weave(T, tasks_abc[3 * t], tasks_abc[3 * t + 1], hcoded.data() + coded_off[(size_t)q]);
-                }
+                level_weave(T, nt, tl, tasks_abc, hcoded.data(), coded_off, n_threads);
                 for (int q = 0; q < nt; q++) {
                         const int t = tl[q];
                         const int a = tasks_abc[3 * t], b = tasks_abc[3 * t + 1], c = tasks_abc[3 * t + 2];
@@ -517,6 +642,11 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                         }
                 }
                 TC(cudaStreamSynchronize(st));
+                if (trace) {
+                        const auto t_end = tnow();
+                        fprintf(stderr, "[kb200 trace] tree level %d: %d tasks prep %.2f bonus %.2f dp %.2f post %.2f weave %.2f ms\n", L, nt,
+                                tms(t_level0, t_prep), tms(t_prep, t_bonus), tms(t_bonus, t_dp), tms(t_dp, t_post), tms(t_post, t_end));
+                }
         }
         for (int i = 0; i < N; i++) {
                 memcpy(gaps_out + S.h_offs[i] + i, T.gaps[i].data(), sizeof(int) * ((size_t)S.h_lens[i] + 1));
@@ -540,10 +670,7 @@ extern "C" int kb200_align_tree(kb200_ctx* ctx, const kb200_params* prm,
         KbSeqs S;
         int rc = S.upload(ctx, seqs, offs, lens, nseq);
         if (rc == KB200_OK) {
-                int nthr = 1;
-#ifdef _OPENMP
-                nthr = omp_get_max_threads();
-#endif
+                const int nthr = kb_default_threads();
                 rc = kb_align_tree_dev(ctx, prm, S, tasks_abc, ntasks, seq_distances, posmaps, K, weight, nthr, gaps_out);
         }
         S.release();
