@@ -37,7 +37,7 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int WARPS_PER_CTA = 4;
-constexpr int TBL_STRIDE = 32;
+constexpr int TBL_MAX = 23 * 32;     // shared table capacity (floats)
 constexpr int PUBLISH_EVERY = 16;    // columns between progress publications
 
 // kernel variants
@@ -163,7 +163,7 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                             const bool first_term, const bool last_term,
                             const Trip in, float4* __restrict__ rowbuf,
                             const unsigned* __restrict__ prev_prog, unsigned* __restrict__ my_prog,
-                            const float* __restrict__ s_tbl, const int lane)
+                            const float* __restrict__ s_tbl, const int tstride, const int lane)
 {
         constexpr int NA = VTraits<V>::NA;
         constexpr int PW4 = (V == V_PP5) ? (PACK5 / 4) : (PACK23 / 4);
@@ -189,7 +189,7 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                 }
                 rc.irow[k] = i;
                 if constexpr (V == V_SS) {
-                        rc.rbase[k] = (int)J.seq_r[i] * TBL_STRIDE;
+                        rc.rbase[k] = (int)J.seq_r[i] * tstride;
                 } else {
                         const float* p = J.prof_r + ((size_t)(i + 1) << 6);
                         const float* pp = bwd ? (p + 64) : (p - 64);
@@ -324,7 +324,7 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
 
 template <int V, bool BONUS>
 __device__ void sweep_unit(const KbJob& J, const KbBox& bx, const int bwd, const int strip, const int thin,
-                           unsigned* __restrict__ prog_self, const float* __restrict__ s_tbl, const int lane)
+                           unsigned* __restrict__ prog_self, const float* __restrict__ s_tbl, const int tstride, const int lane)
 {
         const int mid = (bx.ea - bx.sa) / 2 + bx.sa;
         const int r0 = bwd ? mid : bx.sa;
@@ -347,15 +347,15 @@ __device__ void sweep_unit(const KbJob& J, const KbBox& bx, const int bwd, const
         unsigned* mine = (strip + 1 < nstr) ? prog_self : nullptr;
         const int rem = R - row0;
         if (rps == 32) {
-                sweep_strip<V, 1, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, lane);
+                sweep_strip<V, 1, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane);
         } else if constexpr (V == V_PP23) {
-                if (rem >= 64) sweep_strip<V, 2, false, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, lane);
-                else if (rem > 32) sweep_strip<V, 2, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, lane);
-                else sweep_strip<V, 1, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, lane);
+                if (rem >= 64) sweep_strip<V, 2, false, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane);
+                else if (rem > 32) sweep_strip<V, 2, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane);
+                else sweep_strip<V, 1, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane);
         } else {
-                if (rem >= 128) sweep_strip<V, 4, false, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, lane);
-                else if (rem > 32) sweep_strip<V, 4, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, lane);
-                else sweep_strip<V, 1, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, lane);
+                if (rem >= 128) sweep_strip<V, 4, false, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane);
+                else if (rem > 32) sweep_strip<V, 4, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane);
+                else sweep_strip<V, 1, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane);
         }
 }
 
@@ -363,10 +363,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
 kb_sweep_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes,
                 const KbUnit* __restrict__ units, const unsigned* __restrict__ nunits_p,
                 unsigned int* __restrict__ cursor, unsigned* __restrict__ prog,
-                const float* __restrict__ tbl, const int thin)
+                const float* __restrict__ tbl, const int thin, const int tstride)
 {
-        __shared__ float s_tbl[23 * TBL_STRIDE];
-        for (int i = threadIdx.x; i < 23 * TBL_STRIDE; i += blockDim.x) {
+        __shared__ float s_tbl[TBL_MAX];
+        for (int i = threadIdx.x; i < TBL_MAX; i += blockDim.x) {
                 s_tbl[i] = tbl[i];
         }
         __syncthreads();
@@ -388,17 +388,17 @@ kb_sweep_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes,
                 const bool bonus = (J.bonus != nullptr);
                 unsigned* ps = prog + unit;
                 if (J.kind == KB200_KIND_SS) {
-                        if (bonus) sweep_unit<V_SS, true>(J, bx, bwd, un.strip, thin, ps, s_tbl, lane);
-                        else sweep_unit<V_SS, false>(J, bx, bwd, un.strip, thin, ps, s_tbl, lane);
+                        if (bonus) sweep_unit<V_SS, true>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane);
+                        else sweep_unit<V_SS, false>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane);
                 } else if (J.kind == KB200_KIND_SP) {
-                        if (bonus) sweep_unit<V_SP, true>(J, bx, bwd, un.strip, thin, ps, s_tbl, lane);
-                        else sweep_unit<V_SP, false>(J, bx, bwd, un.strip, thin, ps, s_tbl, lane);
+                        if (bonus) sweep_unit<V_SP, true>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane);
+                        else sweep_unit<V_SP, false>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane);
                 } else if (J.nalpha <= 5) {
-                        if (bonus) sweep_unit<V_PP5, true>(J, bx, bwd, un.strip, thin, ps, s_tbl, lane);
-                        else sweep_unit<V_PP5, false>(J, bx, bwd, un.strip, thin, ps, s_tbl, lane);
+                        if (bonus) sweep_unit<V_PP5, true>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane);
+                        else sweep_unit<V_PP5, false>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane);
                 } else {
-                        if (bonus) sweep_unit<V_PP23, true>(J, bx, bwd, un.strip, thin, ps, s_tbl, lane);
-                        else sweep_unit<V_PP23, false>(J, bx, bwd, un.strip, thin, ps, s_tbl, lane);
+                        if (bonus) sweep_unit<V_PP23, true>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane);
+                        else sweep_unit<V_PP23, false>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane);
                 }
         }
 }
@@ -677,7 +677,7 @@ struct SBox {
 
 template <int V>
 __device__ void small_sweep(const KbJob& J, const int bwd, const int r0, const int r1, const int sb, const int eb,
-                            const Trip in, Trip* __restrict__ S, const float* __restrict__ s_tbl)
+                            const Trip in, Trip* __restrict__ S, const float* __restrict__ s_tbl, const int tstride)
 {
         constexpr int NA = VTraits<V>::NA;
         constexpr int PW = (V == V_PP5) ? PACK5 : PACK23;
@@ -710,7 +710,7 @@ __device__ void small_sweep(const KbJob& J, const int bwd, const int r0, const i
                 const float* prow = nullptr;
                 if constexpr (V == V_SS) {
                         RO = J.o; RE = J.e; RT = J.t; ROp = J.o;
-                        rbase = (int)J.seq_r[i] * TBL_STRIDE;
+                        rbase = (int)J.seq_r[i] * tstride;
                 } else {
                         prow = J.prof_r + ((size_t)(i + 1) << 6);
                         const float* pp = bwd ? (prow + 64) : (prow - 64);
@@ -770,7 +770,7 @@ __device__ void small_sweep(const KbJob& J, const int bwd, const int r0, const i
 }
 
 template <int V>
-__device__ void small_box_run(const KbJob& J, const KbBox& root, const float* __restrict__ s_tbl,
+__device__ void small_box_run(const KbJob& J, const KbBox& root, const float* __restrict__ s_tbl, const int tstride,
                               unsigned long long& ncells)
 {
         Trip F[SMALL_COLS + 1], B[SMALL_COLS + 1];
@@ -791,8 +791,8 @@ __device__ void small_box_run(const KbJob& J, const KbBox& root, const float* __
                 const SBox bx = stack[--sp];
                 const int sa = bx.sa, ea = bx.ea, sb = bx.sb, eb = bx.eb;
                 const int mid = (ea - sa) / 2 + sa;
-                small_sweep<V>(J, 0, sa, mid, sb, eb, bx.f0, F, s_tbl);
-                small_sweep<V>(J, 1, mid, ea, sb, eb, bx.b0, B, s_tbl);
+                small_sweep<V>(J, 0, sa, mid, sb, eb, bx.f0, F, s_tbl, tstride);
+                small_sweep<V>(J, 1, mid, ea, sb, eb, bx.b0, B, s_tbl, tstride);
                 ncells += (unsigned long long)(ea - sa) * (unsigned long long)(eb - sb);
                 // meet-up
                 const float middle = (float)(eb - sb) / 2.0F + (float)sb;
@@ -879,10 +879,10 @@ __device__ void small_box_run(const KbJob& J, const KbBox& root, const float* __
 
 __global__ void __launch_bounds__(128)
 kb_small_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes, const unsigned* __restrict__ nsmall_p,
-                unsigned long long* __restrict__ cells, const float* __restrict__ tbl)
+                unsigned long long* __restrict__ cells, const float* __restrict__ tbl, const int tstride)
 {
-        __shared__ float s_tbl[23 * TBL_STRIDE];
-        for (int i = threadIdx.x; i < 23 * TBL_STRIDE; i += blockDim.x) {
+        __shared__ float s_tbl[TBL_MAX];
+        for (int i = threadIdx.x; i < TBL_MAX; i += blockDim.x) {
                 s_tbl[i] = tbl[i];
         }
         __syncthreads();
@@ -892,10 +892,10 @@ kb_small_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes,
                 const KbBox bx = boxes[b];
                 const KbJob J = jobs[bx.job];
                 unsigned long long nc = 0;
-                if (J.kind == KB200_KIND_SS) small_box_run<V_SS>(J, bx, s_tbl, nc);
-                else if (J.kind == KB200_KIND_SP) small_box_run<V_SP>(J, bx, s_tbl, nc);
-                else if (J.nalpha <= 5) small_box_run<V_PP5>(J, bx, s_tbl, nc);
-                else small_box_run<V_PP23>(J, bx, s_tbl, nc);
+                if (J.kind == KB200_KIND_SS) small_box_run<V_SS>(J, bx, s_tbl, tstride, nc);
+                else if (J.kind == KB200_KIND_SP) small_box_run<V_SP>(J, bx, s_tbl, tstride, nc);
+                else if (J.nalpha <= 5) small_box_run<V_PP5>(J, bx, s_tbl, tstride, nc);
+                else small_box_run<V_PP23>(J, bx, s_tbl, tstride, nc);
                 atomicAdd(cells + 4 + J.kind, nc);
                 if (J.bonus) {
                         atomicAdd(cells + 3, nc);
@@ -961,12 +961,19 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
         KB_RUN(ctx->d_units.ensure(sizeof(KbUnit) * unit_cap));
         KB_RUN(ctx->d_prog.ensure(sizeof(unsigned) * unit_cap));
         KB_RUN(ctx->d_counters.ensure(128));
-        KB_RUN(ctx->d_tbl.ensure(sizeof(float) * 23 * TBL_STRIDE));
+        KB_RUN(ctx->d_tbl.ensure(sizeof(float) * TBL_MAX));
+        // shared-memory score table: row stride = alphabet size, so that a 5-letter table (25
+        // entries) puts every entry in its own bank -- lanes reading different entries never conflict
+        int max_alpha = 5;
+        for (int i = 0; i < n; i++) {
+                max_alpha = std::max(max_alpha, jobs[i].nalpha);
+        }
+        const int tstride = (max_alpha <= 5) ? 5 : 23;
         {
-                std::vector<float> tbl(23 * TBL_STRIDE, 0.0f);
-                for (int i = 0; i < 23; i++) {
-                        for (int j = 0; j < 23; j++) {
-                                tbl[i * TBL_STRIDE + j] = subm_host[i * 23 + j];
+                std::vector<float> tbl(TBL_MAX, 0.0f);
+                for (int i = 0; i < tstride; i++) {
+                        for (int j = 0; j < tstride; j++) {
+                                tbl[i * tstride + j] = subm_host[i * 23 + j];
                         }
                 }
                 KB_CUDA(cudaMemcpyAsync(ctx->d_tbl.p, tbl.data(), sizeof(float) * tbl.size(), cudaMemcpyHostToDevice, st));
@@ -1035,7 +1042,7 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
                 KB_CUDA(cudaEventRecord(ctx->ev2, st));
                 kb_sweep_kernel<<<sweep_ctas, WARPS_PER_CTA * 32, 0, st>>>(ctx->d_jobs.as<KbJob>(), cur, ctx->d_units.as<KbUnit>(),
                                                                             d_nunits, d_cursor, ctx->d_prog.as<unsigned>(),
-                                                                            ctx->d_tbl.as<float>(), thin);
+                                                                            ctx->d_tbl.as<float>(), thin, tstride);
                 KB_CUDA(cudaEventRecord(ctx->ev3, st));
                 int mgrid = (int)std::min<unsigned>((count + 3) / 4, (unsigned)(ctx->sm_count * 16));
                 kb_meetup_kernel<<<mgrid, 128, 0, st>>>(ctx->d_jobs.as<KbJob>(), cur, (int)count, nxt, d_next,
@@ -1066,7 +1073,7 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
         {
                 // every box that became small during the rounds: finish its recursion in one launch
                 KB_CUDA(cudaEventRecord(ctx->ev2, st));
-                kb_small_kernel<<<ctx->sm_count * 8, 128, 0, st>>>(ctx->d_jobs.as<KbJob>(), d_small, d_nsmall, d_cells, ctx->d_tbl.as<float>());
+                kb_small_kernel<<<ctx->sm_count * 8, 128, 0, st>>>(ctx->d_jobs.as<KbJob>(), d_small, d_nsmall, d_cells, ctx->d_tbl.as<float>(), tstride);
                 KB_CUDA(cudaGetLastError());
                 KB_CUDA(cudaEventRecord(ctx->ev3, st));
                 KB_CUDA(cudaEventSynchronize(ctx->ev3));
