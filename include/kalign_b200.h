@@ -91,6 +91,7 @@ typedef struct kb200_stats {
         double align_seconds;     /* device-timed span of kb200_msa_align calls (CUDA events) */
         double small_seconds;     /* device time of the small-box kernel */
         double small_ss, small_sp, small_pp;   /* cells handled by the small-box kernel (subset of cells_*) */
+        double n_collectives, collective_bytes; /* NCCL all-gathers issued / bytes gathered (multi-GPU) */
 } kb200_stats;
 
 int  kb200_device_count(void);
@@ -136,6 +137,19 @@ int kb200_align_tree(kb200_ctx* ctx, const kb200_params* prm,
 int kb200_kalign(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_threads, int type,
                  float gpo, float gpe, float tgpe, int consistency_anchors, float consistency_weight,
                  char*** aligned, int* out_aln_len);
+
+/* Multi-GPU (one process per GPU of one node, NCCL over NVLink): rank 0 creates a unique id,
+   the caller distributes it (e.g. torch.distributed broadcast), every rank attaches its context.
+   With a communicator attached, kb200_msa_align shards the N x K anchor pairs and the tasks of every
+   guide-tree level across the ranks (the reference's independent OpenMP tasks,
+   lib/src/aln_run.c:95-109) and all-gathers position maps / coded paths / merged profiles; every
+   rank ends with the complete result.  kb200_partition is the (host-only) contiguous cost-balanced
+   partition used for both. */
+#define KB200_COMM_ID_BYTES 128
+int  kb200_comm_unique_id(void* id_out, int nbytes);
+int  kb200_ctx_comm_init(kb200_ctx* ctx, int rank, int world, const void* id, int nbytes);
+void kb200_ctx_comm_destroy(kb200_ctx* ctx);
+int  kb200_partition(const double* cost, int n, int world, int* bounds);
 
 /* The same pipeline in stages, so that the DP stages can be run (and timed) on sequences that
    are already resident in HBM:

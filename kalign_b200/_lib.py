@@ -39,14 +39,16 @@ class Stats(C.Structure):
                 ("h2d_bytes", C.c_double), ("d2h_bytes", C.c_double),
                 ("cells_ss", C.c_double), ("cells_sp", C.c_double), ("cells_pp", C.c_double),
                 ("cells_bonus", C.c_double), ("align_seconds", C.c_double), ("small_seconds", C.c_double),
-                ("small_ss", C.c_double), ("small_sp", C.c_double), ("small_pp", C.c_double)]
+                ("small_ss", C.c_double), ("small_sp", C.c_double), ("small_pp", C.c_double),
+                ("n_collectives", C.c_double), ("collective_bytes", C.c_double)]
 
 
 # every symbol include/kalign_b200.h declares
 EXPORTS = ["kb200_device_count", "kb200_ctx_create", "kb200_ctx_destroy", "kb200_get_stats",
            "kb200_version", "kb200_params_init", "kb200_pair_align_batch", "kb200_distances",
            "kb200_anchor_posmaps", "kb200_align_tree", "kb200_kalign",
-           "kb200_msa_create", "kb200_msa_align", "kb200_msa_result", "kb200_msa_info", "kb200_msa_free"]
+           "kb200_msa_create", "kb200_msa_align", "kb200_msa_result", "kb200_msa_info", "kb200_msa_free",
+           "kb200_comm_unique_id", "kb200_ctx_comm_init", "kb200_ctx_comm_destroy", "kb200_partition"]
 
 _lib = None
 
@@ -94,6 +96,14 @@ def load():
     lib.kb200_msa_info.restype = C.c_int
     lib.kb200_msa_free.argtypes = [C.c_void_p]
     lib.kb200_msa_free.restype = None
+    lib.kb200_comm_unique_id.argtypes = [C.c_void_p, C.c_int]
+    lib.kb200_comm_unique_id.restype = C.c_int
+    lib.kb200_ctx_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    lib.kb200_ctx_comm_init.restype = C.c_int
+    lib.kb200_ctx_comm_destroy.argtypes = [C.c_void_p]
+    lib.kb200_ctx_comm_destroy.restype = None
+    lib.kb200_partition.argtypes = [np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS"), C.c_int, C.c_int, i32p]
+    lib.kb200_partition.restype = C.c_int
     _lib = lib
     return lib
 

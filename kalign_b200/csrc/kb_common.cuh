@@ -109,6 +109,8 @@ struct KbArena {
 };
 
 struct kb200_ctx {
+        int rank = 0, world = 1;     // multi-GPU: one process per GPU (kb200_ctx_comm_init)
+        void* comm = nullptr;        // ncclComm_t
         int device = 0;
         int sm_count = 148;
         cudaStream_t stream = nullptr;
@@ -119,7 +121,7 @@ struct kb200_ctx {
         // staging for the host-pointer entry points
         KbDevBuf d_stage0, d_stage1, d_stage2, d_stage3, d_stage4, d_stage5;
         // progressive alignment (kb_tree.cu)
-        KbDevBuf t_subm, t_leaf, t_gapset, t_prefix, t_raw, t_coded, t_scr, t_pjobs, t_mjobs, t_src, t_bonus, t_bidx, t_bval;
+        KbDevBuf t_subm, t_leaf, t_gapset, t_prefix, t_raw, t_coded, t_scr, t_pjobs, t_mjobs, t_src, t_bonus, t_bidx, t_bval, t_posmaps;
         KbArena arena;
 };
 
@@ -130,3 +132,10 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
 // bpm (kb_bpm.cu)
 int kb_bpm_pairs(kb200_ctx* ctx, const uint8_t* d_seqs, const int64_t* d_offs, const int* d_lens,
                  const int* d_rows, int nrows, const int* d_cols, int ncols, float* d_dm);
+
+// multi-GPU helpers (kb_comm.cu)
+// contiguous partition of n items with the given costs into `world` shards: bounds[0..world]
+void kb_partition(const double* cost, int n, int world, int* bounds);
+// all-gather of variable-size contiguous segments of one device buffer:
+// segment r = bytes [seg[r], seg[r+1]) is owned by rank r and ends up on every rank
+int kb_allgatherv(kb200_ctx* ctx, void* dbuf, const size_t* seg);

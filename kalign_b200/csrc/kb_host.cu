@@ -137,8 +137,49 @@ int kb_distances_dev(kb200_ctx* ctx, KbSeqs& S, const int* rows, int nrows, cons
 
 // ---------------------------------------------------------------------------------------------
 
+// multi-GPU: cost-balanced shard of the N x K pair list, local compute, one all-gather
+int kb_anchor_posmaps_sharded(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S, const int* anchor_ids, int K, int* posmaps)
+{
+        const int N = S.n;
+        const long long np = (long long)N * K;
+        if (ctx->world <= 1) {
+                return kb_anchor_posmaps_dev(ctx, prm, S, anchor_ids, K, 0, np, posmaps);
+        }
+        std::vector<double> cost((size_t)np);
+        for (long long p = 0; p < np; p++) {
+                const int i = (int)(p / K), k = (int)(p % K);
+                cost[(size_t)p] = (i == anchor_ids[k]) ? 1.0 : (double)S.h_lens[i] * (double)S.h_lens[anchor_ids[k]] + 1.0;
+        }
+        std::vector<int> b((size_t)ctx->world + 1);
+        kb_partition(cost.data(), (int)np, ctx->world, b.data());
+        auto map_off = [&](long long p) -> size_t {
+                if (p >= np) return (size_t)K * (size_t)S.total;
+                const int i = (int)(p / K), k = (int)(p % K);
+                return (size_t)K * (size_t)S.h_offs[i] + (size_t)k * (size_t)S.h_lens[i];
+        };
+        const size_t full = (size_t)K * (size_t)S.total;
+        KB_RUN(ctx->t_posmaps.ensure(sizeof(int) * (full + 8)));
+        // local shard: results land at their final offsets of the full device array
+        KB_RUN(kb_anchor_posmaps_dev(ctx, prm, S, anchor_ids, K, b[(size_t)ctx->rank], b[(size_t)ctx->rank + 1], nullptr,
+                                     ctx->t_posmaps.as<int>()));
+        std::vector<size_t> seg((size_t)ctx->world + 1);
+        for (int r = 0; r <= ctx->world; r++) seg[(size_t)r] = map_off(b[(size_t)r]) * sizeof(int);
+        KB_RUN(kb_allgatherv(ctx, ctx->t_posmaps.p, seg.data()));
+        KB_CUDA(cudaMemcpyAsync(posmaps, ctx->t_posmaps.p, sizeof(int) * full, cudaMemcpyDeviceToHost, ctx->stream));
+        KB_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->stats.d2h_bytes += (double)(sizeof(int) * full);
+        for (long long p = 0; p < np; p++) {
+                const int i = (int)(p / K), k = (int)(p % K);
+                if (i == anchor_ids[k]) {
+                        int* m = posmaps + map_off(p);
+                        for (int q = 0; q < S.h_lens[i]; q++) m[q] = q;
+                }
+        }
+        return KB200_OK;
+}
+
 int kb_anchor_posmaps_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S, const int* anchor_ids, int K,
-                          long long pair_begin, long long pair_end, int* posmaps)
+                          long long pair_begin, long long pair_end, int* posmaps, int* d_full)
 {
         const int N = S.n;
         if (pair_begin < 0) pair_begin = 0;
@@ -179,11 +220,14 @@ int kb_anchor_posmaps_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S, co
         KB_RUN(ctx->d_stage0.ensure(sizeof(int) * (n_raw + 8)));
         KB_RUN(ctx->d_stage1.ensure(sizeof(int) * (n_coded + 8)));
         KB_RUN(ctx->d_stage2.ensure(sizeof(int) * (n_scr + 8)));
-        KB_RUN(ctx->d_stage3.ensure(sizeof(int) * (out_n + 8)));
+        if (!d_full) {
+                KB_RUN(ctx->d_stage3.ensure(sizeof(int) * (out_n + 8)));
+        }
         int* d_raw = ctx->d_stage0.as<int>();
         int* d_coded = ctx->d_stage1.as<int>();
         int* d_scr = ctx->d_stage2.as<int>();
-        int* d_out = ctx->d_stage3.as<int>();
+        // d_full: results go to their final offsets of a full-size device array (multi-GPU gather)
+        int* d_out = d_full ? (d_full + out_begin) : ctx->d_stage3.as<int>();
         size_t o_raw = 0, o_coded = 0, o_scr = 0;
         for (long long p = pair_begin; p < pair_end; p++) {
                 const int i = (int)(p / K), k = (int)(p % K);
@@ -234,6 +278,10 @@ int kb_anchor_posmaps_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S, co
         if (getenv("KB200_TRACE")) {
                 KB_CUDA(cudaStreamSynchronize(st));
                 t2 = std::chrono::steady_clock::now();
+        }
+        if (!posmaps) {
+                KB_CUDA(cudaStreamSynchronize(st));
+                return KB200_OK;
         }
         KB_CUDA(cudaMemcpyAsync(posmaps + out_begin, d_out, sizeof(int) * out_n, cudaMemcpyDeviceToHost, st));
         KB_CUDA(cudaStreamSynchronize(st));

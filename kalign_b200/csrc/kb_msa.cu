@@ -739,7 +739,7 @@ int kb200_msa_align(kb200_msa* M)
         KB_CUDA(cudaEventCreate(&e1));
         KB_CUDA(cudaEventRecord(e0, ctx->stream));
         if (M->K > 0) {
-                KB_RUN(kb_anchor_posmaps_dev(ctx, &M->prm, M->S, M->anchor_ids.data(), M->K, 0, (long long)M->N * M->K, M->posmaps.data()));
+                KB_RUN(kb_anchor_posmaps_sharded(ctx, &M->prm, M->S, M->anchor_ids.data(), M->K, M->posmaps.data()));
         }
         KB_RUN(kb_align_tree_dev(ctx, &M->prm, M->S, M->abc.data(), M->N - 1, M->seq_distances.data(),
                                  M->K > 0 ? M->posmaps.data() : nullptr, M->K, M->weight, M->n_threads, M->gaps.data()));

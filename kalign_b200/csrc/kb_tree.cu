@@ -195,16 +195,18 @@ void combine_bonus(const Tree& T, const NodePos& A, const NodePos& B, std::vecto
         }
 }
 
-void level_bonus(Tree& T, int nt, const std::vector<int>& rown, const std::vector<int>& rlen,
+void level_bonus(Tree& T, int q0, int q1, const std::vector<int>& rown, const std::vector<int>& rlen,
                  const std::vector<int>& coln, const std::vector<int>& clen, int n_threads,
                  std::vector<std::vector<int>>& colof,
                  std::vector<std::vector<std::pair<long long, float>>>& lists)
 {
         const int K = T.K;
+        const int nt = (int)rown.size();
+        const int nm = q1 - q0;
         (void)n_threads;
-        // members of every profile operand of this level
+        // members of every profile operand of my tasks of this level
         std::vector<int> members;
-        for (int q = 0; q < nt; q++) {
+        for (int q = q0; q < q1; q++) {
                 const int nodes[2] = {rown[(size_t)q], coln[(size_t)q]};
                 for (int s = 0; s < 2; s++) {
                         if (T.nsip[(size_t)nodes[s]] > 1) {
@@ -212,20 +214,20 @@ void level_bonus(Tree& T, int nt, const std::vector<int>& rown, const std::vecto
                         }
                 }
         }
-        std::vector<NodePos> np((size_t)2 * nt);
+        std::vector<NodePos> np((size_t)2 * std::max(nm, 0));
         std::vector<PosChunk> chunks;
         const int BLK = 512;
-        for (int q = 0; q < nt; q++) {
+        for (int q = q0; q < q1; q++) {
                 const int nodes[2] = {rown[(size_t)q], coln[(size_t)q]};
                 const int lens2[2] = {rlen[(size_t)q], clen[(size_t)q]};
                 for (int s = 0; s < 2; s++) {
-                        NodePos& P = np[(size_t)2 * q + s];
+                        NodePos& P = np[(size_t)2 * (q - q0) + s];
                         P.len = lens2[s];
                         P.pos.resize((size_t)K * P.len);
                         P.conf.resize((size_t)K * P.len);
                         for (int c0 = 0; c0 < P.len; c0 += BLK) {
                                 PosChunk w;
-                                w.slot = 2 * q + s; w.node = nodes[s]; w.c0 = c0; w.c1 = std::min(P.len, c0 + BLK);
+                                w.slot = 2 * (q - q0) + s; w.node = nodes[s]; w.c0 = c0; w.c1 = std::min(P.len, c0 + BLK);
                                 chunks.push_back(w);
                         }
                 }
@@ -250,8 +252,8 @@ void level_bonus(Tree& T, int nt, const std::vector<int>& rown, const std::vecto
 #ifdef _OPENMP
 #pragma omp for schedule(dynamic, 1)
 #endif
-                for (int q = 0; q < nt; q++) {
-                        combine_bonus(T, np[(size_t)2 * q], np[(size_t)2 * q + 1], lists[(size_t)q]);
+                for (int q = q0; q < q1; q++) {
+                        combine_bonus(T, np[(size_t)2 * (q - q0)], np[(size_t)2 * (q - q0) + 1], lists[(size_t)q]);
                 }
         }
 }
@@ -409,13 +411,24 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                                 }
                         }
                 }
+                // ---- multi-GPU: contiguous shard of this level's task list, balanced by la*lb ----
+                int q0 = 0, q1 = nt;
+                std::vector<int> tb((size_t)ctx->world + 1, 0);
+                {
+                        std::vector<double> cost((size_t)nt);
+                        for (int q = 0; q < nt; q++) cost[(size_t)q] = (double)la[q] * (double)lb[q] + 1.0;
+                        kb_partition(cost.data(), nt, ctx->world, tb.data());
+                        q0 = tb[(size_t)ctx->rank];
+                        q1 = tb[(size_t)ctx->rank + 1];
+                }
+                const int ntm = q1 - q0;      // my tasks
                 // ---- leaf profiles (make_profile_n with THIS task's offset) and gap rescale ----
                 std::vector<KbLeafProfile> leaves;
                 std::vector<long long> leaf_prefix;
                 std::vector<KbGapSet> gsets;
                 std::vector<long long> gs_prefix;
                 long long leaf_cols = 0, gs_cols = 0;
-                for (int q = 0; q < nt; q++) {
+                for (int q = q0; q < q1; q++) {
                         const int a = tasks_abc[3 * tl[q]], b = tasks_abc[3 * tl[q] + 1];
                         const int nodes[2] = {a, b};
                         const int other[2] = {b, a};
@@ -508,9 +521,9 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                 const auto t_prep = tnow();
                 // ---- consistency bonus (default mode), dense on device ----
                 if (T.posmaps) {
-                        level_bonus(T, nt, rown, rlen, coln, clen, n_threads, colof, bonus_lists);
+                        level_bonus(T, q0, q1, rown, rlen, coln, clen, n_threads, colof, bonus_lists);
                         size_t dense = 0, nent = 0;
-                        for (int q = 0; q < nt; q++) {
+                        for (int q = q0; q < q1; q++) {
                                 dense += (size_t)rlen[q] * (size_t)clen[q];
                                 nent += bonus_lists[(size_t)q].size();
                         }
@@ -520,7 +533,7 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                         std::vector<long long> hidx(nent);
                         std::vector<float> hval(nent);
                         size_t off = 0, e = 0;
-                        for (int q = 0; q < nt; q++) {
+                        for (int q = q0; q < q1; q++) {
                                 jobs[(size_t)q].bonus = d_bonus.as<float>() + off;
                                 for (const auto& pr : bonus_lists[(size_t)q]) {
                                         hidx[e] = (long long)off + pr.first;
@@ -562,11 +575,27 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                         }
                 }
                 TC(cudaMemsetAsync(d_raw.p, 0xFF, sizeof(int) * n_raw, st));
-                TR(kb_run_hirschberg(ctx, prm->subm, jobs));
+                {
+                        std::vector<KbJob> mine(jobs.begin() + q0, jobs.begin() + q1);
+                        TR(kb_run_hirschberg(ctx, prm->subm, mine));
+                }
                 const auto t_dp = tnow();
-                TR(d_pjobs.ensure(sizeof(KbPathJob) * (size_t)nt));
-                TC(cudaMemcpyAsync(d_pjobs.p, pjobs.data(), sizeof(KbPathJob) * (size_t)nt, cudaMemcpyHostToDevice, st));
-                TR(kb_code_paths(ctx, d_pjobs.as<KbPathJob>(), nt));
+                TR(d_pjobs.ensure(sizeof(KbPathJob) * (size_t)nt + 16));
+                if (ntm > 0) {
+                        TC(cudaMemcpyAsync(d_pjobs.p, pjobs.data() + q0, sizeof(KbPathJob) * (size_t)ntm, cudaMemcpyHostToDevice, st));
+                        TR(kb_code_paths(ctx, d_pjobs.as<KbPathJob>(), ntm));
+                }
+                if (ctx->world > 1) {
+                        // coded paths of every rank's shard (segments are contiguous in task order)
+                        std::vector<size_t> seg((size_t)ctx->world + 1, 0);
+                        size_t o = 0;
+                        int r = 0;
+                        for (int q = 0; q <= nt; q++) {
+                                while (r <= ctx->world && q == tb[(size_t)r]) { seg[(size_t)r] = o * sizeof(int); r++; }
+                                if (q < nt) o += (size_t)la[q] + (size_t)lb[q] + 2;
+                        }
+                        TR(kb_allgatherv(ctx, d_coded.p, seg.data()));
+                }
                 std::vector<int> hcoded(n_coded);
                 TC(cudaMemcpyAsync(hcoded.data(), d_coded.p, sizeof(int) * n_coded, cudaMemcpyDeviceToHost, st));
                 TC(cudaStreamSynchronize(st));
@@ -584,33 +613,41 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                                 o += (size_t)la[q] + (size_t)lb[q] + 2;
                         }
                 }
+                std::vector<size_t> prof_off((size_t)nt + 1, 0);     // float offsets inside the level block
                 for (int q = 0; q < nt; q++) {
-                        if (tl[q] == ntasks - 1) continue;
-                        nsrc += (size_t)hcoded[coded_off[(size_t)q]] + 2;
+                        size_t w = 0;
+                        if (tl[q] != ntasks - 1) {
+                                w = ((size_t)hcoded[coded_off[(size_t)q]] + 2) * 64;
+                                if (q >= q0 && q < q1) nsrc += (size_t)hcoded[coded_off[(size_t)q]] + 2;
+                        }
+                        prof_off[(size_t)q + 1] = prof_off[(size_t)q] + w;
                 }
                 TR(d_src.ensure(sizeof(int2) * (nsrc + 16)));
+                float* block = nullptr;
+                if (prof_off[(size_t)nt] > 0) {
+                        block = arena.alloc_floats(prof_off[(size_t)nt]);
+                        if (!block) { cleanup(); return KB200_FAIL; }
+                }
                 {
                         size_t osrc = 0;
                         for (int q = 0; q < nt; q++) {
                                 const int t = tl[q];
                                 const int a = tasks_abc[3 * t], b = tasks_abc[3 * t + 1], c = tasks_abc[3 * t + 2];
                                 const int alnlen = hcoded[coded_off[(size_t)q]];
-                                if (t != ntasks - 1) {
-                                        float* np = arena.alloc_floats((size_t)(alnlen + 2) * 64);
-                                        if (!np) { cleanup(); return KB200_FAIL; }
-                                        T.prof[c] = np;
-                                        KbMergeJob m;
-                                        m.pa = T.prof[a]; m.pb = T.prof[b]; m.newp = np;
-                                        m.path = d_coded.as<int>() + coded_off[(size_t)q];
-                                        m.src = d_src.as<int2>() + osrc;
-                                        m.alnlen = alnlen;
-                                        m.sipa = T.nsip[a]; m.sipb = T.nsip[b];
-                                        m.gpo = prm->gpo; m.gpe = prm->gpe; m.tgpe = prm->tgpe;
-                                        mjobs.push_back(m);
-                                        mprefix.push_back(mcols);
-                                        mcols += alnlen + 2;
-                                        osrc += (size_t)alnlen + 2;
-                                }
+                                if (t == ntasks - 1) continue;
+                                T.prof[c] = block + prof_off[(size_t)q];
+                                if (q < q0 || q >= q1) continue;
+                                KbMergeJob m;
+                                m.pa = T.prof[a]; m.pb = T.prof[b]; m.newp = T.prof[c];
+                                m.path = d_coded.as<int>() + coded_off[(size_t)q];
+                                m.src = d_src.as<int2>() + osrc;
+                                m.alnlen = alnlen;
+                                m.sipa = T.nsip[a]; m.sipb = T.nsip[b];
+                                m.gpo = prm->gpo; m.gpe = prm->gpe; m.tgpe = prm->tgpe;
+                                mjobs.push_back(m);
+                                mprefix.push_back(mcols);
+                                mcols += alnlen + 2;
+                                osrc += (size_t)alnlen + 2;
                         }
                 }
                 if (!mjobs.empty()) {
@@ -619,6 +656,12 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                         TC(cudaMemcpyAsync(d_pref_mg, mprefix.data(), sizeof(long long) * mprefix.size(), cudaMemcpyHostToDevice, st));
                         TR(kb_merge_index(ctx, d_mjobs.as<KbMergeJob>(), (int)mjobs.size()));
                         TR(kb_merge_profiles(ctx, d_mjobs.as<KbMergeJob>(), (int)mjobs.size(), d_pref_mg, mcols));
+                }
+                if (ctx->world > 1 && block) {
+                        // the single all-gather of merged sub-profiles of this level (NCCL over NVLink)
+                        std::vector<size_t> seg((size_t)ctx->world + 1, 0);
+                        for (int r = 0; r <= ctx->world; r++) seg[(size_t)r] = prof_off[(size_t)tb[(size_t)r]] * sizeof(float);
+                        TR(kb_allgatherv(ctx, block, seg.data()));
                 }
                 const auto t_post = tnow();
                 // ---- host bookkeeping while the merge kernels run: gaps, sip, nsip, plen ----
