@@ -175,7 +175,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cfg, type_, K, label = WORKLOADS[args.workload]
-    host_threads = effective_cpus()
+    # the CPU quota is shared by all ranks of the node
+    host_threads = max(1, effective_cpus() // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))))
     default_sample = {"C2": 400, "C3": 160, "C4": 4000}[args.workload]
     n_sample = args.ref_sample or default_sample
 

@@ -53,6 +53,22 @@ EXPORTS = ["kb200_device_count", "kb200_ctx_create", "kb200_ctx_destroy", "kb200
 _lib = None
 
 
+def _preload_nccl():
+    """The library links libnccl.so.2.  If PyTorch is (or will be) imported in this process its bundled
+    NCCL must be the one that gets loaded -- an older system libnccl loaded first breaks
+    `import torch` (undefined symbol in libtorch_cuda).  So load torch's copy first when it exists."""
+    import glob
+    import sys
+    for base in sys.path:
+        for cand in glob.glob(os.path.join(base, "nvidia", "nccl", "lib", "libnccl.so.2")):
+            try:
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+                return cand
+            except OSError:
+                pass
+    return None
+
+
 def load():
     global _lib
     if _lib is not None:
@@ -60,6 +76,7 @@ def load():
     if not os.path.exists(SO_PATH):
         raise RuntimeError("kalign_b200: %s is missing (run `python -c 'import __graft_entry__ as g; g.build()'`); "
                            "there is no CPU fallback" % SO_PATH)
+    _preload_nccl()
     lib = C.CDLL(SO_PATH)
     lib.kb200_device_count.restype = C.c_int
     lib.kb200_version.restype = C.c_char_p
