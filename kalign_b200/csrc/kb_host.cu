@@ -15,9 +15,11 @@
 
 int kb_default_threads()
 {
+        // hardware threads visible to the process, NOT omp_get_max_threads(): launchers such as
+        // torchrun export OMP_NUM_THREADS=1; the num_threads() clauses used here override that.
         int n = 1;
 #ifdef _OPENMP
-        n = omp_get_max_threads();
+        n = omp_get_num_procs();
 #endif
         FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r");
         if (f) {
