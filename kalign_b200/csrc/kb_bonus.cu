@@ -1,0 +1,281 @@
+// kb_bonus.cu -- device-resident gap weaving and anchor-consistency bonus.
+//
+// Replaces, with the same arithmetic and the same tie rules (nothing copied):
+//   make_seq / update_gaps                 lib/src/weave_alignment.c:41,96
+//   get_node_anchor_positions              lib/src/anchor_consistency.c:352-467
+//   anchor_consistency_get_bonus_profile   lib/src/anchor_consistency.c:469-561
+//
+// State kept on the device for the whole tree: gaps[] of every sequence (len+1 ints, the layout of
+// kb200_align_tree's gaps_out) and colof[p] = p + sum_{q<=p} gaps[q], the profile column of
+// residue p in the node the sequence currently belongs to.
+//
+// Weaving: a member's gaps[i] grows by the number of new gap columns that fall into its i-th gap
+// run; with P the prefix sum of the task's new-gap vector that is P[end_i+1] - P[rel_i] with
+// rel_i = colof_old[i-1]+1 and end_i = rel_i + gaps_old[i] -- independent per (sequence, i).
+//
+// Votes: one thread per profile column visits the members in sip[] order ("first seen position
+// wins", anchor_consistency.c:440-445), finds the member's residue in that column by binary search
+// in colof, and counts agreement.  Inverse map: the largest column j wins (atomicMax ==
+// "last write wins" of the ascending loop, :519-524).  Scatter: one thread per DP row adds its
+// <=K terms in anchor order k into the dense matrix, (per_anchor_weight*conf_a)*conf_b, :532-533.
+#include "kb_host.cuh"
+#include "kb_bonus.cuh"
+
+#include <algorithm>
+
+namespace {
+
+constexpr int KMAX = KB_BONUS_KMAX;
+
+// ---- weave -----------------------------------------------------------------------------------
+// per task (serial, O(alnlen)): new-gap counts per profile column of a and of b, as prefix sums
+__global__ void kb_weave_prefix_kernel(const KbWeaveTask* __restrict__ tasks, const int ntasks)
+{
+        const int q = blockIdx.x * blockDim.x + threadIdx.x;
+        if (q >= ntasks) return;
+        const KbWeaveTask T = tasks[q];
+        const int* __restrict__ path = T.path;
+        int* __restrict__ Pa = T.Pa;      // alnlen+2 entries: Pa[x] = # new gaps in columns < x of a
+        int* __restrict__ Pb = T.Pb;
+        const int n = ((T.alnlen >= 0) ? T.alnlen : path[0]) + 2;
+        for (int i = 0; i < n; i++) {
+                Pa[i] = 0; Pb[i] = 0;
+        }
+        int posa = 0, posb = 0;
+        for (int c = 1; path[c] != 3; c++) {
+                const int p = path[c];
+                if (!p) {
+                        posa++; posb++;
+                } else if (p & 1) {
+                        Pa[posa + 1] += 1; posb++;       // gap_a[posa] += 1
+                } else if (p & 2) {
+                        Pb[posb + 1] += 1; posa++;       // gap_b[posb] += 1
+                }
+        }
+        for (int i = 1; i < n; i++) {
+                Pa[i] += Pa[i - 1];
+                Pb[i] += Pb[i - 1];
+        }
+}
+
+// one warp per member sequence: update gaps from the old colof, then rebuild colof
+__global__ void kb_weave_apply_kernel(const KbWeaveMember* __restrict__ members, const int nmembers,
+                                      const int64_t* __restrict__ offs, const int* __restrict__ lens,
+                                      int* __restrict__ gaps, int* __restrict__ colof)
+{
+        const int lane = threadIdx.x & 31;
+        const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        if (w >= nmembers) return;
+        const KbWeaveMember M = members[w];
+        const int si = M.seq;
+        const int len = lens[si];
+        int* __restrict__ g = gaps + offs[si] + si;
+        int* __restrict__ co = colof + offs[si];
+        const int* __restrict__ P = M.P;
+        // pass 1: adds (reads old colof / old gaps only)
+        for (int i = lane; i <= len; i += 32) {
+                const int rel = (i == 0) ? 0 : (co[i - 1] + 1);
+                const int gi = g[i];
+                const int end = rel + gi;
+                const int add = P[end + 1] - P[rel];
+                g[i] = gi + add;
+        }
+        __syncwarp();
+        // pass 2: colof[p] = p + inclusive prefix of gaps
+        int carry = 0;
+        for (int base = 0; base < len; base += 32) {
+                const int p = base + lane;
+                int v = (p < len) ? (g[p] + 1) : 0;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                        const int t = __shfl_up_sync(0xffffffffu, v, o);
+                        if (lane >= o) v += t;
+                }
+                if (p < len) {
+                        co[p] = carry + v - 1;
+                }
+                carry += __shfl_sync(0xffffffffu, v, 31);
+        }
+}
+
+__global__ void kb_init_colof_kernel(const int64_t* __restrict__ offs, const int* __restrict__ lens, const int nseq,
+                                     int* __restrict__ colof)
+{
+        const int lane = threadIdx.x & 31;
+        const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        if (w >= nseq) return;
+        int* co = colof + offs[w];
+        for (int p = lane; p < lens[w]; p += 32) {
+                co[p] = p;
+        }
+}
+
+// ---- votes -----------------------------------------------------------------------------------
+__global__ void kb_bonus_positions_kernel(const KbBonusOperand* __restrict__ ops, const long long* __restrict__ col_prefix,
+                                          const int nops, const long long total_cols, const int K,
+                                          const int* __restrict__ memb, const int64_t* __restrict__ offs,
+                                          const int* __restrict__ lens, const int* __restrict__ colof,
+                                          const int* __restrict__ posmaps)
+{
+        const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        if (gid >= total_cols) return;
+        int lo = 0, hi = nops - 1;
+        while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (col_prefix[mid] <= gid) lo = mid; else hi = mid - 1;
+        }
+        const KbBonusOperand O = ops[lo];
+        const int c = (int)(gid - col_prefix[lo]);
+        int* __restrict__ pos = O.pos;        // [K][len]
+        float* __restrict__ conf = O.conf;
+        if (O.m1 - O.m0 == 1) {
+                // leaf: direct lookup (anchor_consistency.c:360-378)
+                const int si = memb[O.m0];
+                const int seq_len = lens[si];
+                for (int k = 0; k < K; k++) {
+                        int v = -1;
+                        if (c < seq_len) {
+                                v = posmaps[(size_t)K * (size_t)offs[si] + (size_t)k * (size_t)seq_len + c];
+                        }
+                        pos[(size_t)k * O.len + c] = v;
+                        conf[(size_t)k * O.len + c] = (v >= 0) ? 1.0f : 0.0f;
+                }
+                return;
+        }
+        int best[KMAX], agree[KMAX], total[KMAX];
+#pragma unroll
+        for (int k = 0; k < KMAX; k++) {
+                best[k] = -1; agree[k] = 0; total[k] = 0;
+        }
+        for (int m = O.m0; m < O.m1; m++) {
+                const int si = memb[m];
+                const int seq_len = lens[si];
+                const int* __restrict__ co = colof + offs[si];
+                // residue whose column is c (colof is strictly increasing)
+                int a = 0, b = seq_len;
+                while (a < b) {
+                        const int mid = (a + b) >> 1;
+                        if (co[mid] < c) a = mid + 1; else b = mid;
+                }
+                if (a >= seq_len || co[a] != c) continue;
+                const int* __restrict__ map0 = posmaps + (size_t)K * (size_t)offs[si] + a;
+#pragma unroll
+                for (int k = 0; k < KMAX; k++) {
+                        if (k < K) {
+                                const int apos = map0[(size_t)k * seq_len];
+                                if (apos >= 0) {
+                                        total[k]++;
+                                        if (best[k] < 0) {
+                                                best[k] = apos;
+                                                agree[k] = 1;
+                                        } else if (apos == best[k]) {
+                                                agree[k]++;
+                                        }
+                                }
+                        }
+                }
+        }
+#pragma unroll
+        for (int k = 0; k < KMAX; k++) {
+                if (k < K) {
+                        const bool ok = total[k] > 0 && agree[k] > 0;
+                        pos[(size_t)k * O.len + c] = ok ? best[k] : -1;
+                        conf[(size_t)k * O.len + c] = ok ? ((float)agree[k] / (float)total[k]) : 0.0f;
+                }
+        }
+}
+
+// inverse map of the column operand: inv[k][anchor_pos] = largest column j mapping there
+__global__ void kb_bonus_inverse_kernel(const KbBonusTask* __restrict__ tasks, const long long* __restrict__ col_prefix,
+                                        const int ntasks, const long long total_cols, const int K,
+                                        const int* __restrict__ aoff)
+{
+        const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        if (gid >= total_cols) return;
+        int lo = 0, hi = ntasks - 1;
+        while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (col_prefix[mid] <= gid) lo = mid; else hi = mid - 1;
+        }
+        const KbBonusTask T = tasks[lo];
+        const int j = (int)(gid - col_prefix[lo]);
+        for (int k = 0; k < K; k++) {
+                const int ap = T.pos_b[(size_t)k * T.len_b + j];
+                if (ap >= 0) {
+                        atomicMax(T.inv + aoff[k] + ap, j);
+                }
+        }
+}
+
+// one thread per DP row: add the <=K terms in anchor order
+__global__ void kb_bonus_scatter_kernel(const KbBonusTask* __restrict__ tasks, const long long* __restrict__ row_prefix,
+                                        const int ntasks, const long long total_rows, const int K,
+                                        const int* __restrict__ aoff, const float paw)
+{
+        const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        if (gid >= total_rows) return;
+        int lo = 0, hi = ntasks - 1;
+        while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (row_prefix[mid] <= gid) lo = mid; else hi = mid - 1;
+        }
+        const KbBonusTask T = tasks[lo];
+        const int i = (int)(gid - row_prefix[lo]);
+        float* __restrict__ row = T.dense + (size_t)i * (size_t)T.len_b;
+        for (int k = 0; k < K; k++) {
+                const int ak = T.pos_a[(size_t)k * T.len_a + i];
+                if (ak < 0) continue;
+                const int bj = T.inv[aoff[k] + ak];
+                if (bj < 0) continue;
+                const float ca = T.conf_a[(size_t)k * T.len_a + i];
+                const float cb = T.conf_b[(size_t)k * T.len_b + bj];
+                const float v = __fmul_rn(__fmul_rn(paw, ca), cb);
+                row[bj] = __fadd_rn(row[bj], v);
+        }
+}
+
+} // namespace
+
+int kb_bonus_init_state(kb200_ctx* ctx, KbSeqs& S, int* d_gaps, int* d_colof)
+{
+        KB_CUDA(cudaMemsetAsync(d_gaps, 0, sizeof(int) * ((size_t)S.total + (size_t)S.n), ctx->stream));
+        const int warps = S.n;
+        kb_init_colof_kernel<<<(warps * 32 + 127) / 128, 128, 0, ctx->stream>>>(S.d_offs.as<int64_t>(), S.d_lens.as<int>(), S.n, d_colof);
+        KB_CUDA(cudaGetLastError());
+        ctx->stats.n_launches++;
+        return KB200_OK;
+}
+
+int kb_weave_level(kb200_ctx* ctx, KbSeqs& S, const KbWeaveTask* d_tasks, int ntasks,
+                   const KbWeaveMember* d_members, int nmembers, int* d_gaps, int* d_colof)
+{
+        if (ntasks <= 0) return KB200_OK;
+        kb_weave_prefix_kernel<<<(ntasks + 63) / 64, 64, 0, ctx->stream>>>(d_tasks, ntasks);
+        KB_CUDA(cudaGetLastError());
+        if (nmembers > 0) {
+                kb_weave_apply_kernel<<<(nmembers * 32 + 127) / 128, 128, 0, ctx->stream>>>(d_members, nmembers, S.d_offs.as<int64_t>(),
+                                                                                             S.d_lens.as<int>(), d_gaps, d_colof);
+                KB_CUDA(cudaGetLastError());
+        }
+        ctx->stats.n_launches += 2;
+        return KB200_OK;
+}
+
+int kb_bonus_level(kb200_ctx* ctx, KbSeqs& S, int K, float paw,
+                   const KbBonusOperand* d_ops, const long long* d_op_prefix, int nops, long long op_cols,
+                   const int* d_memb, const int* d_colof, const int* d_posmaps,
+                   const KbBonusTask* d_tasks, const long long* d_colb_prefix, long long colb_total,
+                   const long long* d_row_prefix, long long row_total, int ntasks, const int* d_aoff)
+{
+        if (ntasks <= 0) return KB200_OK;
+        kb_bonus_positions_kernel<<<(unsigned)((op_cols + 127) / 128), 128, 0, ctx->stream>>>(d_ops, d_op_prefix, nops, op_cols, K, d_memb,
+                                                                                               S.d_offs.as<int64_t>(), S.d_lens.as<int>(),
+                                                                                               d_colof, d_posmaps);
+        KB_CUDA(cudaGetLastError());
+        kb_bonus_inverse_kernel<<<(unsigned)((colb_total + 127) / 128), 128, 0, ctx->stream>>>(d_tasks, d_colb_prefix, ntasks, colb_total, K, d_aoff);
+        KB_CUDA(cudaGetLastError());
+        kb_bonus_scatter_kernel<<<(unsigned)((row_total + 127) / 128), 128, 0, ctx->stream>>>(d_tasks, d_row_prefix, ntasks, row_total, K, d_aoff, paw);
+        KB_CUDA(cudaGetLastError());
+        ctx->stats.n_launches += 3;
+        return KB200_OK;
+}

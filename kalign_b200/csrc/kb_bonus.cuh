@@ -1,0 +1,40 @@
+// kb_bonus.cuh -- descriptors of the device-side gap weaving / consistency bonus (kb_bonus.cu)
+#pragma once
+#include "kb_host.cuh"
+
+#define KB_BONUS_KMAX 8
+
+struct KbWeaveTask {
+        const int* path;     // coded path (device)
+        int* Pa;             // la+lb+3 ints of scratch
+        int* Pb;
+        int alnlen;          // unused by the kernel when < 0: read from path[0]
+};
+
+struct KbWeaveMember {
+        int seq;
+        const int* P;        // prefix array of the member's side of its task
+};
+
+struct KbBonusOperand {
+        int* pos;            // [K][len]
+        float* conf;
+        int len;
+        int m0, m1;          // member range in the level's member list (sip order)
+};
+
+struct KbBonusTask {
+        const int* pos_a; const float* conf_a; int len_a;    // DP rows operand
+        const int* pos_b; const float* conf_b; int len_b;    // DP cols operand
+        int* inv;            // sum_k anchor_len ints, initialised to -1
+        float* dense;        // len_a*len_b floats, zero filled
+};
+
+int kb_bonus_init_state(kb200_ctx* ctx, KbSeqs& S, int* d_gaps, int* d_colof);
+int kb_weave_level(kb200_ctx* ctx, KbSeqs& S, const KbWeaveTask* d_tasks, int ntasks,
+                   const KbWeaveMember* d_members, int nmembers, int* d_gaps, int* d_colof);
+int kb_bonus_level(kb200_ctx* ctx, KbSeqs& S, int K, float paw,
+                   const KbBonusOperand* d_ops, const long long* d_op_prefix, int nops, long long op_cols,
+                   const int* d_memb, const int* d_colof, const int* d_posmaps,
+                   const KbBonusTask* d_tasks, const long long* d_colb_prefix, long long colb_total,
+                   const long long* d_row_prefix, long long row_total, int ntasks, const int* d_aoff);

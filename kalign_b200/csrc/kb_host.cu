@@ -144,8 +144,23 @@ int kb_anchor_posmaps_sharded(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S
 {
         const int N = S.n;
         const long long np = (long long)N * K;
+        ctx->posmaps_tag = nullptr;
+        ctx->posmaps_n = 0;
         if (ctx->world <= 1) {
-                return kb_anchor_posmaps_dev(ctx, prm, S, anchor_ids, K, 0, np, posmaps);
+                // results stay resident in t_posmaps (the progressive phase reads them on the device)
+                const size_t full1 = (size_t)K * (size_t)S.total;
+                KB_RUN(ctx->t_posmaps.ensure(sizeof(int) * (full1 + 8)));
+                KB_RUN(kb_anchor_posmaps_dev(ctx, prm, S, anchor_ids, K, 0, np, posmaps, ctx->t_posmaps.as<int>()));
+                // identity maps of the anchors are host-filled: mirror them
+                for (int k = 0; k < K; k++) {
+                        const int i = anchor_ids[k];
+                        const size_t o = (size_t)K * (size_t)S.h_offs[i] + (size_t)k * (size_t)S.h_lens[i];
+                        KB_CUDA(cudaMemcpyAsync(ctx->t_posmaps.as<int>() + o, posmaps + o, sizeof(int) * (size_t)S.h_lens[i], cudaMemcpyHostToDevice, ctx->stream));
+                }
+                KB_CUDA(cudaStreamSynchronize(ctx->stream));
+                ctx->posmaps_tag = (const void*)posmaps;
+                ctx->posmaps_n = full1;
+                return KB200_OK;
         }
         std::vector<double> cost((size_t)np);
         for (long long p = 0; p < np; p++) {
@@ -175,8 +190,12 @@ int kb_anchor_posmaps_sharded(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S
                 if (i == anchor_ids[k]) {
                         int* m = posmaps + map_off(p);
                         for (int q = 0; q < S.h_lens[i]; q++) m[q] = q;
+                        KB_CUDA(cudaMemcpyAsync(ctx->t_posmaps.as<int>() + map_off(p), m, sizeof(int) * (size_t)S.h_lens[i], cudaMemcpyHostToDevice, ctx->stream));
                 }
         }
+        KB_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->posmaps_tag = (const void*)posmaps;
+        ctx->posmaps_n = full;
         return KB200_OK;
 }
 

@@ -742,7 +742,7 @@ int kb200_msa_align(kb200_msa* M)
                 KB_RUN(kb_anchor_posmaps_sharded(ctx, &M->prm, M->S, M->anchor_ids.data(), M->K, M->posmaps.data()));
         }
         KB_RUN(kb_align_tree_dev(ctx, &M->prm, M->S, M->abc.data(), M->N - 1, M->seq_distances.data(),
-                                 M->K > 0 ? M->posmaps.data() : nullptr, M->K, M->weight, M->n_threads, M->gaps.data()));
+                                 M->K > 0 ? M->posmaps.data() : nullptr, M->K, M->weight, M->n_threads, M->gaps.data(), 1));
         KB_CUDA(cudaEventRecord(e1, ctx->stream));
         KB_CUDA(cudaEventSynchronize(e1));
         float ms = 0.0f;

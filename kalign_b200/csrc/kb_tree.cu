@@ -14,6 +14,7 @@
 // on device -> profile merge on device -> the coded paths come back to the host for the gap
 // weaving bookkeeping (msa->gaps, sip, nsip, plen).  Profiles never leave the device.
 #include "kb_host.cuh"
+#include "kb_bonus.cuh"
 
 #include <string.h>
 #include <stdlib.h>
@@ -329,7 +330,7 @@ void level_weave(Tree& T, int nt, const std::vector<int>& tl, const int* tasks_a
 
 int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                       const int* tasks_abc, int ntasks, const float* seq_distances,
-                      const int* posmaps, int K, float weight, int n_threads, int* gaps_out)
+                      const int* posmaps, int K, float weight, int n_threads, int* gaps_out, int posmaps_on_device)
 {
         const int N = S.n;
         if (ntasks != N - 1 || N < 2) {
@@ -379,6 +380,38 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
 
         std::vector<std::vector<std::pair<long long, float>>> bonus_lists;
         std::vector<std::vector<int>> colof((size_t)N);
+        // ---- device-resident gaps / colof / position maps (kb_bonus.cu); KB200_HOST_BONUS=1 keeps the
+        //      host implementation of weave_alignment.c / anchor_consistency.c for A/B checks
+        const bool dev_state = (getenv("KB200_HOST_BONUS") == nullptr) && (T.K <= KB_BONUS_KMAX);
+        int* d_gaps = nullptr;
+        int* d_colof = nullptr;
+        const int* d_posmaps = nullptr;
+        int maxlen = 0;
+        for (int i = 0; i < N; i++) maxlen = std::max(maxlen, S.h_lens[i]);
+        if (dev_state) {
+                TR(ctx->t_gaps.ensure(sizeof(int) * ((size_t)S.total + (size_t)N + 8)));
+                TR(ctx->t_colof.ensure(sizeof(int) * ((size_t)S.total + 8)));
+                d_gaps = ctx->t_gaps.as<int>();
+                d_colof = ctx->t_colof.as<int>();
+                TR(kb_bonus_init_state(ctx, S, d_gaps, d_colof));
+                if (T.posmaps) {
+                        const size_t full = (size_t)T.K * (size_t)S.total;
+                        if (!posmaps_on_device || ctx->posmaps_tag != (const void*)T.posmaps || ctx->posmaps_n != full) {
+                                TR(ctx->t_posmaps.ensure(sizeof(int) * (full + 8)));
+                                TC(cudaMemcpyAsync(ctx->t_posmaps.p, T.posmaps, sizeof(int) * full, cudaMemcpyHostToDevice, st));
+                                ctx->stats.h2d_bytes += (double)(sizeof(int) * full);
+                                ctx->posmaps_tag = nullptr;      // a caller-owned array may change behind our back
+                                ctx->posmaps_n = 0;
+                        }
+                        d_posmaps = ctx->t_posmaps.as<int>();
+                        std::vector<int> aoff((size_t)T.K);
+                        for (int k = 0; k < T.K; k++) aoff[(size_t)k] = k * (maxlen + 1);
+                        TR(ctx->t_aoff.ensure(sizeof(int) * (size_t)T.K + 16));
+                        TC(cudaMemcpyAsync(ctx->t_aoff.p, aoff.data(), sizeof(int) * (size_t)T.K, cudaMemcpyHostToDevice, st));
+                        TC(cudaStreamSynchronize(st));
+                }
+        }
+        const size_t inv_per_task = (size_t)T.K * (size_t)(maxlen + 1);
         for (int L = 1; L <= maxlevel; L++) {
                 const std::vector<int>& tl = by_level[(size_t)L];
                 const int nt = (int)tl.size();
@@ -520,7 +553,71 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                 }
                 const auto t_prep = tnow();
                 // ---- consistency bonus (default mode), dense on device ----
-                if (T.posmaps) {
+                if (T.posmaps && dev_state && ntm > 0) {
+                        const int K = T.K;
+                        std::vector<int> memb;
+                        std::vector<KbBonusOperand> ops((size_t)2 * ntm);
+                        std::vector<long long> op_prefix((size_t)2 * ntm), colb_prefix((size_t)ntm), row_prefix((size_t)ntm);
+                        std::vector<KbBonusTask> btasks((size_t)ntm);
+                        size_t pos_items = 0, dense = 0;
+                        long long op_cols = 0, colb_total = 0, row_total = 0;
+                        for (int q = q0; q < q1; q++) {
+                                pos_items += (size_t)K * ((size_t)rlen[q] + (size_t)clen[q]);
+                                dense += (size_t)rlen[q] * (size_t)clen[q];
+                        }
+                        TR(ctx->t_bpos.ensure(sizeof(int) * (pos_items + 16)));
+                        TR(ctx->t_bconf.ensure(sizeof(float) * (pos_items + 16)));
+                        TR(ctx->t_binv.ensure(sizeof(int) * (inv_per_task * (size_t)ntm + 16)));
+                        TR(d_bonus.ensure(sizeof(float) * (dense + 16)));
+                        size_t po = 0, doff = 0;
+                        for (int q = q0; q < q1; q++) {
+                                const int nodes[2] = {rown[q], coln[q]};
+                                const int lens2[2] = {rlen[q], clen[q]};
+                                for (int sd = 0; sd < 2; sd++) {
+                                        KbBonusOperand& O = ops[(size_t)2 * (q - q0) + sd];
+                                        O.pos = ctx->t_bpos.as<int>() + po;
+                                        O.conf = ctx->t_bconf.as<float>() + po;
+                                        O.len = lens2[sd];
+                                        O.m0 = (int)memb.size();
+                                        memb.insert(memb.end(), T.sip[(size_t)nodes[sd]].begin(), T.sip[(size_t)nodes[sd]].end());
+                                        O.m1 = (int)memb.size();
+                                        op_prefix[(size_t)2 * (q - q0) + sd] = op_cols;
+                                        op_cols += lens2[sd];
+                                        po += (size_t)K * (size_t)lens2[sd];
+                                }
+                                KbBonusTask& B = btasks[(size_t)(q - q0)];
+                                const KbBonusOperand& A = ops[(size_t)2 * (q - q0)];
+                                const KbBonusOperand& Bo = ops[(size_t)2 * (q - q0) + 1];
+                                B.pos_a = A.pos; B.conf_a = A.conf; B.len_a = A.len;
+                                B.pos_b = Bo.pos; B.conf_b = Bo.conf; B.len_b = Bo.len;
+                                B.inv = ctx->t_binv.as<int>() + inv_per_task * (size_t)(q - q0);
+                                B.dense = d_bonus.as<float>() + doff;
+                                jobs[(size_t)q].bonus = B.dense;
+                                doff += (size_t)rlen[q] * (size_t)clen[q];
+                                colb_prefix[(size_t)(q - q0)] = colb_total; colb_total += clen[q];
+                                row_prefix[(size_t)(q - q0)] = row_total; row_total += rlen[q];
+                        }
+                        TR(ctx->t_bdesc.ensure(sizeof(int) * memb.size() + sizeof(KbBonusOperand) * ops.size() + sizeof(KbBonusTask) * btasks.size() +
+                                               sizeof(long long) * (op_prefix.size() + colb_prefix.size() + row_prefix.size()) + 256));
+                        char* base = ctx->t_bdesc.as<char>();
+                        KbBonusOperand* d_ops = (KbBonusOperand*)base; base += sizeof(KbBonusOperand) * ops.size();
+                        KbBonusTask* d_bt = (KbBonusTask*)base; base += sizeof(KbBonusTask) * btasks.size();
+                        long long* d_opp = (long long*)base; base += sizeof(long long) * op_prefix.size();
+                        long long* d_cbp = (long long*)base; base += sizeof(long long) * colb_prefix.size();
+                        long long* d_rwp = (long long*)base; base += sizeof(long long) * row_prefix.size();
+                        int* d_memb = (int*)base;
+                        TC(cudaMemcpyAsync(d_ops, ops.data(), sizeof(KbBonusOperand) * ops.size(), cudaMemcpyHostToDevice, st));
+                        TC(cudaMemcpyAsync(d_bt, btasks.data(), sizeof(KbBonusTask) * btasks.size(), cudaMemcpyHostToDevice, st));
+                        TC(cudaMemcpyAsync(d_opp, op_prefix.data(), sizeof(long long) * op_prefix.size(), cudaMemcpyHostToDevice, st));
+                        TC(cudaMemcpyAsync(d_cbp, colb_prefix.data(), sizeof(long long) * colb_prefix.size(), cudaMemcpyHostToDevice, st));
+                        TC(cudaMemcpyAsync(d_rwp, row_prefix.data(), sizeof(long long) * row_prefix.size(), cudaMemcpyHostToDevice, st));
+                        TC(cudaMemcpyAsync(d_memb, memb.data(), sizeof(int) * memb.size(), cudaMemcpyHostToDevice, st));
+                        TC(cudaMemsetAsync(d_bonus.p, 0, sizeof(float) * dense, st));
+                        TC(cudaMemsetAsync(ctx->t_binv.p, 0xFF, sizeof(int) * inv_per_task * (size_t)ntm, st));
+                        TR(kb_bonus_level(ctx, S, K, T.weight / (float)K, d_ops, d_opp, 2 * ntm, op_cols, d_memb, d_colof, d_posmaps,
+                                          d_bt, d_cbp, colb_total, d_rwp, row_total, ntm, ctx->t_aoff.as<int>()));
+                        TC(cudaStreamSynchronize(st));     // host descriptor vectors go out of scope
+                } else if (T.posmaps && !dev_state) {
                         level_bonus(T, q0, q1, rown, rlen, coln, clen, n_threads, colof, bonus_lists);
                         size_t dense = 0, nent = 0;
                         for (int q = q0; q < q1; q++) {
@@ -574,6 +671,14 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                                 o_scr += (size_t)la[q] + 2;
                         }
                 }
+                std::vector<size_t> coded_off((size_t)nt);
+                {
+                        size_t o = 0;
+                        for (int q = 0; q < nt; q++) {
+                                coded_off[(size_t)q] = o;
+                                o += (size_t)la[q] + (size_t)lb[q] + 2;
+                        }
+                }
                 TC(cudaMemsetAsync(d_raw.p, 0xFF, sizeof(int) * n_raw, st));
                 {
                         std::vector<KbJob> mine(jobs.begin() + q0, jobs.begin() + q1);
@@ -596,6 +701,32 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                         }
                         TR(kb_allgatherv(ctx, d_coded.p, seg.data()));
                 }
+                if (dev_state) {
+                        // gap weaving of EVERY task of the level on the device (all ranks keep the full state)
+                        std::vector<KbWeaveTask> wt((size_t)nt);
+                        std::vector<KbWeaveMember> wm;
+                        size_t pneed = 0;
+                        for (int q = 0; q < nt; q++) pneed += 2 * ((size_t)la[q] + (size_t)lb[q] + 4);
+                        TR(ctx->t_wp.ensure(sizeof(int) * (pneed + 16)));
+                        size_t po = 0;
+                        for (int q = 0; q < nt; q++) {
+                                const int t = tl[q];
+                                KbWeaveTask& W = wt[(size_t)q];
+                                W.path = d_coded.as<int>() + coded_off[(size_t)q];
+                                W.Pa = ctx->t_wp.as<int>() + po; po += (size_t)la[q] + (size_t)lb[q] + 4;
+                                W.Pb = ctx->t_wp.as<int>() + po; po += (size_t)la[q] + (size_t)lb[q] + 4;
+                                W.alnlen = -1;
+                                for (int si : T.sip[(size_t)tasks_abc[3 * t]]) wm.push_back({si, W.Pa});
+                                for (int si : T.sip[(size_t)tasks_abc[3 * t + 1]]) wm.push_back({si, W.Pb});
+                        }
+                        TR(ctx->t_wdesc.ensure(sizeof(KbWeaveTask) * wt.size() + sizeof(KbWeaveMember) * wm.size() + 64));
+                        KbWeaveTask* d_wt = ctx->t_wdesc.as<KbWeaveTask>();
+                        KbWeaveMember* d_wm = (KbWeaveMember*)(d_wt + wt.size());
+                        TC(cudaMemcpyAsync(d_wt, wt.data(), sizeof(KbWeaveTask) * wt.size(), cudaMemcpyHostToDevice, st));
+                        TC(cudaMemcpyAsync(d_wm, wm.data(), sizeof(KbWeaveMember) * wm.size(), cudaMemcpyHostToDevice, st));
+                        TR(kb_weave_level(ctx, S, d_wt, nt, d_wm, (int)wm.size(), d_gaps, d_colof));
+                        TC(cudaStreamSynchronize(st));
+                }
                 std::vector<int> hcoded(n_coded);
                 TC(cudaMemcpyAsync(hcoded.data(), d_coded.p, sizeof(int) * n_coded, cudaMemcpyDeviceToHost, st));
                 TC(cudaStreamSynchronize(st));
@@ -603,16 +734,8 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                 // ---- merge profiles on device (update_n), skipped for the root task ----
                 std::vector<KbMergeJob> mjobs;
                 std::vector<long long> mprefix;
-                std::vector<size_t> coded_off((size_t)nt);
                 long long mcols = 0;
                 size_t nsrc = 0;
-                {
-                        size_t o = 0;
-                        for (int q = 0; q < nt; q++) {
-                                coded_off[(size_t)q] = o;
-                                o += (size_t)la[q] + (size_t)lb[q] + 2;
-                        }
-                }
                 std::vector<size_t> prof_off((size_t)nt + 1, 0);     // float offsets inside the level block
                 for (int q = 0; q < nt; q++) {
                         size_t w = 0;
@@ -665,7 +788,9 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                 }
                 const auto t_post = tnow();
                 // ---- host bookkeeping while the merge kernels run: gaps, sip, nsip, plen ----
-                level_weave(T, nt, tl, tasks_abc, hcoded.data(), coded_off, n_threads);
+                if (!dev_state) {
+                        level_weave(T, nt, tl, tasks_abc, hcoded.data(), coded_off, n_threads);
+                }
                 for (int q = 0; q < nt; q++) {
                         const int t = tl[q];
                         const int a = tasks_abc[3 * t], b = tasks_abc[3 * t + 1], c = tasks_abc[3 * t + 2];
@@ -691,8 +816,14 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                                 tms(t_level0, t_prep), tms(t_prep, t_bonus), tms(t_bonus, t_dp), tms(t_dp, t_post), tms(t_post, t_end));
                 }
         }
-        for (int i = 0; i < N; i++) {
-                memcpy(gaps_out + S.h_offs[i] + i, T.gaps[i].data(), sizeof(int) * ((size_t)S.h_lens[i] + 1));
+        if (dev_state) {
+                TC(cudaMemcpyAsync(gaps_out, d_gaps, sizeof(int) * ((size_t)S.total + (size_t)N), cudaMemcpyDeviceToHost, st));
+                TC(cudaStreamSynchronize(st));
+                ctx->stats.d2h_bytes += (double)(sizeof(int) * ((size_t)S.total + (size_t)N));
+        } else {
+                for (int i = 0; i < N; i++) {
+                        memcpy(gaps_out + S.h_offs[i] + i, T.gaps[i].data(), sizeof(int) * ((size_t)S.h_lens[i] + 1));
+                }
         }
         cleanup();
         (void)rc;
@@ -714,7 +845,7 @@ extern "C" int kb200_align_tree(kb200_ctx* ctx, const kb200_params* prm,
         int rc = S.upload(ctx, seqs, offs, lens, nseq);
         if (rc == KB200_OK) {
                 const int nthr = kb_default_threads();
-                rc = kb_align_tree_dev(ctx, prm, S, tasks_abc, ntasks, seq_distances, posmaps, K, weight, nthr, gaps_out);
+                rc = kb_align_tree_dev(ctx, prm, S, tasks_abc, ntasks, seq_distances, posmaps, K, weight, nthr, gaps_out, 0);
         }
         S.release();
         return rc;
