@@ -32,6 +32,7 @@
 
 #include <algorithm>
 #include <stdlib.h>
+#include <type_traits>
 
 namespace {
 
@@ -73,6 +74,9 @@ __device__ __host__ __forceinline__ int rows_per_strip(int kind, int nalpha, int
         }
         if (kind == KB200_KIND_PP && nalpha > 5) {
                 return 64;
+        }
+        if (kind == KB200_KIND_SS) {
+                return 256;
         }
         return 128;
 }
@@ -226,13 +230,16 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                 pre = __ldcg(rowbuf);
         }
         const int steps = C + 32;
-        for (int t = 0; t < steps; t++) {
+        // one step of the wavefront.  STEADY (32 <= t <= C-1): every lane is on an interior column
+        // (1 <= u <= C-1), so the activity test and the boundary-column dispatch disappear.
+        auto step = [&](auto steady_tag, const int t) {
+                constexpr bool STEADY = decltype(steady_tag)::value;
                 const int u = t - lane;
                 Trip up;
                 up.a = __shfl_up_sync(FULL, bot.a, 1);
                 up.ga = __shfl_up_sync(FULL, bot.ga, 1);
                 up.gb = __shfl_up_sync(FULL, bot.gb, 1);
-                const bool act = (u >= 0) && (u <= C);
+                const bool act = STEADY ? true : ((u >= 0) && (u <= C));
                 if (act) {
                         // ---- column context ----
                         ColCtx<V> cc;
@@ -262,16 +269,16 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                                 prevCO = cc.CO;
                         } else {
                                 cc.CO = J.o; cc.CE = J.e; CT = J.t; cc.COp = J.o;
-                                if (u >= 1) {
+                                if (STEADY || u >= 1) {
                                         cc.cres = (int)__ldg(J.seq_c + r);
                                 }
                         }
                         // ---- lane 0: take the row above from the source ----
                         if (lane == 0) {
                                 if (gen) {
-                                        if (u == 0) {
+                                        if (!STEADY && u == 0) {
                                                 up = in;
-                                        } else if (u < C) {
+                                        } else if (STEADY || u < C) {
                                                 float nga;
                                                 if (first_term) {
                                                         nga = kmax(genGA, genA) + CT;
@@ -285,7 +292,7 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                                         }
                                 } else {
                                         up.a = pre.x; up.ga = pre.y; up.gb = pre.z;
-                                        if (u < C) {
+                                        if (STEADY || u < C) {
                                                 const unsigned need = (unsigned)(u + 2);   // column u+1 written
                                                 if (avail < need) {
                                                         do {
@@ -298,25 +305,42 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                                 }
                         }
                         const Trip got = up;
-                        if (u == 0) {
-                                cells<V, K, TAIL, MODE_FIRST, BONUS>(J, rc, vmask, first_term, last_term, cc, s_tbl, sA, sGA, sGB, d, up);
-                        } else if (u < C) {
+                        if constexpr (STEADY) {
                                 cells<V, K, TAIL, MODE_MID, BONUS>(J, rc, vmask, first_term, last_term, cc, s_tbl, sA, sGA, sGB, d, up);
                         } else {
-                                cells<V, K, TAIL, MODE_LAST, BONUS>(J, rc, vmask, first_term, last_term, cc, s_tbl, sA, sGA, sGB, d, up);
+                                if (u == 0) {
+                                        cells<V, K, TAIL, MODE_FIRST, BONUS>(J, rc, vmask, first_term, last_term, cc, s_tbl, sA, sGA, sGB, d, up);
+                                } else if (u < C) {
+                                        cells<V, K, TAIL, MODE_MID, BONUS>(J, rc, vmask, first_term, last_term, cc, s_tbl, sA, sGA, sGB, d, up);
+                                } else {
+                                        cells<V, K, TAIL, MODE_LAST, BONUS>(J, rc, vmask, first_term, last_term, cc, s_tbl, sA, sGA, sGB, d, up);
+                                }
                         }
                         d = got;
                         bot = up;
                 }
                 if (lane == 31) {
                         const int uo = t - 31;
-                        if (uo >= 0 && uo <= C) {
+                        if (STEADY || (uo >= 0 && uo <= C)) {
                                 rowbuf[uo] = make_float4(bot.a, bot.ga, bot.gb, 0.0f);
                                 if (my_prog && (((uo + 1) % PUBLISH_EVERY) == 0 || uo == C)) {
                                         __threadfence();
                                         *((volatile unsigned*)my_prog) = (unsigned)(uo + 1);
                                 }
                         }
+                }
+        };
+        {
+                int t = 0;
+                const int t_fill = (steps < 32) ? steps : 32;
+                for (; t < t_fill; t++) {
+                        step(std::false_type{}, t);
+                }
+                for (; t < C; t++) {            // 32 <= t <= C-1
+                        step(std::true_type{}, t);
+                }
+                for (; t < steps; t++) {
+                        step(std::false_type{}, t);
                 }
         }
         __syncwarp();
@@ -351,6 +375,11 @@ __device__ void sweep_unit(const KbJob& J, const KbBox& bx, const int bwd, const
         } else if constexpr (V == V_PP23) {
                 if (rem >= 64) sweep_strip<V, 2, false, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane);
                 else if (rem > 32) sweep_strip<V, 2, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane);
+                else sweep_strip<V, 1, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane);
+        } else if constexpr (V == V_SS) {
+                if (rem >= 256) sweep_strip<V, 8, false, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane);
+                else if (rem > 128) sweep_strip<V, 8, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane);
+                else if (rem > 32) sweep_strip<V, 4, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane);
                 else sweep_strip<V, 1, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane);
         } else {
                 if (rem >= 128) sweep_strip<V, 4, false, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane);
