@@ -100,7 +100,7 @@ template <int V> struct ColCtx {
 template <int V, int K, bool TAIL, int MODE, bool BONUS>
 __device__ __forceinline__ void cells(const KbJob& J, const RowCtx<V, K>& rc, const unsigned vmask,
                                       const bool first_term, const bool last_term,
-                                      const ColCtx<V>& cc, const float* __restrict__ s_tbl,
+                                      const ColCtx<V>& cc, const float (&bon)[K], const float* __restrict__ s_tbl,
                                       float (&sA)[K], float (&sGA)[K], float (&sGB)[K],
                                       Trip d, Trip& u /* in: up at column u; out: bottom row */)
 {
@@ -132,7 +132,7 @@ __device__ __forceinline__ void cells(const KbJob& J, const RowCtx<V, K>& rc, co
                                 }
                         }
                         if constexpr (BONUS) {
-                                a = a + __ldg(J.bonus + (size_t)rc.irow[k] * (size_t)J.len_b + (size_t)cc.jcol);
+                                a = a + bon[k];      // consistency[i*stride + j], prefetched one step ahead
                         }
                         if constexpr (MODE == MODE_MID) {
                                 ga = kmax(oGA + cc.CE, oA + cc.CO);
@@ -230,6 +230,22 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                 pre = __ldcg(rowbuf);
         }
         const int steps = C + 32;
+        // column input of the current step (filled one step ahead); lane 0 starts on column 0 at t=0
+        float4 curA = make_float4(0.f, 0.f, 0.f, 0.f), curB = curA;
+        int cur_cres = 0;
+        float cur_bon[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) cur_bon[k] = 0.0f;
+        if constexpr (NA > 0 && NA <= 5) {
+                static_assert(PACK5 == 8, "PP5 record is two float4");
+                if (lane == 0) {
+                        const int j0 = bwd ? eb : sb;
+                        const int r0c = bwd ? j0 : (j0 - 1);
+                        const float4* __restrict__ rec = reinterpret_cast<const float4*>(J.cpack) + (size_t)(r0c + 1) * PW4;
+                        curA = __ldg(rec);
+                        curB = __ldg(rec + 1);
+                }
+        }
         // one step of the wavefront.  STEADY (32 <= t <= C-1): every lane is on an interior column
         // (1 <= u <= C-1), so the activity test and the boundary-column dispatch disappear.
         auto step = [&](auto steady_tag, const int t) {
@@ -240,17 +256,50 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                 up.ga = __shfl_up_sync(FULL, bot.ga, 1);
                 up.gb = __shfl_up_sync(FULL, bot.gb, 1);
                 const bool act = STEADY ? true : ((u >= 0) && (u <= C));
+                // ---- column input of the NEXT step (software prefetch: the load latency is off the
+                //      recurrence's critical path, which matters when few warps are resident) ----
+                constexpr bool PREF = (NA <= 5);   // 23-letter records are loaded in-step (register budget)
+                float4 nxtA = make_float4(0.f, 0.f, 0.f, 0.f), nxtB = nxtA;   // PP5 record = 2 x float4
+                int ncres = 0;
+                float nbon[K];
+                if constexpr (BONUS) {
+                        const int pu = u + 1;
+                        if (STEADY || (pu >= 1 && pu <= C)) {
+                                const int pj = bwd ? (eb - pu) : (sb + pu);
+#pragma unroll
+                                for (int k = 0; k < K; k++) {
+                                        nbon[k] = __ldg(J.bonus + (size_t)rc.irow[k] * (size_t)J.len_b + (size_t)pj);
+                                }
+                        } else {
+#pragma unroll
+                                for (int k = 0; k < K; k++) nbon[k] = 0.0f;
+                        }
+                }
+                if constexpr (PREF) {
+                        const int pu = u + 1;
+                        if (STEADY || (pu >= 0 && pu <= C)) {
+                                const int pj = bwd ? (eb - pu) : (sb + pu);
+                                const int pr = bwd ? pj : (pj - 1);
+                                if constexpr (NA > 0) {
+                                        const float4* __restrict__ rec = reinterpret_cast<const float4*>(J.cpack) + (size_t)(pr + 1) * PW4;
+                                        nxtA = __ldg(rec);
+                                        nxtB = __ldg(rec + 1);
+                                } else {
+                                        if (STEADY || pu >= 1) {
+                                                ncres = (int)__ldg(J.seq_c + pr);
+                                        }
+                                }
+                        }
+                }
                 if (act) {
-                        // ---- column context ----
+                        // ---- column context (prefetched during the previous step) ----
                         ColCtx<V> cc;
                         const int j = bwd ? (eb - u) : (sb + u);        // state column
-                        const int r = bwd ? j : (j - 1);                // residue / profile index
                         cc.jcol = j;
-                        cc.cres = 0;
+                        cc.cres = cur_cres;
                         float CT;
-                        if constexpr (NA > 0) {
-                                // packed record of profile column r+1 (for u==0 the boundary column
-                                // visited "before" u==1: only its [27] is used)
+                        if constexpr (NA > 0 && !PREF) {
+                                const int r = bwd ? j : (j - 1);
                                 const float4* __restrict__ rec = reinterpret_cast<const float4*>(J.cpack) + (size_t)(r + 1) * PW4;
                                 float buf[PW4 * 4];
 #pragma unroll
@@ -267,11 +316,17 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                                 CT = buf[NA + 2];
                                 cc.COp = prevCO;
                                 prevCO = cc.CO;
+                        } else if constexpr (NA > 0) {
+                                // PACK5: s0..s3 | s4, [27], [28], [29]
+                                cc.qs[0] = curA.x; cc.qs[1] = curA.y; cc.qs[2] = curA.z; cc.qs[3] = curA.w;
+                                cc.qs[4] = curB.x;
+                                cc.CO = curB.y;
+                                cc.CE = curB.z;
+                                CT = curB.w;
+                                cc.COp = prevCO;
+                                prevCO = cc.CO;
                         } else {
                                 cc.CO = J.o; cc.CE = J.e; CT = J.t; cc.COp = J.o;
-                                if (STEADY || u >= 1) {
-                                        cc.cres = (int)__ldg(J.seq_c + r);
-                                }
                         }
                         // ---- lane 0: take the row above from the source ----
                         if (lane == 0) {
@@ -306,24 +361,33 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                         }
                         const Trip got = up;
                         if constexpr (STEADY) {
-                                cells<V, K, TAIL, MODE_MID, BONUS>(J, rc, vmask, first_term, last_term, cc, s_tbl, sA, sGA, sGB, d, up);
+                                cells<V, K, TAIL, MODE_MID, BONUS>(J, rc, vmask, first_term, last_term, cc, cur_bon, s_tbl, sA, sGA, sGB, d, up);
                         } else {
                                 if (u == 0) {
-                                        cells<V, K, TAIL, MODE_FIRST, BONUS>(J, rc, vmask, first_term, last_term, cc, s_tbl, sA, sGA, sGB, d, up);
+                                        cells<V, K, TAIL, MODE_FIRST, BONUS>(J, rc, vmask, first_term, last_term, cc, cur_bon, s_tbl, sA, sGA, sGB, d, up);
                                 } else if (u < C) {
-                                        cells<V, K, TAIL, MODE_MID, BONUS>(J, rc, vmask, first_term, last_term, cc, s_tbl, sA, sGA, sGB, d, up);
+                                        cells<V, K, TAIL, MODE_MID, BONUS>(J, rc, vmask, first_term, last_term, cc, cur_bon, s_tbl, sA, sGA, sGB, d, up);
                                 } else {
-                                        cells<V, K, TAIL, MODE_LAST, BONUS>(J, rc, vmask, first_term, last_term, cc, s_tbl, sA, sGA, sGB, d, up);
+                                        cells<V, K, TAIL, MODE_LAST, BONUS>(J, rc, vmask, first_term, last_term, cc, cur_bon, s_tbl, sA, sGA, sGB, d, up);
                                 }
                         }
                         d = got;
                         bot = up;
                 }
+                cur_cres = ncres;
+                if constexpr (BONUS) {
+#pragma unroll
+                        for (int k = 0; k < K; k++) cur_bon[k] = nbon[k];
+                }
+                if constexpr (NA > 0 && PREF) {
+                        curA = nxtA;
+                        curB = nxtB;
+                }
                 if (lane == 31) {
                         const int uo = t - 31;
                         if (STEADY || (uo >= 0 && uo <= C)) {
                                 rowbuf[uo] = make_float4(bot.a, bot.ga, bot.gb, 0.0f);
-                                if (my_prog && (((uo + 1) % PUBLISH_EVERY) == 0 || uo == C)) {
+                                if (my_prog && (((uo + 1) % ((K == 1) ? (PUBLISH_EVERY / 2) : PUBLISH_EVERY)) == 0 || uo == C)) {
                                         __threadfence();
                                         *((volatile unsigned*)my_prog) = (unsigned)(uo + 1);
                                 }
