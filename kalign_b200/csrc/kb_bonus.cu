@@ -111,13 +111,17 @@ __global__ void kb_init_colof_kernel(const int64_t* __restrict__ offs, const int
 }
 
 // ---- votes -----------------------------------------------------------------------------------
+// One WARP per profile column: lanes stride over the members.  "First seen position wins"
+// (anchor_consistency.c:440-445) = the position voted by the valid member with the smallest index
+// in sip[] order; pass 1 finds it with a warp min-reduction, pass 2 counts total / agreeing votes.
 __global__ void kb_bonus_positions_kernel(const KbBonusOperand* __restrict__ ops, const long long* __restrict__ col_prefix,
                                           const int nops, const long long total_cols, const int K,
                                           const int* __restrict__ memb, const int64_t* __restrict__ offs,
                                           const int* __restrict__ lens, const int* __restrict__ colof,
                                           const int* __restrict__ posmaps)
 {
-        const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        const int lane = threadIdx.x & 31;
+        const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
         if (gid >= total_cols) return;
         int lo = 0, hi = nops - 1;
         while (lo < hi) {
@@ -128,11 +132,12 @@ __global__ void kb_bonus_positions_kernel(const KbBonusOperand* __restrict__ ops
         const int c = (int)(gid - col_prefix[lo]);
         int* __restrict__ pos = O.pos;        // [K][len]
         float* __restrict__ conf = O.conf;
-        if (O.m1 - O.m0 == 1) {
+        const int nmem = O.m1 - O.m0;
+        if (nmem == 1) {
                 // leaf: direct lookup (anchor_consistency.c:360-378)
                 const int si = memb[O.m0];
                 const int seq_len = lens[si];
-                for (int k = 0; k < K; k++) {
+                for (int k = lane; k < K; k += 32) {
                         int v = -1;
                         if (c < seq_len) {
                                 v = posmaps[(size_t)K * (size_t)offs[si] + (size_t)k * (size_t)seq_len + c];
@@ -142,16 +147,16 @@ __global__ void kb_bonus_positions_kernel(const KbBonusOperand* __restrict__ ops
                 }
                 return;
         }
-        int best[KMAX], agree[KMAX], total[KMAX];
+        // pass 1: per lane, first member (smallest index) with a valid position, per anchor
+        int first_m[KMAX], first_pos[KMAX], total[KMAX];
 #pragma unroll
         for (int k = 0; k < KMAX; k++) {
-                best[k] = -1; agree[k] = 0; total[k] = 0;
+                first_m[k] = 0x7fffffff; first_pos[k] = -1; total[k] = 0;
         }
-        for (int m = O.m0; m < O.m1; m++) {
-                const int si = memb[m];
+        for (int m = lane; m < nmem; m += 32) {
+                const int si = memb[O.m0 + m];
                 const int seq_len = lens[si];
                 const int* __restrict__ co = colof + offs[si];
-                // residue whose column is c (colof is strictly increasing)
                 int a = 0, b = seq_len;
                 while (a < b) {
                         const int mid = (a + b) >> 1;
@@ -165,22 +170,62 @@ __global__ void kb_bonus_positions_kernel(const KbBonusOperand* __restrict__ ops
                                 const int apos = map0[(size_t)k * seq_len];
                                 if (apos >= 0) {
                                         total[k]++;
-                                        if (best[k] < 0) {
-                                                best[k] = apos;
-                                                agree[k] = 1;
-                                        } else if (apos == best[k]) {
-                                                agree[k]++;
+                                        if (m < first_m[k]) {
+                                                first_m[k] = m;
+                                                first_pos[k] = apos;
                                         }
                                 }
                         }
                 }
         }
+        int best[KMAX];
 #pragma unroll
         for (int k = 0; k < KMAX; k++) {
-                if (k < K) {
-                        const bool ok = total[k] > 0 && agree[k] > 0;
+                int fm = first_m[k], fp = first_pos[k], tt = total[k];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                        const int om = __shfl_xor_sync(0xffffffffu, fm, o);
+                        const int op = __shfl_xor_sync(0xffffffffu, fp, o);
+                        tt += __shfl_xor_sync(0xffffffffu, tt, o);
+                        if (om < fm) { fm = om; fp = op; }
+                }
+                best[k] = fp;
+                total[k] = tt;
+        }
+        // pass 2: members agreeing with the first-seen position
+        int agree[KMAX];
+#pragma unroll
+        for (int k = 0; k < KMAX; k++) agree[k] = 0;
+        for (int m = lane; m < nmem; m += 32) {
+                const int si = memb[O.m0 + m];
+                const int seq_len = lens[si];
+                const int* __restrict__ co = colof + offs[si];
+                int a = 0, b = seq_len;
+                while (a < b) {
+                        const int mid = (a + b) >> 1;
+                        if (co[mid] < c) a = mid + 1; else b = mid;
+                }
+                if (a >= seq_len || co[a] != c) continue;
+                const int* __restrict__ map0 = posmaps + (size_t)K * (size_t)offs[si] + a;
+#pragma unroll
+                for (int k = 0; k < KMAX; k++) {
+                        if (k < K) {
+                                const int apos = map0[(size_t)k * seq_len];
+                                if (apos >= 0 && apos == best[k]) agree[k]++;
+                        }
+                }
+        }
+#pragma unroll
+        for (int k = 0; k < KMAX; k++) {
+                int ag = agree[k];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                        ag += __shfl_xor_sync(0xffffffffu, ag, o);
+                }
+                if (lane == 0 && k < K) {
+                        const bool ok = total[k] > 0 && ag > 0;
                         pos[(size_t)k * O.len + c] = ok ? best[k] : -1;
-                        conf[(size_t)k * O.len + c] = ok ? ((float)agree[k] / (float)total[k]) : 0.0f;
+                        conf[(size_t)k * O.len + c] = ok ? ((float)ag / (float)total[k]) : 0.0f;
                 }
         }
 }
@@ -268,7 +313,7 @@ int kb_bonus_level(kb200_ctx* ctx, KbSeqs& S, int K, float paw,
                    const long long* d_row_prefix, long long row_total, int ntasks, const int* d_aoff)
 {
         if (ntasks <= 0) return KB200_OK;
-        kb_bonus_positions_kernel<<<(unsigned)((op_cols + 127) / 128), 128, 0, ctx->stream>>>(d_ops, d_op_prefix, nops, op_cols, K, d_memb,
+        kb_bonus_positions_kernel<<<(unsigned)((op_cols * 32 + 127) / 128), 128, 0, ctx->stream>>>(d_ops, d_op_prefix, nops, op_cols, K, d_memb,
                                                                                                S.d_offs.as<int64_t>(), S.d_lens.as<int>(),
                                                                                                d_colof, d_posmaps);
         KB_CUDA(cudaGetLastError());
