@@ -221,13 +221,28 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
         float prevCO = 0.0f;                // PP: [27] of the column visited one step earlier
         const bool gen = (prev_prog == nullptr);
         unsigned avail = gen ? 0x7fffffffu : 0u;   // columns of the row above known to be written
-        float4 pre = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!gen && lane == 0) {
-                while (avail < 1u) {
-                        avail = ld_volatile_u32(prev_prog);
+        // lane 0 of a consumer strip reads the row above RD columns ahead of its use (register
+        // ring): the L2 latency of the hand-off is then hidden even when this is the only warp
+        // the scheduler can run (one box spread thinly over the machine)
+        constexpr int RD = (K == 1) ? 4 : 1;     // thick strips run with many co-resident warps
+        float4 pre0 = make_float4(0.f, 0.f, 0.f, 0.f), pre1 = pre0, pre2 = pre0, pre3 = pre0;
+        auto fetch_above = [&](const int col) -> float4 {
+                const unsigned need = (unsigned)(col + 1);          // column `col` written
+                if (avail < need) {
+                        do {
+                                avail = ld_volatile_u32(prev_prog);
+                        } while (avail < need);
+                        __threadfence();
                 }
-                __threadfence();
-                pre = __ldcg(rowbuf);
+                return __ldcg(rowbuf + col);
+        };
+        if (!gen && lane == 0) {
+                pre0 = fetch_above(0);
+                if constexpr (RD == 4) {
+                        if (1 <= C) pre1 = fetch_above(1);
+                        if (2 <= C) pre2 = fetch_above(2);
+                        if (3 <= C) pre3 = fetch_above(3);
+                }
         }
         const int steps = C + 32;
         // column input of the current step (filled one step ahead); lane 0 starts on column 0 at t=0
@@ -262,6 +277,22 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                 float4 nxtA = make_float4(0.f, 0.f, 0.f, 0.f), nxtB = nxtA;   // PP5 record = 2 x float4
                 int ncres = 0;
                 float nbon[K];
+                if constexpr (K == 1 && (BONUS || NA > 0)) {
+                        // thin strips: pull the far-ahead inputs towards L1 (no register cost)
+                        const int fu = u + 8;
+                        if (fu >= 1 && fu <= C) {
+                                const int fj = bwd ? (eb - fu) : (sb + fu);
+                                if constexpr (BONUS) {
+                                        const float* fp = J.bonus + (size_t)rc.irow[0] * (size_t)J.len_b + (size_t)fj;
+                                        asm volatile("prefetch.global.L1 [%0];" ::"l"(fp));
+                                }
+                                if constexpr (NA > 0) {
+                                        const int fr = bwd ? fj : (fj - 1);
+                                        const float* fq = J.cpack + (size_t)(fr + 1) * (PW4 * 4);
+                                        asm volatile("prefetch.global.L1 [%0];" ::"l"(fq));
+                                }
+                        }
+                }
                 if constexpr (BONUS) {
                         const int pu = u + 1;
                         if (STEADY || (pu >= 1 && pu <= C)) {
@@ -346,16 +377,16 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                                                 up.a = KB_NEGF; up.ga = KB_NEGF; up.gb = KB_NEGF;
                                         }
                                 } else {
-                                        up.a = pre.x; up.ga = pre.y; up.gb = pre.z;
-                                        if (STEADY || u < C) {
-                                                const unsigned need = (unsigned)(u + 2);   // column u+1 written
-                                                if (avail < need) {
-                                                        do {
-                                                                avail = ld_volatile_u32(prev_prog);
-                                                        } while (avail < need);
-                                                        __threadfence();
+                                        up.a = pre0.x; up.ga = pre0.y; up.gb = pre0.z;
+                                        if constexpr (RD == 4) {
+                                                pre0 = pre1; pre1 = pre2; pre2 = pre3;
+                                                if (u + RD <= C) {
+                                                        pre3 = fetch_above(u + RD);
                                                 }
-                                                pre = __ldcg(rowbuf + u + 1);
+                                        } else {
+                                                if (u + 1 <= C) {
+                                                        pre0 = fetch_above(u + 1);
+                                                }
                                         }
                                 }
                         }
