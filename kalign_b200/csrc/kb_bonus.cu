@@ -28,33 +28,49 @@ namespace {
 constexpr int KMAX = KB_BONUS_KMAX;
 
 // ---- weave -----------------------------------------------------------------------------------
-// per task (serial, O(alnlen)): new-gap counts per profile column of a and of b, as prefix sums
+// per task, one warp: P[x] = number of new gap columns inserted before profile column x of the
+// operand = number of gap entries that precede the x-th operand-consuming entry of the coded path
+// (make_seq's gap_a / gap_b, weave_alignment.c:57-70, as prefix sums).
 __global__ void kb_weave_prefix_kernel(const KbWeaveTask* __restrict__ tasks, const int ntasks)
 {
-        const int q = blockIdx.x * blockDim.x + threadIdx.x;
+        const int lane = threadIdx.x & 31;
+        const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
         if (q >= ntasks) return;
         const KbWeaveTask T = tasks[q];
         const int* __restrict__ path = T.path;
-        int* __restrict__ Pa = T.Pa;      // alnlen+2 entries: Pa[x] = # new gaps in columns < x of a
+        int* __restrict__ Pa = T.Pa;
         int* __restrict__ Pb = T.Pb;
-        const int n = ((T.alnlen >= 0) ? T.alnlen : path[0]) + 2;
-        for (int i = 0; i < n; i++) {
-                Pa[i] = 0; Pb[i] = 0;
-        }
-        int posa = 0, posb = 0;
-        for (int c = 1; path[c] != 3; c++) {
-                const int p = path[c];
-                if (!p) {
-                        posa++; posb++;
-                } else if (p & 1) {
-                        Pa[posa + 1] += 1; posb++;       // gap_a[posa] += 1
-                } else if (p & 2) {
-                        Pb[posb + 1] += 1; posa++;       // gap_b[posb] += 1
+        const int alnlen = (T.alnlen >= 0) ? T.alnlen : path[0];
+        int ka = 0, kb = 0, ga = 0, gb = 0;      // running counts: consumed columns / gap entries
+        for (int base = 1; base <= alnlen; base += 32) {
+                const int c = base + lane;
+                int p = 0;
+                const bool in = c <= alnlen;
+                if (in) p = path[c];
+                const int fa = (in && (!p || (p & 2))) ? 1 : 0;   // consumes a column of a
+                const int fb = (in && (!p || (p & 1))) ? 1 : 0;   // consumes a column of b
+                const int xa = (in && (p & 1)) ? 1 : 0;           // gap column in a
+                const int xb = (in && (p & 2)) ? 1 : 0;           // gap column in b
+                int ia = fa, ib = fb, ja = xa, jb = xb;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                        const int t0 = __shfl_up_sync(0xffffffffu, ia, o);
+                        const int t1 = __shfl_up_sync(0xffffffffu, ib, o);
+                        const int t2 = __shfl_up_sync(0xffffffffu, ja, o);
+                        const int t3 = __shfl_up_sync(0xffffffffu, jb, o);
+                        if (lane >= o) { ia += t0; ib += t1; ja += t2; jb += t3; }
                 }
+                if (fa) Pa[ka + ia] = ga + ja - xa;       // gap entries before this a-consuming entry
+                if (fb) Pb[kb + ib] = gb + jb - xb;
+                ka += __shfl_sync(0xffffffffu, ia, 31);
+                kb += __shfl_sync(0xffffffffu, ib, 31);
+                ga += __shfl_sync(0xffffffffu, ja, 31);
+                gb += __shfl_sync(0xffffffffu, jb, 31);
         }
-        for (int i = 1; i < n; i++) {
-                Pa[i] += Pa[i - 1];
-                Pb[i] += Pb[i - 1];
+        if (lane == 0) {
+                Pa[0] = 0; Pb[0] = 0;
+                Pa[ka + 1] = ga;
+                Pb[kb + 1] = gb;
         }
 }
 
@@ -295,7 +311,7 @@ int kb_weave_level(kb200_ctx* ctx, KbSeqs& S, const KbWeaveTask* d_tasks, int nt
                    const KbWeaveMember* d_members, int nmembers, int* d_gaps, int* d_colof)
 {
         if (ntasks <= 0) return KB200_OK;
-        kb_weave_prefix_kernel<<<(ntasks + 63) / 64, 64, 0, ctx->stream>>>(d_tasks, ntasks);
+        kb_weave_prefix_kernel<<<(ntasks * 32 + 127) / 128, 128, 0, ctx->stream>>>(d_tasks, ntasks);
         KB_CUDA(cudaGetLastError());
         if (nmembers > 0) {
                 kb_weave_apply_kernel<<<(nmembers * 32 + 127) / 128, 128, 0, ctx->stream>>>(d_members, nmembers, S.d_offs.as<int64_t>(),

@@ -70,125 +70,162 @@ __global__ void kb_set_gap_kernel(const KbGapSet* __restrict__ sets, const int n
         }
 }
 
-// raw path -> (mirror) -> coded path (+ optional position map).  One thread per job: the walk is
-// inherently serial and O(len); jobs are independent.
+// ---- warp-parallel path post-processing -------------------------------------------------------
+__device__ __forceinline__ int warp_incl_scan(int v, const int lane)
+{
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += t;
+        }
+        return v;
+}
+
+// entries a row contributes to the coded path: `skip` gap-in-A entries, then one 0 / 2
+// (add_gap_info_to_path_n, aln_setup.c:141-180: the skip is only emitted when the previous row
+// was matched, b != -1, and for row 1 it is path[1]-1)
+__device__ __forceinline__ int row_skip(const int i, const int r, const int rp)
+{
+        if (r == -1) return 0;
+        if (i == 1) return r - 1;
+        return (r - 1 != rp && rp != -1) ? (r - rp - 1) : 0;
+}
+
+// raw path -> (mirror) -> coded path (+ optional position map).  One WARP per job: the walk of
+// the reference is a prefix sum over per-row entry counts, so it is done with warp scans.
 __global__ void kb_code_path_kernel(const KbPathJob* __restrict__ pj, const int njobs)
 {
-        const int j = blockIdx.x * blockDim.x + threadIdx.x;
+        const int lane = threadIdx.x & 31;
+        const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
         if (j >= njobs) {
                 return;
         }
         const KbPathJob P = pj[j];
         const int len_a = P.len_a, len_b = P.len_b;
-        const int n = len_a + len_b + 2;
         const int* raw = P.raw;
-        int* o = P.coded;
+        int* __restrict__ o = P.coded;
         if (P.mirror) {
                 // raw was produced with rows = b (len_b entries); scratch receives the mirrored path
                 int* mr = P.scratch;
-                for (int i = 0; i < len_a + 2; i++) {
+                for (int i = lane; i < len_a + 2; i += 32) {
                         mr[i] = -1;
                 }
-                for (int i = 1; i <= len_b; i++) {
+                __syncwarp();
+                for (int i = 1 + lane; i <= len_b; i += 32) {
                         const int c = raw[i];
                         if (c != -1) {
                                 mr[c] = i;
                         }
                 }
+                __syncwarp();
                 raw = mr;
         }
-        for (int i = 0; i < n; i++) {
-                o[i] = 0;
+        // pass A: total length, first / last matched row and the index of their 0-entry
+        int carry = 1;                       // next free index of o
+        int first_pz = 0x7fffffff, last_pz = -1;
+        for (int base = 1; base <= len_a; base += 32) {
+                const int i = base + lane;
+                int cnt = 0, skip = 0, r = -1;
+                if (i <= len_a) {
+                        r = raw[i];
+                        const int rp = (i > 1) ? raw[i - 1] : -1;
+                        skip = row_skip(i, r, rp);
+                        cnt = skip + 1;
+                }
+                const int incl = warp_incl_scan(cnt, lane);
+                const int start = carry + incl - cnt;
+                if (i <= len_a && r != -1) {
+                        const int pz = start + skip;
+                        first_pz = min(first_pz, pz);
+                        last_pz = max(last_pz, pz);
+                }
+                carry += __shfl_sync(0xffffffffu, incl, 31);
         }
-        int jj = 1;
-        int b = -1;
-        for (int i = 1; i <= len_a; i++) {
-                const int r = raw[i];
-                if (r == -1) {
-                        o[jj++] = 2;
-                } else {
-                        int skip;
-                        if (i == 1) {
-                                skip = r - 1;
-                        } else if (r - 1 != b && b != -1) {
-                                skip = r - b - 1;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+                first_pz = min(first_pz, __shfl_xor_sync(0xffffffffu, first_pz, off));
+                last_pz = max(last_pz, __shfl_xor_sync(0xffffffffu, last_pz, off));
+        }
+        int total = carry;                   // index after the last row entry
+        const int lastr = raw[len_a];
+        const int tail = (lastr != -1 && lastr < len_b) ? (len_b - lastr) : 0;
+        const int end = total + tail;        // index of the terminator
+        // pass B: write the entries (terminal bit 32 on the leading / trailing gap runs,
+        // aln_setup.c:212-222; the open/ext/close loop of the reference never runs, :191-195)
+        carry = 1;
+        int carry_b = 0;                     // residues of b consumed so far (position map)
+        for (int base = 1; base <= len_a; base += 32) {
+                const int i = base + lane;
+                int cnt = 0, skip = 0, r = -1, adv = 0;
+                if (i <= len_a) {
+                        r = raw[i];
+                        const int rp = (i > 1) ? raw[i - 1] : -1;
+                        skip = row_skip(i, r, rp);
+                        cnt = skip + 1;
+                        adv = skip + ((r != -1) ? 1 : 0);
+                }
+                const int incl = warp_incl_scan(cnt, lane);
+                const int inclb = warp_incl_scan(adv, lane);
+                const int start = carry + incl - cnt;
+                if (i <= len_a) {
+                        for (int q = 0; q < skip; q++) {
+                                const int idx = start + q;
+                                o[idx] = 1 | ((idx < first_pz || idx > last_pz) ? 32 : 0);
+                        }
+                        const int idx = start + skip;
+                        if (r == -1) {
+                                o[idx] = 2 | ((idx < first_pz || idx > last_pz) ? 32 : 0);
                         } else {
-                                skip = 0;
+                                o[idx] = 0;
                         }
-                        for (int a = 0; a < skip; a++) {
-                                o[jj++] = 1;
-                        }
-                        o[jj++] = 0;
-                }
-                b = r;
-        }
-        {
-                const int last = raw[len_a];
-                if (last < len_b && last != -1) {
-                        for (int a = 0; a < len_b - last; a++) {
-                                o[jj++] = 1;
+                        if (P.posmap) {
+                                // anchor_consistency.c:85-111: a match maps row i-1 to the b position
+                                P.posmap[i - 1] = (r != -1) ? (carry_b + inclb - adv + skip) : -1;
                         }
                 }
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+                carry_b += __shfl_sync(0xffffffffu, inclb, 31);
         }
-        o[0] = jj - 1;
-        o[jj] = 3;
-        // (the reference's open/ext/close flag loop never runs, aln_setup.c:191-195)
-        int i = 1;
-        while (i < n && o[i] != 0) {
-                o[i] |= 32;
-                i++;
+        for (int q = lane; q < tail; q += 32) {
+                const int idx = total + q;
+                o[idx] = 1 | ((idx < first_pz || idx > last_pz) ? 32 : 0);
         }
-        i = o[0];
-        while (i > 0 && o[i] != 0) {
-                o[i] |= 32;
-                i--;
-        }
-        if (P.posmap) {
-                int* pm = P.posmap;
-                const int len_i = len_a;
-                for (int c = 0; c < len_i; c++) {
-                        pm[c] = -1;
-                }
-                int pos_a = 0, pos_b = 0;
-                for (int c = 1; o[c] != 3; c++) {
-                        const int v = o[c];
-                        if (v == 0) {
-                                if (pos_a < len_i) pm[pos_a] = pos_b;
-                                pos_a++; pos_b++;
-                        } else if (v & 1) {
-                                pos_b++;
-                        } else if (v & 2) {
-                                if (pos_a < len_i) pm[pos_a] = -1;
-                                pos_a++;
-                        }
-                }
+        if (lane == 0) {
+                o[0] = end - 1;
+                o[end] = 3;
         }
 }
 
-// per merge: source column indices of every output column (prefix over the coded path), one
-// thread per job (serial, O(len)), then one warp per output column does the 64-float merge.
+// per merge: source column indices (1-based) of every output column = exclusive counts of the
+// a-consuming / b-consuming entries before it (update_n's profa/profb pointer walk)
 __global__ void kb_merge_index_kernel(const KbMergeJob* __restrict__ mj, const int njobs)
 {
-        const int j = blockIdx.x * blockDim.x + threadIdx.x;
+        const int lane = threadIdx.x & 31;
+        const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
         if (j >= njobs) {
                 return;
         }
         const KbMergeJob M = mj[j];
-        const int* path = M.path;
-        int2* src = M.src;
-        int ia = 1, ib = 1;
-        int c = 1;
-        for (; path[c] != 3; c++) {
-                const int p = path[c];
-                src[c] = make_int2(ia, ib);
-                if (!p) {
-                        ia++; ib++;
-                } else {
-                        if (p & 1) ib++;
-                        if (p & 2) ia++;
+        const int* __restrict__ path = M.path;
+        int2* __restrict__ src = M.src;
+        const int alnlen = M.alnlen;
+        int ca = 1, cb = 1;
+        for (int base = 1; base <= alnlen + 1; base += 32) {
+                const int c = base + lane;
+                int fa = 0, fb = 0;
+                if (c <= alnlen) {
+                        const int p = path[c];
+                        fa = (!p || (p & 2)) ? 1 : 0;
+                        fb = (!p || (p & 1)) ? 1 : 0;
                 }
+                const int ia = warp_incl_scan(fa, lane);
+                const int ib = warp_incl_scan(fb, lane);
+                if (c <= alnlen + 1) {
+                        src[c] = make_int2(ca + ia - fa, cb + ib - fb);
+                }
+                ca += __shfl_sync(0xffffffffu, ia, 31);
+                cb += __shfl_sync(0xffffffffu, ib, 31);
         }
-        src[c] = make_int2(ia, ib);      // last boundary column
 }
 
 __device__ __forceinline__ float gap_adjust_val(float v, const int lane_el, const int p, const float sip,
@@ -296,7 +333,7 @@ int kb_set_gap_penalties(kb200_ctx* ctx, const KbGapSet* d_sets, int nsets,
 int kb_code_paths(kb200_ctx* ctx, const KbPathJob* d_pj, int njobs)
 {
         if (njobs <= 0) return KB200_OK;
-        kb_code_path_kernel<<<(njobs + 63) / 64, 64, 0, ctx->stream>>>(d_pj, njobs);
+        kb_code_path_kernel<<<(njobs * 32 + 127) / 128, 128, 0, ctx->stream>>>(d_pj, njobs);
         KB_CUDA(cudaGetLastError());
         ctx->stats.n_launches++;
         return KB200_OK;
@@ -305,7 +342,7 @@ int kb_code_paths(kb200_ctx* ctx, const KbPathJob* d_pj, int njobs)
 int kb_merge_index(kb200_ctx* ctx, const KbMergeJob* d_mj, int njobs)
 {
         if (njobs <= 0) return KB200_OK;
-        kb_merge_index_kernel<<<(njobs + 63) / 64, 64, 0, ctx->stream>>>(d_mj, njobs);
+        kb_merge_index_kernel<<<(njobs * 32 + 127) / 128, 128, 0, ctx->stream>>>(d_mj, njobs);
         KB_CUDA(cudaGetLastError());
         ctx->stats.n_launches++;
         return KB200_OK;
