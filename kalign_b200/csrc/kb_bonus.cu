@@ -268,7 +268,9 @@ __global__ void kb_bonus_inverse_kernel(const KbBonusTask* __restrict__ tasks, c
         }
 }
 
-// one thread per DP row: add the <=K terms in anchor order
+// one thread per DP row: the row's <=K bonus terms, merged per column in anchor order k (a cell hit
+// by several anchors sums its terms in k order, exactly like the reference's += into a zeroed
+// matrix) and sorted by column: bcol[row*K + e] ascending, unused slots = INT_MAX.
 __global__ void kb_bonus_scatter_kernel(const KbBonusTask* __restrict__ tasks, const long long* __restrict__ row_prefix,
                                         const int ntasks, const long long total_rows, const int K,
                                         const int* __restrict__ aoff, const float paw)
@@ -282,7 +284,9 @@ __global__ void kb_bonus_scatter_kernel(const KbBonusTask* __restrict__ tasks, c
         }
         const KbBonusTask T = tasks[lo];
         const int i = (int)(gid - row_prefix[lo]);
-        float* __restrict__ row = T.dense + (size_t)i * (size_t)T.len_b;
+        int cols[KMAX];
+        float vals[KMAX];
+        int n = 0;
         for (int k = 0; k < K; k++) {
                 const int ak = T.pos_a[(size_t)k * T.len_a + i];
                 if (ak < 0) continue;
@@ -291,7 +295,36 @@ __global__ void kb_bonus_scatter_kernel(const KbBonusTask* __restrict__ tasks, c
                 const float ca = T.conf_a[(size_t)k * T.len_a + i];
                 const float cb = T.conf_b[(size_t)k * T.len_b + bj];
                 const float v = __fmul_rn(__fmul_rn(paw, ca), cb);
-                row[bj] = __fadd_rn(row[bj], v);
+                int e = 0;
+                for (; e < n; e++) {
+                        if (cols[e] == bj) break;
+                }
+                if (e < n) {
+                        vals[e] = __fadd_rn(vals[e], v);           // later anchor, same cell
+                } else {
+                        cols[n] = bj;
+                        vals[n] = __fadd_rn(0.0f, v);               // 0 + v, as += into the zeroed matrix
+                        n++;
+                }
+        }
+        // insertion sort by column (n <= K <= 8)
+        for (int x = 1; x < n; x++) {
+                const int c = cols[x];
+                const float v = vals[x];
+                int y = x - 1;
+                while (y >= 0 && cols[y] > c) {
+                        cols[y + 1] = cols[y];
+                        vals[y + 1] = vals[y];
+                        y--;
+                }
+                cols[y + 1] = c;
+                vals[y + 1] = v;
+        }
+        int* __restrict__ oc = T.bcol + (size_t)i * K;
+        float* __restrict__ ov = T.bval + (size_t)i * K;
+        for (int e = 0; e < K; e++) {
+                oc[e] = (e < n) ? cols[e] : 0x7fffffff;
+                ov[e] = (e < n) ? vals[e] : 0.0f;
         }
 }
 

@@ -27,7 +27,8 @@ struct KbBonusTask {
         const int* pos_a; const float* conf_a; int len_a;    // DP rows operand
         const int* pos_b; const float* conf_b; int len_b;    // DP cols operand
         int* inv;            // sum_k anchor_len ints, initialised to -1
-        float* dense;        // len_a*len_b floats, zero filled
+        int* bcol;           // out: len_a*K sorted bonus columns per row (INT_MAX = unused)
+        float* bval;         // out: len_a*K values
 };
 
 int kb_bonus_init_state(kb200_ctx* ctx, KbSeqs& S, int* d_gaps, int* d_colof);

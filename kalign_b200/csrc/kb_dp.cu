@@ -67,7 +67,7 @@ enum { MODE_FIRST = 0, MODE_MID = 1, MODE_LAST = 2 };
 
 // rows per strip of a job in a round: "wide" rounds (few big boxes) use thin strips so that one
 // box spreads over many warps; otherwise thick strips amortise the per-step overhead.
-__device__ __host__ __forceinline__ int rows_per_strip(int kind, int nalpha, int thin)
+__device__ __host__ __forceinline__ int rows_per_strip(int kind, int nalpha, int thin, bool has_bonus)
 {
         if (thin) {
                 return 32;
@@ -75,8 +75,8 @@ __device__ __host__ __forceinline__ int rows_per_strip(int kind, int nalpha, int
         if (kind == KB200_KIND_PP && nalpha > 5) {
                 return 64;
         }
-        if (kind == KB200_KIND_SS) {
-                return 256;
+        if (kind == KB200_KIND_SS && !has_bonus) {
+                return 256;          // K = 8 rows per lane; the bonus variants keep K = 4 (register budget)
         }
         return 128;
 }
@@ -100,7 +100,10 @@ template <int V> struct ColCtx {
 template <int V, int K, bool TAIL, int MODE, bool BONUS>
 __device__ __forceinline__ void cells(const KbJob& J, const RowCtx<V, K>& rc, const unsigned vmask,
                                       const bool first_term, const bool last_term,
-                                      const ColCtx<V>& cc, const float (&bon)[K], const float* __restrict__ s_tbl,
+                                      const ColCtx<V>& cc, const float (&bon)[K],
+                                      const bool sparse, const int bdir, int (&sp_i)[K], int (&sp_c)[K], float (&sp_v)[K],
+                                      const float (&sp_wrap)[K],
+                                      const float* __restrict__ s_tbl,
                                       float (&sA)[K], float (&sGA)[K], float (&sGB)[K],
                                       Trip d, Trip& u /* in: up at column u; out: bottom row */)
 {
@@ -132,7 +135,24 @@ __device__ __forceinline__ void cells(const KbJob& J, const RowCtx<V, K>& rc, co
                                 }
                         }
                         if constexpr (BONUS) {
-                                a = a + bon[k];      // consistency[i*stride + j], prefetched one step ahead
+                                if (sparse) {
+                                        // sorted per-row list walked in sweep direction: at most K hits per row
+                                        if (cc.jcol == sp_c[k]) {
+                                                a = a + sp_v[k];
+                                                sp_i[k] += bdir;
+                                                const int e = sp_i[k];
+                                                const bool ok = (e >= 0) && (e < J.nb);
+                                                const size_t o = (size_t)rc.irow[k] * (size_t)J.nb + (size_t)(ok ? e : 0);
+                                                sp_c[k] = ok ? __ldg(J.bkey + o) : ((bdir > 0) ? 0x7fffffff : -1);
+                                                sp_v[k] = ok ? __ldg(J.bval + o) : 0.0f;
+                                        }
+                                        if constexpr (MODE == MODE_LAST) {
+                                                a = a + sp_wrap[k];   // forward sweep, j == len_b: flat index wraps to (i+1, 0)
+                                        }
+                                } else if (J.bonus) {
+                                        // dense matrix supplied by the caller (kb200_pair_align_batch)
+                                        a = a + __ldg(J.bonus + (size_t)rc.irow[k] * (size_t)J.len_b + (size_t)cc.jcol);
+                                }
                         }
                         if constexpr (MODE == MODE_MID) {
                                 ga = kmax(oGA + cc.CE, oA + cc.CO);
@@ -251,6 +271,43 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
         float cur_bon[K];
 #pragma unroll
         for (int k = 0; k < K; k++) cur_bon[k] = 0.0f;
+        // sparse consistency bonus: per row the index / column / value of the next entry in sweep
+        // direction, and the value the forward sweep picks up at j == len_b (flat index (i+1, 0))
+        const bool sparse = BONUS && (J.bkey != nullptr);
+        const int bdir = bwd ? -1 : 1;
+        int sp_i[K], sp_c[K];
+        float sp_v[K], sp_wrap[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+                sp_i[k] = 0; sp_c[k] = bwd ? -1 : 0x7fffffff; sp_v[k] = 0.0f; sp_wrap[k] = 0.0f;
+        }
+        if constexpr (BONUS) {
+                if (sparse) {
+                        const int KS = J.nb;
+#pragma unroll
+                        for (int k = 0; k < K; k++) {
+                                const int* __restrict__ bc = J.bkey + (size_t)rc.irow[k] * (size_t)KS;
+                                const float* __restrict__ bv = J.bval + (size_t)rc.irow[k] * (size_t)KS;
+                                int e;
+                                if (!bwd) {
+                                        // cells visit j = sb+1 .. eb ascending
+                                        e = 0;
+                                        while (e < KS && __ldg(bc + e) < sb + 1) e++;
+                                        if (e < KS) { sp_c[k] = __ldg(bc + e); sp_v[k] = __ldg(bv + e); }
+                                        if (eb == J.len_b && rc.irow[k] + 1 < J.len_a) {
+                                                const int* __restrict__ nc = bc + KS;
+                                                if (__ldg(nc) == 0) sp_wrap[k] = __ldg(bv + KS);
+                                        }
+                                } else {
+                                        // cells visit j = eb-1 .. sb descending
+                                        e = KS - 1;
+                                        while (e >= 0 && __ldg(bc + e) > eb - 1) e--;
+                                        if (e >= 0) { sp_c[k] = __ldg(bc + e); sp_v[k] = __ldg(bv + e); }
+                                }
+                                sp_i[k] = e;
+                        }
+                }
+        }
         if constexpr (NA > 0 && NA <= 5) {
                 static_assert(PACK5 == 8, "PP5 record is two float4");
                 if (lane == 0) {
@@ -276,34 +333,14 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                 constexpr bool PREF = (NA <= 5);   // 23-letter records are loaded in-step (register budget)
                 float4 nxtA = make_float4(0.f, 0.f, 0.f, 0.f), nxtB = nxtA;   // PP5 record = 2 x float4
                 int ncres = 0;
-                float nbon[K];
-                if constexpr (K == 1 && (BONUS || NA > 0)) {
-                        // thin strips: pull the far-ahead inputs towards L1 (no register cost)
+                if constexpr (K == 1 && NA > 0) {
+                        // thin strips: pull the far-ahead column record towards L1 (no register cost)
                         const int fu = u + 8;
                         if (fu >= 1 && fu <= C) {
                                 const int fj = bwd ? (eb - fu) : (sb + fu);
-                                if constexpr (BONUS) {
-                                        const float* fp = J.bonus + (size_t)rc.irow[0] * (size_t)J.len_b + (size_t)fj;
-                                        asm volatile("prefetch.global.L1 [%0];" ::"l"(fp));
-                                }
-                                if constexpr (NA > 0) {
-                                        const int fr = bwd ? fj : (fj - 1);
-                                        const float* fq = J.cpack + (size_t)(fr + 1) * (PW4 * 4);
-                                        asm volatile("prefetch.global.L1 [%0];" ::"l"(fq));
-                                }
-                        }
-                }
-                if constexpr (BONUS) {
-                        const int pu = u + 1;
-                        if (STEADY || (pu >= 1 && pu <= C)) {
-                                const int pj = bwd ? (eb - pu) : (sb + pu);
-#pragma unroll
-                                for (int k = 0; k < K; k++) {
-                                        nbon[k] = __ldg(J.bonus + (size_t)rc.irow[k] * (size_t)J.len_b + (size_t)pj);
-                                }
-                        } else {
-#pragma unroll
-                                for (int k = 0; k < K; k++) nbon[k] = 0.0f;
+                                const int fr = bwd ? fj : (fj - 1);
+                                const float* fq = J.cpack + (size_t)(fr + 1) * (PW4 * 4);
+                                asm volatile("prefetch.global.L1 [%0];" ::"l"(fq));
                         }
                 }
                 if constexpr (PREF) {
@@ -392,24 +429,20 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                         }
                         const Trip got = up;
                         if constexpr (STEADY) {
-                                cells<V, K, TAIL, MODE_MID, BONUS>(J, rc, vmask, first_term, last_term, cc, cur_bon, s_tbl, sA, sGA, sGB, d, up);
+                                cells<V, K, TAIL, MODE_MID, BONUS>(J, rc, vmask, first_term, last_term, cc, cur_bon, sparse, bdir, sp_i, sp_c, sp_v, sp_wrap, s_tbl, sA, sGA, sGB, d, up);
                         } else {
                                 if (u == 0) {
-                                        cells<V, K, TAIL, MODE_FIRST, BONUS>(J, rc, vmask, first_term, last_term, cc, cur_bon, s_tbl, sA, sGA, sGB, d, up);
+                                        cells<V, K, TAIL, MODE_FIRST, BONUS>(J, rc, vmask, first_term, last_term, cc, cur_bon, sparse, bdir, sp_i, sp_c, sp_v, sp_wrap, s_tbl, sA, sGA, sGB, d, up);
                                 } else if (u < C) {
-                                        cells<V, K, TAIL, MODE_MID, BONUS>(J, rc, vmask, first_term, last_term, cc, cur_bon, s_tbl, sA, sGA, sGB, d, up);
+                                        cells<V, K, TAIL, MODE_MID, BONUS>(J, rc, vmask, first_term, last_term, cc, cur_bon, sparse, bdir, sp_i, sp_c, sp_v, sp_wrap, s_tbl, sA, sGA, sGB, d, up);
                                 } else {
-                                        cells<V, K, TAIL, MODE_LAST, BONUS>(J, rc, vmask, first_term, last_term, cc, cur_bon, s_tbl, sA, sGA, sGB, d, up);
+                                        cells<V, K, TAIL, MODE_LAST, BONUS>(J, rc, vmask, first_term, last_term, cc, cur_bon, sparse, bdir, sp_i, sp_c, sp_v, sp_wrap, s_tbl, sA, sGA, sGB, d, up);
                                 }
                         }
                         d = got;
                         bot = up;
                 }
                 cur_cres = ncres;
-                if constexpr (BONUS) {
-#pragma unroll
-                        for (int k = 0; k < K; k++) cur_bon[k] = nbon[k];
-                }
                 if constexpr (NA > 0 && PREF) {
                         curA = nxtA;
                         curB = nxtB;
@@ -459,7 +492,7 @@ __device__ void sweep_unit(const KbJob& J, const KbBox& bx, const int bwd, const
         } else {
                 in.a = bx.f0a; in.ga = bx.f0ga; in.gb = bx.f0gb;
         }
-        const int rps = rows_per_strip(J.kind, J.nalpha, thin);
+        const int rps = rows_per_strip(J.kind, J.nalpha, thin, BONUS);
         const int nstr = (R + rps - 1) / rps > 0 ? (R + rps - 1) / rps : 1;
         const int row0 = strip * rps;
         const unsigned* prev = (strip > 0) ? (prog_self - 1) : nullptr;
@@ -471,7 +504,7 @@ __device__ void sweep_unit(const KbJob& J, const KbBox& bx, const int bwd, const
                 if (rem >= 64) sweep_strip<V, 2, false, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane);
                 else if (rem > 32) sweep_strip<V, 2, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane);
                 else sweep_strip<V, 1, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane);
-        } else if constexpr (V == V_SS) {
+        } else if constexpr (V == V_SS && !BONUS) {
                 if (rem >= 256) sweep_strip<V, 8, false, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane);
                 else if (rem > 128) sweep_strip<V, 8, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane);
                 else if (rem > 32) sweep_strip<V, 4, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane);
@@ -483,6 +516,10 @@ __device__ void sweep_unit(const KbJob& J, const KbBox& bx, const int bwd, const
         }
 }
 
+// BONUS is a kernel-level template parameter: a batch either carries consistency bonuses for all
+// of its jobs (tree levels in default mode) or for none (anchor batch, --fast), and the two
+// families get independent register allocation / code size.
+template <bool BONUS>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
 kb_sweep_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes,
                 const KbUnit* __restrict__ units, const unsigned* __restrict__ nunits_p,
@@ -509,20 +546,15 @@ kb_sweep_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes,
                 const KbBox bx = boxes[un.item >> 1];
                 const int bwd = un.item & 1;
                 const KbJob J = jobs[bx.job];
-                const bool bonus = (J.bonus != nullptr);
                 unsigned* ps = prog + unit;
                 if (J.kind == KB200_KIND_SS) {
-                        if (bonus) sweep_unit<V_SS, true>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane);
-                        else sweep_unit<V_SS, false>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane);
+                        sweep_unit<V_SS, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane);
                 } else if (J.kind == KB200_KIND_SP) {
-                        if (bonus) sweep_unit<V_SP, true>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane);
-                        else sweep_unit<V_SP, false>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane);
+                        sweep_unit<V_SP, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane);
                 } else if (J.nalpha <= 5) {
-                        if (bonus) sweep_unit<V_PP5, true>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane);
-                        else sweep_unit<V_PP5, false>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane);
+                        sweep_unit<V_PP5, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane);
                 } else {
-                        if (bonus) sweep_unit<V_PP23, true>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane);
-                        else sweep_unit<V_PP23, false>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane);
+                        sweep_unit<V_PP23, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane);
                 }
         }
 }
@@ -530,7 +562,7 @@ kb_sweep_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes,
 // ---------------------------------------------------------------------------------------------
 // plan: cut every (box, direction) into strips, reserve a contiguous, ordered unit range
 __global__ void kb_plan_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes, const int nboxes,
-                               const int thin, KbUnit* __restrict__ units, unsigned* __restrict__ prog,
+                               const int thin, const int batch_bonus, KbUnit* __restrict__ units, unsigned* __restrict__ prog,
                                unsigned* __restrict__ nunits)
 {
         const int lane = threadIdx.x & 31;
@@ -541,7 +573,7 @@ __global__ void kb_plan_kernel(const KbJob* __restrict__ jobs, const KbBox* __re
                 const int bwd = (int)(item & 1);
                 const int mid = (bx.ea - bx.sa) / 2 + bx.sa;
                 const int R = bwd ? (bx.ea - mid) : (mid - bx.sa);
-                const int rps = rows_per_strip(jobs[bx.job].kind, jobs[bx.job].nalpha, thin);
+                const int rps = rows_per_strip(jobs[bx.job].kind, jobs[bx.job].nalpha, thin, batch_bonus != 0);
                 nstr = (R + rps - 1) / rps;
                 if (nstr < 1) nstr = 1;
         }
@@ -699,7 +731,7 @@ kb_meetup_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes
                 if (lane == 0) {
                         const unsigned long long nc = (unsigned long long)(ea - sa) * (unsigned long long)(eb - sb);
                         atomicAdd(cells + J.kind, nc);
-                        if (J.bonus) {
+                        if (J.bonus || J.bkey) {
                                 atomicAdd(cells + 3, nc);
                         }
                         if (bx.depth == 0 && J.score) {
@@ -875,6 +907,18 @@ __device__ void small_sweep(const KbJob& J, const int bwd, const int r0, const i
                         }
                         if (J.bonus) {
                                 a = a + __ldg(J.bonus + (size_t)i * (size_t)J.len_b + (size_t)j);
+                        } else if (J.bkey) {
+                                // flat index i*len_b + j of the reference: j == len_b is (i+1, 0)
+                                const int bi = (j == J.len_b) ? (i + 1) : i;
+                                const int bj = (j == J.len_b) ? 0 : j;
+                                float v = 0.0f;
+                                const int* __restrict__ bc = J.bkey + (size_t)bi * (size_t)J.nb;
+                                for (int e = 0; e < J.nb; e++) {
+                                        const int cc2 = __ldg(bc + e);
+                                        if (cc2 == bj) { v = __ldg(J.bval + (size_t)bi * (size_t)J.nb + e); break; }
+                                        if (cc2 > bj) break;
+                                }
+                                a = a + v;
                         }
                         S[u].a = a;
                         pga = S[u].ga;
@@ -1021,7 +1065,7 @@ kb_small_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes,
                 else if (J.nalpha <= 5) small_box_run<V_PP5>(J, bx, s_tbl, tstride, nc);
                 else small_box_run<V_PP23>(J, bx, s_tbl, tstride, nc);
                 atomicAdd(cells + 4 + J.kind, nc);
-                if (J.bonus) {
+                if (J.bonus || J.bkey) {
                         atomicAdd(cells + 3, nc);
                 }
         }
@@ -1150,6 +1194,11 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
         float sweep_ms = 0.0f;
         const bool trace = getenv("KB200_TRACE") != nullptr;
         int round = 0;
+        // all-or-nothing: a job without bonus in a bonus batch simply has an empty list / null dense
+        bool batch_bonus = false;
+        for (int i = 0; i < n; i++) {
+                if (jobs[i].bonus || jobs[i].bkey) batch_bonus = true;
+        }
         // resident warps of the persistent sweep grid
         const int sweep_ctas = ctx->sm_count * 4;
         const size_t resident_warps = (size_t)sweep_ctas * WARPS_PER_CTA;
@@ -1161,12 +1210,18 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
                 const size_t thick_units = rows_total / 128 + 2 * (size_t)count;
                 const int thin = (thick_units < 2 * resident_warps) ? 1 : 0;
                 const unsigned items = 2u * count;
-                kb_plan_kernel<<<(items + 127) / 128, 128, 0, st>>>(ctx->d_jobs.as<KbJob>(), cur, (int)count, thin,
+                kb_plan_kernel<<<(items + 127) / 128, 128, 0, st>>>(ctx->d_jobs.as<KbJob>(), cur, (int)count, thin, batch_bonus ? 1 : 0,
                                                                      ctx->d_units.as<KbUnit>(), ctx->d_prog.as<unsigned>(), d_nunits);
                 KB_CUDA(cudaEventRecord(ctx->ev2, st));
-                kb_sweep_kernel<<<sweep_ctas, WARPS_PER_CTA * 32, 0, st>>>(ctx->d_jobs.as<KbJob>(), cur, ctx->d_units.as<KbUnit>(),
-                                                                            d_nunits, d_cursor, ctx->d_prog.as<unsigned>(),
-                                                                            ctx->d_tbl.as<float>(), thin, tstride);
+                if (batch_bonus) {
+                        kb_sweep_kernel<true><<<sweep_ctas, WARPS_PER_CTA * 32, 0, st>>>(ctx->d_jobs.as<KbJob>(), cur, ctx->d_units.as<KbUnit>(),
+                                                                                          d_nunits, d_cursor, ctx->d_prog.as<unsigned>(),
+                                                                                          ctx->d_tbl.as<float>(), thin, tstride);
+                } else {
+                        kb_sweep_kernel<false><<<sweep_ctas, WARPS_PER_CTA * 32, 0, st>>>(ctx->d_jobs.as<KbJob>(), cur, ctx->d_units.as<KbUnit>(),
+                                                                                           d_nunits, d_cursor, ctx->d_prog.as<unsigned>(),
+                                                                                           ctx->d_tbl.as<float>(), thin, tstride);
+                }
                 KB_CUDA(cudaEventRecord(ctx->ev3, st));
                 int mgrid = (int)std::min<unsigned>((count + 3) / 4, (unsigned)(ctx->sm_count * 16));
                 kb_meetup_kernel<<<mgrid, 128, 0, st>>>(ctx->d_jobs.as<KbJob>(), cur, (int)count, nxt, d_next,

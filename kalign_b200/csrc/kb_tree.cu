@@ -559,16 +559,17 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                         std::vector<KbBonusOperand> ops((size_t)2 * ntm);
                         std::vector<long long> op_prefix((size_t)2 * ntm), colb_prefix((size_t)ntm), row_prefix((size_t)ntm);
                         std::vector<KbBonusTask> btasks((size_t)ntm);
-                        size_t pos_items = 0, dense = 0;
+                        size_t pos_items = 0, sparse_items = 0;
                         long long op_cols = 0, colb_total = 0, row_total = 0;
                         for (int q = q0; q < q1; q++) {
                                 pos_items += (size_t)K * ((size_t)rlen[q] + (size_t)clen[q]);
-                                dense += (size_t)rlen[q] * (size_t)clen[q];
+                                sparse_items += (size_t)K * (size_t)rlen[q];
                         }
                         TR(ctx->t_bpos.ensure(sizeof(int) * (pos_items + 16)));
                         TR(ctx->t_bconf.ensure(sizeof(float) * (pos_items + 16)));
                         TR(ctx->t_binv.ensure(sizeof(int) * (inv_per_task * (size_t)ntm + 16)));
-                        TR(d_bonus.ensure(sizeof(float) * (dense + 16)));
+                        TR(d_bidx.ensure(sizeof(int) * (sparse_items + 16)));
+                        TR(d_bval.ensure(sizeof(float) * (sparse_items + 16)));
                         size_t po = 0, doff = 0;
                         for (int q = q0; q < q1; q++) {
                                 const int nodes[2] = {rown[q], coln[q]};
@@ -591,9 +592,12 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                                 B.pos_a = A.pos; B.conf_a = A.conf; B.len_a = A.len;
                                 B.pos_b = Bo.pos; B.conf_b = Bo.conf; B.len_b = Bo.len;
                                 B.inv = ctx->t_binv.as<int>() + inv_per_task * (size_t)(q - q0);
-                                B.dense = d_bonus.as<float>() + doff;
-                                jobs[(size_t)q].bonus = B.dense;
-                                doff += (size_t)rlen[q] * (size_t)clen[q];
+                                B.bcol = d_bidx.as<int>() + doff;
+                                B.bval = d_bval.as<float>() + doff;
+                                jobs[(size_t)q].bkey = B.bcol;
+                                jobs[(size_t)q].bval = B.bval;
+                                jobs[(size_t)q].nb = K;
+                                doff += (size_t)K * (size_t)rlen[q];
                                 colb_prefix[(size_t)(q - q0)] = colb_total; colb_total += clen[q];
                                 row_prefix[(size_t)(q - q0)] = row_total; row_total += rlen[q];
                         }
@@ -612,7 +616,6 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                         TC(cudaMemcpyAsync(d_cbp, colb_prefix.data(), sizeof(long long) * colb_prefix.size(), cudaMemcpyHostToDevice, st));
                         TC(cudaMemcpyAsync(d_rwp, row_prefix.data(), sizeof(long long) * row_prefix.size(), cudaMemcpyHostToDevice, st));
                         TC(cudaMemcpyAsync(d_memb, memb.data(), sizeof(int) * memb.size(), cudaMemcpyHostToDevice, st));
-                        TC(cudaMemsetAsync(d_bonus.p, 0, sizeof(float) * dense, st));
                         TC(cudaMemsetAsync(ctx->t_binv.p, 0xFF, sizeof(int) * inv_per_task * (size_t)ntm, st));
                         TR(kb_bonus_level(ctx, S, K, T.weight / (float)K, d_ops, d_opp, 2 * ntm, op_cols, d_memb, d_colof, d_posmaps,
                                           d_bt, d_cbp, colb_total, d_rwp, row_total, ntm, ctx->t_aoff.as<int>()));
