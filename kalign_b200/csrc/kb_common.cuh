@@ -112,6 +112,7 @@ struct kb200_ctx {
         int rank = 0, world = 1;     // multi-GPU: one process per GPU (kb200_ctx_comm_init)
         void* comm = nullptr;        // ncclComm_t
         int device = 0;
+        unsigned tag_counter = 8192u;  // row-buffer hand-off tags (kb_dp.cu)
         int sm_count = 148;
         cudaStream_t stream = nullptr;
         cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;

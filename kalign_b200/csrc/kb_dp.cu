@@ -22,7 +22,8 @@
 // shuffle.  The row that leaves a strip (H/E/F = a/ga/gb, one float4 per column) is streamed
 // through the job's row buffer in global memory; the NEXT strip of the same sweep -- run
 // concurrently by another warp, possibly on another SM -- consumes it a few columns behind
-// (progress flags, release/acquire through __threadfence), so one big box is spread over many SMs
+// (each float4 carries a per-launch strip tag in its 4th word: data and "ready" flag travel in ONE
+// 16-byte store, no fences, no L1 invalidation), so one big box is spread over many SMs
 // (pipelined multi-CTA wavefront) while a batch of many boxes simply fills the machine with
 // independent strips.  Work units (box, direction, strip) are handed out in order by an atomic
 // cursor to a persistent grid: a strip only ever waits for a unit that was handed out earlier.
@@ -39,7 +40,6 @@ namespace {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int WARPS_PER_CTA = 4;
 constexpr int TBL_MAX = 23 * 32;     // shared table capacity (floats)
-constexpr int PUBLISH_EVERY = 16;    // columns between progress publications
 
 // kernel variants
 enum { V_SS = 0, V_SP = 1, V_PP5 = 2, V_PP23 = 3 };
@@ -173,20 +173,18 @@ __device__ __forceinline__ void cells(const KbJob& J, const RowCtx<V, K>& rc, co
         }
 }
 
-__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p)
-{
-        return *((const volatile unsigned*)p);
-}
-
 // One strip of 32*K rows starting at logical row `row0` of the sweep.
-//   prev_prog : progress flag of the strip above (nullptr for strip 0: the init row is generated)
-//   my_prog   : progress flag this strip publishes (nullptr when nobody consumes it)
+//   in_tag  : tag the row above must carry (0 for strip 0: the init row is generated)
+//   out_tag : tag this strip stamps on the row it emits
+// Hand-off protocol: the producer writes {a, ga, gb, tag} with one 16-byte store; the consumer
+// re-reads the slot (ld.volatile.v4, L2) until the tag matches.  Tags are unique per launch and
+// strip, so a slot still holding an older row (an earlier strip, an earlier round) never matches.
 template <int V, int K, bool TAIL, bool BONUS>
 __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const int eb,
                             const int r0, const int r1, const int row0,
                             const bool first_term, const bool last_term,
                             const Trip in, float4* __restrict__ rowbuf,
-                            const unsigned* __restrict__ prev_prog, unsigned* __restrict__ my_prog,
+                            const unsigned in_tag, const unsigned out_tag,
                             const float* __restrict__ s_tbl, const int tstride, const int lane)
 {
         constexpr int NA = VTraits<V>::NA;
@@ -239,29 +237,35 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
         Trip bot = {KB_NEGF, KB_NEGF, KB_NEGF};
         float genA = in.a, genGA = in.ga;   // init-row generator (strip 0, lane 0)
         float prevCO = 0.0f;                // PP: [27] of the column visited one step earlier
-        const bool gen = (prev_prog == nullptr);
-        unsigned avail = gen ? 0x7fffffffu : 0u;   // columns of the row above known to be written
+        const bool gen = (in_tag == 0u);
         // lane 0 of a consumer strip reads the row above RD columns ahead of its use (register
         // ring): the L2 latency of the hand-off is then hidden even when this is the only warp
         // the scheduler can run (one box spread thinly over the machine)
         constexpr int RD = (K == 1) ? 4 : 1;     // thick strips run with many co-resident warps
         float4 pre0 = make_float4(0.f, 0.f, 0.f, 0.f), pre1 = pre0, pre2 = pre0, pre3 = pre0;
+        // speculative read (no wait): issued RD columns ahead, validated by its tag when it is used
+        auto peek_above = [&](const int col) -> float4 {
+                float4 v;
+                const float4* p = rowbuf + col;
+                asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                             : "l"(p)
+                             : "memory");
+                return v;
+        };
         auto fetch_above = [&](const int col) -> float4 {
-                const unsigned need = (unsigned)(col + 1);          // column `col` written
-                if (avail < need) {
-                        do {
-                                avail = ld_volatile_u32(prev_prog);
-                        } while (avail < need);
-                        __threadfence();
-                }
-                return __ldcg(rowbuf + col);
+                float4 v;
+                do {
+                        v = peek_above(col);
+                } while (__float_as_uint(v.w) != in_tag);
+                return v;
         };
         if (!gen && lane == 0) {
                 pre0 = fetch_above(0);
                 if constexpr (RD == 4) {
-                        if (1 <= C) pre1 = fetch_above(1);
-                        if (2 <= C) pre2 = fetch_above(2);
-                        if (3 <= C) pre3 = fetch_above(3);
+                        if (1 <= C) pre1 = peek_above(1);
+                        if (2 <= C) pre2 = peek_above(2);
+                        if (3 <= C) pre3 = peek_above(3);
                 }
         }
         const int steps = C + 32;
@@ -318,6 +322,18 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                         curB = __ldg(rec + 1);
                 }
         }
+        // running pointers instead of per-step index arithmetic: the column visited NEXT (pu = u+1;
+        // 1-lane at t=0) and the state column of the current u
+        const int dstep = bwd ? -1 : 1;
+        int jcur = bwd ? (eb + lane) : (sb - lane);
+        const long long pr_first = bwd ? (long long)(eb - (1 - lane)) : (long long)(sb + (1 - lane)) - 1;
+        const float4* recp = nullptr;          // packed record of the next column (PP)
+        const uint8_t* seqp = nullptr;         // residue of the next column (SS, SP)
+        if constexpr (NA > 0) {
+                recp = reinterpret_cast<const float4*>(J.cpack) + (pr_first + 1) * PW4;
+        } else {
+                seqp = J.seq_c + pr_first;
+        }
         // one step of the wavefront.  STEADY (32 <= t <= C-1): every lane is on an interior column
         // (1 <= u <= C-1), so the activity test and the boundary-column dispatch disappear.
         auto step = [&](auto steady_tag, const int t) {
@@ -337,24 +353,19 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                         // thin strips: pull the far-ahead column record towards L1 (no register cost)
                         const int fu = u + 8;
                         if (fu >= 1 && fu <= C) {
-                                const int fj = bwd ? (eb - fu) : (sb + fu);
-                                const int fr = bwd ? fj : (fj - 1);
-                                const float* fq = J.cpack + (size_t)(fr + 1) * (PW4 * 4);
+                                const float4* fq = recp + 7 * dstep * PW4;
                                 asm volatile("prefetch.global.L1 [%0];" ::"l"(fq));
                         }
                 }
                 if constexpr (PREF) {
                         const int pu = u + 1;
                         if (STEADY || (pu >= 0 && pu <= C)) {
-                                const int pj = bwd ? (eb - pu) : (sb + pu);
-                                const int pr = bwd ? pj : (pj - 1);
                                 if constexpr (NA > 0) {
-                                        const float4* __restrict__ rec = reinterpret_cast<const float4*>(J.cpack) + (size_t)(pr + 1) * PW4;
-                                        nxtA = __ldg(rec);
-                                        nxtB = __ldg(rec + 1);
+                                        nxtA = __ldg(recp);
+                                        nxtB = __ldg(recp + 1);
                                 } else {
                                         if (STEADY || pu >= 1) {
-                                                ncres = (int)__ldg(J.seq_c + pr);
+                                                ncres = (int)__ldg(seqp);
                                         }
                                 }
                         }
@@ -362,13 +373,12 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                 if (act) {
                         // ---- column context (prefetched during the previous step) ----
                         ColCtx<V> cc;
-                        const int j = bwd ? (eb - u) : (sb + u);        // state column
+                        const int j = jcur;                             // state column: eb-u / sb+u
                         cc.jcol = j;
                         cc.cres = cur_cres;
                         float CT;
                         if constexpr (NA > 0 && !PREF) {
-                                const int r = bwd ? j : (j - 1);
-                                const float4* __restrict__ rec = reinterpret_cast<const float4*>(J.cpack) + (size_t)(r + 1) * PW4;
+                                const float4* __restrict__ rec = recp - dstep * PW4;   // record of the current column
                                 float buf[PW4 * 4];
 #pragma unroll
                                 for (int w = 0; w < PW4; w++) {
@@ -414,15 +424,18 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                                                 up.a = KB_NEGF; up.ga = KB_NEGF; up.gb = KB_NEGF;
                                         }
                                 } else {
+                                        if (__float_as_uint(pre0.w) != in_tag) {
+                                                pre0 = fetch_above(u);       // the early read raced the producer: wait
+                                        }
                                         up.a = pre0.x; up.ga = pre0.y; up.gb = pre0.z;
                                         if constexpr (RD == 4) {
                                                 pre0 = pre1; pre1 = pre2; pre2 = pre3;
                                                 if (u + RD <= C) {
-                                                        pre3 = fetch_above(u + RD);
+                                                        pre3 = peek_above(u + RD);
                                                 }
                                         } else {
                                                 if (u + 1 <= C) {
-                                                        pre0 = fetch_above(u + 1);
+                                                        pre0 = peek_above(u + 1);
                                                 }
                                         }
                                 }
@@ -447,14 +460,16 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                         curA = nxtA;
                         curB = nxtB;
                 }
+                jcur += dstep;
+                if constexpr (NA > 0) {
+                        recp += dstep * PW4;
+                } else {
+                        seqp += dstep;
+                }
                 if (lane == 31) {
                         const int uo = t - 31;
                         if (STEADY || (uo >= 0 && uo <= C)) {
-                                rowbuf[uo] = make_float4(bot.a, bot.ga, bot.gb, 0.0f);
-                                if (my_prog && (((uo + 1) % ((K == 1) ? (PUBLISH_EVERY / 2) : PUBLISH_EVERY)) == 0 || uo == C)) {
-                                        __threadfence();
-                                        *((volatile unsigned*)my_prog) = (unsigned)(uo + 1);
-                                }
+                                rowbuf[uo] = make_float4(bot.a, bot.ga, bot.gb, __uint_as_float(out_tag));
                         }
                 }
         };
@@ -476,7 +491,7 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
 
 template <int V, bool BONUS>
 __device__ void sweep_unit(const KbJob& J, const KbBox& bx, const int bwd, const int strip, const int thin,
-                           unsigned* __restrict__ prog_self, const float* __restrict__ s_tbl, const int tstride, const int lane)
+                           const unsigned tag_base, const float* __restrict__ s_tbl, const int tstride, const int lane)
 {
         const int mid = (bx.ea - bx.sa) / 2 + bx.sa;
         const int r0 = bwd ? mid : bx.sa;
@@ -495,8 +510,9 @@ __device__ void sweep_unit(const KbJob& J, const KbBox& bx, const int bwd, const
         const int rps = rows_per_strip(J.kind, J.nalpha, thin, BONUS);
         const int nstr = (R + rps - 1) / rps > 0 ? (R + rps - 1) / rps : 1;
         const int row0 = strip * rps;
-        const unsigned* prev = (strip > 0) ? (prog_self - 1) : nullptr;
-        unsigned* mine = (strip + 1 < nstr) ? prog_self : nullptr;
+        (void)nstr;
+        const unsigned prev = (strip > 0) ? (tag_base + (unsigned)strip) : 0u;      // tag written by strip-1
+        const unsigned mine = tag_base + (unsigned)strip + 1u;
         const int rem = R - row0;
         if (rps == 32) {
                 sweep_strip<V, 1, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane);
@@ -523,7 +539,7 @@ template <bool BONUS>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
 kb_sweep_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes,
                 const KbUnit* __restrict__ units, const unsigned* __restrict__ nunits_p,
-                unsigned int* __restrict__ cursor, unsigned* __restrict__ prog,
+                unsigned int* __restrict__ cursor, const unsigned tag_base,
                 const float* __restrict__ tbl, const int thin, const int tstride)
 {
         __shared__ float s_tbl[TBL_MAX];
@@ -546,7 +562,7 @@ kb_sweep_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes,
                 const KbBox bx = boxes[un.item >> 1];
                 const int bwd = un.item & 1;
                 const KbJob J = jobs[bx.job];
-                unsigned* ps = prog + unit;
+                const unsigned ps = tag_base;
                 if (J.kind == KB200_KIND_SS) {
                         sweep_unit<V_SS, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane);
                 } else if (J.kind == KB200_KIND_SP) {
@@ -562,7 +578,7 @@ kb_sweep_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes,
 // ---------------------------------------------------------------------------------------------
 // plan: cut every (box, direction) into strips, reserve a contiguous, ordered unit range
 __global__ void kb_plan_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes, const int nboxes,
-                               const int thin, const int batch_bonus, KbUnit* __restrict__ units, unsigned* __restrict__ prog,
+                               const int thin, const int batch_bonus, KbUnit* __restrict__ units,
                                unsigned* __restrict__ nunits)
 {
         const int lane = threadIdx.x & 31;
@@ -596,7 +612,6 @@ __global__ void kb_plan_kernel(const KbJob* __restrict__ jobs, const KbBox* __re
                 un.item = (int)item;
                 un.strip = s;
                 units[mine + s] = un;
-                prog[mine + s] = 0u;
         }
 }
 
@@ -1104,6 +1119,8 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
                 }
         }
         KB_RUN(ctx->d_rows.ensure(2 * total_cols * sizeof(float4)));
+        // stale rows (an earlier batch, an earlier context) must never carry a live hand-off tag
+        KB_CUDA(cudaMemsetAsync(ctx->d_rows.p, 0, 2 * total_cols * sizeof(float4), st));
         KB_RUN(ctx->d_pack.ensure(pack_floats * sizeof(float) + 64));
         {
                 float4* base = ctx->d_rows.as<float4>();
@@ -1127,7 +1144,6 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
         KB_RUN(ctx->d_boxB.ensure(sizeof(KbBox) * box_cap));
         KB_RUN(ctx->d_boxS.ensure(sizeof(KbBox) * box_cap));
         KB_RUN(ctx->d_units.ensure(sizeof(KbUnit) * unit_cap));
-        KB_RUN(ctx->d_prog.ensure(sizeof(unsigned) * unit_cap));
         KB_RUN(ctx->d_counters.ensure(128));
         KB_RUN(ctx->d_tbl.ensure(sizeof(float) * TBL_MAX));
         // shared-memory score table: row stride = alphabet size, so that a 5-letter table (25
@@ -1210,16 +1226,20 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
                 const size_t thick_units = rows_total / 128 + 2 * (size_t)count;
                 const int thin = (thick_units < 2 * resident_warps) ? 1 : 0;
                 const unsigned items = 2u * count;
+                // tags: unique per launch (8192 strips per sweep at most: 256k rows), never 0
+                ctx->tag_counter += 8192u;
+                if (ctx->tag_counter > 0xffff0000u) ctx->tag_counter = 8192u;
+                const unsigned tag_base = ctx->tag_counter;
                 kb_plan_kernel<<<(items + 127) / 128, 128, 0, st>>>(ctx->d_jobs.as<KbJob>(), cur, (int)count, thin, batch_bonus ? 1 : 0,
-                                                                     ctx->d_units.as<KbUnit>(), ctx->d_prog.as<unsigned>(), d_nunits);
+                                                                     ctx->d_units.as<KbUnit>(), d_nunits);
                 KB_CUDA(cudaEventRecord(ctx->ev2, st));
                 if (batch_bonus) {
                         kb_sweep_kernel<true><<<sweep_ctas, WARPS_PER_CTA * 32, 0, st>>>(ctx->d_jobs.as<KbJob>(), cur, ctx->d_units.as<KbUnit>(),
-                                                                                          d_nunits, d_cursor, ctx->d_prog.as<unsigned>(),
+                                                                                          d_nunits, d_cursor, tag_base,
                                                                                           ctx->d_tbl.as<float>(), thin, tstride);
                 } else {
                         kb_sweep_kernel<false><<<sweep_ctas, WARPS_PER_CTA * 32, 0, st>>>(ctx->d_jobs.as<KbJob>(), cur, ctx->d_units.as<KbUnit>(),
-                                                                                           d_nunits, d_cursor, ctx->d_prog.as<unsigned>(),
+                                                                                           d_nunits, d_cursor, tag_base,
                                                                                            ctx->d_tbl.as<float>(), thin, tstride);
                 }
                 KB_CUDA(cudaEventRecord(ctx->ev3, st));
