@@ -173,29 +173,18 @@ __device__ __forceinline__ void cells(const KbJob& J, const RowCtx<V, K>& rc, co
         }
 }
 
-// One strip of 32*K rows starting at logical row `row0` of the sweep.
-//   in_tag  : tag the row above must carry (0 for strip 0: the init row is generated)
-//   out_tag : tag this strip stamps on the row it emits
-// Hand-off protocol: the producer writes {a, ga, gb, tag} with one 16-byte store; the consumer
-// re-reads the slot (ld.volatile.v4, L2) until the tag matches.  Tags are unique per launch and
-// strip, so a slot still holding an older row (an earlier strip, an earlier round) never matches.
-template <int V, int K, bool TAIL, bool BONUS>
-__device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const int eb,
-                            const int r0, const int r1, const int row0,
-                            const bool first_term, const bool last_term,
-                            const Trip in, float4* __restrict__ rowbuf,
-                            const unsigned in_tag, const unsigned out_tag,
-                            const float* __restrict__ s_tbl, const int tstride, const int lane)
+// rows first .. first+K-1 of a sweep (logical numbering: 0 is the row next to the init row); rows
+// past the end repeat the last one and are masked out (pass-through) by the returned bit mask
+template <int V, int K>
+__device__ __forceinline__ unsigned load_rows(const KbJob& J, const int bwd, const int r0, const int r1, const int first,
+                                               const int tstride, RowCtx<V, K>& rc)
 {
         constexpr int NA = VTraits<V>::NA;
-        constexpr int PW4 = (V == V_PP5) ? (PACK5 / 4) : (PACK23 / 4);
-        const int C = eb - sb;
         const int R = r1 - r0;
-        RowCtx<V, K> rc;
         unsigned vmask = 0;
 #pragma unroll
         for (int k = 0; k < K; k++) {
-                int g = row0 + lane * K + k;
+                int g = first + k;
                 const bool valid = g < R;
                 if (valid) {
                         vmask |= (1u << k);
@@ -228,6 +217,60 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                         }
                 }
         }
+        return vmask;
+}
+
+// sparse consistency bonus: per row the index / column / value of the next entry in sweep
+// direction, and the value the forward sweep picks up at j == len_b (flat index (i+1, 0))
+template <int V, int K>
+__device__ __forceinline__ void sparse_init(const KbJob& J, const int bwd, const int sb, const int eb, const RowCtx<V, K>& rc,
+                                            int (&sp_i)[K], int (&sp_c)[K], float (&sp_v)[K], float (&sp_wrap)[K])
+{
+        const int KS = J.nb;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+                const int* __restrict__ bc = J.bkey + (size_t)rc.irow[k] * (size_t)KS;
+                const float* __restrict__ bv = J.bval + (size_t)rc.irow[k] * (size_t)KS;
+                int e;
+                if (!bwd) {
+                        // cells visit j = sb+1 .. eb ascending
+                        e = 0;
+                        while (e < KS && __ldg(bc + e) < sb + 1) e++;
+                        if (e < KS) { sp_c[k] = __ldg(bc + e); sp_v[k] = __ldg(bv + e); }
+                        if (eb == J.len_b && rc.irow[k] + 1 < J.len_a) {
+                                const int* __restrict__ nc = bc + KS;
+                                if (__ldg(nc) == 0) sp_wrap[k] = __ldg(bv + KS);
+                        }
+                } else {
+                        // cells visit j = eb-1 .. sb descending
+                        e = KS - 1;
+                        while (e >= 0 && __ldg(bc + e) > eb - 1) e--;
+                        if (e >= 0) { sp_c[k] = __ldg(bc + e); sp_v[k] = __ldg(bv + e); }
+                }
+                sp_i[k] = e;
+        }
+}
+
+// One strip of 32*K rows starting at logical row `row0` of the sweep.
+//   in_tag  : tag the row above must carry (0 for strip 0: the init row is generated)
+//   out_tag : tag this strip stamps on the row it emits
+// Hand-off protocol: the producer writes {a, ga, gb, tag} with one 16-byte store; the consumer
+// re-reads the slot (ld.volatile.v4, L2) until the tag matches.  Tags are unique per launch and
+// strip, so a slot still holding an older row (an earlier strip, an earlier round) never matches.
+template <int V, int K, bool TAIL, bool BONUS>
+__device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const int eb,
+                            const int r0, const int r1, const int row0,
+                            const bool first_term, const bool last_term,
+                            const Trip in, float4* __restrict__ rowbuf,
+                            const unsigned in_tag, const unsigned out_tag,
+                            const float* __restrict__ s_tbl, const int tstride, const int lane)
+{
+        constexpr int NA = VTraits<V>::NA;
+        constexpr int PW4 = (V == V_PP5) ? (PACK5 / 4) : (PACK23 / 4);
+        const int C = eb - sb;
+        const int R = r1 - r0;
+        RowCtx<V, K> rc;
+        const unsigned vmask = load_rows<V, K>(J, bwd, r0, r1, row0 + lane * K, tstride, rc);
         float sA[K], sGA[K], sGB[K];
 #pragma unroll
         for (int k = 0; k < K; k++) {
@@ -287,29 +330,7 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
         }
         if constexpr (BONUS) {
                 if (sparse) {
-                        const int KS = J.nb;
-#pragma unroll
-                        for (int k = 0; k < K; k++) {
-                                const int* __restrict__ bc = J.bkey + (size_t)rc.irow[k] * (size_t)KS;
-                                const float* __restrict__ bv = J.bval + (size_t)rc.irow[k] * (size_t)KS;
-                                int e;
-                                if (!bwd) {
-                                        // cells visit j = sb+1 .. eb ascending
-                                        e = 0;
-                                        while (e < KS && __ldg(bc + e) < sb + 1) e++;
-                                        if (e < KS) { sp_c[k] = __ldg(bc + e); sp_v[k] = __ldg(bv + e); }
-                                        if (eb == J.len_b && rc.irow[k] + 1 < J.len_a) {
-                                                const int* __restrict__ nc = bc + KS;
-                                                if (__ldg(nc) == 0) sp_wrap[k] = __ldg(bv + KS);
-                                        }
-                                } else {
-                                        // cells visit j = eb-1 .. sb descending
-                                        e = KS - 1;
-                                        while (e >= 0 && __ldg(bc + e) > eb - 1) e--;
-                                        if (e >= 0) { sp_c[k] = __ldg(bc + e); sp_v[k] = __ldg(bv + e); }
-                                }
-                                sp_i[k] = e;
-                        }
+                        sparse_init<V, K>(J, bwd, sb, eb, rc, sp_i, sp_c, sp_v, sp_wrap);
                 }
         }
         if constexpr (NA > 0 && NA <= 5) {
@@ -678,7 +699,7 @@ __device__ __forceinline__ void put_child(KbBox* __restrict__ next, int slot, in
 __global__ void __launch_bounds__(128)
 kb_meetup_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes, const int nboxes,
                  KbBox* __restrict__ next, unsigned int* __restrict__ next_count,
-                 KbBox* __restrict__ small, unsigned int* __restrict__ small_count,
+                 KbBox* __restrict__ small, unsigned int* __restrict__ small_count, const int small_rows, const int small_cols,
                  unsigned long long* __restrict__ cells)
 {
         const int lane = threadIdx.x & 31;
@@ -797,8 +818,8 @@ kb_meetup_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes
                                 }
                                 const bool hasL = (lsa < lea) && (lsb < leb);
                                 const bool hasR = (rsa < rea) && (rsb < reb);
-                                const bool smL = hasL && small && ((lea - lsa) <= 16) && ((leb - lsb) <= 48);
-                                const bool smR = hasR && small && ((rea - rsa) <= 16) && ((reb - rsb) <= 48);
+                                const bool smL = hasL && small && ((lea - lsa) <= small_rows) && ((leb - lsb) <= small_cols);
+                                const bool smR = hasR && small && ((rea - rsa) <= small_rows) && ((reb - rsb) <= small_cols);
                                 const int nbig = ((hasL && !smL) ? 1 : 0) + ((hasR && !smR) ? 1 : 0);
                                 const int nsml = (smL ? 1 : 0) + (smR ? 1 : 0);
                                 if (nbig) {
@@ -832,23 +853,23 @@ kb_meetup_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes
 // and columns (serial sweeps exactly as the reference runs them, explicit DFS stack), so the deep
 // recursion levels -- millions of boxes of a handful of cells -- cost one launch instead of one
 // round each.  Arithmetic is the same cell recurrence in the same order.
-constexpr int SMALL_ROWS = 16;
+constexpr int SMALL_ROWS = 16;        // default thresholds (few jobs: deeper sweeps stay parallel)
 constexpr int SMALL_COLS = 48;
+constexpr int SMALL_ROWS_MAX = 128;   // many jobs: the machine is full anyway, skip the lane-starved rounds
+constexpr int SMALL_COLS_MAX = 256;
 constexpr int SMALL_STACK = 12;
-
-__device__ __forceinline__ bool is_small(int sa, int ea, int sb, int eb)
-{
-        return (ea - sa) <= SMALL_ROWS && (eb - sb) <= SMALL_COLS;
-}
 
 struct SBox {
         int sa, ea, sb, eb;
         Trip f0, b0;
 };
 
-template <int V>
+// One sweep of a small box by ONE thread: the rows are taken K at a time through the shared cell
+// routine (cells<>, the same code the warp strips run: K cells of a column chained in registers),
+// so the row array S -- thread-local memory -- is read and written once per K rows.
+template <int V, int K, bool BONUS>
 __device__ void small_sweep(const KbJob& J, const int bwd, const int r0, const int r1, const int sb, const int eb,
-                            const Trip in, Trip* __restrict__ S, const float* __restrict__ s_tbl, const int tstride)
+                            const Trip in, float4* __restrict__ S, const float* __restrict__ s_tbl, const int tstride)
 {
         constexpr int NA = VTraits<V>::NA;
         constexpr int PW = (V == V_PP5) ? PACK5 : PACK23;
@@ -856,107 +877,109 @@ __device__ void small_sweep(const KbJob& J, const int bwd, const int r0, const i
         const int R = r1 - r0;
         const bool first_term = bwd ? (eb == J.len_b) : (sb == 0);
         const bool last_term = bwd ? (sb == 0) : (eb == J.len_b);
-        S[0] = in;
-        for (int u = 1; u < C; u++) {
-                float CO, CE, CT;
-                if constexpr (NA > 0) {
-                        const int j = bwd ? (eb - u) : (sb + u);
-                        const int r = bwd ? j : (j - 1);
-                        const float* rec = J.cpack + (size_t)(r + 1) * PW;
-                        CO = __ldg(rec + NA); CE = __ldg(rec + NA + 1); CT = __ldg(rec + NA + 2);
-                } else {
-                        CO = J.o; CE = J.e; CT = J.t;
+        const int dstep = bwd ? -1 : 1;
+        // record / residue of state column u: r = bwd ? eb-u : sb+u-1
+        const long long rfirst = bwd ? (long long)eb : (long long)sb - 1;
+        {
+                // init row
+                float pa = in.a, pga = in.ga;
+                S[0] = make_float4(in.a, in.ga, in.gb, 0.0f);
+                for (int u = 1; u < C; u++) {
+                        float CO, CE, CT;
+                        if constexpr (NA > 0) {
+                                const float* rec = J.cpack + (size_t)(rfirst + (long long)dstep * u + 1) * PW;
+                                CO = __ldg(rec + NA); CE = __ldg(rec + NA + 1); CT = __ldg(rec + NA + 2);
+                        } else {
+                                CO = J.o; CE = J.e; CT = J.t;
+                        }
+                        const float ga = first_term ? (kmax(pga, pa) + CT) : kmax(pga + CE, pa + CO);
+                        S[u] = make_float4(KB_NEGF, ga, KB_NEGF, 0.0f);
+                        pa = KB_NEGF;
+                        pga = ga;
                 }
-                Trip t;
-                t.a = KB_NEGF;
-                t.gb = KB_NEGF;
-                t.ga = first_term ? (kmax(S[u - 1].ga, S[u - 1].a) + CT) : kmax(S[u - 1].ga + CE, S[u - 1].a + CO);
-                S[u] = t;
+                S[C] = make_float4(KB_NEGF, KB_NEGF, KB_NEGF, 0.0f);
         }
-        S[C].a = KB_NEGF; S[C].ga = KB_NEGF; S[C].gb = KB_NEGF;
-        for (int v = 0; v < R; v++) {
-                const int i = bwd ? (r1 - 1 - v) : (r0 + v);
-                float RO, RE, RT, ROp;
-                int rbase = 0;
-                const float* prow = nullptr;
-                if constexpr (V == V_SS) {
-                        RO = J.o; RE = J.e; RT = J.t; ROp = J.o;
-                        rbase = (int)J.seq_r[i] * tstride;
-                } else {
-                        prow = J.prof_r + ((size_t)(i + 1) << 6);
-                        const float* pp = bwd ? (prow + 64) : (prow - 64);
-                        RO = __ldg(prow + 27); RE = __ldg(prow + 28); RT = __ldg(prow + 29); ROp = __ldg(pp + 27);
-                }
-                float pa = S[0].a, pga = S[0].ga, pgb = S[0].gb;
-                float xa = KB_NEGF, xga = KB_NEGF;
-                S[0].a = KB_NEGF;
-                S[0].ga = KB_NEGF;
-                S[0].gb = first_term ? (kmax(pgb, pa) + RT) : kmax(pgb + RE, pa + RO);
-                float COp;
-                if constexpr (NA > 0) {
-                        const int r = bwd ? eb : (sb - 1);
-                        COp = __ldg(J.cpack + (size_t)(r + 1) * PW + NA);
-                } else {
-                        COp = J.o;
-                }
-                for (int u = 1; u <= C; u++) {
-                        const int j = bwd ? (eb - u) : (sb + u);
-                        const int r = bwd ? j : (j - 1);
-                        float CO, CE;
-                        const float ca = S[u].a;
-                        float a = kmax(kmax(pa, pga + COp), pgb + ROp);
-                        if constexpr (V == V_SS) {
-                                CO = J.o; CE = J.e;
-                                const float x = s_tbl[rbase + (int)__ldg(J.seq_c + r)] + J.nsoff;
-                                a = a + x;
-                        } else if constexpr (V == V_SP) {
-                                CO = J.o; CE = J.e;
-                                a = a + __ldg(prow + 32 + (int)__ldg(J.seq_c + r));
-                        } else {
-                                const float* rec = J.cpack + (size_t)(r + 1) * PW;
-                                CO = __ldg(rec + NA); CE = __ldg(rec + NA + 1);
+        const bool sparse = BONUS && (J.bkey != nullptr);
+        for (int v0 = 0; v0 < R; v0 += K) {
+                RowCtx<V, K> rc;
+                const unsigned vmask = load_rows<V, K>(J, bwd, r0, r1, v0, tstride, rc);
+                float sA[K], sGA[K], sGB[K], bon[K];
+                int sp_i[K], sp_c[K];
+                float sp_v[K], sp_wrap[K];
 #pragma unroll
-                                for (int c = NA - 1; c >= 0; c--) {
-                                        a = __fadd_rn(a, __fmul_rn(__ldg(prow + c), __ldg(rec + c)));
-                                }
+                for (int k = 0; k < K; k++) {
+                        sA[k] = KB_NEGF; sGA[k] = KB_NEGF; sGB[k] = KB_NEGF; bon[k] = 0.0f;
+                        sp_i[k] = 0; sp_c[k] = bwd ? -1 : 0x7fffffff; sp_v[k] = 0.0f; sp_wrap[k] = 0.0f;
+                }
+                if constexpr (BONUS) {
+                        if (sparse) {
+                                sparse_init<V, K>(J, bwd, sb, eb, rc, sp_i, sp_c, sp_v, sp_wrap);
                         }
-                        if (J.bonus) {
-                                a = a + __ldg(J.bonus + (size_t)i * (size_t)J.len_b + (size_t)j);
-                        } else if (J.bkey) {
-                                // flat index i*len_b + j of the reference: j == len_b is (i+1, 0)
-                                const int bi = (j == J.len_b) ? (i + 1) : i;
-                                const int bj = (j == J.len_b) ? 0 : j;
-                                float v = 0.0f;
-                                const int* __restrict__ bc = J.bkey + (size_t)bi * (size_t)J.nb;
-                                for (int e = 0; e < J.nb; e++) {
-                                        const int cc2 = __ldg(bc + e);
-                                        if (cc2 == bj) { v = __ldg(J.bval + (size_t)bi * (size_t)J.nb + e); break; }
-                                        if (cc2 > bj) break;
+                }
+                Trip d = {KB_NEGF, KB_NEGF, KB_NEGF};
+                ColCtx<V> cc;
+                cc.cres = 0;
+                cc.CO = J.o; cc.CE = J.e; cc.COp = J.o;
+                float prevCO = 0.0f;
+                auto column = [&](const int u) {
+                        cc.jcol = bwd ? (eb - u) : (sb + u);
+                        const long long r = rfirst + (long long)dstep * u;
+                        if constexpr (NA > 0) {
+                                const float* __restrict__ rec = J.cpack + (size_t)(r + 1) * PW;
+                                if constexpr (PW % 4 == 0) {
+                                        float buf[PW];
+#pragma unroll
+                                        for (int w = 0; w < PW / 4; w++) {
+                                                const float4 q = __ldg(reinterpret_cast<const float4*>(rec) + w);
+                                                buf[4 * w] = q.x; buf[4 * w + 1] = q.y; buf[4 * w + 2] = q.z; buf[4 * w + 3] = q.w;
+                                        }
+#pragma unroll
+                                        for (int c = 0; c < NA; c++) cc.qs[c] = buf[c];
+                                        cc.CO = buf[NA]; cc.CE = buf[NA + 1];
                                 }
-                                a = a + v;
-                        }
-                        S[u].a = a;
-                        pga = S[u].ga;
-                        S[u].ga = (u < C) ? kmax(xga + CE, xa + CO) : KB_NEGF;
-                        pgb = S[u].gb;
-                        if (u == C && last_term) {
-                                S[u].gb = kmax(pgb, ca) + RT;
+                                cc.COp = prevCO;
+                                prevCO = cc.CO;
                         } else {
-                                S[u].gb = kmax(pgb + RE, ca + RO);
+                                if (u >= 1) {
+                                        cc.cres = (int)__ldg(J.seq_c + r);
+                                }
                         }
-                        pa = ca;
-                        xa = a;
-                        xga = S[u].ga;
-                        COp = CO;
+                };
+                // column 0
+                {
+                        column(0);
+                        const float4 q = S[0];
+                        Trip up = {q.x, q.y, q.z};
+                        const Trip got = up;
+                        cells<V, K, true, MODE_FIRST, BONUS>(J, rc, vmask, first_term, last_term, cc, bon, sparse, dstep, sp_i, sp_c, sp_v, sp_wrap, s_tbl, sA, sGA, sGB, d, up);
+                        d = got;
+                        S[0] = make_float4(up.a, up.ga, up.gb, 0.0f);
+                }
+                for (int u = 1; u < C; u++) {
+                        column(u);
+                        const float4 q = S[u];
+                        Trip up = {q.x, q.y, q.z};
+                        const Trip got = up;
+                        cells<V, K, true, MODE_MID, BONUS>(J, rc, vmask, first_term, last_term, cc, bon, sparse, dstep, sp_i, sp_c, sp_v, sp_wrap, s_tbl, sA, sGA, sGB, d, up);
+                        d = got;
+                        S[u] = make_float4(up.a, up.ga, up.gb, 0.0f);
+                }
+                {
+                        column(C);
+                        const float4 q = S[C];
+                        Trip up = {q.x, q.y, q.z};
+                        cells<V, K, true, MODE_LAST, BONUS>(J, rc, vmask, first_term, last_term, cc, bon, sparse, dstep, sp_i, sp_c, sp_v, sp_wrap, s_tbl, sA, sGA, sGB, d, up);
+                        S[C] = make_float4(up.a, up.ga, up.gb, 0.0f);
                 }
         }
 }
 
-template <int V>
+template <int V, int MAXC, bool BONUS>
 __device__ void small_box_run(const KbJob& J, const KbBox& root, const float* __restrict__ s_tbl, const int tstride,
                               unsigned long long& ncells)
 {
-        Trip F[SMALL_COLS + 1], B[SMALL_COLS + 1];
+        constexpr int KR = (V == V_PP23) ? 2 : 4;     // rows per pass (register budget as in the strips)
+        float4 F[MAXC + 1], B[MAXC + 1];
         SBox stack[SMALL_STACK];
         int sp = 0;
         {
@@ -974,8 +997,8 @@ __device__ void small_box_run(const KbJob& J, const KbBox& root, const float* __
                 const SBox bx = stack[--sp];
                 const int sa = bx.sa, ea = bx.ea, sb = bx.sb, eb = bx.eb;
                 const int mid = (ea - sa) / 2 + sa;
-                small_sweep<V>(J, 0, sa, mid, sb, eb, bx.f0, F, s_tbl, tstride);
-                small_sweep<V>(J, 1, mid, ea, sb, eb, bx.b0, B, s_tbl, tstride);
+                small_sweep<V, KR, BONUS>(J, 0, sa, mid, sb, eb, bx.f0, F, s_tbl, tstride);
+                small_sweep<V, KR, BONUS>(J, 1, mid, ea, sb, eb, bx.b0, B, s_tbl, tstride);
                 ncells += (unsigned long long)(ea - sa) * (unsigned long long)(eb - sb);
                 // meet-up
                 const float middle = (float)(eb - sb) / 2.0F + (float)sb;
@@ -995,8 +1018,10 @@ __device__ void small_box_run(const KbJob& J, const KbBox& root, const float* __
                 Best m;
                 m.max = KB_NEGF; m.max2 = KB_NEGF; m.key = 0x7fffffff;
                 for (int i = sb; i <= eb; i++) {
-                        const Trip f = F[i - sb];
-                        const Trip b = B[eb - i];
+                        const float4 fq = F[i - sb];
+                        const float4 bq = B[eb - i];
+                        const Trip f = {fq.x, fq.y, fq.z};
+                        const Trip b = {bq.x, bq.y, bq.z};
                         float sub = fabsf(middle - (float)i);
                         sub = __fdiv_rn(sub, 1000.0F);
                         const int kb = (i - sb) * 8;
@@ -1060,7 +1085,8 @@ __device__ void small_box_run(const KbJob& J, const KbBox& root, const float* __
         }
 }
 
-__global__ void __launch_bounds__(128)
+template <int MAXC, bool BONUS>
+__global__ void __launch_bounds__(128, 4)
 kb_small_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes, const unsigned* __restrict__ nsmall_p,
                 unsigned long long* __restrict__ cells, const float* __restrict__ tbl, const int tstride)
 {
@@ -1075,10 +1101,10 @@ kb_small_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes,
                 const KbBox bx = boxes[b];
                 const KbJob J = jobs[bx.job];
                 unsigned long long nc = 0;
-                if (J.kind == KB200_KIND_SS) small_box_run<V_SS>(J, bx, s_tbl, tstride, nc);
-                else if (J.kind == KB200_KIND_SP) small_box_run<V_SP>(J, bx, s_tbl, tstride, nc);
-                else if (J.nalpha <= 5) small_box_run<V_PP5>(J, bx, s_tbl, tstride, nc);
-                else small_box_run<V_PP23>(J, bx, s_tbl, tstride, nc);
+                if (J.kind == KB200_KIND_SS) small_box_run<V_SS, MAXC, BONUS>(J, bx, s_tbl, tstride, nc);
+                else if (J.kind == KB200_KIND_SP) small_box_run<V_SP, MAXC, BONUS>(J, bx, s_tbl, tstride, nc);
+                else if (J.nalpha <= 5) small_box_run<V_PP5, MAXC, BONUS>(J, bx, s_tbl, tstride, nc);
+                else small_box_run<V_PP23, MAXC, BONUS>(J, bx, s_tbl, tstride, nc);
                 atomicAdd(cells + 4 + J.kind, nc);
                 if (J.bonus || J.bkey) {
                         atomicAdd(cells + 3, nc);
@@ -1207,6 +1233,20 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
         unsigned int* d_nsmall = d_cursor + 3;
         KbBox* d_small = ctx->d_boxS.as<KbBox>();
         const bool use_small = getenv("KB200_NO_SMALL") == nullptr;
+        // thread-per-box threshold: with enough jobs to fill the machine the deep rounds (boxes of a
+        // few dozen rows: 1-2 live lanes per warp in a sweep) are cheaper as serial per-thread work
+        int small_rows = SMALL_ROWS, small_cols = SMALL_COLS;
+        {
+                // largest power of two T such that the boxes of T rows (about rows_total / T of them)
+                // still give every resident thread of half the machine a box of its own
+                const size_t want = (size_t)ctx->sm_count * 256;
+                while (small_rows * 2 <= SMALL_ROWS_MAX && rows_total / (size_t)(small_rows * 2) >= want) {
+                        small_rows *= 2;
+                }
+                if (small_rows > SMALL_ROWS) small_cols = std::min(2 * small_rows + small_rows / 2, SMALL_COLS_MAX);
+        }
+        if (const char* e = getenv("KB200_SMALL_ROWS")) small_rows = std::min(std::max(atoi(e), 1), SMALL_ROWS_MAX);
+        if (const char* e = getenv("KB200_SMALL_COLS")) small_cols = std::min(std::max(atoi(e), 4), SMALL_COLS_MAX);
         float sweep_ms = 0.0f;
         const bool trace = getenv("KB200_TRACE") != nullptr;
         int round = 0;
@@ -1227,8 +1267,8 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
                 const int thin = (thick_units < 2 * resident_warps) ? 1 : 0;
                 const unsigned items = 2u * count;
                 // tags: unique per launch (8192 strips per sweep at most: 256k rows), never 0
-                ctx->tag_counter += 8192u;
-                if (ctx->tag_counter > 0xffff0000u) ctx->tag_counter = 8192u;
+                ctx->tag_counter += 65536u;
+                if (ctx->tag_counter > 0xfff00000u) ctx->tag_counter = 65536u;
                 const unsigned tag_base = ctx->tag_counter;
                 kb_plan_kernel<<<(items + 127) / 128, 128, 0, st>>>(ctx->d_jobs.as<KbJob>(), cur, (int)count, thin, batch_bonus ? 1 : 0,
                                                                      ctx->d_units.as<KbUnit>(), d_nunits);
@@ -1245,7 +1285,7 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
                 KB_CUDA(cudaEventRecord(ctx->ev3, st));
                 int mgrid = (int)std::min<unsigned>((count + 3) / 4, (unsigned)(ctx->sm_count * 16));
                 kb_meetup_kernel<<<mgrid, 128, 0, st>>>(ctx->d_jobs.as<KbJob>(), cur, (int)count, nxt, d_next,
-                                                        use_small ? d_small : nullptr, d_nsmall, d_cells);
+                                                        use_small ? d_small : nullptr, d_nsmall, small_rows, small_cols, d_cells);
                 KB_CUDA(cudaGetLastError());
                 unsigned host_counts[4] = {0, 0, 0, 0};
                 KB_CUDA(cudaMemcpyAsync(host_counts, d_cursor, sizeof(host_counts), cudaMemcpyDeviceToHost, st));
@@ -1272,7 +1312,16 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
         {
                 // every box that became small during the rounds: finish its recursion in one launch
                 KB_CUDA(cudaEventRecord(ctx->ev2, st));
-                kb_small_kernel<<<ctx->sm_count * 8, 128, 0, st>>>(ctx->d_jobs.as<KbJob>(), d_small, d_nsmall, d_cells, ctx->d_tbl.as<float>(), tstride);
+                const int sgrid = ctx->sm_count * 4;
+                const KbJob* dj = ctx->d_jobs.as<KbJob>();
+                const float* dt = ctx->d_tbl.as<float>();
+                if (small_cols <= SMALL_COLS) {
+                        if (batch_bonus) kb_small_kernel<SMALL_COLS, true><<<sgrid, 128, 0, st>>>(dj, d_small, d_nsmall, d_cells, dt, tstride);
+                        else kb_small_kernel<SMALL_COLS, false><<<sgrid, 128, 0, st>>>(dj, d_small, d_nsmall, d_cells, dt, tstride);
+                } else {
+                        if (batch_bonus) kb_small_kernel<SMALL_COLS_MAX, true><<<sgrid, 128, 0, st>>>(dj, d_small, d_nsmall, d_cells, dt, tstride);
+                        else kb_small_kernel<SMALL_COLS_MAX, false><<<sgrid, 128, 0, st>>>(dj, d_small, d_nsmall, d_cells, dt, tstride);
+                }
                 KB_CUDA(cudaGetLastError());
                 KB_CUDA(cudaEventRecord(ctx->ev3, st));
                 KB_CUDA(cudaEventSynchronize(ctx->ev3));
@@ -1283,7 +1332,7 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
                 if (trace) {
                         unsigned ns = 0;
                         cudaMemcpy(&ns, d_nsmall, sizeof(unsigned), cudaMemcpyDeviceToHost);
-                        fprintf(stderr, "[kb200 trace] jobs=%d small boxes=%u small_ms=%.3f\n", n, ns, sms);
+                        fprintf(stderr, "[kb200 trace] jobs=%d small(<=%dx%d) boxes=%u small_ms=%.3f\n", n, small_rows, small_cols, ns, sms);
                 }
         }
         KB_CUDA(cudaEventRecord(ctx->ev1, st));
