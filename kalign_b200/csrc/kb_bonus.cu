@@ -68,6 +68,7 @@ __global__ void kb_weave_prefix_kernel(const KbWeaveTask* __restrict__ tasks, co
                 gb += __shfl_sync(0xffffffffu, jb, 31);
         }
         if (lane == 0) {
+                if (T.out_len) *T.out_len = alnlen;
                 Pa[0] = 0; Pb[0] = 0;
                 Pa[ka + 1] = ga;
                 Pb[kb + 1] = gb;
@@ -127,24 +128,124 @@ __global__ void kb_init_colof_kernel(const int64_t* __restrict__ offs, const int
 }
 
 // ---- votes -----------------------------------------------------------------------------------
-// One WARP per profile column: lanes stride over the members.  "First seen position wins"
-// (anchor_consistency.c:440-445) = the position voted by the valid member with the smallest index
-// in sip[] order; pass 1 finds it with a warp min-reduction, pass 2 counts total / agreeing votes.
-__global__ void kb_bonus_positions_kernel(const KbBonusOperand* __restrict__ ops, const long long* __restrict__ col_prefix,
-                                          const int nops, const long long total_cols, const int K,
-                                          const int* __restrict__ memb, const int64_t* __restrict__ offs,
-                                          const int* __restrict__ lens, const int* __restrict__ colof,
-                                          const int* __restrict__ posmaps)
+// Operands with many members: one WARP per chunk of 32 profile columns walks ALL members in
+// sip[] order (so "first seen position wins", total and agreeing votes come out of one pass,
+// exactly the reference's loop, anchor_consistency.c:405-446).  Members are taken 32 at a time:
+// first every lane finds, for its own member, the first residue at or after the chunk's first
+// column (binary search in colof); then the 32 members are visited in order, lane j reading the
+// member's residue a_lo+j -- the residues that fall into the chunk are consecutive -- and its K
+// anchor positions (coalesced); the owner lane of a column picks them up by shuffle: residue
+// columns are strictly increasing, so the j-th residue in the chunk is the j-th set bit of the
+// chunk's occupancy mask.
+__global__ void __launch_bounds__(128)
+kb_bonus_positions_kernel(const KbBonusOperand* __restrict__ ops, const int* __restrict__ op_list,
+                          const long long* __restrict__ chunk_prefix,
+                          const int nops, const long long total_chunks, const int K,
+                          const int* __restrict__ memb, const int64_t* __restrict__ offs,
+                          const int* __restrict__ lens, const int* __restrict__ colof,
+                          const int* __restrict__ posmaps)
 {
         const int lane = threadIdx.x & 31;
         const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        if (gid >= total_chunks) return;
+        int lo = 0, hi = nops - 1;
+        while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (chunk_prefix[mid] <= gid) lo = mid; else hi = mid - 1;
+        }
+        const KbBonusOperand O = ops[op_list[lo]];
+        const int c0 = (int)(gid - chunk_prefix[lo]) * 32;
+        const int c = c0 + lane;                 // the column this lane owns
+        const int nmem = O.m1 - O.m0;
+        int best[KMAX], total[KMAX], agree[KMAX];
+#pragma unroll
+        for (int k = 0; k < KMAX; k++) {
+                best[k] = -1; total[k] = 0; agree[k] = 0;
+        }
+        const unsigned lt_mask = (1u << lane) - 1u;
+        for (int mb = 0; mb < nmem; mb += 32) {
+                // ---- lane = member: locate the chunk in the member's residues ----
+                int my_len = 0, my_alo = 0;
+                long long my_off = 0;
+                if (mb + lane < nmem) {
+                        const int si = memb[O.m0 + mb + lane];
+                        my_len = lens[si];
+                        my_off = (long long)offs[si];
+                        const int* __restrict__ co = colof + my_off;
+                        int a = 0, b = my_len;
+                        while (a < b) {
+                                const int mid = (a + b) >> 1;
+                                if (co[mid] < c0) a = mid + 1; else b = mid;
+                        }
+                        my_alo = a;
+                }
+                const int cnt = min(32, nmem - mb);
+                // ---- members in sip order; lane = residue a_lo + lane, then lane = column ----
+#pragma unroll 4
+                for (int i = 0; i < cnt; i++) {
+                        const int len = __shfl_sync(0xffffffffu, my_len, i);
+                        const int alo = __shfl_sync(0xffffffffu, my_alo, i);
+                        const long long off = __shfl_sync(0xffffffffu, my_off, i);
+                        const int idx = alo + lane;
+                        int rel = 32;
+                        if (idx < len) {
+                                rel = colof[off + idx] - c0;
+                        }
+                        const bool in = rel < 32;
+                        const unsigned occ = __reduce_or_sync(0xffffffffu, in ? (1u << rel) : 0u);
+                        if (occ == 0u) continue;
+                        const int src = __popc(occ & lt_mask);
+                        const bool has = (occ >> lane) & 1u;
+                        const int* __restrict__ map0 = posmaps + (size_t)K * (size_t)off + idx;
+#pragma unroll
+                        for (int k = 0; k < KMAX; k++) {
+                                if (k < K) {
+                                        const int mine = in ? map0[(size_t)k * len] : -1;
+                                        const int apos = __shfl_sync(0xffffffffu, mine, src);
+                                        if (has && apos >= 0) {
+                                                if (total[k] == 0) best[k] = apos;
+                                                total[k]++;
+                                                if (apos == best[k]) agree[k]++;
+                                        }
+                                }
+                        }
+                }
+        }
+        if (c < O.len) {
+                int* __restrict__ pos = O.pos;        // [K][len]
+                float* __restrict__ conf = O.conf;
+#pragma unroll
+                for (int k = 0; k < KMAX; k++) {
+                        if (k < K) {
+                                const bool ok = total[k] > 0 && agree[k] > 0;
+                                pos[(size_t)k * O.len + c] = ok ? best[k] : -1;
+                                conf[(size_t)k * O.len + c] = ok ? ((float)agree[k] / (float)total[k]) : 0.0f;
+                        }
+                }
+        }
+}
+
+// Operands with few members (the bulk of the low tree levels: leaves and profiles of a handful of
+// sequences): one THREAD per profile column walks the members serially in sip[] order -- first seen
+// position, total and agreeing votes in ONE pass, exactly the reference's loop order -- finding the
+// member's residue in its column by binary search in colof.  Adjacent threads are adjacent columns
+// of one operand.
+
+__global__ void kb_bonus_positions_small_kernel(const KbBonusOperand* __restrict__ ops, const int* __restrict__ op_list,
+                                                const long long* __restrict__ col_prefix,
+                                                const int nops, const long long total_cols, const int K,
+                                                const int* __restrict__ memb, const int64_t* __restrict__ offs,
+                                                const int* __restrict__ lens, const int* __restrict__ colof,
+                                                const int* __restrict__ posmaps)
+{
+        const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
         if (gid >= total_cols) return;
         int lo = 0, hi = nops - 1;
         while (lo < hi) {
                 const int mid = (lo + hi + 1) >> 1;
                 if (col_prefix[mid] <= gid) lo = mid; else hi = mid - 1;
         }
-        const KbBonusOperand O = ops[lo];
+        const KbBonusOperand O = ops[op_list[lo]];
         const int c = (int)(gid - col_prefix[lo]);
         int* __restrict__ pos = O.pos;        // [K][len]
         float* __restrict__ conf = O.conf;
@@ -153,7 +254,7 @@ __global__ void kb_bonus_positions_kernel(const KbBonusOperand* __restrict__ ops
                 // leaf: direct lookup (anchor_consistency.c:360-378)
                 const int si = memb[O.m0];
                 const int seq_len = lens[si];
-                for (int k = lane; k < K; k += 32) {
+                for (int k = 0; k < K; k++) {
                         int v = -1;
                         if (c < seq_len) {
                                 v = posmaps[(size_t)K * (size_t)offs[si] + (size_t)k * (size_t)seq_len + c];
@@ -163,13 +264,13 @@ __global__ void kb_bonus_positions_kernel(const KbBonusOperand* __restrict__ ops
                 }
                 return;
         }
-        // pass 1: per lane, first member (smallest index) with a valid position, per anchor
-        int first_m[KMAX], first_pos[KMAX], total[KMAX];
+        int best[KMAX], total[KMAX], agree[KMAX];
 #pragma unroll
         for (int k = 0; k < KMAX; k++) {
-                first_m[k] = 0x7fffffff; first_pos[k] = -1; total[k] = 0;
+                best[k] = -1; total[k] = 0; agree[k] = 0;
         }
-        for (int m = lane; m < nmem; m += 32) {
+#pragma unroll 1
+        for (int m = 0; m < nmem; m++) {
                 const int si = memb[O.m0 + m];
                 const int seq_len = lens[si];
                 const int* __restrict__ co = colof + offs[si];
@@ -178,70 +279,27 @@ __global__ void kb_bonus_positions_kernel(const KbBonusOperand* __restrict__ ops
                         const int mid = (a + b) >> 1;
                         if (co[mid] < c) a = mid + 1; else b = mid;
                 }
-                if (a >= seq_len || co[a] != c) continue;
+                const bool hit = (a < seq_len) && (co[a] == c);
+                if (!hit) continue;
                 const int* __restrict__ map0 = posmaps + (size_t)K * (size_t)offs[si] + a;
 #pragma unroll
                 for (int k = 0; k < KMAX; k++) {
                         if (k < K) {
                                 const int apos = map0[(size_t)k * seq_len];
                                 if (apos >= 0) {
+                                        if (total[k] == 0) best[k] = apos;       // first seen position wins
                                         total[k]++;
-                                        if (m < first_m[k]) {
-                                                first_m[k] = m;
-                                                first_pos[k] = apos;
-                                        }
+                                        if (apos == best[k]) agree[k]++;          // best is final once set
                                 }
                         }
                 }
         }
-        int best[KMAX];
 #pragma unroll
         for (int k = 0; k < KMAX; k++) {
-                int fm = first_m[k], fp = first_pos[k], tt = total[k];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                        const int om = __shfl_xor_sync(0xffffffffu, fm, o);
-                        const int op = __shfl_xor_sync(0xffffffffu, fp, o);
-                        tt += __shfl_xor_sync(0xffffffffu, tt, o);
-                        if (om < fm) { fm = om; fp = op; }
-                }
-                best[k] = fp;
-                total[k] = tt;
-        }
-        // pass 2: members agreeing with the first-seen position
-        int agree[KMAX];
-#pragma unroll
-        for (int k = 0; k < KMAX; k++) agree[k] = 0;
-        for (int m = lane; m < nmem; m += 32) {
-                const int si = memb[O.m0 + m];
-                const int seq_len = lens[si];
-                const int* __restrict__ co = colof + offs[si];
-                int a = 0, b = seq_len;
-                while (a < b) {
-                        const int mid = (a + b) >> 1;
-                        if (co[mid] < c) a = mid + 1; else b = mid;
-                }
-                if (a >= seq_len || co[a] != c) continue;
-                const int* __restrict__ map0 = posmaps + (size_t)K * (size_t)offs[si] + a;
-#pragma unroll
-                for (int k = 0; k < KMAX; k++) {
-                        if (k < K) {
-                                const int apos = map0[(size_t)k * seq_len];
-                                if (apos >= 0 && apos == best[k]) agree[k]++;
-                        }
-                }
-        }
-#pragma unroll
-        for (int k = 0; k < KMAX; k++) {
-                int ag = agree[k];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                        ag += __shfl_xor_sync(0xffffffffu, ag, o);
-                }
-                if (lane == 0 && k < K) {
-                        const bool ok = total[k] > 0 && ag > 0;
+                if (k < K) {
+                        const bool ok = total[k] > 0 && agree[k] > 0;
                         pos[(size_t)k * O.len + c] = ok ? best[k] : -1;
-                        conf[(size_t)k * O.len + c] = ok ? ((float)ag / (float)total[k]) : 0.0f;
+                        conf[(size_t)k * O.len + c] = ok ? ((float)agree[k] / (float)total[k]) : 0.0f;
                 }
         }
 }
@@ -356,20 +414,33 @@ int kb_weave_level(kb200_ctx* ctx, KbSeqs& S, const KbWeaveTask* d_tasks, int nt
 }
 
 int kb_bonus_level(kb200_ctx* ctx, KbSeqs& S, int K, float paw,
-                   const KbBonusOperand* d_ops, const long long* d_op_prefix, int nops, long long op_cols,
+                   const KbBonusOperand* d_ops,
+                   const int* d_small_list, const long long* d_small_prefix, int n_small, long long small_cols,
+                   const int* d_large_list, const long long* d_large_prefix, int n_large, long long large_cols,
                    const int* d_memb, const int* d_colof, const int* d_posmaps,
                    const KbBonusTask* d_tasks, const long long* d_colb_prefix, long long colb_total,
                    const long long* d_row_prefix, long long row_total, int ntasks, const int* d_aoff)
 {
         if (ntasks <= 0) return KB200_OK;
-        kb_bonus_positions_kernel<<<(unsigned)((op_cols * 32 + 127) / 128), 128, 0, ctx->stream>>>(d_ops, d_op_prefix, nops, op_cols, K, d_memb,
-                                                                                               S.d_offs.as<int64_t>(), S.d_lens.as<int>(),
-                                                                                               d_colof, d_posmaps);
-        KB_CUDA(cudaGetLastError());
+        if (n_small > 0) {
+                kb_bonus_positions_small_kernel<<<(unsigned)((small_cols + 127) / 128), 128, 0, ctx->stream>>>(
+                        d_ops, d_small_list, d_small_prefix, n_small, small_cols, K, d_memb, S.d_offs.as<int64_t>(), S.d_lens.as<int>(),
+                        d_colof, d_posmaps);
+                KB_CUDA(cudaGetLastError());
+                ctx->stats.n_launches++;
+        }
+        if (n_large > 0) {
+                // large_cols counts 32-column chunks here (one warp each)
+                kb_bonus_positions_kernel<<<(unsigned)((large_cols * 32 + 127) / 128), 128, 0, ctx->stream>>>(
+                        d_ops, d_large_list, d_large_prefix, n_large, large_cols, K, d_memb, S.d_offs.as<int64_t>(), S.d_lens.as<int>(),
+                        d_colof, d_posmaps);
+                KB_CUDA(cudaGetLastError());
+                ctx->stats.n_launches++;
+        }
         kb_bonus_inverse_kernel<<<(unsigned)((colb_total + 127) / 128), 128, 0, ctx->stream>>>(d_tasks, d_colb_prefix, ntasks, colb_total, K, d_aoff);
         KB_CUDA(cudaGetLastError());
         kb_bonus_scatter_kernel<<<(unsigned)((row_total + 127) / 128), 128, 0, ctx->stream>>>(d_tasks, d_row_prefix, ntasks, row_total, K, d_aoff, paw);
         KB_CUDA(cudaGetLastError());
-        ctx->stats.n_launches += 3;
+        ctx->stats.n_launches += 2;
         return KB200_OK;
 }

@@ -2,13 +2,13 @@
 #pragma once
 #include "kb_host.cuh"
 
-#define KB_BONUS_KMAX 8
 
 struct KbWeaveTask {
         const int* path;     // coded path (device)
         int* Pa;             // la+lb+3 ints of scratch
         int* Pb;
         int alnlen;          // unused by the kernel when < 0: read from path[0]
+        int* out_len;        // optional: receives the alignment length (the only thing the host needs of the path)
 };
 
 struct KbWeaveMember {
@@ -34,8 +34,13 @@ struct KbBonusTask {
 int kb_bonus_init_state(kb200_ctx* ctx, KbSeqs& S, int* d_gaps, int* d_colof);
 int kb_weave_level(kb200_ctx* ctx, KbSeqs& S, const KbWeaveTask* d_tasks, int ntasks,
                    const KbWeaveMember* d_members, int nmembers, int* d_gaps, int* d_colof);
+// operands with at most KB_BONUS_SMALL_NMEM members go to the thread-per-column kernel (small list),
+// the others to the warp-per-column kernel (large list); prefixes are per list
+#define KB_BONUS_SMALL_NMEM 16
 int kb_bonus_level(kb200_ctx* ctx, KbSeqs& S, int K, float paw,
-                   const KbBonusOperand* d_ops, const long long* d_op_prefix, int nops, long long op_cols,
+                   const KbBonusOperand* d_ops,
+                   const int* d_small_list, const long long* d_small_prefix, int n_small, long long small_cols,
+                   const int* d_large_list, const long long* d_large_prefix, int n_large, long long large_cols,
                    const int* d_memb, const int* d_colof, const int* d_posmaps,
                    const KbBonusTask* d_tasks, const long long* d_colb_prefix, long long colb_total,
                    const long long* d_row_prefix, long long row_total, int ntasks, const int* d_aoff);

@@ -64,6 +64,8 @@ struct KbUnit {
 __device__ __forceinline__ float kmax(float a, float b) { return fmaxf(a, b); }
 
 enum { MODE_FIRST = 0, MODE_MID = 1, MODE_LAST = 2 };
+// consistency bonus of a batch: none / sparse per-row lists (tree levels) / caller-supplied dense matrix
+enum { BONUS_NONE = 0, BONUS_SPARSE = 1, BONUS_DENSE = 2 };
 
 // rows per strip of a job in a round: "wide" rounds (few big boxes) use thin strips so that one
 // box spreads over many warps; otherwise thick strips amortise the per-step overhead.
@@ -97,16 +99,39 @@ template <int V> struct ColCtx {
         int jcol;
 };
 
-template <int V, int K, bool TAIL, int MODE, bool BONUS>
+// Sparse consistency bonus of a row: <= nb (column, value) entries sorted by column.  The warp
+// strips stage the lists of their rows in shared memory (lane-private slots, [entry][row][lane]:
+// conflict-free), so that stepping to the next entry after a hit is an LDS instead of a dependent
+// L2 access that would stall the whole warp; the thread-per-box kernel reads them from global.
+constexpr int BON_SLOTS = KB_BONUS_KMAX;
+constexpr int BON_KMAX_ROWS = 4;      // rows per lane of the widest strip that carries a bonus
+
+template <int K, bool BSM>
+__device__ __forceinline__ void bonus_entry(const KbJob& J, const int2* __restrict__ s_bon, const int irow, const int k, const int e,
+                                            int& c, float& v)
+{
+        if constexpr (BSM) {
+                const int2 q = s_bon[(e * K + k) * 32];
+                c = q.x;
+                v = __int_as_float(q.y);
+        } else {
+                const size_t o = (size_t)irow * (size_t)J.nb + (size_t)e;
+                c = __ldg(J.bkey + o);
+                v = __ldg(J.bval + o);
+        }
+}
+
+template <int V, int K, bool TAIL, int MODE, int BONUS, bool BSM = false>
 __device__ __forceinline__ void cells(const KbJob& J, const RowCtx<V, K>& rc, const unsigned vmask,
                                       const bool first_term, const bool last_term,
                                       const ColCtx<V>& cc, const float (&bon)[K],
                                       const bool sparse, const int bdir, int (&sp_i)[K], int (&sp_c)[K], float (&sp_v)[K],
-                                      const float (&sp_wrap)[K],
+                                      const float (&sp_wrap)[K], const int2* __restrict__ s_bon,
                                       const float* __restrict__ s_tbl,
                                       float (&sA)[K], float (&sGA)[K], float (&sGB)[K],
                                       Trip d, Trip& u /* in: up at column u; out: bottom row */)
 {
+        unsigned hits = 0;
 #pragma unroll
         for (int k = 0; k < K; k++) {
                 const float oA = sA[k], oGA = sGA[k], oGB = sGB[k];
@@ -134,22 +159,19 @@ __device__ __forceinline__ void cells(const KbJob& J, const RowCtx<V, K>& rc, co
                                         a = __fadd_rn(a, __fmul_rn(rc.cnt[k][c], cc.qs[c]));
                                 }
                         }
-                        if constexpr (BONUS) {
-                                if (sparse) {
-                                        // sorted per-row list walked in sweep direction: at most K hits per row
-                                        if (cc.jcol == sp_c[k]) {
-                                                a = a + sp_v[k];
-                                                sp_i[k] += bdir;
-                                                const int e = sp_i[k];
-                                                const bool ok = (e >= 0) && (e < J.nb);
-                                                const size_t o = (size_t)rc.irow[k] * (size_t)J.nb + (size_t)(ok ? e : 0);
-                                                sp_c[k] = ok ? __ldg(J.bkey + o) : ((bdir > 0) ? 0x7fffffff : -1);
-                                                sp_v[k] = ok ? __ldg(J.bval + o) : 0.0f;
-                                        }
-                                        if constexpr (MODE == MODE_LAST) {
-                                                a = a + sp_wrap[k];   // forward sweep, j == len_b: flat index wraps to (i+1, 0)
-                                        }
-                                } else if (J.bonus) {
+                        if constexpr (BONUS == BONUS_SPARSE) {
+                                // sorted per-row list walked in sweep direction: at most nb hits per row.
+                                // The reference adds its dense matrix entry to EVERY cell
+                                // (aln_seqseq.c:83-85): + 0.0f where the list has no entry.  A job
+                                // without a list keeps the never-matching sentinel in sp_c.
+                                const bool hit = (cc.jcol == sp_c[k]);
+                                a = a + (hit ? sp_v[k] : 0.0f);
+                                hits |= hit ? (1u << k) : 0u;
+                                if constexpr (MODE == MODE_LAST) {
+                                        a = a + sp_wrap[k];   // forward sweep, j == len_b: flat index wraps to (i+1, 0)
+                                }
+                        } else if constexpr (BONUS == BONUS_DENSE) {
+                                if (J.bonus) {
                                         // dense matrix supplied by the caller (kb200_pair_align_batch)
                                         a = a + __ldg(J.bonus + (size_t)rc.irow[k] * (size_t)J.len_b + (size_t)cc.jcol);
                                 }
@@ -170,6 +192,24 @@ __device__ __forceinline__ void cells(const KbJob& J, const RowCtx<V, K>& rc, co
                 sA[k] = a; sGA[k] = ga; sGB[k] = gb;
                 d.a = oA; d.ga = oGA; d.gb = oGB;
                 u.a = a; u.ga = ga; u.gb = gb;
+        }
+        if constexpr (BONUS == BONUS_SPARSE && MODE != MODE_FIRST) {
+                // step the lists that were hit to their next entry: ONE divergent region per step
+                if (hits) {
+#pragma unroll
+                        for (int k = 0; k < K; k++) {
+                                if ((hits >> k) & 1u) {
+                                        sp_i[k] += bdir;
+                                        const int e = sp_i[k];
+                                        const bool ok = (e >= 0) && (e < J.nb);
+                                        int nc;
+                                        float nv;
+                                        bonus_entry<K, BSM>(J, s_bon, rc.irow[k], k, ok ? e : 0, nc, nv);
+                                        sp_c[k] = ok ? nc : ((bdir > 0) ? 0x7fffffff : -1);
+                                        sp_v[k] = ok ? nv : 0.0f;
+                                }
+                        }
+                }
         }
 }
 
@@ -222,30 +262,52 @@ __device__ __forceinline__ unsigned load_rows(const KbJob& J, const int bwd, con
 
 // sparse consistency bonus: per row the index / column / value of the next entry in sweep
 // direction, and the value the forward sweep picks up at j == len_b (flat index (i+1, 0))
-template <int V, int K>
+template <int V, int K, bool BSM>
 __device__ __forceinline__ void sparse_init(const KbJob& J, const int bwd, const int sb, const int eb, const RowCtx<V, K>& rc,
+                                            int2* __restrict__ s_bon,
                                             int (&sp_i)[K], int (&sp_c)[K], float (&sp_v)[K], float (&sp_wrap)[K])
 {
         const int KS = J.nb;
+        if constexpr (BSM) {
+                // stage the lists of this lane's rows (lane-private slots; s_bon is already offset by the lane)
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                        const int* __restrict__ bc = J.bkey + (size_t)rc.irow[k] * (size_t)KS;
+                        const float* __restrict__ bv = J.bval + (size_t)rc.irow[k] * (size_t)KS;
+                        for (int e = 0; e < KS; e++) {
+                                s_bon[(e * K + k) * 32] = make_int2(__ldg(bc + e), __float_as_int(__ldg(bv + e)));
+                        }
+                }
+                __syncwarp();
+        }
 #pragma unroll
         for (int k = 0; k < K; k++) {
-                const int* __restrict__ bc = J.bkey + (size_t)rc.irow[k] * (size_t)KS;
-                const float* __restrict__ bv = J.bval + (size_t)rc.irow[k] * (size_t)KS;
                 int e;
+                int c = 0;
+                float v = 0.0f;
                 if (!bwd) {
                         // cells visit j = sb+1 .. eb ascending
                         e = 0;
-                        while (e < KS && __ldg(bc + e) < sb + 1) e++;
-                        if (e < KS) { sp_c[k] = __ldg(bc + e); sp_v[k] = __ldg(bv + e); }
+                        while (e < KS) {
+                                bonus_entry<K, BSM>(J, s_bon, rc.irow[k], k, e, c, v);
+                                if (c >= sb + 1) break;
+                                e++;
+                        }
+                        if (e < KS) { sp_c[k] = c; sp_v[k] = v; }
                         if (eb == J.len_b && rc.irow[k] + 1 < J.len_a) {
-                                const int* __restrict__ nc = bc + KS;
-                                if (__ldg(nc) == 0) sp_wrap[k] = __ldg(bv + KS);
+                                // flat index (i, len_b) of the reference's dense matrix is (i+1, 0)
+                                const size_t o = (size_t)(rc.irow[k] + 1) * (size_t)KS;
+                                if (__ldg(J.bkey + o) == 0) sp_wrap[k] = __ldg(J.bval + o);
                         }
                 } else {
                         // cells visit j = eb-1 .. sb descending
                         e = KS - 1;
-                        while (e >= 0 && __ldg(bc + e) > eb - 1) e--;
-                        if (e >= 0) { sp_c[k] = __ldg(bc + e); sp_v[k] = __ldg(bv + e); }
+                        while (e >= 0) {
+                                bonus_entry<K, BSM>(J, s_bon, rc.irow[k], k, e, c, v);
+                                if (c <= eb - 1) break;
+                                e--;
+                        }
+                        if (e >= 0) { sp_c[k] = c; sp_v[k] = v; }
                 }
                 sp_i[k] = e;
         }
@@ -257,14 +319,15 @@ __device__ __forceinline__ void sparse_init(const KbJob& J, const int bwd, const
 // Hand-off protocol: the producer writes {a, ga, gb, tag} with one 16-byte store; the consumer
 // re-reads the slot (ld.volatile.v4, L2) until the tag matches.  Tags are unique per launch and
 // strip, so a slot still holding an older row (an earlier strip, an earlier round) never matches.
-template <int V, int K, bool TAIL, bool BONUS>
+template <int V, int K, bool TAIL, int BONUS>
 __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const int eb,
                             const int r0, const int r1, const int row0,
                             const bool first_term, const bool last_term,
                             const Trip in, float4* __restrict__ rowbuf,
                             const unsigned in_tag, const unsigned out_tag,
-                            const float* __restrict__ s_tbl, const int tstride, const int lane)
+                            const float* __restrict__ s_tbl, const int tstride, const int lane, float4* s_ring, int2* s_bon)
 {
+        static_assert(BONUS != BONUS_SPARSE || K <= BON_KMAX_ROWS, "bonus staging area is sized for K <= 4");
         constexpr int NA = VTraits<V>::NA;
         constexpr int PW4 = (V == V_PP5) ? (PACK5 / 4) : (PACK23 / 4);
         const int C = eb - sb;
@@ -281,12 +344,19 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
         float genA = in.a, genGA = in.ga;   // init-row generator (strip 0, lane 0)
         float prevCO = 0.0f;                // PP: [27] of the column visited one step earlier
         const bool gen = (in_tag == 0u);
-        // lane 0 of a consumer strip reads the row above RD columns ahead of its use (register
-        // ring): the L2 latency of the hand-off is then hidden even when this is the only warp
-        // the scheduler can run (one box spread thinly over the machine)
-        constexpr int RD = (K == 1) ? 4 : 1;     // thick strips run with many co-resident warps
-        float4 pre0 = make_float4(0.f, 0.f, 0.f, 0.f), pre1 = pre0, pre2 = pre0, pre3 = pre0;
-        // speculative read (no wait): issued RD columns ahead, validated by its tag when it is used
+        // Hand-off read side.  Thick strips (K > 1) run with many co-resident warps: lane 0 reads the
+        // row above one column ahead (ld.volatile into a register, validated by its tag when used).
+        // Thin strips (K == 1) are run by a LONE warp per scheduler (one big box spread over the
+        // machine), so the L2 latency of the hand-off must be hidden inside the warp: lane 0 streams
+        // the row above through a shared-memory ring with cp.async (global -> shared, no register
+        // is tied to the in-flight load, so nothing stalls on it), RLEAD columns ahead of its use;
+        // the entry is moved ring -> register one step before it is consumed.  An entry that was
+        // copied before the producer wrote it fails its tag check and is re-read by polling.
+        constexpr bool RING = (K == 1);
+        constexpr int RDEPTH = 16;               // ring slots (power of two, > RLEAD)
+        constexpr int RLEAD = 8;                 // columns of read-ahead
+        float4 pre0 = make_float4(0.f, 0.f, 0.f, 0.f);
+        // speculative read (no wait), validated by its tag when it is used
         auto peek_above = [&](const int col) -> float4 {
                 float4 v;
                 const float4* p = rowbuf + col;
@@ -303,12 +373,35 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                 } while (__float_as_uint(v.w) != in_tag);
                 return v;
         };
+        const unsigned ring_base = RING ? (unsigned)__cvta_generic_to_shared(s_ring) : 0u;
+        auto ring_issue = [&](const int col) {
+                // one commit group per column, empty past the end of the row
+                if (col <= C) {
+                        const unsigned dst = ring_base + (unsigned)((col & (RDEPTH - 1)) * 16);
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(rowbuf + col) : "memory");
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        auto ring_take = [&](const int col) -> float4 {
+                // the group of column `col` is the RLEAD-th youngest: all but RLEAD-1 groups complete
+                float4 v;
+                asm volatile("cp.async.wait_group %0;" ::"n"(RLEAD - 1) : "memory");
+                const unsigned src = ring_base + (unsigned)((col & (RDEPTH - 1)) * 16);
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                             : "r"(src)
+                             : "memory");
+                return v;
+        };
         if (!gen && lane == 0) {
-                pre0 = fetch_above(0);
-                if constexpr (RD == 4) {
-                        if (1 <= C) pre1 = peek_above(1);
-                        if (2 <= C) pre2 = peek_above(2);
-                        if (3 <= C) pre3 = peek_above(3);
+                if constexpr (RING) {
+#pragma unroll
+                        for (int c = 0; c < RLEAD; c++) {
+                                ring_issue(c);
+                        }
+                        pre0 = ring_take(0);
+                } else {
+                        pre0 = fetch_above(0);
                 }
         }
         const int steps = C + 32;
@@ -320,7 +413,8 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
         for (int k = 0; k < K; k++) cur_bon[k] = 0.0f;
         // sparse consistency bonus: per row the index / column / value of the next entry in sweep
         // direction, and the value the forward sweep picks up at j == len_b (flat index (i+1, 0))
-        const bool sparse = BONUS && (J.bkey != nullptr);
+        const bool sparse = (BONUS == BONUS_SPARSE) && (J.bkey != nullptr);
+        int2* const my_bon = s_bon + lane;       // lane-private slots [entry][row k][lane]
         const int bdir = bwd ? -1 : 1;
         int sp_i[K], sp_c[K];
         float sp_v[K], sp_wrap[K];
@@ -330,7 +424,7 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
         }
         if constexpr (BONUS) {
                 if (sparse) {
-                        sparse_init<V, K>(J, bwd, sb, eb, rc, sp_i, sp_c, sp_v, sp_wrap);
+                        sparse_init<V, K, true>(J, bwd, sb, eb, rc, my_bon, sp_i, sp_c, sp_v, sp_wrap);
                 }
         }
         if constexpr (NA > 0 && NA <= 5) {
@@ -449,11 +543,9 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                                                 pre0 = fetch_above(u);       // the early read raced the producer: wait
                                         }
                                         up.a = pre0.x; up.ga = pre0.y; up.gb = pre0.z;
-                                        if constexpr (RD == 4) {
-                                                pre0 = pre1; pre1 = pre2; pre2 = pre3;
-                                                if (u + RD <= C) {
-                                                        pre3 = peek_above(u + RD);
-                                                }
+                                        if constexpr (RING) {
+                                                ring_issue(u + RLEAD);
+                                                pre0 = ring_take(u + 1);     // consumed by the next step
                                         } else {
                                                 if (u + 1 <= C) {
                                                         pre0 = peek_above(u + 1);
@@ -463,14 +555,14 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                         }
                         const Trip got = up;
                         if constexpr (STEADY) {
-                                cells<V, K, TAIL, MODE_MID, BONUS>(J, rc, vmask, first_term, last_term, cc, cur_bon, sparse, bdir, sp_i, sp_c, sp_v, sp_wrap, s_tbl, sA, sGA, sGB, d, up);
+                                cells<V, K, TAIL, MODE_MID, BONUS, true>(J, rc, vmask, first_term, last_term, cc, cur_bon, sparse, bdir, sp_i, sp_c, sp_v, sp_wrap, my_bon, s_tbl, sA, sGA, sGB, d, up);
                         } else {
                                 if (u == 0) {
-                                        cells<V, K, TAIL, MODE_FIRST, BONUS>(J, rc, vmask, first_term, last_term, cc, cur_bon, sparse, bdir, sp_i, sp_c, sp_v, sp_wrap, s_tbl, sA, sGA, sGB, d, up);
+                                        cells<V, K, TAIL, MODE_FIRST, BONUS, true>(J, rc, vmask, first_term, last_term, cc, cur_bon, sparse, bdir, sp_i, sp_c, sp_v, sp_wrap, my_bon, s_tbl, sA, sGA, sGB, d, up);
                                 } else if (u < C) {
-                                        cells<V, K, TAIL, MODE_MID, BONUS>(J, rc, vmask, first_term, last_term, cc, cur_bon, sparse, bdir, sp_i, sp_c, sp_v, sp_wrap, s_tbl, sA, sGA, sGB, d, up);
+                                        cells<V, K, TAIL, MODE_MID, BONUS, true>(J, rc, vmask, first_term, last_term, cc, cur_bon, sparse, bdir, sp_i, sp_c, sp_v, sp_wrap, my_bon, s_tbl, sA, sGA, sGB, d, up);
                                 } else {
-                                        cells<V, K, TAIL, MODE_LAST, BONUS>(J, rc, vmask, first_term, last_term, cc, cur_bon, sparse, bdir, sp_i, sp_c, sp_v, sp_wrap, s_tbl, sA, sGA, sGB, d, up);
+                                        cells<V, K, TAIL, MODE_LAST, BONUS, true>(J, rc, vmask, first_term, last_term, cc, cur_bon, sparse, bdir, sp_i, sp_c, sp_v, sp_wrap, my_bon, s_tbl, sA, sGA, sGB, d, up);
                                 }
                         }
                         d = got;
@@ -510,9 +602,10 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
         __syncwarp();
 }
 
-template <int V, bool BONUS>
+template <int V, int BONUS>
 __device__ void sweep_unit(const KbJob& J, const KbBox& bx, const int bwd, const int strip, const int thin,
-                           const unsigned tag_base, const float* __restrict__ s_tbl, const int tstride, const int lane)
+                           const unsigned tag_base, const float* __restrict__ s_tbl, const int tstride, const int lane,
+                           float4* s_ring, int2* s_bon)
 {
         const int mid = (bx.ea - bx.sa) / 2 + bx.sa;
         const int r0 = bwd ? mid : bx.sa;
@@ -528,7 +621,7 @@ __device__ void sweep_unit(const KbJob& J, const KbBox& bx, const int bwd, const
         } else {
                 in.a = bx.f0a; in.ga = bx.f0ga; in.gb = bx.f0gb;
         }
-        const int rps = rows_per_strip(J.kind, J.nalpha, thin, BONUS);
+        const int rps = rows_per_strip(J.kind, J.nalpha, thin, BONUS != BONUS_NONE);
         const int nstr = (R + rps - 1) / rps > 0 ? (R + rps - 1) / rps : 1;
         const int row0 = strip * rps;
         (void)nstr;
@@ -536,27 +629,27 @@ __device__ void sweep_unit(const KbJob& J, const KbBox& bx, const int bwd, const
         const unsigned mine = tag_base + (unsigned)strip + 1u;
         const int rem = R - row0;
         if (rps == 32) {
-                sweep_strip<V, 1, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane);
+                sweep_strip<V, 1, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_bon);
         } else if constexpr (V == V_PP23) {
-                if (rem >= 64) sweep_strip<V, 2, false, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane);
-                else if (rem > 32) sweep_strip<V, 2, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane);
-                else sweep_strip<V, 1, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane);
+                if (rem >= 64) sweep_strip<V, 2, false, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_bon);
+                else if (rem > 32) sweep_strip<V, 2, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_bon);
+                else sweep_strip<V, 1, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_bon);
         } else if constexpr (V == V_SS && !BONUS) {
-                if (rem >= 256) sweep_strip<V, 8, false, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane);
-                else if (rem > 128) sweep_strip<V, 8, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane);
-                else if (rem > 32) sweep_strip<V, 4, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane);
-                else sweep_strip<V, 1, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane);
+                if (rem >= 256) sweep_strip<V, 8, false, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_bon);
+                else if (rem > 128) sweep_strip<V, 8, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_bon);
+                else if (rem > 32) sweep_strip<V, 4, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_bon);
+                else sweep_strip<V, 1, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_bon);
         } else {
-                if (rem >= 128) sweep_strip<V, 4, false, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane);
-                else if (rem > 32) sweep_strip<V, 4, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane);
-                else sweep_strip<V, 1, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane);
+                if (rem >= 128) sweep_strip<V, 4, false, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_bon);
+                else if (rem > 32) sweep_strip<V, 4, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_bon);
+                else sweep_strip<V, 1, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_bon);
         }
 }
 
 // BONUS is a kernel-level template parameter: a batch either carries consistency bonuses for all
 // of its jobs (tree levels in default mode) or for none (anchor batch, --fast), and the two
 // families get independent register allocation / code size.
-template <bool BONUS>
+template <int BONUS>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
 kb_sweep_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes,
                 const KbUnit* __restrict__ units, const unsigned* __restrict__ nunits_p,
@@ -564,11 +657,16 @@ kb_sweep_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes,
                 const float* __restrict__ tbl, const int thin, const int tstride)
 {
         __shared__ float s_tbl[TBL_MAX];
+        __shared__ float4 s_ring_all[WARPS_PER_CTA][16];     // thin strips: hand-off read-ahead ring, one per warp
         for (int i = threadIdx.x; i < TBL_MAX; i += blockDim.x) {
                 s_tbl[i] = tbl[i];
         }
         __syncthreads();
         const int lane = threadIdx.x & 31;
+        // sparse bonus lists of the rows of the strip a warp is sweeping (bonus kernel family only)
+        __shared__ int2 s_bon_all[(BONUS == BONUS_SPARSE) ? WARPS_PER_CTA * BON_SLOTS * BON_KMAX_ROWS * 32 : 1];
+        float4* s_ring = s_ring_all[threadIdx.x >> 5];
+        int2* s_bon = (BONUS == BONUS_SPARSE) ? (s_bon_all + (threadIdx.x >> 5) * (BON_SLOTS * BON_KMAX_ROWS * 32)) : s_bon_all;
         const unsigned total = *nunits_p;
         while (true) {
                 unsigned unit = 0;
@@ -585,13 +683,13 @@ kb_sweep_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes,
                 const KbJob J = jobs[bx.job];
                 const unsigned ps = tag_base;
                 if (J.kind == KB200_KIND_SS) {
-                        sweep_unit<V_SS, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane);
+                        sweep_unit<V_SS, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane, s_ring, s_bon);
                 } else if (J.kind == KB200_KIND_SP) {
-                        sweep_unit<V_SP, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane);
+                        sweep_unit<V_SP, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane, s_ring, s_bon);
                 } else if (J.nalpha <= 5) {
-                        sweep_unit<V_PP5, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane);
+                        sweep_unit<V_PP5, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane, s_ring, s_bon);
                 } else {
-                        sweep_unit<V_PP23, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane);
+                        sweep_unit<V_PP23, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane, s_ring, s_bon);
                 }
         }
 }
@@ -867,7 +965,7 @@ struct SBox {
 // One sweep of a small box by ONE thread: the rows are taken K at a time through the shared cell
 // routine (cells<>, the same code the warp strips run: K cells of a column chained in registers),
 // so the row array S -- thread-local memory -- is read and written once per K rows.
-template <int V, int K, bool BONUS>
+template <int V, int K, int BONUS>
 __device__ void small_sweep(const KbJob& J, const int bwd, const int r0, const int r1, const int sb, const int eb,
                             const Trip in, float4* __restrict__ S, const float* __restrict__ s_tbl, const int tstride)
 {
@@ -899,7 +997,7 @@ __device__ void small_sweep(const KbJob& J, const int bwd, const int r0, const i
                 }
                 S[C] = make_float4(KB_NEGF, KB_NEGF, KB_NEGF, 0.0f);
         }
-        const bool sparse = BONUS && (J.bkey != nullptr);
+        const bool sparse = (BONUS == BONUS_SPARSE) && (J.bkey != nullptr);
         for (int v0 = 0; v0 < R; v0 += K) {
                 RowCtx<V, K> rc;
                 const unsigned vmask = load_rows<V, K>(J, bwd, r0, r1, v0, tstride, rc);
@@ -913,7 +1011,7 @@ __device__ void small_sweep(const KbJob& J, const int bwd, const int r0, const i
                 }
                 if constexpr (BONUS) {
                         if (sparse) {
-                                sparse_init<V, K>(J, bwd, sb, eb, rc, sp_i, sp_c, sp_v, sp_wrap);
+                                sparse_init<V, K, false>(J, bwd, sb, eb, rc, nullptr, sp_i, sp_c, sp_v, sp_wrap);
                         }
                 }
                 Trip d = {KB_NEGF, KB_NEGF, KB_NEGF};
@@ -951,7 +1049,7 @@ __device__ void small_sweep(const KbJob& J, const int bwd, const int r0, const i
                         const float4 q = S[0];
                         Trip up = {q.x, q.y, q.z};
                         const Trip got = up;
-                        cells<V, K, true, MODE_FIRST, BONUS>(J, rc, vmask, first_term, last_term, cc, bon, sparse, dstep, sp_i, sp_c, sp_v, sp_wrap, s_tbl, sA, sGA, sGB, d, up);
+                        cells<V, K, true, MODE_FIRST, BONUS, false>(J, rc, vmask, first_term, last_term, cc, bon, sparse, dstep, sp_i, sp_c, sp_v, sp_wrap, nullptr, s_tbl, sA, sGA, sGB, d, up);
                         d = got;
                         S[0] = make_float4(up.a, up.ga, up.gb, 0.0f);
                 }
@@ -960,7 +1058,7 @@ __device__ void small_sweep(const KbJob& J, const int bwd, const int r0, const i
                         const float4 q = S[u];
                         Trip up = {q.x, q.y, q.z};
                         const Trip got = up;
-                        cells<V, K, true, MODE_MID, BONUS>(J, rc, vmask, first_term, last_term, cc, bon, sparse, dstep, sp_i, sp_c, sp_v, sp_wrap, s_tbl, sA, sGA, sGB, d, up);
+                        cells<V, K, true, MODE_MID, BONUS, false>(J, rc, vmask, first_term, last_term, cc, bon, sparse, dstep, sp_i, sp_c, sp_v, sp_wrap, nullptr, s_tbl, sA, sGA, sGB, d, up);
                         d = got;
                         S[u] = make_float4(up.a, up.ga, up.gb, 0.0f);
                 }
@@ -968,13 +1066,13 @@ __device__ void small_sweep(const KbJob& J, const int bwd, const int r0, const i
                         column(C);
                         const float4 q = S[C];
                         Trip up = {q.x, q.y, q.z};
-                        cells<V, K, true, MODE_LAST, BONUS>(J, rc, vmask, first_term, last_term, cc, bon, sparse, dstep, sp_i, sp_c, sp_v, sp_wrap, s_tbl, sA, sGA, sGB, d, up);
+                        cells<V, K, true, MODE_LAST, BONUS, false>(J, rc, vmask, first_term, last_term, cc, bon, sparse, dstep, sp_i, sp_c, sp_v, sp_wrap, nullptr, s_tbl, sA, sGA, sGB, d, up);
                         S[C] = make_float4(up.a, up.ga, up.gb, 0.0f);
                 }
         }
 }
 
-template <int V, int MAXC, bool BONUS>
+template <int V, int MAXC, int BONUS>
 __device__ void small_box_run(const KbJob& J, const KbBox& root, const float* __restrict__ s_tbl, const int tstride,
                               unsigned long long& ncells)
 {
@@ -1085,7 +1183,7 @@ __device__ void small_box_run(const KbJob& J, const KbBox& root, const float* __
         }
 }
 
-template <int MAXC, bool BONUS>
+template <int MAXC, int BONUS>
 __global__ void __launch_bounds__(128, 4)
 kb_small_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes, const unsigned* __restrict__ nsmall_p,
                 unsigned long long* __restrict__ cells, const float* __restrict__ tbl, const int tstride)
@@ -1247,13 +1345,29 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
         }
         if (const char* e = getenv("KB200_SMALL_ROWS")) small_rows = std::min(std::max(atoi(e), 1), SMALL_ROWS_MAX);
         if (const char* e = getenv("KB200_SMALL_COLS")) small_cols = std::min(std::max(atoi(e), 4), SMALL_COLS_MAX);
+        // KB200_THIN=0|1 forces thick / thin strips (tests run every batch both ways)
+        int force_thin = -1;
+        if (const char* e = getenv("KB200_THIN")) force_thin = (atoi(e) != 0) ? 1 : 0;
         float sweep_ms = 0.0f;
         const bool trace = getenv("KB200_TRACE") != nullptr;
         int round = 0;
         // all-or-nothing: a job without bonus in a bonus batch simply has an empty list / null dense
-        bool batch_bonus = false;
+        bool batch_bonus = false, batch_dense = false;
         for (int i = 0; i < n; i++) {
                 if (jobs[i].bonus || jobs[i].bkey) batch_bonus = true;
+                if (jobs[i].bonus) batch_dense = true;
+                if (jobs[i].bkey && jobs[i].nb > KB_BONUS_KMAX) {
+                        fprintf(stderr, "[kalign_b200] sparse bonus with %d entries per row (max %d)\n", jobs[i].nb, KB_BONUS_KMAX);
+                        return KB200_FAIL;
+                }
+        }
+        {
+                // 4 resident CTAs per SM: the bonus family stages its lists in 36 KB of shared memory per CTA
+                static bool carveout_set = false;
+                if (!carveout_set) {
+                        cudaFuncSetAttribute(kb_sweep_kernel<BONUS_SPARSE>, cudaFuncAttributePreferredSharedMemoryCarveout, 70);
+                        carveout_set = true;
+                }
         }
         // resident warps of the persistent sweep grid
         const int sweep_ctas = ctx->sm_count * 4;
@@ -1264,7 +1378,8 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
                 // thin strips when thick ones could not occupy the machine: the rows still alive
                 // at this depth are at most rows_total, spread over `count` boxes
                 const size_t thick_units = rows_total / 128 + 2 * (size_t)count;
-                const int thin = (thick_units < 2 * resident_warps) ? 1 : 0;
+                int thin = (thick_units < 2 * resident_warps) ? 1 : 0;
+                if (force_thin >= 0) thin = force_thin;
                 const unsigned items = 2u * count;
                 // tags: unique per launch (8192 strips per sweep at most: 256k rows), never 0
                 ctx->tag_counter += 65536u;
@@ -1273,14 +1388,18 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
                 kb_plan_kernel<<<(items + 127) / 128, 128, 0, st>>>(ctx->d_jobs.as<KbJob>(), cur, (int)count, thin, batch_bonus ? 1 : 0,
                                                                      ctx->d_units.as<KbUnit>(), d_nunits);
                 KB_CUDA(cudaEventRecord(ctx->ev2, st));
-                if (batch_bonus) {
-                        kb_sweep_kernel<true><<<sweep_ctas, WARPS_PER_CTA * 32, 0, st>>>(ctx->d_jobs.as<KbJob>(), cur, ctx->d_units.as<KbUnit>(),
-                                                                                          d_nunits, d_cursor, tag_base,
-                                                                                          ctx->d_tbl.as<float>(), thin, tstride);
-                } else {
-                        kb_sweep_kernel<false><<<sweep_ctas, WARPS_PER_CTA * 32, 0, st>>>(ctx->d_jobs.as<KbJob>(), cur, ctx->d_units.as<KbUnit>(),
-                                                                                           d_nunits, d_cursor, tag_base,
-                                                                                           ctx->d_tbl.as<float>(), thin, tstride);
+                {
+                        const KbJob* dj = ctx->d_jobs.as<KbJob>();
+                        const KbUnit* du = ctx->d_units.as<KbUnit>();
+                        const float* dt = ctx->d_tbl.as<float>();
+                        const int thr = WARPS_PER_CTA * 32;
+                        if (batch_dense) {
+                                kb_sweep_kernel<BONUS_DENSE><<<sweep_ctas, thr, 0, st>>>(dj, cur, du, d_nunits, d_cursor, tag_base, dt, thin, tstride);
+                        } else if (batch_bonus) {
+                                kb_sweep_kernel<BONUS_SPARSE><<<sweep_ctas, thr, 0, st>>>(dj, cur, du, d_nunits, d_cursor, tag_base, dt, thin, tstride);
+                        } else {
+                                kb_sweep_kernel<BONUS_NONE><<<sweep_ctas, thr, 0, st>>>(dj, cur, du, d_nunits, d_cursor, tag_base, dt, thin, tstride);
+                        }
                 }
                 KB_CUDA(cudaEventRecord(ctx->ev3, st));
                 int mgrid = (int)std::min<unsigned>((count + 3) / 4, (unsigned)(ctx->sm_count * 16));
@@ -1315,12 +1434,15 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
                 const int sgrid = ctx->sm_count * 4;
                 const KbJob* dj = ctx->d_jobs.as<KbJob>();
                 const float* dt = ctx->d_tbl.as<float>();
+                const int fam = batch_dense ? BONUS_DENSE : (batch_bonus ? BONUS_SPARSE : BONUS_NONE);
                 if (small_cols <= SMALL_COLS) {
-                        if (batch_bonus) kb_small_kernel<SMALL_COLS, true><<<sgrid, 128, 0, st>>>(dj, d_small, d_nsmall, d_cells, dt, tstride);
-                        else kb_small_kernel<SMALL_COLS, false><<<sgrid, 128, 0, st>>>(dj, d_small, d_nsmall, d_cells, dt, tstride);
+                        if (fam == BONUS_DENSE) kb_small_kernel<SMALL_COLS, BONUS_DENSE><<<sgrid, 128, 0, st>>>(dj, d_small, d_nsmall, d_cells, dt, tstride);
+                        else if (fam == BONUS_SPARSE) kb_small_kernel<SMALL_COLS, BONUS_SPARSE><<<sgrid, 128, 0, st>>>(dj, d_small, d_nsmall, d_cells, dt, tstride);
+                        else kb_small_kernel<SMALL_COLS, BONUS_NONE><<<sgrid, 128, 0, st>>>(dj, d_small, d_nsmall, d_cells, dt, tstride);
                 } else {
-                        if (batch_bonus) kb_small_kernel<SMALL_COLS_MAX, true><<<sgrid, 128, 0, st>>>(dj, d_small, d_nsmall, d_cells, dt, tstride);
-                        else kb_small_kernel<SMALL_COLS_MAX, false><<<sgrid, 128, 0, st>>>(dj, d_small, d_nsmall, d_cells, dt, tstride);
+                        if (fam == BONUS_DENSE) kb_small_kernel<SMALL_COLS_MAX, BONUS_DENSE><<<sgrid, 128, 0, st>>>(dj, d_small, d_nsmall, d_cells, dt, tstride);
+                        else if (fam == BONUS_SPARSE) kb_small_kernel<SMALL_COLS_MAX, BONUS_SPARSE><<<sgrid, 128, 0, st>>>(dj, d_small, d_nsmall, d_cells, dt, tstride);
+                        else kb_small_kernel<SMALL_COLS_MAX, BONUS_NONE><<<sgrid, 128, 0, st>>>(dj, d_small, d_nsmall, d_cells, dt, tstride);
                 }
                 KB_CUDA(cudaGetLastError());
                 KB_CUDA(cudaEventRecord(ctx->ev3, st));

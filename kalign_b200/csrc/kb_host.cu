@@ -140,35 +140,17 @@ int kb_distances_dev(kb200_ctx* ctx, KbSeqs& S, const int* rows, int nrows, cons
 // ---------------------------------------------------------------------------------------------
 
 // multi-GPU: cost-balanced shard of the N x K pair list, local compute, one all-gather
-int kb_anchor_posmaps_sharded(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S, const int* anchor_ids, int K, int* posmaps)
+int kb_anchor_posmaps_sharded(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S, const int* anchor_ids, int K, int* posmaps,
+                              int host_copy)
 {
+        // Position maps are produced into ctx->t_posmaps and STAY there: the progressive phase reads
+        // them on the device.  `posmaps` (host) is only filled when host_copy != 0 (the host
+        // restatement of the bonus, KB200_HOST_BONUS); otherwise it merely tags the device copy.
         const int N = S.n;
         const long long np = (long long)N * K;
         ctx->posmaps_tag = nullptr;
         ctx->posmaps_n = 0;
-        if (ctx->world <= 1) {
-                // results stay resident in t_posmaps (the progressive phase reads them on the device)
-                const size_t full1 = (size_t)K * (size_t)S.total;
-                KB_RUN(ctx->t_posmaps.ensure(sizeof(int) * (full1 + 8)));
-                KB_RUN(kb_anchor_posmaps_dev(ctx, prm, S, anchor_ids, K, 0, np, posmaps, ctx->t_posmaps.as<int>()));
-                // identity maps of the anchors are host-filled: mirror them
-                for (int k = 0; k < K; k++) {
-                        const int i = anchor_ids[k];
-                        const size_t o = (size_t)K * (size_t)S.h_offs[i] + (size_t)k * (size_t)S.h_lens[i];
-                        KB_CUDA(cudaMemcpyAsync(ctx->t_posmaps.as<int>() + o, posmaps + o, sizeof(int) * (size_t)S.h_lens[i], cudaMemcpyHostToDevice, ctx->stream));
-                }
-                KB_CUDA(cudaStreamSynchronize(ctx->stream));
-                ctx->posmaps_tag = (const void*)posmaps;
-                ctx->posmaps_n = full1;
-                return KB200_OK;
-        }
-        std::vector<double> cost((size_t)np);
-        for (long long p = 0; p < np; p++) {
-                const int i = (int)(p / K), k = (int)(p % K);
-                cost[(size_t)p] = (i == anchor_ids[k]) ? 1.0 : (double)S.h_lens[i] * (double)S.h_lens[anchor_ids[k]] + 1.0;
-        }
-        std::vector<int> b((size_t)ctx->world + 1);
-        kb_partition(cost.data(), (int)np, ctx->world, b.data());
+        cudaStream_t st = ctx->stream;
         auto map_off = [&](long long p) -> size_t {
                 if (p >= np) return (size_t)K * (size_t)S.total;
                 const int i = (int)(p / K), k = (int)(p % K);
@@ -176,24 +158,38 @@ int kb_anchor_posmaps_sharded(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S
         };
         const size_t full = (size_t)K * (size_t)S.total;
         KB_RUN(ctx->t_posmaps.ensure(sizeof(int) * (full + 8)));
-        // local shard: results land at their final offsets of the full device array
-        KB_RUN(kb_anchor_posmaps_dev(ctx, prm, S, anchor_ids, K, b[(size_t)ctx->rank], b[(size_t)ctx->rank + 1], nullptr,
-                                     ctx->t_posmaps.as<int>()));
-        std::vector<size_t> seg((size_t)ctx->world + 1);
-        for (int r = 0; r <= ctx->world; r++) seg[(size_t)r] = map_off(b[(size_t)r]) * sizeof(int);
-        KB_RUN(kb_allgatherv(ctx, ctx->t_posmaps.p, seg.data()));
-        KB_CUDA(cudaMemcpyAsync(posmaps, ctx->t_posmaps.p, sizeof(int) * full, cudaMemcpyDeviceToHost, ctx->stream));
-        KB_CUDA(cudaStreamSynchronize(ctx->stream));
-        ctx->stats.d2h_bytes += (double)(sizeof(int) * full);
-        for (long long p = 0; p < np; p++) {
-                const int i = (int)(p / K), k = (int)(p % K);
-                if (i == anchor_ids[k]) {
-                        int* m = posmaps + map_off(p);
-                        for (int q = 0; q < S.h_lens[i]; q++) m[q] = q;
-                        KB_CUDA(cudaMemcpyAsync(ctx->t_posmaps.as<int>() + map_off(p), m, sizeof(int) * (size_t)S.h_lens[i], cudaMemcpyHostToDevice, ctx->stream));
+        int* d_maps = ctx->t_posmaps.as<int>();
+        if (ctx->world <= 1) {
+                KB_RUN(kb_anchor_posmaps_dev(ctx, prm, S, anchor_ids, K, 0, np, nullptr, d_maps));
+        } else {
+                std::vector<double> cost((size_t)np);
+                for (long long p = 0; p < np; p++) {
+                        const int i = (int)(p / K), k = (int)(p % K);
+                        cost[(size_t)p] = (i == anchor_ids[k]) ? 1.0 : (double)S.h_lens[i] * (double)S.h_lens[anchor_ids[k]] + 1.0;
                 }
+                std::vector<int> b((size_t)ctx->world + 1);
+                kb_partition(cost.data(), (int)np, ctx->world, b.data());
+                // local shard: results land at their final offsets of the full device array
+                KB_RUN(kb_anchor_posmaps_dev(ctx, prm, S, anchor_ids, K, b[(size_t)ctx->rank], b[(size_t)ctx->rank + 1], nullptr, d_maps));
+                std::vector<size_t> seg((size_t)ctx->world + 1);
+                for (int r = 0; r <= ctx->world; r++) seg[(size_t)r] = map_off(b[(size_t)r]) * sizeof(int);
+                KB_RUN(kb_allgatherv(ctx, ctx->t_posmaps.p, seg.data()));
         }
-        KB_CUDA(cudaStreamSynchronize(ctx->stream));
+        // identity maps of the anchors themselves (anchor_consistency.c:252-258)
+        int maxlen = 0;
+        for (int k = 0; k < K; k++) maxlen = std::max(maxlen, S.h_lens[anchor_ids[k]]);
+        std::vector<int> iota((size_t)maxlen + 1);
+        for (int q = 0; q <= maxlen; q++) iota[(size_t)q] = q;
+        for (int k = 0; k < K; k++) {
+                const int i = anchor_ids[k];
+                const size_t o = map_off((long long)i * K + k);
+                KB_CUDA(cudaMemcpyAsync(d_maps + o, iota.data(), sizeof(int) * (size_t)S.h_lens[i], cudaMemcpyHostToDevice, st));
+        }
+        if (host_copy && posmaps) {
+                KB_CUDA(cudaMemcpyAsync(posmaps, d_maps, sizeof(int) * full, cudaMemcpyDeviceToHost, st));
+                ctx->stats.d2h_bytes += (double)(sizeof(int) * full);
+        }
+        KB_CUDA(cudaStreamSynchronize(st));
         ctx->posmaps_tag = (const void*)posmaps;
         ctx->posmaps_n = full;
         return KB200_OK;

@@ -30,7 +30,11 @@ int kb_distances_dev(kb200_ctx* ctx, KbSeqs& S, const int* rows, int nrows, cons
 
 int kb_anchor_posmaps_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S, const int* anchor_ids, int K,
                           long long pair_begin, long long pair_end, int* posmaps_host, int* d_full = nullptr);
-int kb_anchor_posmaps_sharded(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S, const int* anchor_ids, int K, int* posmaps_host);
+int kb_anchor_posmaps_sharded(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S, const int* anchor_ids, int K, int* posmaps_host,
+                              int host_copy);
+// the progressive phase needs the position maps on the HOST only in the A/B mode KB200_HOST_BONUS
+// (or when K exceeds the device kernels' compile-time bound)
+int kb_bonus_on_host(int K);
 
 int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                       const int* tasks_abc, int ntasks, const float* seq_distances,

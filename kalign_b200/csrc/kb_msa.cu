@@ -717,7 +717,8 @@ int kb200_msa_create(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_thr
         if (rc == KB200_OK && consistency_anchors > 0 && N >= 3) {
                 M->K = std::min(consistency_anchors, N);
                 select_anchors(M->seq_distances.data(), N, M->K, M->anchor_ids);
-                M->posmaps.assign((size_t)total * (size_t)M->K, -1);
+                // host copy of the position maps only in the host-bonus A/B mode; otherwise the vector is a tag
+                M->posmaps.assign(kb_bonus_on_host(M->K) ? (size_t)total * (size_t)M->K : (size_t)8, -1);
         }
         if (rc != KB200_OK) {
                 kb200_msa_free(M);
@@ -739,7 +740,7 @@ int kb200_msa_align(kb200_msa* M)
         KB_CUDA(cudaEventCreate(&e1));
         KB_CUDA(cudaEventRecord(e0, ctx->stream));
         if (M->K > 0) {
-                KB_RUN(kb_anchor_posmaps_sharded(ctx, &M->prm, M->S, M->anchor_ids.data(), M->K, M->posmaps.data()));
+                KB_RUN(kb_anchor_posmaps_sharded(ctx, &M->prm, M->S, M->anchor_ids.data(), M->K, M->posmaps.data(), kb_bonus_on_host(M->K)));
         }
         KB_RUN(kb_align_tree_dev(ctx, &M->prm, M->S, M->abc.data(), M->N - 1, M->seq_distances.data(),
                                  M->K > 0 ? M->posmaps.data() : nullptr, M->K, M->weight, M->n_threads, M->gaps.data(), 1));

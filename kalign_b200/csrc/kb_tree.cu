@@ -328,6 +328,11 @@ void level_weave(Tree& T, int nt, const std::vector<int>& tl, const int* tasks_a
 
 } // namespace
 
+int kb_bonus_on_host(int K)
+{
+        return (getenv("KB200_HOST_BONUS") != nullptr) || (K > KB_BONUS_KMAX);
+}
+
 int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                       const int* tasks_abc, int ntasks, const float* seq_distances,
                       const int* posmaps, int K, float weight, int n_threads, int* gaps_out, int posmaps_on_device)
@@ -382,7 +387,7 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
         std::vector<std::vector<int>> colof((size_t)N);
         // ---- device-resident gaps / colof / position maps (kb_bonus.cu); KB200_HOST_BONUS=1 keeps the
         //      host implementation of weave_alignment.c / anchor_consistency.c for A/B checks
-        const bool dev_state = (getenv("KB200_HOST_BONUS") == nullptr) && (T.K <= KB_BONUS_KMAX);
+        const bool dev_state = !kb_bonus_on_host(T.K);
         int* d_gaps = nullptr;
         int* d_colof = nullptr;
         const int* d_posmaps = nullptr;
@@ -601,23 +606,48 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                                 colb_prefix[(size_t)(q - q0)] = colb_total; colb_total += clen[q];
                                 row_prefix[(size_t)(q - q0)] = row_total; row_total += rlen[q];
                         }
-                        TR(ctx->t_bdesc.ensure(sizeof(int) * memb.size() + sizeof(KbBonusOperand) * ops.size() + sizeof(KbBonusTask) * btasks.size() +
+                        // operands by member count: thread-per-column kernel (few members) / warp-per-column
+                        std::vector<int> small_list, large_list;
+                        std::vector<long long> small_prefix, large_prefix;
+                        long long small_cols = 0, large_cols = 0;
+                        for (size_t o = 0; o < ops.size(); o++) {
+                                if (ops[o].m1 - ops[o].m0 <= KB_BONUS_SMALL_NMEM) {
+                                        small_list.push_back((int)o); small_prefix.push_back(small_cols); small_cols += ops[o].len;
+                                } else {
+                                        large_list.push_back((int)o); large_prefix.push_back(large_cols); large_cols += (ops[o].len + 31) / 32;   // 32-column chunks
+                                }
+                        }
+                        (void)op_cols;
+                        TR(ctx->t_bdesc.ensure(sizeof(int) * (memb.size() + 2 * ops.size()) + sizeof(KbBonusOperand) * ops.size() + sizeof(KbBonusTask) * btasks.size() +
                                                sizeof(long long) * (op_prefix.size() + colb_prefix.size() + row_prefix.size()) + 256));
                         char* base = ctx->t_bdesc.as<char>();
                         KbBonusOperand* d_ops = (KbBonusOperand*)base; base += sizeof(KbBonusOperand) * ops.size();
                         KbBonusTask* d_bt = (KbBonusTask*)base; base += sizeof(KbBonusTask) * btasks.size();
-                        long long* d_opp = (long long*)base; base += sizeof(long long) * op_prefix.size();
+                        long long* d_smp = (long long*)base; base += sizeof(long long) * small_prefix.size();
+                        long long* d_lgp = (long long*)base; base += sizeof(long long) * large_prefix.size();
                         long long* d_cbp = (long long*)base; base += sizeof(long long) * colb_prefix.size();
                         long long* d_rwp = (long long*)base; base += sizeof(long long) * row_prefix.size();
+                        int* d_sml = (int*)base; base += sizeof(int) * small_list.size();
+                        int* d_lgl = (int*)base; base += sizeof(int) * large_list.size();
                         int* d_memb = (int*)base;
                         TC(cudaMemcpyAsync(d_ops, ops.data(), sizeof(KbBonusOperand) * ops.size(), cudaMemcpyHostToDevice, st));
                         TC(cudaMemcpyAsync(d_bt, btasks.data(), sizeof(KbBonusTask) * btasks.size(), cudaMemcpyHostToDevice, st));
-                        TC(cudaMemcpyAsync(d_opp, op_prefix.data(), sizeof(long long) * op_prefix.size(), cudaMemcpyHostToDevice, st));
+                        if (!small_list.empty()) {
+                                TC(cudaMemcpyAsync(d_smp, small_prefix.data(), sizeof(long long) * small_prefix.size(), cudaMemcpyHostToDevice, st));
+                                TC(cudaMemcpyAsync(d_sml, small_list.data(), sizeof(int) * small_list.size(), cudaMemcpyHostToDevice, st));
+                        }
+                        if (!large_list.empty()) {
+                                TC(cudaMemcpyAsync(d_lgp, large_prefix.data(), sizeof(long long) * large_prefix.size(), cudaMemcpyHostToDevice, st));
+                                TC(cudaMemcpyAsync(d_lgl, large_list.data(), sizeof(int) * large_list.size(), cudaMemcpyHostToDevice, st));
+                        }
                         TC(cudaMemcpyAsync(d_cbp, colb_prefix.data(), sizeof(long long) * colb_prefix.size(), cudaMemcpyHostToDevice, st));
                         TC(cudaMemcpyAsync(d_rwp, row_prefix.data(), sizeof(long long) * row_prefix.size(), cudaMemcpyHostToDevice, st));
                         TC(cudaMemcpyAsync(d_memb, memb.data(), sizeof(int) * memb.size(), cudaMemcpyHostToDevice, st));
                         TC(cudaMemsetAsync(ctx->t_binv.p, 0xFF, sizeof(int) * inv_per_task * (size_t)ntm, st));
-                        TR(kb_bonus_level(ctx, S, K, T.weight / (float)K, d_ops, d_opp, 2 * ntm, op_cols, d_memb, d_colof, d_posmaps,
+                        TR(kb_bonus_level(ctx, S, K, T.weight / (float)K, d_ops,
+                                          d_sml, d_smp, (int)small_list.size(), small_cols,
+                                          d_lgl, d_lgp, (int)large_list.size(), large_cols,
+                                          d_memb, d_colof, d_posmaps,
                                           d_bt, d_cbp, colb_total, d_rwp, row_total, ntm, ctx->t_aoff.as<int>()));
                         TC(cudaStreamSynchronize(st));     // host descriptor vectors go out of scope
                 } else if (T.posmaps && !dev_state) {
@@ -711,6 +741,7 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                         size_t pneed = 0;
                         for (int q = 0; q < nt; q++) pneed += 2 * ((size_t)la[q] + (size_t)lb[q] + 4);
                         TR(ctx->t_wp.ensure(sizeof(int) * (pneed + 16)));
+                        TR(ctx->t_alen.ensure(sizeof(int) * ((size_t)nt + 16)));
                         size_t po = 0;
                         for (int q = 0; q < nt; q++) {
                                 const int t = tl[q];
@@ -719,6 +750,7 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                                 W.Pa = ctx->t_wp.as<int>() + po; po += (size_t)la[q] + (size_t)lb[q] + 4;
                                 W.Pb = ctx->t_wp.as<int>() + po; po += (size_t)la[q] + (size_t)lb[q] + 4;
                                 W.alnlen = -1;
+                                W.out_len = ctx->t_alen.as<int>() + q;
                                 for (int si : T.sip[(size_t)tasks_abc[3 * t]]) wm.push_back({si, W.Pa});
                                 for (int si : T.sip[(size_t)tasks_abc[3 * t + 1]]) wm.push_back({si, W.Pb});
                         }
@@ -730,10 +762,21 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                         TR(kb_weave_level(ctx, S, d_wt, nt, d_wm, (int)wm.size(), d_gaps, d_colof));
                         TC(cudaStreamSynchronize(st));
                 }
-                std::vector<int> hcoded(n_coded);
-                TC(cudaMemcpyAsync(hcoded.data(), d_coded.p, sizeof(int) * n_coded, cudaMemcpyDeviceToHost, st));
-                TC(cudaStreamSynchronize(st));
-                ctx->stats.d2h_bytes += (double)(sizeof(int) * n_coded);
+                // the host only needs every task's alignment length (plen bookkeeping, merged profile
+                // sizes); the coded paths themselves stay on the device (KB200_HOST_BONUS: full copy)
+                std::vector<int> hcoded;
+                std::vector<int> alen((size_t)nt);
+                if (dev_state) {
+                        TC(cudaMemcpyAsync(alen.data(), ctx->t_alen.p, sizeof(int) * (size_t)nt, cudaMemcpyDeviceToHost, st));
+                        TC(cudaStreamSynchronize(st));
+                        ctx->stats.d2h_bytes += (double)(sizeof(int) * (size_t)nt);
+                } else {
+                        hcoded.resize(n_coded);
+                        TC(cudaMemcpyAsync(hcoded.data(), d_coded.p, sizeof(int) * n_coded, cudaMemcpyDeviceToHost, st));
+                        TC(cudaStreamSynchronize(st));
+                        ctx->stats.d2h_bytes += (double)(sizeof(int) * n_coded);
+                        for (int q = 0; q < nt; q++) alen[(size_t)q] = hcoded[coded_off[(size_t)q]];
+                }
                 // ---- merge profiles on device (update_n), skipped for the root task ----
                 std::vector<KbMergeJob> mjobs;
                 std::vector<long long> mprefix;
@@ -743,8 +786,8 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                 for (int q = 0; q < nt; q++) {
                         size_t w = 0;
                         if (tl[q] != ntasks - 1) {
-                                w = ((size_t)hcoded[coded_off[(size_t)q]] + 2) * 64;
-                                if (q >= q0 && q < q1) nsrc += (size_t)hcoded[coded_off[(size_t)q]] + 2;
+                                w = ((size_t)alen[(size_t)q] + 2) * 64;
+                                if (q >= q0 && q < q1) nsrc += (size_t)alen[(size_t)q] + 2;
                         }
                         prof_off[(size_t)q + 1] = prof_off[(size_t)q] + w;
                 }
@@ -759,7 +802,7 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                         for (int q = 0; q < nt; q++) {
                                 const int t = tl[q];
                                 const int a = tasks_abc[3 * t], b = tasks_abc[3 * t + 1], c = tasks_abc[3 * t + 2];
-                                const int alnlen = hcoded[coded_off[(size_t)q]];
+                                const int alnlen = alen[(size_t)q];
                                 if (t == ntasks - 1) continue;
                                 T.prof[c] = block + prof_off[(size_t)q];
                                 if (q < q0 || q >= q1) continue;
@@ -797,7 +840,7 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                 for (int q = 0; q < nt; q++) {
                         const int t = tl[q];
                         const int a = tasks_abc[3 * t], b = tasks_abc[3 * t + 1], c = tasks_abc[3 * t + 2];
-                        T.plen[c] = hcoded[coded_off[(size_t)q]];
+                        T.plen[c] = alen[(size_t)q];
                         T.nsip[c] = T.nsip[a] + T.nsip[b];
                         std::vector<int>& sc = T.sip[c];
                         sc.clear();

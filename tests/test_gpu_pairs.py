@@ -65,17 +65,36 @@ def ctx():
     c.close()
 
 
+@pytest.fixture(params=["auto", "thick", "thick_nosmall"])
+def strips(request):
+    """the engine picks thin (32-row) strips for small batches; KB200_THIN=0 forces the thick-strip
+    code paths (K = 8 / 4 / 2 rows per lane) the big batches use, KB200_NO_SMALL keeps every box
+    in the warp kernel down to the last recursion level"""
+    import os
+    old = {k: os.environ.get(k) for k in ("KB200_THIN", "KB200_NO_SMALL")}
+    if request.param != "auto":
+        os.environ["KB200_THIN"] = "0"
+    if request.param == "thick_nosmall":
+        os.environ["KB200_NO_SMALL"] = "1"
+    yield request.param
+    for k, v in old.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+
+
 @pytest.mark.parametrize("name,A,gpo,gpe,tgpe", [("protein", 20, 7.0, 1.25, 1.0),
                                                   ("rna", 4, 217.0, 39.4, 292.6),
                                                   ("dna", 4, 8.0, 6.0, 0.0)])
-def test_seqseq_batch(ctx, name, A, gpo, gpe, tgpe):
+def test_seqseq_batch(ctx, strips, name, A, gpo, gpe, tgpe):
     from kalign_b200 import _lib
     rng = np.random.default_rng(101)
     subm = pfasum_like(rng) if name == "protein" else np.ascontiguousarray(
         rng.integers(-4, 6, size=(23, 23)).astype(np.float32) * (50.0 if name == "rna" else 1.0))
     prm = _lib.params_from(subm, gpo, gpe, tgpe, nalpha=23 if name == "protein" else 5)
     jobs, kws = [], []
-    sizes = [1, 2, 3, 5, 17, 31, 32, 33, 64, 65, 100, 127, 128, 129, 200, 257, 300, 450]
+    sizes = [1, 2, 3, 5, 17, 31, 32, 33, 64, 65, 100, 127, 128, 129, 200, 257, 300, 450, 600, 1100]
     for t, la in enumerate(sizes * 2):
         s1 = rng.integers(0, A, size=la).astype(np.uint8)
         s2 = mutate(rng, s1, A) if t % 3 else rng.integers(0, A, size=int(rng.integers(la, 2 * la + 2))).astype(np.uint8)
@@ -88,7 +107,7 @@ def test_seqseq_batch(ctx, name, A, gpo, gpe, tgpe):
     check(ctx, prm, jobs, kws)
 
 
-def test_seqseq_bonus(ctx):
+def test_seqseq_bonus(ctx, strips):
     from kalign_b200 import _lib
     rng = np.random.default_rng(7)
     subm = pfasum_like(rng)
@@ -110,7 +129,7 @@ def test_seqseq_bonus(ctx):
 
 @pytest.mark.parametrize("name,A,gpo,gpe,tgpe", [("protein", 20, 7.0, 1.25, 1.0),
                                                   ("rna", 4, 217.0, 39.4, 292.6)])
-def test_profile_batch(ctx, name, A, gpo, gpe, tgpe):
+def test_profile_batch(ctx, strips, name, A, gpo, gpe, tgpe):
     from kalign_b200 import _lib
     rng = np.random.default_rng(55)
     subm = pfasum_like(rng) if name == "protein" else np.ascontiguousarray(
@@ -118,7 +137,7 @@ def test_profile_batch(ctx, name, A, gpo, gpe, tgpe):
     prm = _lib.params_from(subm, gpo, gpe, tgpe, nalpha=23 if name == "protein" else 5)
     o = kbind.oracle()
     jobs, kws = [], []
-    for t, L in enumerate([4, 20, 40, 70, 140, 180]):
+    for t, L in enumerate([4, 20, 40, 70, 140, 180, 300, 560]):
         p1, l1, n1 = oracle_profile(rng, A, L, subm, gpo, gpe, tgpe, depth=1 + t % 3)
         p2, l2, n2 = oracle_profile(rng, A, L, subm, gpo, gpe, tgpe, depth=1 + (t + 1) % 3)
         if l1 >= l2:

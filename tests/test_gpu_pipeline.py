@@ -18,6 +18,20 @@ def ctx():
     c.close()
 
 
+@pytest.fixture(params=["auto", "thick"])
+def strips(request):
+    """KB200_THIN=0: the thick-strip code paths of the big batches, on the small test families"""
+    import os
+    old = os.environ.get("KB200_THIN")
+    if request.param == "thick":
+        os.environ["KB200_THIN"] = "0"
+    yield request.param
+    if old is None:
+        os.environ.pop("KB200_THIN", None)
+    else:
+        os.environ["KB200_THIN"] = old
+
+
 def ref_state(seqs, consistency, type_=8):
     run = kbind.RefRun(seqs, n_threads=2, type_=type_, consistency=consistency, weight=2.0)
     return run
@@ -33,7 +47,7 @@ FAMILIES = [
 
 @pytest.mark.parametrize("name,gen,type_", FAMILIES)
 @pytest.mark.parametrize("consistency", [0, 5])
-def test_seams_and_msa(ctx, name, gen, type_, consistency):
+def test_seams_and_msa(ctx, strips, name, gen, type_, consistency):
     from kalign_b200 import _lib
     seqs = gen()
     run = ref_state(seqs, consistency, type_)
