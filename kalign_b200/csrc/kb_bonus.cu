@@ -128,46 +128,63 @@ __global__ void kb_init_colof_kernel(const int64_t* __restrict__ offs, const int
 }
 
 // ---- votes -----------------------------------------------------------------------------------
-// Operands with many members: one WARP per chunk of 32 profile columns walks ALL members in
-// sip[] order (so "first seen position wins", total and agreeing votes come out of one pass,
-// exactly the reference's loop, anchor_consistency.c:405-446).  Members are taken 32 at a time:
-// first every lane finds, for its own member, the first residue at or after the chunk's first
-// column (binary search in colof); then the 32 members are visited in order, lane j reading the
-// member's residue a_lo+j -- the residues that fall into the chunk are consecutive -- and its K
-// anchor positions (coalesced); the owner lane of a column picks them up by shuffle: residue
-// columns are strictly increasing, so the j-th residue in the chunk is the j-th set bit of the
-// chunk's occupancy mask.
+// Operands with many members.  Work unit = (chunk of 32 profile columns, slice of VOTE_SLICE
+// members), one WARP each, so that the top tree levels (a handful of operands with thousands of
+// members) still spread over the whole machine.  Members are taken 32 at a time: first every lane
+// finds, for its own member, the first residue at or after the chunk's first column (binary search
+// in colof); then the 32 members are visited in sip[] order, lane j reading the member's residue
+// a_lo+j -- the residues that fall into the chunk are consecutive -- and its K anchor positions
+// (coalesced); the owner lane of a column picks them up by shuffle: residue columns are strictly
+// increasing, so the j-th residue in the chunk is the j-th set bit of the chunk's occupancy mask.
+//   pass 0: "first seen position wins" (anchor_consistency.c:440-445) = the vote of the valid
+//           member with the smallest index: atomicMin of (member index, position) per column;
+//           total votes by atomicAdd
+//   pass 1: votes agreeing with the winner, atomicAdd
+//   finalize: positions / confidence = agree / total (:449-457)
+constexpr int VOTE_SLICE = 64;
+
+template <int PASS>
 __global__ void __launch_bounds__(128)
-kb_bonus_positions_kernel(const KbBonusOperand* __restrict__ ops, const int* __restrict__ op_list,
-                          const long long* __restrict__ chunk_prefix,
-                          const int nops, const long long total_chunks, const int K,
-                          const int* __restrict__ memb, const int64_t* __restrict__ offs,
-                          const int* __restrict__ lens, const int* __restrict__ colof,
-                          const int* __restrict__ posmaps)
+kb_bonus_votes_kernel(const KbBonusOperand* __restrict__ ops, const KbVoteOp* __restrict__ vops, const int nvops,
+                      const long long total_units, const int K,
+                      const int* __restrict__ memb, const int64_t* __restrict__ offs,
+                      const int* __restrict__ lens, const int* __restrict__ colof,
+                      const int* __restrict__ posmaps,
+                      unsigned long long* __restrict__ vkey, int* __restrict__ vtotal, int* __restrict__ vagree)
 {
         const int lane = threadIdx.x & 31;
         const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-        if (gid >= total_chunks) return;
-        int lo = 0, hi = nops - 1;
+        if (gid >= total_units) return;
+        int lo = 0, hi = nvops - 1;
         while (lo < hi) {
                 const int mid = (lo + hi + 1) >> 1;
-                if (chunk_prefix[mid] <= gid) lo = mid; else hi = mid - 1;
+                if (vops[mid].unit0 <= gid) lo = mid; else hi = mid - 1;
         }
-        const KbBonusOperand O = ops[op_list[lo]];
-        const int c0 = (int)(gid - chunk_prefix[lo]) * 32;
+        const KbVoteOp VO = vops[lo];
+        const KbBonusOperand O = ops[VO.op];
+        const long long lu = gid - VO.unit0;
+        const int chunk = (int)(lu / VO.nslices);
+        const int slice = (int)(lu % VO.nslices);
+        const int c0 = chunk * 32;
         const int c = c0 + lane;                 // the column this lane owns
         const int nmem = O.m1 - O.m0;
-        int best[KMAX], total[KMAX], agree[KMAX];
+        const int m_begin = slice * VOTE_SLICE;
+        const int m_end = min(nmem, m_begin + VOTE_SLICE);
+        int best[KMAX], first_m[KMAX], count[KMAX];
 #pragma unroll
         for (int k = 0; k < KMAX; k++) {
-                best[k] = -1; total[k] = 0; agree[k] = 0;
+                best[k] = -1; first_m[k] = -1; count[k] = 0;
+                if (PASS == 1 && k < K && c < O.len) {
+                        const unsigned long long key = vkey[VO.vote0 + (long long)k * O.len + c];
+                        best[k] = (key == ~0ull) ? -1 : (int)(unsigned)(key & 0xffffffffull);
+                }
         }
         const unsigned lt_mask = (1u << lane) - 1u;
-        for (int mb = 0; mb < nmem; mb += 32) {
+        for (int mb = m_begin; mb < m_end; mb += 32) {
                 // ---- lane = member: locate the chunk in the member's residues ----
                 int my_len = 0, my_alo = 0;
                 long long my_off = 0;
-                if (mb + lane < nmem) {
+                if (mb + lane < m_end) {
                         const int si = memb[O.m0 + mb + lane];
                         my_len = lens[si];
                         my_off = (long long)offs[si];
@@ -179,7 +196,7 @@ kb_bonus_positions_kernel(const KbBonusOperand* __restrict__ ops, const int* __r
                         }
                         my_alo = a;
                 }
-                const int cnt = min(32, nmem - mb);
+                const int cnt = min(32, m_end - mb);
                 // ---- members in sip order; lane = residue a_lo + lane, then lane = column ----
 #pragma unroll 4
                 for (int i = 0; i < cnt; i++) {
@@ -203,25 +220,55 @@ kb_bonus_positions_kernel(const KbBonusOperand* __restrict__ ops, const int* __r
                                         const int mine = in ? map0[(size_t)k * len] : -1;
                                         const int apos = __shfl_sync(0xffffffffu, mine, src);
                                         if (has && apos >= 0) {
-                                                if (total[k] == 0) best[k] = apos;
-                                                total[k]++;
-                                                if (apos == best[k]) agree[k]++;
+                                                if (PASS == 0) {
+                                                        if (count[k] == 0) { best[k] = apos; first_m[k] = mb + i; }
+                                                        count[k]++;
+                                                } else {
+                                                        if (apos == best[k]) count[k]++;
+                                                }
                                         }
                                 }
                         }
                 }
         }
         if (c < O.len) {
-                int* __restrict__ pos = O.pos;        // [K][len]
-                float* __restrict__ conf = O.conf;
 #pragma unroll
                 for (int k = 0; k < KMAX; k++) {
-                        if (k < K) {
-                                const bool ok = total[k] > 0 && agree[k] > 0;
-                                pos[(size_t)k * O.len + c] = ok ? best[k] : -1;
-                                conf[(size_t)k * O.len + c] = ok ? ((float)agree[k] / (float)total[k]) : 0.0f;
+                        if (k < K && count[k] > 0) {
+                                const long long slot = VO.vote0 + (long long)k * O.len + c;
+                                if (PASS == 0) {
+                                        atomicMin(vkey + slot, ((unsigned long long)(unsigned)first_m[k] << 32) | (unsigned long long)(unsigned)best[k]);
+                                        atomicAdd(vtotal + slot, count[k]);
+                                } else {
+                                        atomicAdd(vagree + slot, count[k]);
+                                }
                         }
                 }
+        }
+}
+
+__global__ void kb_bonus_votes_final_kernel(const KbBonusOperand* __restrict__ ops, const KbVoteOp* __restrict__ vops, const int nvops,
+                                            const long long total_cols, const int K,
+                                            const unsigned long long* __restrict__ vkey, const int* __restrict__ vtotal,
+                                            const int* __restrict__ vagree)
+{
+        const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        if (gid >= total_cols) return;
+        int lo = 0, hi = nvops - 1;
+        while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (vops[mid].col0 <= gid) lo = mid; else hi = mid - 1;
+        }
+        const KbVoteOp VO = vops[lo];
+        const KbBonusOperand O = ops[VO.op];
+        const int c = (int)(gid - VO.col0);
+        for (int k = 0; k < K; k++) {
+                const long long slot = VO.vote0 + (long long)k * O.len + c;
+                const unsigned long long key = vkey[slot];
+                const int total = vtotal[slot], agree = vagree[slot];
+                const bool ok = (key != ~0ull) && total > 0 && agree > 0;
+                O.pos[(size_t)k * O.len + c] = ok ? (int)(unsigned)(key & 0xffffffffull) : -1;
+                O.conf[(size_t)k * O.len + c] = ok ? ((float)agree / (float)total) : 0.0f;
         }
 }
 
@@ -416,30 +463,42 @@ int kb_weave_level(kb200_ctx* ctx, KbSeqs& S, const KbWeaveTask* d_tasks, int nt
 int kb_bonus_level(kb200_ctx* ctx, KbSeqs& S, int K, float paw,
                    const KbBonusOperand* d_ops,
                    const int* d_small_list, const long long* d_small_prefix, int n_small, long long small_cols,
-                   const int* d_large_list, const long long* d_large_prefix, int n_large, long long large_cols,
+                   const KbVoteOp* d_vops, int n_large, long long large_units, long long large_cols, long long vote_slots,
                    const int* d_memb, const int* d_colof, const int* d_posmaps,
                    const KbBonusTask* d_tasks, const long long* d_colb_prefix, long long colb_total,
                    const long long* d_row_prefix, long long row_total, int ntasks, const int* d_aoff)
 {
         if (ntasks <= 0) return KB200_OK;
+        cudaStream_t st = ctx->stream;
         if (n_small > 0) {
-                kb_bonus_positions_small_kernel<<<(unsigned)((small_cols + 127) / 128), 128, 0, ctx->stream>>>(
+                kb_bonus_positions_small_kernel<<<(unsigned)((small_cols + 127) / 128), 128, 0, st>>>(
                         d_ops, d_small_list, d_small_prefix, n_small, small_cols, K, d_memb, S.d_offs.as<int64_t>(), S.d_lens.as<int>(),
                         d_colof, d_posmaps);
                 KB_CUDA(cudaGetLastError());
                 ctx->stats.n_launches++;
         }
         if (n_large > 0) {
-                // large_cols counts 32-column chunks here (one warp each)
-                kb_bonus_positions_kernel<<<(unsigned)((large_cols * 32 + 127) / 128), 128, 0, ctx->stream>>>(
-                        d_ops, d_large_list, d_large_prefix, n_large, large_cols, K, d_memb, S.d_offs.as<int64_t>(), S.d_lens.as<int>(),
-                        d_colof, d_posmaps);
+                // vote scratch: [keys u64 | totals int | agreeing int], one slot per (operand column, anchor)
+                KB_RUN(ctx->t_bvote.ensure((size_t)vote_slots * 16 + 64));
+                unsigned long long* vkey = ctx->t_bvote.as<unsigned long long>();
+                int* vtotal = (int*)(vkey + vote_slots);
+                int* vagree = vtotal + vote_slots;
+                KB_CUDA(cudaMemsetAsync(vkey, 0xFF, (size_t)vote_slots * 8, st));
+                KB_CUDA(cudaMemsetAsync(vtotal, 0, (size_t)vote_slots * 8, st));
+                const unsigned grid = (unsigned)((large_units * 32 + 127) / 128);
+                kb_bonus_votes_kernel<0><<<grid, 128, 0, st>>>(d_ops, d_vops, n_large, large_units, K, d_memb, S.d_offs.as<int64_t>(),
+                                                                 S.d_lens.as<int>(), d_colof, d_posmaps, vkey, vtotal, vagree);
                 KB_CUDA(cudaGetLastError());
-                ctx->stats.n_launches++;
+                kb_bonus_votes_kernel<1><<<grid, 128, 0, st>>>(d_ops, d_vops, n_large, large_units, K, d_memb, S.d_offs.as<int64_t>(),
+                                                                 S.d_lens.as<int>(), d_colof, d_posmaps, vkey, vtotal, vagree);
+                KB_CUDA(cudaGetLastError());
+                kb_bonus_votes_final_kernel<<<(unsigned)((large_cols + 127) / 128), 128, 0, st>>>(d_ops, d_vops, n_large, large_cols, K, vkey, vtotal, vagree);
+                KB_CUDA(cudaGetLastError());
+                ctx->stats.n_launches += 3;
         }
-        kb_bonus_inverse_kernel<<<(unsigned)((colb_total + 127) / 128), 128, 0, ctx->stream>>>(d_tasks, d_colb_prefix, ntasks, colb_total, K, d_aoff);
+        kb_bonus_inverse_kernel<<<(unsigned)((colb_total + 127) / 128), 128, 0, st>>>(d_tasks, d_colb_prefix, ntasks, colb_total, K, d_aoff);
         KB_CUDA(cudaGetLastError());
-        kb_bonus_scatter_kernel<<<(unsigned)((row_total + 127) / 128), 128, 0, ctx->stream>>>(d_tasks, d_row_prefix, ntasks, row_total, K, d_aoff, paw);
+        kb_bonus_scatter_kernel<<<(unsigned)((row_total + 127) / 128), 128, 0, st>>>(d_tasks, d_row_prefix, ntasks, row_total, K, d_aoff, paw);
         KB_CUDA(cudaGetLastError());
         ctx->stats.n_launches += 2;
         return KB200_OK;

@@ -34,13 +34,25 @@ struct KbBonusTask {
 int kb_bonus_init_state(kb200_ctx* ctx, KbSeqs& S, int* d_gaps, int* d_colof);
 int kb_weave_level(kb200_ctx* ctx, KbSeqs& S, const KbWeaveTask* d_tasks, int ntasks,
                    const KbWeaveMember* d_members, int nmembers, int* d_gaps, int* d_colof);
+// one many-member operand of the sliced vote kernels (kb_bonus_votes_kernel)
+struct KbVoteOp {
+        int op;              // index into the level's operand array
+        int nchunks;         // 32-column chunks
+        int nslices;         // slices of KB_BONUS_VOTE_SLICE members
+        int pad;
+        long long unit0;     // first (chunk, slice) work unit of this operand
+        long long vote0;     // first slot of the vote scratch (K * len slots)
+        long long col0;      // first column in the concatenated column space of these operands
+};
+#define KB_BONUS_VOTE_SLICE 64
+
 // operands with at most KB_BONUS_SMALL_NMEM members go to the thread-per-column kernel (small list),
-// the others to the warp-per-column kernel (large list); prefixes are per list
+// the others to the sliced warp kernels (vops)
 #define KB_BONUS_SMALL_NMEM 16
 int kb_bonus_level(kb200_ctx* ctx, KbSeqs& S, int K, float paw,
                    const KbBonusOperand* d_ops,
                    const int* d_small_list, const long long* d_small_prefix, int n_small, long long small_cols,
-                   const int* d_large_list, const long long* d_large_prefix, int n_large, long long large_cols,
+                   const KbVoteOp* d_vops, int n_large, long long large_units, long long large_cols, long long vote_slots,
                    const int* d_memb, const int* d_colof, const int* d_posmaps,
                    const KbBonusTask* d_tasks, const long long* d_colb_prefix, long long colb_total,
                    const long long* d_row_prefix, long long row_total, int ntasks, const int* d_aoff);

@@ -125,7 +125,7 @@ struct kb200_ctx {
         KbDevBuf d_stage0, d_stage1, d_stage2, d_stage3, d_stage4, d_stage5;
         // progressive alignment (kb_tree.cu)
         KbDevBuf t_subm, t_leaf, t_gapset, t_prefix, t_raw, t_coded, t_scr, t_pjobs, t_mjobs, t_src, t_bonus, t_bidx, t_bval, t_posmaps,
-                 t_gaps, t_colof, t_aoff, t_bpos, t_bconf, t_binv, t_bdesc, t_wp, t_wdesc, t_alen;
+                 t_gaps, t_colof, t_aoff, t_bpos, t_bconf, t_binv, t_bdesc, t_wp, t_wdesc, t_alen, t_bvote;
         const void* posmaps_tag = nullptr;   // host array currently mirrored in t_posmaps
         size_t posmaps_n = 0;
         KbArena arena;

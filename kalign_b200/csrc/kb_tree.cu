@@ -606,29 +606,39 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                                 colb_prefix[(size_t)(q - q0)] = colb_total; colb_total += clen[q];
                                 row_prefix[(size_t)(q - q0)] = row_total; row_total += rlen[q];
                         }
-                        // operands by member count: thread-per-column kernel (few members) / warp-per-column
-                        std::vector<int> small_list, large_list;
-                        std::vector<long long> small_prefix, large_prefix;
-                        long long small_cols = 0, large_cols = 0;
+                        // operands by member count: thread-per-column kernel (few members) / sliced warp kernels
+                        std::vector<int> small_list;
+                        std::vector<long long> small_prefix;
+                        std::vector<KbVoteOp> vops;
+                        long long small_cols = 0, large_units = 0, large_cols = 0, vote_slots = 0;
                         for (size_t o = 0; o < ops.size(); o++) {
-                                if (ops[o].m1 - ops[o].m0 <= KB_BONUS_SMALL_NMEM) {
+                                const int nmem = ops[o].m1 - ops[o].m0;
+                                if (nmem <= KB_BONUS_SMALL_NMEM) {
                                         small_list.push_back((int)o); small_prefix.push_back(small_cols); small_cols += ops[o].len;
                                 } else {
-                                        large_list.push_back((int)o); large_prefix.push_back(large_cols); large_cols += (ops[o].len + 31) / 32;   // 32-column chunks
+                                        KbVoteOp v;
+                                        v.op = (int)o;
+                                        v.nchunks = (ops[o].len + 31) / 32;
+                                        v.nslices = (nmem + KB_BONUS_VOTE_SLICE - 1) / KB_BONUS_VOTE_SLICE;
+                                        v.pad = 0;
+                                        v.unit0 = large_units; large_units += (long long)v.nchunks * v.nslices;
+                                        v.vote0 = vote_slots; vote_slots += (long long)K * ops[o].len;
+                                        v.col0 = large_cols; large_cols += ops[o].len;
+                                        vops.push_back(v);
                                 }
                         }
                         (void)op_cols;
-                        TR(ctx->t_bdesc.ensure(sizeof(int) * (memb.size() + 2 * ops.size()) + sizeof(KbBonusOperand) * ops.size() + sizeof(KbBonusTask) * btasks.size() +
+                        TR(ctx->t_bdesc.ensure(sizeof(int) * (memb.size() + ops.size()) + sizeof(KbBonusOperand) * ops.size() + sizeof(KbBonusTask) * btasks.size() +
+                                               sizeof(KbVoteOp) * vops.size() +
                                                sizeof(long long) * (op_prefix.size() + colb_prefix.size() + row_prefix.size()) + 256));
                         char* base = ctx->t_bdesc.as<char>();
                         KbBonusOperand* d_ops = (KbBonusOperand*)base; base += sizeof(KbBonusOperand) * ops.size();
                         KbBonusTask* d_bt = (KbBonusTask*)base; base += sizeof(KbBonusTask) * btasks.size();
+                        KbVoteOp* d_vops = (KbVoteOp*)base; base += sizeof(KbVoteOp) * vops.size();
                         long long* d_smp = (long long*)base; base += sizeof(long long) * small_prefix.size();
-                        long long* d_lgp = (long long*)base; base += sizeof(long long) * large_prefix.size();
                         long long* d_cbp = (long long*)base; base += sizeof(long long) * colb_prefix.size();
                         long long* d_rwp = (long long*)base; base += sizeof(long long) * row_prefix.size();
                         int* d_sml = (int*)base; base += sizeof(int) * small_list.size();
-                        int* d_lgl = (int*)base; base += sizeof(int) * large_list.size();
                         int* d_memb = (int*)base;
                         TC(cudaMemcpyAsync(d_ops, ops.data(), sizeof(KbBonusOperand) * ops.size(), cudaMemcpyHostToDevice, st));
                         TC(cudaMemcpyAsync(d_bt, btasks.data(), sizeof(KbBonusTask) * btasks.size(), cudaMemcpyHostToDevice, st));
@@ -636,9 +646,8 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                                 TC(cudaMemcpyAsync(d_smp, small_prefix.data(), sizeof(long long) * small_prefix.size(), cudaMemcpyHostToDevice, st));
                                 TC(cudaMemcpyAsync(d_sml, small_list.data(), sizeof(int) * small_list.size(), cudaMemcpyHostToDevice, st));
                         }
-                        if (!large_list.empty()) {
-                                TC(cudaMemcpyAsync(d_lgp, large_prefix.data(), sizeof(long long) * large_prefix.size(), cudaMemcpyHostToDevice, st));
-                                TC(cudaMemcpyAsync(d_lgl, large_list.data(), sizeof(int) * large_list.size(), cudaMemcpyHostToDevice, st));
+                        if (!vops.empty()) {
+                                TC(cudaMemcpyAsync(d_vops, vops.data(), sizeof(KbVoteOp) * vops.size(), cudaMemcpyHostToDevice, st));
                         }
                         TC(cudaMemcpyAsync(d_cbp, colb_prefix.data(), sizeof(long long) * colb_prefix.size(), cudaMemcpyHostToDevice, st));
                         TC(cudaMemcpyAsync(d_rwp, row_prefix.data(), sizeof(long long) * row_prefix.size(), cudaMemcpyHostToDevice, st));
@@ -646,7 +655,7 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                         TC(cudaMemsetAsync(ctx->t_binv.p, 0xFF, sizeof(int) * inv_per_task * (size_t)ntm, st));
                         TR(kb_bonus_level(ctx, S, K, T.weight / (float)K, d_ops,
                                           d_sml, d_smp, (int)small_list.size(), small_cols,
-                                          d_lgl, d_lgp, (int)large_list.size(), large_cols,
+                                          d_vops, (int)vops.size(), large_units, large_cols, vote_slots,
                                           d_memb, d_colof, d_posmaps,
                                           d_bt, d_cbp, colb_total, d_rwp, row_total, ntm, ctx->t_aoff.as<int>()));
                         TC(cudaStreamSynchronize(st));     // host descriptor vectors go out of scope
