@@ -121,6 +121,10 @@ int kb200_anchor_posmaps(kb200_ctx* ctx, const kb200_params* prm,
                          const int* anchor_ids, int K,
                          long long pair_begin, long long pair_end, int* posmaps);
 
+/* Anchor choice of anchor_consistency_build (static select_anchors, anchor_consistency.c:124-198):
+   K diverse sequences by farthest-point sampling on seq_distances.  Host-only. */
+int kb200_select_anchors(const float* seq_distances, int nseq, int K, int* anchor_ids);
+
 /* Progressive alignment over a guide tree (create_msa_tree, aln_run.c:43).
    tasks_abc: ntasks x 3 (a, b, c) sorted by c (task.c:151-161); seq_distances: nseq floats
    (bisectingKmeans.c:247-256) or NULL; posmaps/K/weight: consistency table or NULL/0.

@@ -46,7 +46,7 @@ class Stats(C.Structure):
 # every symbol include/kalign_b200.h declares
 EXPORTS = ["kb200_device_count", "kb200_ctx_create", "kb200_ctx_destroy", "kb200_get_stats",
            "kb200_version", "kb200_params_init", "kb200_pair_align_batch", "kb200_distances",
-           "kb200_anchor_posmaps", "kb200_align_tree", "kb200_kalign",
+           "kb200_anchor_posmaps", "kb200_select_anchors", "kb200_align_tree", "kb200_kalign",
            "kb200_msa_create", "kb200_msa_align", "kb200_msa_result", "kb200_msa_info", "kb200_msa_free",
            "kb200_comm_unique_id", "kb200_ctx_comm_init", "kb200_ctx_comm_destroy", "kb200_partition"]
 
@@ -95,6 +95,8 @@ def load():
     lib.kb200_anchor_posmaps.argtypes = [C.c_void_p, C.POINTER(Params), u8p, i64p, i32p, C.c_int,
                                          i32p, C.c_int, C.c_longlong, C.c_longlong, i32p]
     lib.kb200_anchor_posmaps.restype = C.c_int
+    lib.kb200_select_anchors.argtypes = [f32p, C.c_int, C.c_int, i32p]
+    lib.kb200_select_anchors.restype = C.c_int
     lib.kb200_align_tree.argtypes = [C.c_void_p, C.POINTER(Params), u8p, i64p, i32p, C.c_int,
                                      i32p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float, i32p]
     lib.kb200_align_tree.restype = C.c_int

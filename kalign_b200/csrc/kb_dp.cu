@@ -325,7 +325,8 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                             const bool first_term, const bool last_term,
                             const Trip in, float4* __restrict__ rowbuf,
                             const unsigned in_tag, const unsigned out_tag,
-                            const float* __restrict__ s_tbl, const int tstride, const int lane, float4* s_ring, int2* s_bon)
+                            const float* __restrict__ s_tbl, const int tstride, const int lane, float4* s_ring, float4* s_rec,
+                            int2* s_bon)
 {
         static_assert(BONUS != BONUS_SPARSE || K <= BON_KMAX_ROWS, "bonus staging area is sized for K <= 4");
         constexpr int NA = VTraits<V>::NA;
@@ -344,19 +345,15 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
         float genA = in.a, genGA = in.ga;   // init-row generator (strip 0, lane 0)
         float prevCO = 0.0f;                // PP: [27] of the column visited one step earlier
         const bool gen = (in_tag == 0u);
-        // Hand-off read side.  Thick strips (K > 1) run with many co-resident warps: lane 0 reads the
-        // row above one column ahead (ld.volatile into a register, validated by its tag when used).
-        // Thin strips (K == 1) are run by a LONE warp per scheduler (one big box spread over the
-        // machine), so the L2 latency of the hand-off must be hidden inside the warp: lane 0 streams
-        // the row above through a shared-memory ring with cp.async (global -> shared, no register
-        // is tied to the in-flight load, so nothing stalls on it), RLEAD columns ahead of its use;
-        // the entry is moved ring -> register one step before it is consumed.  An entry that was
-        // copied before the producer wrote it fails its tag check and is re-read by polling.
-        constexpr bool RING = (K == 1);
-        constexpr int RDEPTH = 16;               // ring slots (power of two, > RLEAD)
-        constexpr int RLEAD = 8;                 // columns of read-ahead
-        float4 pre0 = make_float4(0.f, 0.f, 0.f, 0.f);
-        // speculative read (no wait), validated by its tag when it is used
+        // Hand-off read side.  The row above is pulled in BLOCKS of HB columns, well ahead of its use:
+        // column c is loaded by lane (c & 31) (ld.volatile.v4 into a register: a coalesced 128-byte
+        // request per block), validated by its tag every HB steps (warp-uniform poll), and
+        // committed to a 64-column shared-memory ring from which lane 0 takes one entry per step
+        // (broadcast LDS).  Four blocks are in flight (24..32 steps of read-ahead), so that neither
+        // the L2 latency nor the poll sits on the per-step path -- which is what bounds a warp that
+        // runs alone on its scheduler (few big boxes: top of the guide tree, long sequences).
+        constexpr int HB = 8;
+        float4 blk = make_float4(0.f, 0.f, 0.f, 0.f);
         auto peek_above = [&](const int col) -> float4 {
                 float4 v;
                 const float4* p = rowbuf + col;
@@ -366,44 +363,65 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                              : "memory");
                 return v;
         };
-        auto fetch_above = [&](const int col) -> float4 {
-                float4 v;
-                do {
-                        v = peek_above(col);
-                } while (__float_as_uint(v.w) != in_tag);
-                return v;
-        };
-        const unsigned ring_base = RING ? (unsigned)__cvta_generic_to_shared(s_ring) : 0u;
-        auto ring_issue = [&](const int col) {
-                // one commit group per column, empty past the end of the row
-                if (col <= C) {
-                        const unsigned dst = ring_base + (unsigned)((col & (RDEPTH - 1)) * 16);
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(rowbuf + col) : "memory");
-                }
-                asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        auto ring_take = [&](const int col) -> float4 {
-                // the group of column `col` is the RLEAD-th youngest: all but RLEAD-1 groups complete
-                float4 v;
-                asm volatile("cp.async.wait_group %0;" ::"n"(RLEAD - 1) : "memory");
-                const unsigned src = ring_base + (unsigned)((col & (RDEPTH - 1)) * 16);
-                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                             : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                             : "r"(src)
-                             : "memory");
-                return v;
-        };
-        if (!gen && lane == 0) {
-                if constexpr (RING) {
-#pragma unroll
-                        for (int c = 0; c < RLEAD; c++) {
-                                ring_issue(c);
-                        }
-                        pre0 = ring_take(0);
-                } else {
-                        pre0 = fetch_above(0);
-                }
+        if (!gen && lane <= C) {
+                blk = peek_above(lane);
         }
+        // Column records of 5-letter profile-profile sweeps go through a 64-column shared-memory
+        // ring as well (cp.async, 16 columns at a time, a block ahead): the per-step record read is
+        // an LDS.128 pair instead of an L1-missing global load every fourth column.
+        constexpr bool RECRING = (NA > 0 && NA <= 5);
+        float4* const s_recA = s_rec;
+        float4* const s_recB = s_rec + 64;
+        auto rec_issue = [&](const int col0, const int ncols) {
+                if constexpr (RECRING) {
+                        const int col = col0 + (lane >> 1);
+                        const int half = lane & 1;
+                        if ((lane >> 1) < ncols && col <= C) {
+                                const long long ridx = bwd ? (long long)(eb - col + 1) : (long long)(sb + col);
+                                const float4* src = reinterpret_cast<const float4*>(J.cpack) + ridx * 2 + half;
+                                const unsigned dst = (unsigned)__cvta_generic_to_shared((half ? s_recB : s_recA) + (col & 63));
+                                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                        }
+                }
+        };
+        auto rec_wait = [&]() {
+                if constexpr (RECRING) {
+                        asm volatile("cp.async.wait_all;" ::: "memory");
+                        __syncwarp();
+                }
+        };
+        // every HB steps (t % HB == 0): commit the hand-off block of columns t .. t+HB-1 and start
+        // the load of the block 32 columns further; every 16 steps the same for the record ring
+        auto boundary = [&](const int t) {
+                if (!gen && t <= C) {
+                        const bool mine = (lane >> 3) == ((t >> 3) & 3);
+                        const int col = t + (lane & 7);
+                        const bool need = mine && (col <= C);
+                        while (true) {
+                                const bool ok = !need || (__float_as_uint(blk.w) == in_tag);
+                                if (__all_sync(FULL, ok)) {
+                                        break;
+                                }
+                                if (!ok) {
+                                        blk = peek_above(col);
+                                }
+                        }
+                        if (need) {
+                                s_ring[col & 63] = blk;
+                        }
+                        __syncwarp();
+                        if (mine && col + 32 <= C) {
+                                blk = peek_above(col + 32);
+                        }
+                }
+                if constexpr (RECRING) {
+                        if ((t & 15) == 0 && t > 0) {
+                                rec_wait();                      // columns t+1 .. t+16 (issued 16 steps ago)
+                                rec_issue(t + 17, 16);           // slots of columns t-47 .. t-32: last read at step t-2
+                        }
+                }
+        };
+        static_assert(HB == 8, "lane groups of 8");
         const int steps = C + 32;
         // column input of the current step (filled one step ahead); lane 0 starts on column 0 at t=0
         float4 curA = make_float4(0.f, 0.f, 0.f, 0.f), curB = curA;
@@ -427,15 +445,15 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                         sparse_init<V, K, true>(J, bwd, sb, eb, rc, my_bon, sp_i, sp_c, sp_v, sp_wrap);
                 }
         }
-        if constexpr (NA > 0 && NA <= 5) {
+        if constexpr (RECRING) {
                 static_assert(PACK5 == 8, "PP5 record is two float4");
-                if (lane == 0) {
-                        const int j0 = bwd ? eb : sb;
-                        const int r0c = bwd ? j0 : (j0 - 1);
-                        const float4* __restrict__ rec = reinterpret_cast<const float4*>(J.cpack) + (size_t)(r0c + 1) * PW4;
-                        curA = __ldg(rec);
-                        curB = __ldg(rec + 1);
-                }
+                rec_issue(0, 16);
+                rec_issue(16, 16);
+                rec_issue(32, 1);
+                rec_wait();
+                // lane 0 is on column 0 at step 0; the other lanes read their column 0 one step ahead
+                curA = s_recA[0];
+                curB = s_recB[0];
         }
         // running pointers instead of per-step index arithmetic: the column visited NEXT (pu = u+1;
         // 1-lane at t=0) and the state column of the current u
@@ -444,9 +462,9 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
         const long long pr_first = bwd ? (long long)(eb - (1 - lane)) : (long long)(sb + (1 - lane)) - 1;
         const float4* recp = nullptr;          // packed record of the next column (PP)
         const uint8_t* seqp = nullptr;         // residue of the next column (SS, SP)
-        if constexpr (NA > 0) {
+        if constexpr (NA > 5) {
                 recp = reinterpret_cast<const float4*>(J.cpack) + (pr_first + 1) * PW4;
-        } else {
+        } else if constexpr (NA == 0) {
                 seqp = J.seq_c + pr_first;
         }
         // one step of the wavefront.  STEADY (32 <= t <= C-1): every lane is on an interior column
@@ -454,6 +472,11 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
         auto step = [&](auto steady_tag, const int t) {
                 constexpr bool STEADY = decltype(steady_tag)::value;
                 const int u = t - lane;
+                // row above, column t, for lane 0 (consumer strips): committed by boundary()
+                float4 hin = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (!gen) {
+                        hin = s_ring[t & 63];
+                }
                 Trip up;
                 up.a = __shfl_up_sync(FULL, bot.a, 1);
                 up.ga = __shfl_up_sync(FULL, bot.ga, 1);
@@ -464,25 +487,14 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                 constexpr bool PREF = (NA <= 5);   // 23-letter records are loaded in-step (register budget)
                 float4 nxtA = make_float4(0.f, 0.f, 0.f, 0.f), nxtB = nxtA;   // PP5 record = 2 x float4
                 int ncres = 0;
-                if constexpr (K == 1 && NA > 0) {
-                        // thin strips: pull the far-ahead column record towards L1 (no register cost)
-                        const int fu = u + 8;
-                        if (fu >= 1 && fu <= C) {
-                                const float4* fq = recp + 7 * dstep * PW4;
-                                asm volatile("prefetch.global.L1 [%0];" ::"l"(fq));
-                        }
-                }
-                if constexpr (PREF) {
+                if constexpr (RECRING) {
+                        // ring slot of column u+1 (lanes outside the box read a slot they never use)
+                        nxtA = s_recA[(u + 1) & 63];
+                        nxtB = s_recB[(u + 1) & 63];
+                } else if constexpr (PREF) {
                         const int pu = u + 1;
-                        if (STEADY || (pu >= 0 && pu <= C)) {
-                                if constexpr (NA > 0) {
-                                        nxtA = __ldg(recp);
-                                        nxtB = __ldg(recp + 1);
-                                } else {
-                                        if (STEADY || pu >= 1) {
-                                                ncres = (int)__ldg(seqp);
-                                        }
-                                }
+                        if (STEADY || (pu >= 1 && pu <= C)) {
+                                ncres = (int)__ldg(seqp);
                         }
                 }
                 if (act) {
@@ -539,18 +551,7 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                                                 up.a = KB_NEGF; up.ga = KB_NEGF; up.gb = KB_NEGF;
                                         }
                                 } else {
-                                        if (__float_as_uint(pre0.w) != in_tag) {
-                                                pre0 = fetch_above(u);       // the early read raced the producer: wait
-                                        }
-                                        up.a = pre0.x; up.ga = pre0.y; up.gb = pre0.z;
-                                        if constexpr (RING) {
-                                                ring_issue(u + RLEAD);
-                                                pre0 = ring_take(u + 1);     // consumed by the next step
-                                        } else {
-                                                if (u + 1 <= C) {
-                                                        pre0 = peek_above(u + 1);
-                                                }
-                                        }
+                                        up.a = hin.x; up.ga = hin.y; up.gb = hin.z;
                                 }
                         }
                         const Trip got = up;
@@ -574,9 +575,9 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                         curB = nxtB;
                 }
                 jcur += dstep;
-                if constexpr (NA > 0) {
+                if constexpr (NA > 5) {
                         recp += dstep * PW4;
-                } else {
+                } else if constexpr (NA == 0) {
                         seqp += dstep;
                 }
                 if (lane == 31) {
@@ -590,12 +591,22 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                 int t = 0;
                 const int t_fill = (steps < 32) ? steps : 32;
                 for (; t < t_fill; t++) {
+                        if ((t & (HB - 1)) == 0) {
+                                boundary(t);
+                        }
                         step(std::false_type{}, t);
                 }
-                for (; t < C; t++) {            // 32 <= t <= C-1
-                        step(std::true_type{}, t);
+                while (t < C) {                 // 32 <= t <= C-1, in runs of HB steps
+                        boundary(t);
+                        const int te = (t + HB < C) ? (t + HB) : C;
+                        for (; t < te; t++) {
+                                step(std::true_type{}, t);
+                        }
                 }
                 for (; t < steps; t++) {
+                        if ((t & (HB - 1)) == 0) {
+                                boundary(t);
+                        }
                         step(std::false_type{}, t);
                 }
         }
@@ -605,7 +616,7 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
 template <int V, int BONUS>
 __device__ void sweep_unit(const KbJob& J, const KbBox& bx, const int bwd, const int strip, const int thin,
                            const unsigned tag_base, const float* __restrict__ s_tbl, const int tstride, const int lane,
-                           float4* s_ring, int2* s_bon)
+                           float4* s_ring, float4* s_rec, int2* s_bon)
 {
         const int mid = (bx.ea - bx.sa) / 2 + bx.sa;
         const int r0 = bwd ? mid : bx.sa;
@@ -629,20 +640,20 @@ __device__ void sweep_unit(const KbJob& J, const KbBox& bx, const int bwd, const
         const unsigned mine = tag_base + (unsigned)strip + 1u;
         const int rem = R - row0;
         if (rps == 32) {
-                sweep_strip<V, 1, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_bon);
+                sweep_strip<V, 1, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
         } else if constexpr (V == V_PP23) {
-                if (rem >= 64) sweep_strip<V, 2, false, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_bon);
-                else if (rem > 32) sweep_strip<V, 2, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_bon);
-                else sweep_strip<V, 1, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_bon);
+                if (rem >= 64) sweep_strip<V, 2, false, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
+                else if (rem > 32) sweep_strip<V, 2, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
+                else sweep_strip<V, 1, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
         } else if constexpr (V == V_SS && !BONUS) {
-                if (rem >= 256) sweep_strip<V, 8, false, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_bon);
-                else if (rem > 128) sweep_strip<V, 8, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_bon);
-                else if (rem > 32) sweep_strip<V, 4, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_bon);
-                else sweep_strip<V, 1, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_bon);
+                if (rem >= 256) sweep_strip<V, 8, false, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
+                else if (rem > 128) sweep_strip<V, 8, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
+                else if (rem > 32) sweep_strip<V, 4, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
+                else sweep_strip<V, 1, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
         } else {
-                if (rem >= 128) sweep_strip<V, 4, false, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_bon);
-                else if (rem > 32) sweep_strip<V, 4, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_bon);
-                else sweep_strip<V, 1, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_bon);
+                if (rem >= 128) sweep_strip<V, 4, false, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
+                else if (rem > 32) sweep_strip<V, 4, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
+                else sweep_strip<V, 1, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
         }
 }
 
@@ -657,7 +668,8 @@ kb_sweep_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes,
                 const float* __restrict__ tbl, const int thin, const int tstride)
 {
         __shared__ float s_tbl[TBL_MAX];
-        __shared__ float4 s_ring_all[WARPS_PER_CTA][16];     // thin strips: hand-off read-ahead ring, one per warp
+        __shared__ float4 s_ring_all[WARPS_PER_CTA][64];     // hand-off ring (row above), one per warp
+        __shared__ float4 s_rec_all[WARPS_PER_CTA][128];     // 5-letter column records: two 64-column rings per warp
         for (int i = threadIdx.x; i < TBL_MAX; i += blockDim.x) {
                 s_tbl[i] = tbl[i];
         }
@@ -666,6 +678,7 @@ kb_sweep_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes,
         // sparse bonus lists of the rows of the strip a warp is sweeping (bonus kernel family only)
         __shared__ int2 s_bon_all[(BONUS == BONUS_SPARSE) ? WARPS_PER_CTA * BON_SLOTS * BON_KMAX_ROWS * 32 : 1];
         float4* s_ring = s_ring_all[threadIdx.x >> 5];
+        float4* s_rec = s_rec_all[threadIdx.x >> 5];
         int2* s_bon = (BONUS == BONUS_SPARSE) ? (s_bon_all + (threadIdx.x >> 5) * (BON_SLOTS * BON_KMAX_ROWS * 32)) : s_bon_all;
         const unsigned total = *nunits_p;
         while (true) {
@@ -683,13 +696,13 @@ kb_sweep_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes,
                 const KbJob J = jobs[bx.job];
                 const unsigned ps = tag_base;
                 if (J.kind == KB200_KIND_SS) {
-                        sweep_unit<V_SS, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane, s_ring, s_bon);
+                        sweep_unit<V_SS, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
                 } else if (J.kind == KB200_KIND_SP) {
-                        sweep_unit<V_SP, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane, s_ring, s_bon);
+                        sweep_unit<V_SP, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
                 } else if (J.nalpha <= 5) {
-                        sweep_unit<V_PP5, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane, s_ring, s_bon);
+                        sweep_unit<V_PP5, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
                 } else {
-                        sweep_unit<V_PP23, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane, s_ring, s_bon);
+                        sweep_unit<V_PP23, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
                 }
         }
 }
@@ -1362,10 +1375,13 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
                 }
         }
         {
-                // 4 resident CTAs per SM: the bonus family stages its lists in 36 KB of shared memory per CTA
+                // 4 resident CTAs per SM: 15 KB of rings and tables per CTA, + 32 KB of staged bonus lists
+                // in the bonus family (4 x 48 KB: the whole shared-memory carve-out)
                 static bool carveout_set = false;
                 if (!carveout_set) {
-                        cudaFuncSetAttribute(kb_sweep_kernel<BONUS_SPARSE>, cudaFuncAttributePreferredSharedMemoryCarveout, 70);
+                        cudaFuncSetAttribute(kb_sweep_kernel<BONUS_SPARSE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+                        cudaFuncSetAttribute(kb_sweep_kernel<BONUS_NONE>, cudaFuncAttributePreferredSharedMemoryCarveout, 40);
+                        cudaFuncSetAttribute(kb_sweep_kernel<BONUS_DENSE>, cudaFuncAttributePreferredSharedMemoryCarveout, 40);
                         carveout_set = true;
                 }
         }

@@ -599,6 +599,22 @@ static void encode_seqs(kb200_msa* M, int alpha)
 
 extern "C" {
 
+// host-only helper for a binding that replaces anchor_consistency_build: the reference's anchor
+// choice is a static function (select_anchors, lib/src/anchor_consistency.c:124-198)
+int kb200_select_anchors(const float* seq_distances, int nseq, int K, int* anchor_ids)
+{
+        if (!seq_distances || !anchor_ids || nseq < 1 || K < 1 || K > nseq) {
+                fprintf(stderr, "[kalign_b200] kb200_select_anchors: bad arguments\n");
+                return KB200_FAIL;
+        }
+        std::vector<int> ids;
+        select_anchors(seq_distances, nseq, K, ids);
+        for (int k = 0; k < K; k++) {
+                anchor_ids[k] = ids[(size_t)k];
+        }
+        return KB200_OK;
+}
+
 void kb200_msa_free(kb200_msa* M)
 {
         if (!M) return;
