@@ -1,0 +1,386 @@
+/*
+ * kalign_gpu_seams.c -- the reference-side binding of INTEGRATION.md, built for real.
+ *
+ * This file is the ONE host-side C file a kalign maintainer adds.  It is compiled together with the
+ * reference's own, unmodified lib/src/*.c (in place, see integration/Makefile) and linked with
+ *
+ *     -Wl,--wrap=d_estimation -Wl,--wrap=anchor_consistency_build -Wl,--wrap=create_msa_tree
+ *
+ * so that the three calls kalign_run_seeded() makes into its hot path
+ *
+ *     d_estimation()              lib/src/sequence_distance.c:37   (from bisectingKmeans.c:205,294)
+ *     anchor_consistency_build()  lib/src/anchor_consistency.c:200 (from aln_wrap.c:211)
+ *     create_msa_tree()           lib/src/aln_run.c:43             (from aln_wrap.c:225)
+ *
+ * resolve to the functions below, which flatten struct msa into plain arrays and call the C ABI of
+ * libkalign_b200.so (include/kalign_b200.h).  Everything else -- kalign.h, struct msa, I/O, the
+ * guide tree, parameter handling, finalise_alignment, the CLI -- is the reference's code, untouched.
+ * The result is a libkalign.so.3 + kalign executable that are drop-in for the alignment path.
+ *
+ * There is no CPU fallback: when no CUDA device is usable every seam returns FAIL, and
+ * kalign_run()/kalign() fail with it.  Environment: KALIGN_B200_DEVICE selects the GPU (default 0).
+ *
+ * Not covered (out of scope): --refine all/confident and the inline-refine tree
+ * (create_msa_tree_inline_refine stays the reference's CPU code; the two-pass refinement needs
+ * msa->sip/nsip/plen of the internal nodes, which this seam does not reconstruct).
+ */
+#include <pthread.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef HAVE_AVX2
+#include <xmmintrin.h>
+#include <mm_malloc.h>
+#endif
+
+#include "tldevel.h"
+#include "msa_struct.h"
+#include "task.h"
+#include "aln_param.h"
+#include "anchor_consistency.h"
+
+#include "kalign_b200.h"
+
+static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;   /* d_estimation(pair=1) is called from OpenMP tasks */
+static kb200_ctx* g_ctx = NULL;
+
+/* flat copy of the last consistency table (host): handed to kb200_align_tree without re-packing */
+static struct consistency_table* g_ct_owner = NULL;
+static int* g_posmaps = NULL;
+
+static kb200_ctx* seam_ctx(void)
+{
+        if(!g_ctx){
+                int dev = 0;
+                const char* e = getenv("KALIGN_B200_DEVICE");
+                if(e){
+                        dev = atoi(e);
+                }
+                if(kb200_ctx_create(dev, &g_ctx) != KB200_OK){
+                        g_ctx = NULL;
+                        fprintf(stderr, "[kalign/b200] no usable CUDA device %d: the alignment path has no CPU fallback\n", dev);
+                }
+        }
+        return g_ctx;
+}
+
+struct flat_msa{
+        uint8_t* seqs;
+        int64_t* offs;
+        int* lens;
+        int n;
+};
+
+static void flat_free(struct flat_msa* f)
+{
+        free(f->seqs);
+        free(f->offs);
+        free(f->lens);
+        f->seqs = NULL; f->offs = NULL; f->lens = NULL;
+}
+
+/* msa->sequences[i]->s / ->len (sorted, encoded by convert_msa_to_internal) as one code array */
+static int flatten(struct msa* msa, struct flat_msa* f)
+{
+        int64_t total = 0;
+        int i;
+        f->n = msa->numseq;
+        f->offs = malloc(sizeof(int64_t) * (size_t)f->n);
+        f->lens = malloc(sizeof(int) * (size_t)f->n);
+        f->seqs = NULL;
+        if(!f->offs || !f->lens){
+                flat_free(f);
+                return FAIL;
+        }
+        for(i = 0; i < f->n; i++){
+                f->offs[i] = total;
+                f->lens[i] = msa->sequences[i]->len;
+                total += f->lens[i];
+        }
+        f->seqs = malloc((size_t)total + 1);
+        if(!f->seqs){
+                flat_free(f);
+                return FAIL;
+        }
+        for(i = 0; i < f->n; i++){
+                memcpy(f->seqs + f->offs[i], msa->sequences[i]->s, (size_t)f->lens[i]);
+        }
+        return OK;
+}
+
+static void fill_params(struct msa* msa, struct aln_param* ap, kb200_params* prm)
+{
+        int i, j;
+        for(i = 0; i < 23; i++){
+                for(j = 0; j < 23; j++){
+                        prm->subm[i * 23 + j] = ap->subm[i][j];
+                }
+        }
+        prm->gpo = ap->gpo;
+        prm->gpe = ap->gpe;
+        prm->tgpe = ap->tgpe;
+        prm->vsm_amax = ap->vsm_amax;
+        prm->nalpha = (msa->biotype == ALN_BIOTYPE_DNA) ? 5 : 23;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * d_estimation (sequence_distance.c:37): pair == 0 -> numseq rows x num_samples (rows padded to a
+ * multiple of 8 floats, 32-byte aligned under AVX2, freed row by row by the caller); pair == 1 ->
+ * galloc'd num_samples x num_samples matrix (freed with gfree), where the reference's double loop
+ * leaves dm[i][j] = dm[j][i] = calc_distance(seq[max(i,j)], seq[min(i,j)]) + length term. */
+float** __wrap_d_estimation(struct msa* msa, int* samples, int num_samples, int pair)
+{
+        float** dm = NULL;
+        float* flat = NULL;
+        int* rows = NULL;
+        struct flat_msa f = {NULL, NULL, NULL, 0};
+        kb200_ctx* ctx = NULL;
+        int numseq = msa->numseq;
+        int i, j;
+        int rc;
+
+        pthread_mutex_lock(&g_lock);
+        ctx = seam_ctx();
+        if(!ctx || flatten(msa, &f) != OK){
+                pthread_mutex_unlock(&g_lock);
+                goto ERROR;
+        }
+        if(pair){
+                flat = malloc(sizeof(float) * (size_t)num_samples * (size_t)num_samples);
+                rc = flat ? kb200_distances(ctx, f.seqs, f.offs, f.lens, numseq, samples, num_samples, samples, num_samples, flat) : KB200_FAIL;
+        }else{
+                rows = malloc(sizeof(int) * (size_t)numseq);
+                flat = malloc(sizeof(float) * (size_t)numseq * (size_t)num_samples);
+                if(rows){
+                        for(i = 0; i < numseq; i++){
+                                rows[i] = i;
+                        }
+                }
+                rc = (rows && flat) ? kb200_distances(ctx, f.seqs, f.offs, f.lens, numseq, rows, numseq, samples, num_samples, flat) : KB200_FAIL;
+        }
+        pthread_mutex_unlock(&g_lock);
+        if(rc != KB200_OK){
+                goto ERROR;
+        }
+        if(pair){
+                RUN(galloc(&dm, num_samples, num_samples));
+                for(i = 0; i < num_samples; i++){
+                        for(j = 0; j <= i; j++){
+                                float v = flat[(size_t)i * (size_t)num_samples + (size_t)j];
+                                dm[i][j] = v;
+                                dm[j][i] = v;
+                        }
+                }
+        }else{
+                int a = num_samples / 8;
+                if(num_samples % 8){
+                        a++;
+                }
+                a = a << 3;
+                MMALLOC(dm, sizeof(float*) * numseq);
+                for(i = 0; i < numseq; i++){
+                        dm[i] = NULL;
+                }
+                for(i = 0; i < numseq; i++){
+#ifdef HAVE_AVX2
+                        dm[i] = _mm_malloc(sizeof(float) * a, 32);
+#else
+                        MMALLOC(dm[i], sizeof(float) * a);
+#endif
+                        if(!dm[i]){
+                                goto ERROR;
+                        }
+                        for(j = 0; j < num_samples; j++){
+                                dm[i][j] = flat[(size_t)i * (size_t)num_samples + (size_t)j];
+                        }
+                        for(j = num_samples; j < a; j++){
+                                dm[i][j] = 0.0F;
+                        }
+                }
+        }
+        free(flat);
+        free(rows);
+        flat_free(&f);
+        return dm;
+ERROR:
+        free(flat);
+        free(rows);
+        flat_free(&f);
+        return NULL;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * anchor_consistency_build (anchor_consistency.c:200): same table, same ownership (every map is
+ * its own allocation, released by anchor_consistency_free); the N x K pairwise alignments run as
+ * one batch on the GPU. */
+int __wrap_anchor_consistency_build(struct msa* msa, struct aln_param* ap, int n_anchors, float weight,
+                                    struct consistency_table** ct_out)
+{
+        struct consistency_table* ct = NULL;
+        struct flat_msa f = {NULL, NULL, NULL, 0};
+        kb200_params prm;
+        kb200_ctx* ctx = NULL;
+        int* posmaps = NULL;
+        int N = msa->numseq;
+        int K = n_anchors;
+        int i, k;
+        int64_t total = 0;
+
+        if(K <= 0 || N < 3){
+                *ct_out = NULL;
+                return OK;
+        }
+        if(K > N){
+                K = N;
+        }
+        if(msa->seq_distances == NULL){
+                *ct_out = NULL;
+                return OK;
+        }
+        ctx = seam_ctx();
+        if(!ctx){
+                *ct_out = NULL;
+                return FAIL;
+        }
+        MMALLOC(ct, sizeof(struct consistency_table));
+        ct->pos_maps = NULL;
+        ct->map_lengths = NULL;
+        ct->anchor_ids = NULL;
+        ct->n_anchors = K;
+        ct->numseq = N;
+        ct->weight = weight;
+        MMALLOC(ct->anchor_ids, sizeof(int) * K);
+        MMALLOC(ct->pos_maps, sizeof(int*) * N * K);
+        MMALLOC(ct->map_lengths, sizeof(int) * N * K);
+        for(i = 0; i < N * K; i++){
+                ct->pos_maps[i] = NULL;
+                ct->map_lengths[i] = 0;
+        }
+        if(kb200_select_anchors(msa->seq_distances, N, K, ct->anchor_ids) != KB200_OK){
+                goto ERROR;
+        }
+        if(!msa->quiet){
+                LOG_MSG("Anchor consistency: K=%d, weight=%.1f (GPU batch)", K, weight);
+        }
+        RUN(flatten(msa, &f));
+        fill_params(msa, ap, &prm);
+        for(i = 0; i < N; i++){
+                total += f.lens[i];
+        }
+        posmaps = malloc(sizeof(int) * (size_t)total * (size_t)K + sizeof(int));
+        if(!posmaps){
+                goto ERROR;
+        }
+        if(kb200_anchor_posmaps(ctx, &prm, f.seqs, f.offs, f.lens, N, ct->anchor_ids, K, 0, (long long)N * K, posmaps) != KB200_OK){
+                goto ERROR;
+        }
+        for(i = 0; i < N; i++){
+                for(k = 0; k < K; k++){
+                        const int len_i = f.lens[i];
+                        ct->map_lengths[i * K + k] = len_i;
+                        MMALLOC(ct->pos_maps[i * K + k], sizeof(int) * (len_i > 0 ? len_i : 1));
+                        memcpy(ct->pos_maps[i * K + k], posmaps + (size_t)K * (size_t)f.offs[i] + (size_t)k * (size_t)len_i,
+                               sizeof(int) * (size_t)len_i);
+                }
+        }
+        /* keep the flat copy for create_msa_tree */
+        free(g_posmaps);
+        g_posmaps = posmaps;
+        g_ct_owner = ct;
+        flat_free(&f);
+        *ct_out = ct;
+        return OK;
+ERROR:
+        free(posmaps);
+        flat_free(&f);
+        anchor_consistency_free(ct);
+        *ct_out = NULL;
+        return FAIL;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * create_msa_tree (aln_run.c:43): same arguments; post-condition used by finalise_alignment
+ * (msa_op.c:546): every sequences[i]->gaps[0..len] filled. */
+int __wrap_create_msa_tree(struct msa* msa, struct aln_param* ap, struct aln_tasks* t)
+{
+        struct flat_msa f = {NULL, NULL, NULL, 0};
+        struct consistency_table* ct = (struct consistency_table*)msa->consistency_table;
+        kb200_params prm;
+        kb200_ctx* ctx = NULL;
+        int* abc = NULL;
+        int* gaps = NULL;
+        int* posmaps = NULL;
+        int own_posmaps = 0;
+        int K = 0;
+        float weight = 0.0F;
+        int N = msa->numseq;
+        int i, k;
+        int64_t total = 0;
+
+        ctx = seam_ctx();
+        if(!ctx){
+                return FAIL;
+        }
+        RUN(sort_tasks(t, TASK_ORDER_TREE));             /* as aln_run.c:48 */
+        RUN(flatten(msa, &f));
+        fill_params(msa, ap, &prm);
+        for(i = 0; i < N; i++){
+                total += f.lens[i];
+        }
+        abc = malloc(sizeof(int) * 3 * (size_t)(t->n_tasks > 0 ? t->n_tasks : 1));
+        gaps = malloc(sizeof(int) * ((size_t)total + (size_t)N));
+        if(!abc || !gaps){
+                goto ERROR;
+        }
+        for(i = 0; i < t->n_tasks; i++){
+                abc[3 * i] = t->list[i]->a;
+                abc[3 * i + 1] = t->list[i]->b;
+                abc[3 * i + 2] = t->list[i]->c;
+        }
+        if(ct){
+                K = ct->n_anchors;
+                weight = ct->weight;
+                if(ct == g_ct_owner && g_posmaps){
+                        posmaps = g_posmaps;
+                }else{
+                        /* a table built elsewhere (e.g. by the reference's CPU path): pack it */
+                        posmaps = malloc(sizeof(int) * (size_t)total * (size_t)K + sizeof(int));
+                        if(!posmaps){
+                                goto ERROR;
+                        }
+                        own_posmaps = 1;
+                        for(i = 0; i < N; i++){
+                                for(k = 0; k < K; k++){
+                                        memcpy(posmaps + (size_t)K * (size_t)f.offs[i] + (size_t)k * (size_t)f.lens[i],
+                                               ct->pos_maps[i * K + k], sizeof(int) * (size_t)f.lens[i]);
+                                }
+                        }
+                }
+        }
+        if(kb200_align_tree(ctx, &prm, f.seqs, f.offs, f.lens, N, abc, t->n_tasks, msa->seq_distances,
+                            posmaps, K, weight, gaps) != KB200_OK){
+                goto ERROR;
+        }
+        for(i = 0; i < N; i++){
+                memcpy(msa->sequences[i]->gaps, gaps + f.offs[i] + i, sizeof(int) * (size_t)(f.lens[i] + 1));
+        }
+        if(own_posmaps){
+                free(posmaps);
+        }
+        free(g_posmaps);
+        g_posmaps = NULL;
+        g_ct_owner = NULL;
+        free(abc);
+        free(gaps);
+        flat_free(&f);
+        return OK;
+ERROR:
+        if(own_posmaps){
+                free(posmaps);
+        }
+        free(abc);
+        free(gaps);
+        flat_free(&f);
+        return FAIL;
+}

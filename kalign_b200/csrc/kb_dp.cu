@@ -121,7 +121,150 @@ __device__ __forceinline__ void bonus_entry(const KbJob& J, const int2* __restri
         }
 }
 
-template <int V, int K, bool TAIL, int MODE, int BONUS, bool BSM = false>
+// Packed fp32x2 addition (Blackwell FADD2): two independent IEEE round-to-nearest
+// additions per instruction -- the same values as two scalar operations, at half the issue slots
+// and half the load on the FP pipe that bounds the sweep.
+__device__ __forceinline__ float2 add2(const float2 a, const float2 b)
+{
+        unsigned long long ra, rb, rd;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+        asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+        float2 d;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+        return d;
+}
+
+// NOTE: there is deliberately no packed multiply here.  ptxas contracts mul.rn.f32x2 (and even
+// fma.rn.f32x2 with a -0 addend) followed by add.rn.f32x2 into ONE FFMA2 -- a single rounding --
+// regardless of -fmad=false, which would break bit-identity with the reference's separately rounded
+// multiply and add (aln_profileprofile.c:99-106).  Products are therefore scalar __fmul_rn; only
+// the additions are packed.  tests/test_sass_contract.py checks the SASS for fused multiply-adds.
+
+template <int V, int K, bool TAIL, int MODE, int BONUS, bool BSM>
+__device__ __forceinline__ void cells(const KbJob& J, const RowCtx<V, K>& rc, const unsigned vmask,
+                                      const bool first_term, const bool last_term,
+                                      const ColCtx<V>& cc, const float (&bon)[K],
+                                      const bool sparse, const int bdir, int (&sp_i)[K], int (&sp_c)[K], float (&sp_v)[K],
+                                      const float (&sp_wrap)[K], const int2* __restrict__ s_bon,
+                                      const float* __restrict__ s_tbl,
+                                      float (&sA)[K], float (&sGA)[K], float (&sGB)[K],
+                                      Trip d, Trip& u);
+
+// Interior columns, rows taken two at a time: the same operations on the same operands as the
+// scalar routine below (every add / multiply is still rounded on its own), issued as packed pairs:
+//   (oGA_k + COp, oGA_k + CE)            -> diagonal term of row k+1 and the row's own ga
+//   (oA_k + CO, oA_k+1 + CO)             -> ga of both rows
+//   (oGB_k + ROp_k+1, oGB_k+1 + ROp_k+2) -> diagonal terms of rows k+1, k+2
+//   (m_k + x_k, m_k+1 + x_k+1) and the profile-profile dot product of both rows
+// Only the gb chain down the column (row k+1 needs the new a / gb of row k) stays scalar.
+template <int V, int K, bool TAIL, int BONUS, bool BSM>
+__device__ __forceinline__ void cells_mid2(const KbJob& J, const RowCtx<V, K>& rc, const unsigned vmask,
+                                           const ColCtx<V>& cc,
+                                           const int bdir, int (&sp_i)[K], int (&sp_c)[K], float (&sp_v)[K],
+                                           const int2* __restrict__ s_bon, const float* __restrict__ s_tbl,
+                                           float (&sA)[K], float (&sGA)[K], float (&sGB)[K],
+                                           const Trip d, Trip& u)
+{
+        static_assert(K % 2 == 0, "rows in pairs");
+        constexpr int NA = VTraits<V>::NA;
+        unsigned hits = 0;
+        const float2 colGA = make_float2(cc.COp, cc.CE);
+        const float2 colCO = make_float2(cc.CO, cc.CO);
+        float ROp0;
+        if constexpr (V == V_SS) {
+                ROp0 = J.o;
+        } else {
+                ROp0 = rc.ROp[0];
+        }
+        // diagonal of row 0: the lane above, one column back
+        float dA = d.a;
+        float tGA = d.ga + cc.COp;
+        float tGB = d.gb + ROp0;
+#pragma unroll
+        for (int k = 0; k < K; k += 2) {
+                const float oA0 = sA[k], oA1 = sA[k + 1];
+                const float oGA0 = sGA[k], oGA1 = sGA[k + 1];
+                const float oGB0 = sGB[k], oGB1 = sGB[k + 1];
+                float RO0, RE0, RO1, RE1, ROpA, ROpB;
+                if constexpr (V == V_SS) {
+                        RO0 = RO1 = J.o; RE0 = RE1 = J.e; ROpA = ROpB = J.o;
+                } else {
+                        RO0 = rc.RO[k]; RE0 = rc.RE[k]; RO1 = rc.RO[k + 1]; RE1 = rc.RE[k + 1];
+                        ROpA = rc.ROp[k + 1];
+                        ROpB = rc.ROp[(k + 2 < K) ? (k + 2) : k];        // last pair: second half unused
+                }
+                const float2 g0 = add2(make_float2(oGA0, oGA0), colGA);      // .x: + COp (row k+1), .y: + CE (own ga)
+                const float2 g1 = add2(make_float2(oGA1, oGA1), colGA);
+                const float2 h = add2(make_float2(oA0, oA1), colCO);
+                const float2 b = add2(make_float2(oGB0, oGB1), make_float2(ROpA, ROpB));
+                const float m0 = kmax(kmax(dA, tGA), tGB);
+                const float m1 = kmax(kmax(oA0, g0.x), b.x);
+                float2 a01 = make_float2(m0, m1);
+                if constexpr (V == V_SS) {
+                        const float2 x = add2(make_float2(s_tbl[rc.rbase[k] + cc.cres], s_tbl[rc.rbase[k + 1] + cc.cres]),
+                                              make_float2(J.nsoff, J.nsoff));
+                        a01 = add2(a01, x);
+                } else if constexpr (V == V_SP) {
+                        a01 = add2(a01, make_float2(__ldg(rc.prow[k] + 32 + cc.cres), __ldg(rc.prow[k + 1] + 32 + cc.cres)));
+                } else {
+#pragma unroll
+                        for (int c = NA - 1; c >= 0; c--) {
+                                const float2 p = make_float2(__fmul_rn(rc.cnt[k][c], cc.qs[c]), __fmul_rn(rc.cnt[k + 1][c], cc.qs[c]));
+                                a01 = add2(a01, p);
+                        }
+                }
+                if constexpr (BONUS == BONUS_SPARSE) {
+                        const bool hit0 = (cc.jcol == sp_c[k]);
+                        const bool hit1 = (cc.jcol == sp_c[k + 1]);
+                        a01 = add2(a01, make_float2(hit0 ? sp_v[k] : 0.0f, hit1 ? sp_v[k + 1] : 0.0f));
+                        hits |= (hit0 ? (1u << k) : 0u) | (hit1 ? (2u << k) : 0u);
+                } else if constexpr (BONUS == BONUS_DENSE) {
+                        if (J.bonus) {
+                                a01 = add2(a01, make_float2(__ldg(J.bonus + (size_t)rc.irow[k] * (size_t)J.len_b + (size_t)cc.jcol),
+                                                            __ldg(J.bonus + (size_t)rc.irow[k + 1] * (size_t)J.len_b + (size_t)cc.jcol)));
+                        }
+                }
+                float a0 = a01.x, a1 = a01.y;
+                float ga0 = kmax(g0.y, h.x);
+                float ga1 = kmax(g1.y, h.y);
+                float gb0 = kmax(u.gb + RE0, u.a + RO0);
+                if constexpr (TAIL) {
+                        if (!((vmask >> k) & 1u)) {
+                                a0 = u.a; ga0 = u.ga; gb0 = u.gb;
+                        }
+                }
+                float gb1 = kmax(gb0 + RE1, a0 + RO1);
+                if constexpr (TAIL) {
+                        if (!((vmask >> (k + 1)) & 1u)) {
+                                a1 = a0; ga1 = ga0; gb1 = gb0;
+                        }
+                }
+                sA[k] = a0; sGA[k] = ga0; sGB[k] = gb0;
+                sA[k + 1] = a1; sGA[k + 1] = ga1; sGB[k + 1] = gb1;
+                u.a = a1; u.ga = ga1; u.gb = gb1;
+                dA = oA1; tGA = g1.x; tGB = b.y;
+        }
+        if constexpr (BONUS == BONUS_SPARSE) {
+                if (hits) {
+#pragma unroll
+                        for (int k = 0; k < K; k++) {
+                                if ((hits >> k) & 1u) {
+                                        sp_i[k] += bdir;
+                                        const int e = sp_i[k];
+                                        const bool ok = (e >= 0) && (e < J.nb);
+                                        int nc;
+                                        float nv;
+                                        bonus_entry<K, BSM>(J, s_bon, rc.irow[k], k, ok ? e : 0, nc, nv);
+                                        sp_c[k] = ok ? nc : ((bdir > 0) ? 0x7fffffff : -1);
+                                        sp_v[k] = ok ? nv : 0.0f;
+                                }
+                        }
+                }
+        }
+}
+
+template <int V, int K, bool TAIL, int MODE, int BONUS, bool BSM>
 __device__ __forceinline__ void cells(const KbJob& J, const RowCtx<V, K>& rc, const unsigned vmask,
                                       const bool first_term, const bool last_term,
                                       const ColCtx<V>& cc, const float (&bon)[K],
@@ -131,6 +274,10 @@ __device__ __forceinline__ void cells(const KbJob& J, const RowCtx<V, K>& rc, co
                                       float (&sA)[K], float (&sGA)[K], float (&sGB)[K],
                                       Trip d, Trip& u /* in: up at column u; out: bottom row */)
 {
+        if constexpr (MODE == MODE_MID && (K % 2) == 0) {
+                cells_mid2<V, K, TAIL, BONUS, BSM>(J, rc, vmask, cc, bdir, sp_i, sp_c, sp_v, s_bon, s_tbl, sA, sGA, sGB, d, u);
+                return;
+        }
         unsigned hits = 0;
 #pragma unroll
         for (int k = 0; k < K; k++) {
