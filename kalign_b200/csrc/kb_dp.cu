@@ -743,10 +743,29 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                         }
                         step(std::false_type{}, t);
                 }
-                while (t < C) {                 // 32 <= t <= C-1, in runs of HB steps
+                while (t + HB <= C) {           // 32 <= t <= C-1, in runs of HB steps
                         boundary(t);
-                        const int te = (t + HB < C) ? (t + HB) : C;
-                        for (; t < te; t++) {
+                        // two steps per iteration: the register rotation of the software pipeline
+                        // (current <- next column, diagonal <- row above) becomes renaming
+                        // (not in the sparse-bonus family: its list cursors already fill the register file)
+                        if constexpr (BONUS == BONUS_SPARSE) {
+#pragma unroll 1
+                                for (int q = 0; q < HB; q++) {
+                                        step(std::true_type{}, t);
+                                        t++;
+                                }
+                        } else {
+#pragma unroll 1
+                                for (int q = 0; q < HB; q += 2) {
+                                        step(std::true_type{}, t);
+                                        step(std::true_type{}, t + 1);
+                                        t += 2;
+                                }
+                        }
+                }
+                if (t < C) {
+                        boundary(t);
+                        for (; t < C; t++) {
                                 step(std::true_type{}, t);
                         }
                 }
@@ -786,22 +805,30 @@ __device__ void sweep_unit(const KbJob& J, const KbBox& bx, const int bwd, const
         const unsigned prev = (strip > 0) ? (tag_base + (unsigned)strip) : 0u;      // tag written by strip-1
         const unsigned mine = tag_base + (unsigned)strip + 1u;
         const int rem = R - row0;
-        if (rps == 32) {
-                sweep_strip<V, 1, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
+        // rows per lane of this strip: the full width of the kind's strips, or -- last strip of a
+        // sweep, boxes of the deeper rounds -- the smallest K that covers the remaining rows, so that
+        // a 187-row half box runs with 6 rows per lane (97 % of the lanes' rows live) instead of 8
+#define KB_STRIP(KK, TT) sweep_strip<V, KK, TT, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_rec, s_bon)
+        const int kneed = (rem + 31) >> 5;
+        if (rps == 32 || kneed <= 1) {
+                KB_STRIP(1, true);
         } else if constexpr (V == V_PP23) {
-                if (rem >= 64) sweep_strip<V, 2, false, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
-                else if (rem > 32) sweep_strip<V, 2, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
-                else sweep_strip<V, 1, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
+                if (rem >= 64) KB_STRIP(2, false);
+                else KB_STRIP(2, true);
         } else if constexpr (V == V_SS && !BONUS) {
-                if (rem >= 256) sweep_strip<V, 8, false, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
-                else if (rem > 128) sweep_strip<V, 8, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
-                else if (rem > 32) sweep_strip<V, 4, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
-                else sweep_strip<V, 1, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
+                if (rem >= 256) KB_STRIP(8, false);
+                else if (kneed > 6) KB_STRIP(8, true);
+                else if (kneed > 4) KB_STRIP(6, true);
+                else if (kneed == 4) KB_STRIP(4, true);
+                else if (kneed == 3) KB_STRIP(3, true);
+                else KB_STRIP(2, true);
         } else {
-                if (rem >= 128) sweep_strip<V, 4, false, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
-                else if (rem > 32) sweep_strip<V, 4, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
-                else sweep_strip<V, 1, true, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
+                if (rem >= 128) KB_STRIP(4, false);
+                else if (kneed == 4) KB_STRIP(4, true);
+                else if (kneed == 3) KB_STRIP(3, true);
+                else KB_STRIP(2, true);
         }
+#undef KB_STRIP
 }
 
 // BONUS is a kernel-level template parameter: a batch either carries consistency bonuses for all

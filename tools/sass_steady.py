@@ -24,12 +24,12 @@ for f in re.split(r"\n\s*Function : ", out)[1:]:
         if not m:
             continue
         tgt = int(m.group(1), 16)
-        if tgt <= a and tgt in idx and 40 <= i - idx[tgt] + 1 < 320:
+        if tgt <= a and tgt in idx and 40 <= i - idx[tgt] + 1 < 640:
             body = ins[idx[tgt]:i + 1]
             c = Counter()
             for _, tt in body:
                 op = tt.split()[1] if tt.startswith("@") else tt.split()[0]
                 c[op.split(".")[0]] += 1
-            if c["SHFL"] == 3 and c["VOTE"] == 0:      # innermost steady loops only
+            if c["SHFL"] in (3, 6) and c["VOTE"] == 0:      # innermost steady loops only
                 keys = ["FADD", "FADD2", "FMUL", "FMNMX", "FMNMX3", "FSEL", "MOV", "IMAD", "LDS", "LDG", "LDL", "STL", "ISETP", "BRA"]
                 print("  @%05x %4d instr  " % (ins[idx[tgt]][0], len(body)) + " ".join("%s=%d" % (k, c[k]) for k in keys if c[k]))
