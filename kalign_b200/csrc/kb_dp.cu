@@ -63,7 +63,10 @@ struct KbUnit {
 
 __device__ __forceinline__ float kmax(float a, float b) { return fmaxf(a, b); }
 
-enum { MODE_FIRST = 0, MODE_MID = 1, MODE_LAST = 2 };
+// MODE_EDGE: one routine for the fill / drain steps of a strip, where the lanes of a warp sit on
+// different kinds of column (first / interior / last): the column kind is a per-lane flag resolved
+// with selects instead of three divergent code paths.
+enum { MODE_FIRST = 0, MODE_MID = 1, MODE_LAST = 2, MODE_EDGE = 3 };
 // consistency bonus of a batch: none / sparse per-row lists (tree levels) / caller-supplied dense matrix
 enum { BONUS_NONE = 0, BONUS_SPARSE = 1, BONUS_DENSE = 2 };
 
@@ -149,7 +152,7 @@ __device__ __forceinline__ void cells(const KbJob& J, const RowCtx<V, K>& rc, co
                                       const float (&sp_wrap)[K], const int2* __restrict__ s_bon,
                                       const float* __restrict__ s_tbl,
                                       float (&sA)[K], float (&sGA)[K], float (&sGB)[K],
-                                      Trip d, Trip& u);
+                                      Trip d, Trip& u, const bool e_first = false, const bool e_last = false);
 
 // Interior columns, rows taken two at a time: the same operations on the same operands as the
 // scalar routine below (every add / multiply is still rounded on its own), issued as packed pairs:
@@ -158,14 +161,19 @@ __device__ __forceinline__ void cells(const KbJob& J, const RowCtx<V, K>& rc, co
 //   (oGB_k + ROp_k+1, oGB_k+1 + ROp_k+2) -> diagonal terms of rows k+1, k+2
 //   (m_k + x_k, m_k+1 + x_k+1) and the profile-profile dot product of both rows
 // Only the gb chain down the column (row k+1 needs the new a / gb of row k) stays scalar.
-template <int V, int K, bool TAIL, int BONUS, bool BSM>
+template <int V, int K, bool TAIL, int BONUS, bool BSM, bool EDGE>
 __device__ __forceinline__ void cells_mid2(const KbJob& J, const RowCtx<V, K>& rc, const unsigned vmask,
                                            const ColCtx<V>& cc,
                                            const int bdir, int (&sp_i)[K], int (&sp_c)[K], float (&sp_v)[K],
                                            const int2* __restrict__ s_bon, const float* __restrict__ s_tbl,
                                            float (&sA)[K], float (&sGA)[K], float (&sGB)[K],
-                                           const Trip d, Trip& u)
+                                           const Trip d, Trip& u,
+                                           const bool first_term, const bool last_term, const float (&sp_wrap)[K],
+                                           const bool e_first, const bool e_last)
 {
+        // EDGE: e_first / e_last flag the lane's column as the first / last one of the box
+        const bool e_any = EDGE && (e_first || e_last);
+        const bool e_term = EDGE && ((e_first && first_term) || (e_last && last_term));
         static_assert(K % 2 == 0, "rows in pairs");
         constexpr int NA = VTraits<V>::NA;
         unsigned hits = 0;
@@ -215,12 +223,17 @@ __device__ __forceinline__ void cells_mid2(const KbJob& J, const RowCtx<V, K>& r
                         }
                 }
                 if constexpr (BONUS == BONUS_SPARSE) {
-                        const bool hit0 = (cc.jcol == sp_c[k]);
-                        const bool hit1 = (cc.jcol == sp_c[k + 1]);
+                        const bool hit0 = (cc.jcol == sp_c[k]) && !(EDGE && e_first);
+                        const bool hit1 = (cc.jcol == sp_c[k + 1]) && !(EDGE && e_first);
                         a01 = add2(a01, make_float2(hit0 ? sp_v[k] : 0.0f, hit1 ? sp_v[k + 1] : 0.0f));
                         hits |= (hit0 ? (1u << k) : 0u) | (hit1 ? (2u << k) : 0u);
+                        if constexpr (EDGE) {
+                                if (e_last) {
+                                        a01 = add2(a01, make_float2(sp_wrap[k], sp_wrap[k + 1]));   // j == len_b wraps to (i+1, 0)
+                                }
+                        }
                 } else if constexpr (BONUS == BONUS_DENSE) {
-                        if (J.bonus) {
+                        if (J.bonus && !(EDGE && e_first)) {
                                 a01 = add2(a01, make_float2(__ldg(J.bonus + (size_t)rc.irow[k] * (size_t)J.len_b + (size_t)cc.jcol),
                                                             __ldg(J.bonus + (size_t)rc.irow[k + 1] * (size_t)J.len_b + (size_t)cc.jcol)));
                         }
@@ -229,12 +242,36 @@ __device__ __forceinline__ void cells_mid2(const KbJob& J, const RowCtx<V, K>& r
                 float ga0 = kmax(g0.y, h.x);
                 float ga1 = kmax(g1.y, h.y);
                 float gb0 = kmax(u.gb + RE0, u.a + RO0);
+                if constexpr (EDGE) {
+                        float RT0;
+                        if constexpr (V == V_SS) {
+                                RT0 = J.t;
+                        } else {
+                                RT0 = rc.RT[k];
+                        }
+                        const float gt0 = kmax(u.gb, u.a) + RT0;
+                        gb0 = e_term ? gt0 : gb0;
+                        a0 = e_first ? KB_NEGF : a0;
+                        ga0 = e_any ? KB_NEGF : ga0;
+                }
                 if constexpr (TAIL) {
                         if (!((vmask >> k) & 1u)) {
                                 a0 = u.a; ga0 = u.ga; gb0 = u.gb;
                         }
                 }
                 float gb1 = kmax(gb0 + RE1, a0 + RO1);
+                if constexpr (EDGE) {
+                        float RT1;
+                        if constexpr (V == V_SS) {
+                                RT1 = J.t;
+                        } else {
+                                RT1 = rc.RT[k + 1];
+                        }
+                        const float gt1 = kmax(gb0, a0) + RT1;
+                        gb1 = e_term ? gt1 : gb1;
+                        a1 = e_first ? KB_NEGF : a1;
+                        ga1 = e_any ? KB_NEGF : ga1;
+                }
                 if constexpr (TAIL) {
                         if (!((vmask >> (k + 1)) & 1u)) {
                                 a1 = a0; ga1 = ga0; gb1 = gb0;
@@ -272,12 +309,16 @@ __device__ __forceinline__ void cells(const KbJob& J, const RowCtx<V, K>& rc, co
                                       const float (&sp_wrap)[K], const int2* __restrict__ s_bon,
                                       const float* __restrict__ s_tbl,
                                       float (&sA)[K], float (&sGA)[K], float (&sGB)[K],
-                                      Trip d, Trip& u /* in: up at column u; out: bottom row */)
+                                      Trip d, Trip& u /* in: up at column u; out: bottom row */,
+                                      const bool e_first, const bool e_last)
 {
-        if constexpr (MODE == MODE_MID && (K % 2) == 0) {
-                cells_mid2<V, K, TAIL, BONUS, BSM>(J, rc, vmask, cc, bdir, sp_i, sp_c, sp_v, s_bon, s_tbl, sA, sGA, sGB, d, u);
+        if constexpr ((MODE == MODE_MID || MODE == MODE_EDGE) && (K % 2) == 0) {
+                cells_mid2<V, K, TAIL, BONUS, BSM, MODE == MODE_EDGE>(J, rc, vmask, cc, bdir, sp_i, sp_c, sp_v, s_bon, s_tbl, sA, sGA, sGB,
+                                                                      d, u, first_term, last_term, sp_wrap, e_first, e_last);
                 return;
         }
+        const bool e_any = (MODE == MODE_EDGE) && (e_first || e_last);
+        const bool e_term = (MODE == MODE_EDGE) && ((e_first && first_term) || (e_last && last_term));
         unsigned hits = 0;
 #pragma unroll
         for (int k = 0; k < K; k++) {
@@ -311,14 +352,18 @@ __device__ __forceinline__ void cells(const KbJob& J, const RowCtx<V, K>& rc, co
                                 // The reference adds its dense matrix entry to EVERY cell
                                 // (aln_seqseq.c:83-85): + 0.0f where the list has no entry.  A job
                                 // without a list keeps the never-matching sentinel in sp_c.
-                                const bool hit = (cc.jcol == sp_c[k]);
+                                const bool hit = (cc.jcol == sp_c[k]) && !(MODE == MODE_EDGE && e_first);
                                 a = a + (hit ? sp_v[k] : 0.0f);
                                 hits |= hit ? (1u << k) : 0u;
                                 if constexpr (MODE == MODE_LAST) {
                                         a = a + sp_wrap[k];   // forward sweep, j == len_b: flat index wraps to (i+1, 0)
+                                } else if constexpr (MODE == MODE_EDGE) {
+                                        if (e_last) {
+                                                a = a + sp_wrap[k];
+                                        }
                                 }
                         } else if constexpr (BONUS == BONUS_DENSE) {
-                                if (J.bonus) {
+                                if (J.bonus && !(MODE == MODE_EDGE && e_first)) {
                                         // dense matrix supplied by the caller (kb200_pair_align_batch)
                                         a = a + __ldg(J.bonus + (size_t)rc.irow[k] * (size_t)J.len_b + (size_t)cc.jcol);
                                 }
@@ -326,6 +371,12 @@ __device__ __forceinline__ void cells(const KbJob& J, const RowCtx<V, K>& rc, co
                         if constexpr (MODE == MODE_MID) {
                                 ga = kmax(oGA + cc.CE, oA + cc.CO);
                                 gb = kmax(u.gb + RE, u.a + RO);
+                        } else if constexpr (MODE == MODE_EDGE) {
+                                const float gm = kmax(u.gb + RE, u.a + RO);
+                                const float gt = kmax(u.gb, u.a) + RT;
+                                ga = e_any ? KB_NEGF : kmax(oGA + cc.CE, oA + cc.CO);
+                                gb = e_term ? gt : gm;
+                                a = e_first ? KB_NEGF : a;
                         } else {
                                 ga = KB_NEGF;
                                 gb = last_term ? (kmax(u.gb, u.a) + RT) : kmax(u.gb + RE, u.a + RO);
@@ -705,13 +756,7 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                         if constexpr (STEADY) {
                                 cells<V, K, TAIL, MODE_MID, BONUS, true>(J, rc, vmask, first_term, last_term, cc, cur_bon, sparse, bdir, sp_i, sp_c, sp_v, sp_wrap, my_bon, s_tbl, sA, sGA, sGB, d, up);
                         } else {
-                                if (u == 0) {
-                                        cells<V, K, TAIL, MODE_FIRST, BONUS, true>(J, rc, vmask, first_term, last_term, cc, cur_bon, sparse, bdir, sp_i, sp_c, sp_v, sp_wrap, my_bon, s_tbl, sA, sGA, sGB, d, up);
-                                } else if (u < C) {
-                                        cells<V, K, TAIL, MODE_MID, BONUS, true>(J, rc, vmask, first_term, last_term, cc, cur_bon, sparse, bdir, sp_i, sp_c, sp_v, sp_wrap, my_bon, s_tbl, sA, sGA, sGB, d, up);
-                                } else {
-                                        cells<V, K, TAIL, MODE_LAST, BONUS, true>(J, rc, vmask, first_term, last_term, cc, cur_bon, sparse, bdir, sp_i, sp_c, sp_v, sp_wrap, my_bon, s_tbl, sA, sGA, sGB, d, up);
-                                }
+                                cells<V, K, TAIL, MODE_EDGE, BONUS, true>(J, rc, vmask, first_term, last_term, cc, cur_bon, sparse, bdir, sp_i, sp_c, sp_v, sp_wrap, my_bon, s_tbl, sA, sGA, sGB, d, up, u == 0, u == C);
                         }
                         d = got;
                         bot = up;
