@@ -42,13 +42,16 @@ constexpr int WARPS_PER_CTA = 4;
 constexpr int TBL_MAX = 23 * 32;     // shared table capacity (floats)
 
 // kernel variants
-enum { V_SS = 0, V_SP = 1, V_PP5 = 2, V_PP23 = 3 };
+// V_SP5: profile(rows) x sequence over a 5-letter alphabet -- the rows' score vectors are staged in
+// shared memory (lane-private, conflict-free) instead of being gathered from global memory per cell
+enum { V_SS = 0, V_SP = 1, V_PP5 = 2, V_PP23 = 3, V_SP5 = 4 };
 constexpr int PACK5 = 8;             // packed column record, 5-letter alphabets: s0..s4, [27],[28],[29]
 constexpr int PACK23 = 28;           // 23-letter: s0..s22, [27],[28],[29], pad, pad
 
 template <int V> struct VTraits;
 template <> struct VTraits<V_SS> { static constexpr int NA = 0; };
 template <> struct VTraits<V_SP> { static constexpr int NA = 0; };
+template <> struct VTraits<V_SP5> { static constexpr int NA = 0; };
 template <> struct VTraits<V_PP5> { static constexpr int NA = 5; };
 template <> struct VTraits<V_PP23> { static constexpr int NA = 23; };
 
@@ -90,6 +93,7 @@ __device__ __host__ __forceinline__ int rows_per_strip(int kind, int nalpha, int
 template <int V, int K> struct RowCtx {
         int rbase[K];                                   // SS
         const float* prow[K];                           // SP
+        const float* sprow;                             // SP5: this lane's slot of the staged score vectors [k][letter][lane]
         float cnt[K][VTraits<V>::NA > 0 ? VTraits<V>::NA : 1];   // PP: residue counts of the row
         float RO[K], RE[K], RT[K], ROp[K];              // SP, PP
         int irow[K];
@@ -215,6 +219,9 @@ __device__ __forceinline__ void cells_mid2(const KbJob& J, const RowCtx<V, K>& r
                         a01 = add2(a01, x);
                 } else if constexpr (V == V_SP) {
                         a01 = add2(a01, make_float2(__ldg(rc.prow[k] + 32 + cc.cres), __ldg(rc.prow[k + 1] + 32 + cc.cres)));
+                } else if constexpr (V == V_SP5) {
+                        const float* sv = rc.sprow + cc.cres * 32;
+                        a01 = add2(a01, make_float2(sv[k * 160], sv[(k + 1) * 160]));
                 } else {
 #pragma unroll
                         for (int c = NA - 1; c >= 0; c--) {
@@ -341,6 +348,8 @@ __device__ __forceinline__ void cells(const KbJob& J, const RowCtx<V, K>& rc, co
                                 a = a + x;
                         } else if constexpr (V == V_SP) {
                                 a = a + __ldg(rc.prow[k] + 32 + cc.cres);
+                        } else if constexpr (V == V_SP5) {
+                                a = a + rc.sprow[k * 160 + cc.cres * 32];
                         } else {
 #pragma unroll
                                 for (int c = VTraits<V>::NA - 1; c >= 0; c--) {
@@ -533,6 +542,21 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
         const int R = r1 - r0;
         RowCtx<V, K> rc;
         const unsigned vmask = load_rows<V, K>(J, bwd, r0, r1, row0 + lane * K, tstride, rc);
+        if constexpr (V == V_SP5) {
+                // stage the score vectors of this lane's rows: the per-cell lookup becomes a conflict-free
+                // LDS (every lane reads its own bank) instead of an uncoalesced gather that misses L1
+                static_assert(K <= 4, "score-vector staging area holds 4 rows per lane");
+                float* sp = reinterpret_cast<float*>(s_rec) + lane;
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+#pragma unroll
+                        for (int c = 0; c < 5; c++) {
+                                sp[(k * 5 + c) * 32] = __ldg(rc.prow[k] + 32 + c);
+                        }
+                }
+                rc.sprow = sp;
+        }
         float sA[K], sGA[K], sGB[K];
 #pragma unroll
         for (int k = 0; k < K; k++) {
@@ -546,7 +570,7 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
         // Hand-off read side.  The row above is pulled in BLOCKS of HB columns, well ahead of its use:
         // column c is loaded by lane (c & 31) (ld.volatile.v4 into a register: a coalesced 128-byte
         // request per block), validated by its tag every HB steps (warp-uniform poll), and
-        // committed to a 64-column shared-memory ring from which lane 0 takes one entry per step
+        // committed to a 16-column shared-memory ring from which lane 0 takes one entry per step
         // (broadcast LDS).  Four blocks are in flight (24..32 steps of read-ahead), so that neither
         // the L2 latency nor the poll sits on the per-step path -- which is what bounds a warp that
         // runs alone on its scheduler (few big boxes: top of the guide tree, long sequences).
@@ -605,7 +629,7 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                                 }
                         }
                         if (need) {
-                                s_ring[col & 63] = blk;
+                                s_ring[col & 15] = blk;
                         }
                         __syncwarp();
                         if (mine && col + 32 <= C) {
@@ -673,7 +697,7 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                 // row above, column t, for lane 0 (consumer strips): committed by boundary()
                 float4 hin = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (!gen) {
-                        hin = s_ring[t & 63];
+                        hin = s_ring[t & 15];
                 }
                 Trip up;
                 up.a = __shfl_up_sync(FULL, bot.a, 1);
@@ -821,6 +845,7 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                         step(std::false_type{}, t);
                 }
         }
+        rec_wait();      // no copy into the record ring may outlive the strip (the area is reused)
         __syncwarp();
 }
 
@@ -887,8 +912,10 @@ kb_sweep_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes,
                 const float* __restrict__ tbl, const int thin, const int tstride)
 {
         __shared__ float s_tbl[TBL_MAX];
-        __shared__ float4 s_ring_all[WARPS_PER_CTA][64];     // hand-off ring (row above), one per warp
-        __shared__ float4 s_rec_all[WARPS_PER_CTA][128];     // 5-letter column records: two 64-column rings per warp
+        __shared__ float4 s_ring_all[WARPS_PER_CTA][16];     // hand-off ring (row above), one per warp
+        // per warp: 5-letter profile-profile column records (two 64-column rings, 2 KB) or the staged
+        // score vectors of a 5-letter profile-sequence strip ([4 rows][5 letters][32 lanes] floats)
+        __shared__ float4 s_rec_all[WARPS_PER_CTA][160];
         for (int i = threadIdx.x; i < TBL_MAX; i += blockDim.x) {
                 s_tbl[i] = tbl[i];
         }
@@ -917,7 +944,11 @@ kb_sweep_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes,
                 if (J.kind == KB200_KIND_SS) {
                         sweep_unit<V_SS, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
                 } else if (J.kind == KB200_KIND_SP) {
-                        sweep_unit<V_SP, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
+                        if (J.nalpha <= 5) {
+                                sweep_unit<V_SP5, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
+                        } else {
+                                sweep_unit<V_SP, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
+                        }
                 } else if (J.nalpha <= 5) {
                         sweep_unit<V_PP5, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
                 } else {
