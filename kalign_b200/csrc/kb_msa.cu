@@ -18,6 +18,7 @@
 #include "kb_host.cuh"
 
 #include <math.h>
+#include <time.h>
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
@@ -28,6 +29,19 @@
 #endif
 
 namespace {
+
+// host-stage timing for KB200_TRACE=1
+inline double kb_now()
+{
+        struct timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+inline bool kb_trace_on()
+{
+        static const bool on = getenv("KB200_TRACE") != nullptr;
+        return on;
+}
 
 // ---- alphabets (alphabet.c) ------------------------------------------------------------------
 enum { ALPHA_DNA = 5, ALPHA_RED = 13, ALPHA_AMB = 23 };
@@ -441,6 +455,7 @@ void select_anchors(const float* sd, int N, int K, std::vector<int>& ids)
 int kb_build_tree(kb200_ctx* ctx, KbSeqs& S, int n_threads, std::vector<int>& abc, std::vector<float>& seq_distances)
 {
         const int N = S.n;
+        const double tt0 = kb_now();
         TreeBuilder B;
         B.N = N;
         // pick_anchor / select_seqs (pick_anchor.c:17-72)
@@ -477,11 +492,13 @@ int kb_build_tree(kb200_ctx* ctx, KbSeqs& S, int n_threads, std::vector<int>& ab
         std::vector<int> samples((size_t)N);
         for (int i = 0; i < N; i++) samples[(size_t)i] = i;
         int root = -1;
+        const double tt1 = kb_now();
 #ifdef _OPENMP
 #pragma omp parallel num_threads(n_threads > 0 ? n_threads : 1)
 #pragma omp single
 #endif
         root = bisect(B, samples);
+        const double tt2 = kb_now();
         // leaf clusters: one batched launch for every i<j pair of every cluster.
         // d_estimation(pair=1) leaves dm[i][j] (i<j) = calc_distance(seq_j, seq_i)
         // (sequence_distance.c:53-81: the later (j,i) iteration overwrites both entries).
@@ -528,9 +545,14 @@ int kb_build_tree(kb200_ctx* ctx, KbSeqs& S, int n_threads, std::vector<int>& ab
                         B.nodes[(size_t)B.clusters[ci].placeholder] = B.nodes[(size_t)cluster_root[ci]];
                 }
         }
+        const double tt3 = kb_now();
         abc.clear();
         abc.reserve((size_t)3 * (N - 1));
         emit_tasks(B, root, N, abc);
+        if (kb_trace_on()) {
+                fprintf(stderr, "[kb200 trace] guide tree: anchor distances %.1f ms, bisecting k-means %.1f ms (%d threads), leaf distances + upgma %.1f ms\n",
+                        1e3 * (tt1 - tt0), 1e3 * (tt2 - tt1), n_threads, 1e3 * (tt3 - tt2));
+        }
         if ((int)abc.size() != 3 * (N - 1)) {
                 fprintf(stderr, "[kalign_b200] guide tree: %zu tasks for %d sequences\n", abc.size() / 3, N);
                 return KB200_FAIL;
@@ -635,6 +657,7 @@ int kb200_msa_create(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_thr
         if (n_threads < 1) n_threads = 1;
         n_threads = std::min(n_threads, kb_default_threads());   // never more than the CPU quota
         KB_CUDA(cudaSetDevice(ctx->device));
+        const double tc0 = kb_now();
         // ---- kalign_arr_to_msa: letter frequencies, alphabet detection (msa_op.c:440-520,142-215)
         int letter_freq[128];
         memset(letter_freq, 0, sizeof(letter_freq));
@@ -710,8 +733,14 @@ int kb200_msa_create(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_thr
         M->codes.resize((size_t)total + 16);
         M->gaps.assign((size_t)total + (size_t)N, 0);
         encode_seqs(M, biotype == 1 ? ALPHA_DNA : ALPHA_RED);
+        const double tc1 = kb_now();
         int rc = M->S.upload(ctx, M->codes.data(), M->offs.data(), M->lens.data(), N);
+        const double tc2 = kb_now();
         if (rc == KB200_OK) rc = kb_build_tree(ctx, M->S, n_threads, M->abc, M->seq_distances);
+        if (kb_trace_on()) {
+                fprintf(stderr, "[kb200 trace] msa_create: detect/sort/encode %.1f ms, upload %.1f ms, guide tree %.1f ms\n",
+                        1e3 * (tc1 - tc0), 1e3 * (tc2 - tc1), 1e3 * (kb_now() - tc2));
+        }
         if (rc == KB200_OK && biotype == 0) {
                 encode_seqs(M, ALPHA_AMB);
                 rc = M->S.upload(ctx, M->codes.data(), M->offs.data(), M->lens.data(), N);
@@ -775,6 +804,7 @@ int kb200_msa_align(kb200_msa* M)
 int kb200_msa_result(kb200_msa* M, char*** aligned, int* out_aln_len)
 {
         if (!M || !M->aligned || !aligned || !out_aln_len) return KB200_FAIL;
+        const double tr0 = kb_now();
         const int N = M->N;
         int aln_len = M->lens[0];
         {
@@ -805,6 +835,9 @@ int kb200_msa_result(kb200_msa* M, char*** aligned, int* out_aln_len)
         }
         *aligned = out;
         *out_aln_len = aln_len;
+        if (kb_trace_on()) {
+                fprintf(stderr, "[kb200 trace] msa_result: %d rows x %d columns in %.1f ms\n", N, aln_len, 1e3 * (kb_now() - tr0));
+        }
         return KB200_OK;
 }
 
@@ -827,9 +860,14 @@ int kb200_kalign(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_threads
         kb200_msa* M = nullptr;
         KB_RUN(kb200_msa_create(ctx, seq, len, numseq, n_threads, type, gpo, gpe, tgpe,
                                 consistency_anchors, consistency_weight, &M));
+        const double ta0 = kb_now();
         int rc = kb200_msa_align(M);
+        const double ta1 = kb_now();
         if (rc == KB200_OK) rc = kb200_msa_result(M, aligned, out_aln_len);
         kb200_msa_free(M);
+        if (kb_trace_on()) {
+                fprintf(stderr, "[kb200 trace] kalign: align %.1f ms, result + free %.1f ms\n", 1e3 * (ta1 - ta0), 1e3 * (kb_now() - ta1));
+        }
         return rc;
 }
 
