@@ -67,6 +67,10 @@ void kb200_ctx_destroy(kb200_ctx* ctx)
                 b->release();
         }
         ctx->arena.release();
+        for (KbDevBuf& b : ctx->seq_pool) {
+                b.release();
+        }
+        ctx->seq_pool.clear();
         if (ctx->ev0) cudaEventDestroy(ctx->ev0);
         if (ctx->ev1) cudaEventDestroy(ctx->ev1);
         if (ctx->ev2) cudaEventDestroy(ctx->ev2);

@@ -121,6 +121,9 @@ struct kb200_ctx {
         kb200_stats stats;
         // engine scratch
         KbDevBuf d_jobs, d_boxA, d_boxB, d_boxS, d_counters, d_rows, d_tbl, d_units, d_prog, d_pack, d_ppidx;
+        // device buffers of released sequence sets, reused by the next upload (cudaMalloc / cudaFree
+        // per public call cost up to hundreds of ms next to a 10 GB profile arena)
+        std::vector<KbDevBuf> seq_pool;
         // staging for the host-pointer entry points
         KbDevBuf d_stage0, d_stage1, d_stage2, d_stage3, d_stage4, d_stage5;
         // progressive alignment (kb_tree.cu)

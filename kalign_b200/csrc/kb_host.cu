@@ -36,6 +36,44 @@ int kb_default_threads()
         return std::max(1, std::min(n, 16));
 }
 
+// smallest pooled buffer that is large enough, else the largest one (ensure() regrows it)
+static void take_pooled(kb200_ctx* ctx, KbDevBuf& b, size_t bytes)
+{
+        if (b.p || ctx->seq_pool.empty()) {
+                return;
+        }
+        size_t best = 0;
+        bool fits = false;
+        for (size_t i = 0; i < ctx->seq_pool.size(); i++) {
+                const size_t c = ctx->seq_pool[i].cap;
+                const size_t cb = ctx->seq_pool[best].cap;
+                if (c >= bytes) {
+                        if (!fits || c < cb) {
+                                best = i;
+                        }
+                        fits = true;
+                } else if (!fits && c > cb) {
+                        best = i;
+                }
+        }
+        b = ctx->seq_pool[best];
+        ctx->seq_pool.erase(ctx->seq_pool.begin() + (long)best);
+}
+
+void KbSeqs::release()
+{
+        KbDevBuf* bufs[3] = {&d_seqs, &d_offs, &d_lens};
+        for (KbDevBuf* b : bufs) {
+                if (b->p && owner && owner->seq_pool.size() < 24) {
+                        owner->seq_pool.push_back(*b);
+                        b->p = nullptr;
+                        b->cap = 0;
+                } else {
+                        b->release();
+                }
+        }
+}
+
 int KbSeqs::upload(kb200_ctx* ctx, const uint8_t* seqs, const int64_t* offs, const int* lens, int nseq)
 {
         h_seqs = seqs;
@@ -46,6 +84,10 @@ int KbSeqs::upload(kb200_ctx* ctx, const uint8_t* seqs, const int64_t* offs, con
         for (int i = 0; i < nseq; i++) {
                 total = std::max<int64_t>(total, offs[i] + lens[i]);
         }
+        owner = ctx;
+        take_pooled(ctx, d_seqs, (size_t)total + 16);
+        take_pooled(ctx, d_offs, sizeof(int64_t) * (size_t)nseq);
+        take_pooled(ctx, d_lens, sizeof(int) * (size_t)nseq);
         KB_RUN(d_seqs.ensure((size_t)total + 16));
         KB_RUN(d_offs.ensure(sizeof(int64_t) * (size_t)nseq));
         KB_RUN(d_lens.ensure(sizeof(int) * (size_t)nseq));

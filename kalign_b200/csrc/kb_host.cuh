@@ -13,13 +13,9 @@ struct KbSeqs {
         int n = 0;
         int64_t total = 0;
         KbDevBuf d_seqs, d_offs, d_lens;
+        kb200_ctx* owner = nullptr;      // buffers go back to owner->seq_pool on release
         int upload(kb200_ctx* ctx, const uint8_t* seqs, const int64_t* offs, const int* lens, int nseq);
-        void release()
-        {
-                d_seqs.release();
-                d_offs.release();
-                d_lens.release();
-        }
+        void release();
         const uint8_t* dseq(int i) const { return d_seqs.as<uint8_t>() + h_offs[i]; }
 };
 

@@ -329,16 +329,19 @@ int bisect(TreeBuilder& B, std::vector<int>& samples)
 }
 
 // upgma, bisectingKmeans.c:974-1053.  dm: n x n (modified in place).  Returns sub-tree root.
-int upgma(TreeBuilder& B, float* dm, const std::vector<int>& samples)
+// The sub-tree's 2n-1 nodes are written to B.nodes[base ..] (reserved by the caller), so that the
+// leaf clusters can be processed concurrently.
+int upgma(TreeBuilder& B, float* dm, const std::vector<int>& samples, const int base)
 {
         const int n = (int)samples.size();
+        int next_node = base;
         std::vector<int> as(n), tree(n);
         for (int i = 0; i < n; i++) {
                 as[i] = i + 1;
                 Node nd;
                 nd.id = samples[i];
-                tree[i] = (int)B.nodes.size();
-                B.nodes.push_back(nd);
+                tree[i] = next_node;
+                B.nodes[(size_t)next_node++] = nd;
         }
         int node_a = 0, node_b = 0;
         for (int cnode = n; cnode != 2 * n - 1; cnode++) {
@@ -356,8 +359,8 @@ int upgma(TreeBuilder& B, float* dm, const std::vector<int>& samples)
                 Node nd;
                 nd.left = tree[node_a];
                 nd.right = tree[node_b];
-                tree[node_a] = (int)B.nodes.size();
-                B.nodes.push_back(nd);
+                tree[node_a] = next_node;
+                B.nodes[(size_t)next_node++] = nd;
                 tree[node_b] = -1;
                 as[node_a] = cnode + 1;
                 as[node_b] = 0;
@@ -524,12 +527,32 @@ int kb_build_tree(kb200_ctx* ctx, KbSeqs& S, int n_threads, std::vector<int>& ab
                 if (npairs) {
                         KB_RUN(kb_distances_dev(ctx, S, pa.data(), (int)npairs, pb.data(), 0, 1, pd.data()));
                 }
-                e = 0;
-                // clusters were recorded in completion order; the result is order independent
-                std::vector<int> cluster_root(B.clusters.size());
-                for (size_t ci = 0; ci < B.clusters.size(); ci++) {
+                // clusters were recorded in completion order; the result is order independent.
+                // Every cluster gets its node range and its slice of the pair list up front.
+                const size_t ncl = B.clusters.size();
+                std::vector<int> cluster_root(ncl);
+                std::vector<size_t> pair0(ncl);
+                std::vector<int> node0(ncl);
+                {
+                        size_t pe = 0;
+                        int nb = (int)B.nodes.size();
+                        for (size_t ci = 0; ci < ncl; ci++) {
+                                const size_t n = B.clusters[ci].samples.size();
+                                pair0[ci] = pe;
+                                node0[ci] = nb;
+                                pe += n * (n - 1) / 2;
+                                nb += (n > 0) ? (int)(2 * n - 1) : 0;
+                        }
+                        B.nodes.resize((size_t)nb);
+                }
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads > 0 ? n_threads : 1)
+#endif
+                for (long long cl = 0; cl < (long long)ncl; cl++) {
+                        const size_t ci = (size_t)cl;
                         const Cluster& c = B.clusters[ci];
                         const int n = (int)c.samples.size();
+                        size_t e = pair0[ci];
                         std::vector<float> cdm((size_t)n * n, 0.0f);
                         for (int i = 0; i < n; i++) {
                                 for (int j = i + 1; j < n; j++) {
@@ -538,7 +561,7 @@ int kb_build_tree(kb200_ctx* ctx, KbSeqs& S, int n_threads, std::vector<int>& ab
                                         e++;
                                 }
                         }
-                        cluster_root[ci] = upgma(B, cdm.data(), c.samples);
+                        cluster_root[ci] = upgma(B, cdm.data(), c.samples, node0[ci]);
                 }
                 // splice the UPGMA sub-trees in place of the placeholders
                 for (size_t ci = 0; ci < B.clusters.size(); ci++) {
@@ -596,10 +619,13 @@ struct kb200_msa {
         double t_create = 0, t_tree = 0;
 };
 
-static void encode_seqs(kb200_msa* M, int alpha)
+static void encode_seqs(kb200_msa* M, int alpha, int n_threads)
 {
         const Alphabet a = make_alphabet(alpha);
         bool warned = false;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(n_threads) firstprivate(warned)
+#endif
         for (int i = 0; i < M->N; i++) {
                 const char* s = M->order[(size_t)i]->seq;
                 uint8_t* d = M->codes.data() + M->offs[(size_t)i];
@@ -661,11 +687,25 @@ int kb200_msa_create(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_thr
         // ---- kalign_arr_to_msa: letter frequencies, alphabet detection (msa_op.c:440-520,142-215)
         int letter_freq[128];
         memset(letter_freq, 0, sizeof(letter_freq));
-        for (int i = 0; i < numseq; i++) {
-                for (int j = 0; j < len[i]; j++) {
-                        const int ch = (int)(unsigned char)seq[i][j];
-                        if (ch < 128) letter_freq[ch]++;
+#ifdef _OPENMP
+#pragma omp parallel num_threads(n_threads)
+#endif
+        {
+                int local[128];
+                memset(local, 0, sizeof(local));
+#ifdef _OPENMP
+#pragma omp for schedule(static) nowait
+#endif
+                for (int i = 0; i < numseq; i++) {
+                        for (int j = 0; j < len[i]; j++) {
+                                const int ch = (int)(unsigned char)seq[i][j];
+                                if (ch < 128) local[ch]++;
+                        }
                 }
+#ifdef _OPENMP
+#pragma omp critical
+#endif
+                for (int c = 0; c < 128; c++) letter_freq[c] += local[c];
         }
         int biotype = 2;
         {
@@ -732,7 +772,7 @@ int kb200_msa_create(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_thr
         M->total = total;
         M->codes.resize((size_t)total + 16);
         M->gaps.assign((size_t)total + (size_t)N, 0);
-        encode_seqs(M, biotype == 1 ? ALPHA_DNA : ALPHA_RED);
+        encode_seqs(M, biotype == 1 ? ALPHA_DNA : ALPHA_RED, n_threads);
         const double tc1 = kb_now();
         int rc = M->S.upload(ctx, M->codes.data(), M->offs.data(), M->lens.data(), N);
         const double tc2 = kb_now();
@@ -742,7 +782,7 @@ int kb200_msa_create(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_thr
                         1e3 * (tc1 - tc0), 1e3 * (tc2 - tc1), 1e3 * (kb_now() - tc2));
         }
         if (rc == KB200_OK && biotype == 0) {
-                encode_seqs(M, ALPHA_AMB);
+                encode_seqs(M, ALPHA_AMB, n_threads);
                 rc = M->S.upload(ctx, M->codes.data(), M->offs.data(), M->lens.data(), N);
         }
         if (rc == KB200_OK) {
@@ -814,13 +854,20 @@ int kb200_msa_result(kb200_msa* M, char*** aligned, int* out_aln_len)
         std::vector<int> by_rank((size_t)N);
         for (int i = 0; i < N; i++) by_rank[(size_t)i] = i;
         std::sort(by_rank.begin(), by_rank.end(), [&](int x, int y) { return M->order[(size_t)x]->rank < M->order[(size_t)y]->rank; });
-        char** out = (char**)malloc(sizeof(char*) * (size_t)N);
+        char** out = (char**)calloc((size_t)N, sizeof(char*));
         if (!out) return KB200_FAIL;
+        bool oom = false;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(kb_default_threads())
+#endif
         for (int r = 0; r < N; r++) {
                 const int i = by_rank[(size_t)r];
                 const int* g = M->gaps.data() + M->offs[(size_t)i] + i;
                 char* row = (char*)malloc((size_t)aln_len + 1);
-                if (!row) return KB200_FAIL;
+                if (!row) {
+                        oom = true;
+                        continue;
+                }
                 int f = 0;
                 const char* s = M->order[(size_t)i]->seq;
                 const int li = M->lens[(size_t)i];
@@ -832,6 +879,11 @@ int kb200_msa_result(kb200_msa* M, char*** aligned, int* out_aln_len)
                 while (f < aln_len) row[f++] = '-';
                 row[aln_len] = 0;
                 out[r] = row;
+        }
+        if (oom) {
+                for (int r = 0; r < N; r++) free(out[r]);
+                free(out);
+                return KB200_FAIL;
         }
         *aligned = out;
         *out_aln_len = aln_len;
