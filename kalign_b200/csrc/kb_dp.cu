@@ -1339,7 +1339,8 @@ template <int V, int MAXC, int BONUS>
 __device__ void small_box_run(const KbJob& J, const KbBox& root, const float* __restrict__ s_tbl, const int tstride,
                               unsigned long long& ncells)
 {
-        constexpr int KR = (V == V_PP23) ? 2 : 4;     // rows per pass (register budget as in the strips)
+        // rows per pass (register budget as in the strips: 8 for plain seq-seq, 4, 2 for 23-letter profiles)
+        constexpr int KR = (V == V_PP23) ? 2 : ((V == V_SS && BONUS == BONUS_NONE) ? 8 : 4);
         float4 F[MAXC + 1], B[MAXC + 1];
         SBox stack[SMALL_STACK];
         int sp = 0;
