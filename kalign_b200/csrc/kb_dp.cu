@@ -44,7 +44,10 @@ constexpr int TBL_MAX = 23 * 32;     // shared table capacity (floats)
 // kernel variants
 // V_SP5: profile(rows) x sequence over a 5-letter alphabet -- the rows' score vectors are staged in
 // shared memory (lane-private, conflict-free) instead of being gathered from global memory per cell
-enum { V_SS = 0, V_SP = 1, V_PP5 = 2, V_PP23 = 3, V_SP5 = 4 };
+// V_SS5: sequence x sequence over a 5-letter alphabet -- each row's five (score - offset) values are
+// staged the same way, which removes the per-cell table-address arithmetic and the offset add
+enum { V_SS = 0, V_SP = 1, V_PP5 = 2, V_PP23 = 3, V_SP5 = 4, V_SS5 = 5 };
+template <int V> __host__ __device__ constexpr bool is_ss() { return V == V_SS || V == V_SS5; }
 constexpr int PACK5 = 8;             // packed column record, 5-letter alphabets: s0..s4, [27],[28],[29]
 constexpr int PACK23 = 28;           // 23-letter: s0..s22, [27],[28],[29], pad, pad
 
@@ -52,6 +55,7 @@ template <int V> struct VTraits;
 template <> struct VTraits<V_SS> { static constexpr int NA = 0; };
 template <> struct VTraits<V_SP> { static constexpr int NA = 0; };
 template <> struct VTraits<V_SP5> { static constexpr int NA = 0; };
+template <> struct VTraits<V_SS5> { static constexpr int NA = 0; };
 template <> struct VTraits<V_PP5> { static constexpr int NA = 5; };
 template <> struct VTraits<V_PP23> { static constexpr int NA = 23; };
 
@@ -184,7 +188,7 @@ __device__ __forceinline__ void cells_mid2(const KbJob& J, const RowCtx<V, K>& r
         const float2 colGA = make_float2(cc.COp, cc.CE);
         const float2 colCO = make_float2(cc.CO, cc.CO);
         float ROp0;
-        if constexpr (V == V_SS) {
+        if constexpr (is_ss<V>()) {
                 ROp0 = J.o;
         } else {
                 ROp0 = rc.ROp[0];
@@ -199,7 +203,7 @@ __device__ __forceinline__ void cells_mid2(const KbJob& J, const RowCtx<V, K>& r
                 const float oGA0 = sGA[k], oGA1 = sGA[k + 1];
                 const float oGB0 = sGB[k], oGB1 = sGB[k + 1];
                 float RO0, RE0, RO1, RE1, ROpA, ROpB;
-                if constexpr (V == V_SS) {
+                if constexpr (is_ss<V>()) {
                         RO0 = RO1 = J.o; RE0 = RE1 = J.e; ROpA = ROpB = J.o;
                 } else {
                         RO0 = rc.RO[k]; RE0 = rc.RE[k]; RO1 = rc.RO[k + 1]; RE1 = rc.RE[k + 1];
@@ -219,7 +223,7 @@ __device__ __forceinline__ void cells_mid2(const KbJob& J, const RowCtx<V, K>& r
                         a01 = add2(a01, x);
                 } else if constexpr (V == V_SP) {
                         a01 = add2(a01, make_float2(__ldg(rc.prow[k] + 32 + cc.cres), __ldg(rc.prow[k + 1] + 32 + cc.cres)));
-                } else if constexpr (V == V_SP5) {
+                } else if constexpr (V == V_SP5 || V == V_SS5) {
                         const float* sv = rc.sprow + cc.cres * 32;
                         a01 = add2(a01, make_float2(sv[k * 160], sv[(k + 1) * 160]));
                 } else {
@@ -251,7 +255,7 @@ __device__ __forceinline__ void cells_mid2(const KbJob& J, const RowCtx<V, K>& r
                 float gb0 = kmax(u.gb + RE0, u.a + RO0);
                 if constexpr (EDGE) {
                         float RT0;
-                        if constexpr (V == V_SS) {
+                        if constexpr (is_ss<V>()) {
                                 RT0 = J.t;
                         } else {
                                 RT0 = rc.RT[k];
@@ -269,7 +273,7 @@ __device__ __forceinline__ void cells_mid2(const KbJob& J, const RowCtx<V, K>& r
                 float gb1 = kmax(gb0 + RE1, a0 + RO1);
                 if constexpr (EDGE) {
                         float RT1;
-                        if constexpr (V == V_SS) {
+                        if constexpr (is_ss<V>()) {
                                 RT1 = J.t;
                         } else {
                                 RT1 = rc.RT[k + 1];
@@ -331,7 +335,7 @@ __device__ __forceinline__ void cells(const KbJob& J, const RowCtx<V, K>& rc, co
         for (int k = 0; k < K; k++) {
                 const float oA = sA[k], oGA = sGA[k], oGB = sGB[k];
                 float RO, RE, RT, ROp;
-                if constexpr (V == V_SS) {
+                if constexpr (is_ss<V>()) {
                         RO = J.o; RE = J.e; RT = J.t; ROp = J.o;
                 } else {
                         RO = rc.RO[k]; RE = rc.RE[k]; RT = rc.RT[k]; ROp = rc.ROp[k];
@@ -348,7 +352,7 @@ __device__ __forceinline__ void cells(const KbJob& J, const RowCtx<V, K>& rc, co
                                 a = a + x;
                         } else if constexpr (V == V_SP) {
                                 a = a + __ldg(rc.prow[k] + 32 + cc.cres);
-                        } else if constexpr (V == V_SP5) {
+                        } else if constexpr (V == V_SP5 || V == V_SS5) {
                                 a = a + rc.sprow[k * 160 + cc.cres * 32];
                         } else {
 #pragma unroll
@@ -446,7 +450,7 @@ __device__ __forceinline__ unsigned load_rows(const KbJob& J, const int bwd, con
                         if (i < 0) i = 0;
                 }
                 rc.irow[k] = i;
-                if constexpr (V == V_SS) {
+                if constexpr (is_ss<V>()) {
                         rc.rbase[k] = (int)J.seq_r[i] * tstride;
                 } else {
                         const float* p = J.prof_r + ((size_t)(i + 1) << 6);
@@ -542,17 +546,23 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
         const int R = r1 - r0;
         RowCtx<V, K> rc;
         const unsigned vmask = load_rows<V, K>(J, bwd, r0, r1, row0 + lane * K, tstride, rc);
-        if constexpr (V == V_SP5) {
+        if constexpr (V == V_SP5 || V == V_SS5) {
                 // stage the score vectors of this lane's rows: the per-cell lookup becomes a conflict-free
-                // LDS (every lane reads its own bank) instead of an uncoalesced gather that misses L1
-                static_assert(K <= 4, "score-vector staging area holds 4 rows per lane");
+                // LDS (every lane reads its own bank) with an immediate row offset -- instead of an
+                // uncoalesced gather that misses L1 (profile rows) or two address multiply-adds per
+                // cell plus the offset add (sequence rows: (subm[r][c] - offset) is formed here, once)
+                static_assert(K <= ((BONUS == BONUS_NONE) ? 8 : 4), "score-vector staging area");
                 float* sp = reinterpret_cast<float*>(s_rec) + lane;
                 __syncwarp();
 #pragma unroll
                 for (int k = 0; k < K; k++) {
 #pragma unroll
                         for (int c = 0; c < 5; c++) {
-                                sp[(k * 5 + c) * 32] = __ldg(rc.prow[k] + 32 + c);
+                                if constexpr (V == V_SP5) {
+                                        sp[(k * 5 + c) * 32] = __ldg(rc.prow[k] + 32 + c);
+                                } else {
+                                        sp[(k * 5 + c) * 32] = s_tbl[rc.rbase[k] + c] + J.nsoff;
+                                }
                         }
                 }
                 rc.sprow = sp;
@@ -756,7 +766,20 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                                 cc.CO = J.o; cc.CE = J.e; CT = J.t; cc.COp = J.o;
                         }
                         // ---- lane 0: take the row above from the source ----
-                        if (lane == 0) {
+                        if constexpr (STEADY) {
+                                // branch-free: every lane evaluates the init-row generator (three
+                                // operations), lane 0 keeps the result -- no divergent region per step
+                                const float nga = first_term ? (kmax(genGA, genA) + CT) : kmax(genGA + cc.CE, genA + cc.CO);
+                                const bool l0 = (lane == 0);
+                                const float sa = gen ? KB_NEGF : hin.x;
+                                const float sga = gen ? nga : hin.y;
+                                const float sgb = gen ? KB_NEGF : hin.z;
+                                up.a = l0 ? sa : up.a;
+                                up.ga = l0 ? sga : up.ga;
+                                up.gb = l0 ? sgb : up.gb;
+                                genA = KB_NEGF;
+                                genGA = nga;
+                        } else if (lane == 0) {
                                 if (gen) {
                                         if (!STEADY && u == 0) {
                                                 up = in;
@@ -885,7 +908,7 @@ __device__ void sweep_unit(const KbJob& J, const KbBox& bx, const int bwd, const
         } else if constexpr (V == V_PP23) {
                 if (rem >= 64) KB_STRIP(2, false);
                 else KB_STRIP(2, true);
-        } else if constexpr (V == V_SS && !BONUS) {
+        } else if constexpr (is_ss<V>() && !BONUS) {
                 if (rem >= 256) KB_STRIP(8, false);
                 else if (kneed > 6) KB_STRIP(8, true);
                 else if (kneed > 4) KB_STRIP(6, true);
@@ -914,8 +937,9 @@ kb_sweep_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes,
         __shared__ float s_tbl[TBL_MAX];
         __shared__ float4 s_ring_all[WARPS_PER_CTA][16];     // hand-off ring (row above), one per warp
         // per warp: 5-letter profile-profile column records (two 64-column rings, 2 KB) or the staged
-        // score vectors of a 5-letter profile-sequence strip ([4 rows][5 letters][32 lanes] floats)
-        __shared__ float4 s_rec_all[WARPS_PER_CTA][160];
+        // score vectors of a 5-letter sequence / profile-sequence strip ([K rows][5 letters][32 lanes] floats)
+        constexpr int REC_F4 = (BONUS == BONUS_NONE) ? 320 : 160;     // K = 8 rows per lane without a bonus
+        __shared__ float4 s_rec_all[WARPS_PER_CTA][REC_F4];
         for (int i = threadIdx.x; i < TBL_MAX; i += blockDim.x) {
                 s_tbl[i] = tbl[i];
         }
@@ -942,7 +966,11 @@ kb_sweep_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes,
                 const KbJob J = jobs[bx.job];
                 const unsigned ps = tag_base;
                 if (J.kind == KB200_KIND_SS) {
-                        sweep_unit<V_SS, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
+                        if (tstride == 5) {
+                                sweep_unit<V_SS5, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
+                        } else {
+                                sweep_unit<V_SS, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
+                        }
                 } else if (J.kind == KB200_KIND_SP) {
                         if (J.nalpha <= 5) {
                                 sweep_unit<V_SP5, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
@@ -1365,7 +1393,7 @@ __device__ void small_box_run(const KbJob& J, const KbBox& root, const float* __
                 // meet-up
                 const float middle = (float)(eb - sb) / 2.0F + (float)sb;
                 float x2, x3, x5, x6, x6last, x7;
-                if constexpr (V == V_SS) {
+                if constexpr (is_ss<V>()) {
                         x2 = x3 = x5 = x7 = J.o;
                         x6 = (sb == 0) ? J.t : J.e;
                         x6last = (eb == J.len_b) ? J.t : J.e;
@@ -1631,7 +1659,7 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
                 static bool carveout_set = false;
                 if (!carveout_set) {
                         cudaFuncSetAttribute(kb_sweep_kernel<BONUS_SPARSE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-                        cudaFuncSetAttribute(kb_sweep_kernel<BONUS_NONE>, cudaFuncAttributePreferredSharedMemoryCarveout, 40);
+                        cudaFuncSetAttribute(kb_sweep_kernel<BONUS_NONE>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
                         cudaFuncSetAttribute(kb_sweep_kernel<BONUS_DENSE>, cudaFuncAttributePreferredSharedMemoryCarveout, 40);
                         carveout_set = true;
                 }
