@@ -1,12 +1,12 @@
 #!/usr/bin/env python3
 """Instruction mix of the steady-state inner loops (one wavefront step) of the sweep kernels, read
-from the SASS -- no GPU needed.  usage: tools/sass_steady.py [kalign_b200/csrc/kb_dp.o]"""
+from the SASS -- no GPU needed.  usage: tools/sass_steady.py [kalign_b200/libkalign_b200.so]"""
 import re
 import subprocess
 import sys
 from collections import Counter
 
-obj = sys.argv[1] if len(sys.argv) > 1 else "kalign_b200/csrc/kb_dp.o"
+obj = sys.argv[1] if len(sys.argv) > 1 else "kalign_b200/libkalign_b200.so"
 out = subprocess.run(["cuobjdump", "-sass", obj], stdout=subprocess.PIPE, text=True).stdout
 for f in re.split(r"\n\s*Function : ", out)[1:]:
     name = f.split("\n", 1)[0]
