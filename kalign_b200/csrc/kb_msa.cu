@@ -23,6 +23,7 @@
 #include <string.h>
 #include <algorithm>
 #include <string>
+#include <thread>
 
 #ifdef _OPENMP
 #include <omp.h>
@@ -455,11 +456,23 @@ void select_anchors(const float* sd, int N, int K, std::vector<int>& ids)
 
 // Guide tree on device-resident tree-alphabet sequences: tasks (a,b,c) sorted by c and
 // msa->seq_distances (build_tree_kmeans, bisectingKmeans.c:177-271).
-int kb_build_tree(kb200_ctx* ctx, KbSeqs& S, int n_threads, std::vector<int>& abc, std::vector<float>& seq_distances)
+// The guide tree in three stages, so that the host-only middle one can run beside GPU work:
+//   prepare : anchors, N x 32 distance matrix (GPU), msa->seq_distances
+//   bisect  : bisecting k-means over the distance rows (host, OpenMP tasks)
+//   finish  : leaf-cluster distances (GPU), UPGMA per cluster, task list
+struct KbTreeJob {
+        TreeBuilder B;
+        std::vector<float> dm;
+        int num_anchor = 0;
+        int stride = 0;
+        int root = -1;
+};
+
+int kb_tree_prepare(kb200_ctx* ctx, KbSeqs& S, KbTreeJob& T, std::vector<float>& seq_distances)
 {
         const int N = S.n;
         const double tt0 = kb_now();
-        TreeBuilder B;
+        TreeBuilder& B = T.B;
         B.N = N;
         // pick_anchor / select_seqs (pick_anchor.c:17-72)
         const int num_anchor = std::min(32, N);
@@ -478,30 +491,60 @@ int kb_build_tree(kb200_ctx* ctx, KbSeqs& S, int n_threads, std::vector<int>& ab
         }
         // d_estimation(pair = 0): N x num_anchor, rows padded to a multiple of 8 with zeros
         const int stride = ((num_anchor + 7) / 8) * 8;
-        std::vector<float> dm((size_t)N * stride, 0.0f);
+        T.dm.assign((size_t)N * stride, 0.0f);
         {
                 std::vector<int> rows((size_t)N);
                 for (int i = 0; i < N; i++) rows[(size_t)i] = i;
                 std::vector<float> tmp((size_t)N * num_anchor);
                 KB_RUN(kb_distances_dev(ctx, S, rows.data(), N, anchors.data(), num_anchor, 0, tmp.data()));
                 for (int i = 0; i < N; i++) {
-                        memcpy(dm.data() + (size_t)i * stride, tmp.data() + (size_t)i * num_anchor, sizeof(float) * (size_t)num_anchor);
+                        memcpy(T.dm.data() + (size_t)i * stride, tmp.data() + (size_t)i * num_anchor, sizeof(float) * (size_t)num_anchor);
                 }
         }
-        B.dm = dm.data();
+        T.num_anchor = num_anchor;
+        T.stride = stride;
+        B.dm = T.dm.data();
         B.stride = stride;
         B.num_anchors = num_anchor;
         B.nodes.reserve((size_t)2 * N + 64);
+        // msa->seq_distances (bisectingKmeans.c:247-256)
+        seq_distances.resize((size_t)N);
+        for (int i = 0; i < N; i++) {
+                float sum = 0.0f;
+                for (int j = 0; j < num_anchor; j++) sum += T.dm[(size_t)i * stride + j];
+                const float mean_dist = sum / (float)num_anchor;
+                const float seq_len = (float)S.h_lens[i];
+                seq_distances[(size_t)i] = (seq_len > 0.0f) ? mean_dist / seq_len : 0.0f;
+        }
+        if (kb_trace_on()) {
+                fprintf(stderr, "[kb200 trace] guide tree: anchor distances %.1f ms\n", 1e3 * (kb_now() - tt0));
+        }
+        return KB200_OK;
+}
+
+void kb_tree_bisect(KbTreeJob& T, int n_threads)
+{
+        const double tt1 = kb_now();
+        const int N = T.B.N;
         std::vector<int> samples((size_t)N);
         for (int i = 0; i < N; i++) samples[(size_t)i] = i;
         int root = -1;
-        const double tt1 = kb_now();
 #ifdef _OPENMP
 #pragma omp parallel num_threads(n_threads > 0 ? n_threads : 1)
 #pragma omp single
 #endif
-        root = bisect(B, samples);
+        root = bisect(T.B, samples);
+        T.root = root;
+        if (kb_trace_on()) {
+                fprintf(stderr, "[kb200 trace] guide tree: bisecting k-means %.1f ms (%d threads)\n", 1e3 * (kb_now() - tt1), n_threads);
+        }
+}
+
+int kb_tree_finish(kb200_ctx* ctx, KbSeqs& S, KbTreeJob& T, int n_threads, std::vector<int>& abc)
+{
         const double tt2 = kb_now();
+        TreeBuilder& B = T.B;
+        const int N = B.N;
         // leaf clusters: one batched launch for every i<j pair of every cluster.
         // d_estimation(pair=1) leaves dm[i][j] (i<j) = calc_distance(seq_j, seq_i)
         // (sequence_distance.c:53-81: the later (j,i) iteration overwrites both entries).
@@ -552,13 +595,13 @@ int kb_build_tree(kb200_ctx* ctx, KbSeqs& S, int n_threads, std::vector<int>& ab
                         const size_t ci = (size_t)cl;
                         const Cluster& c = B.clusters[ci];
                         const int n = (int)c.samples.size();
-                        size_t e = pair0[ci];
+                        size_t e2 = pair0[ci];
                         std::vector<float> cdm((size_t)n * n, 0.0f);
                         for (int i = 0; i < n; i++) {
                                 for (int j = i + 1; j < n; j++) {
-                                        cdm[(size_t)i * n + j] = pd[e];
-                                        cdm[(size_t)j * n + i] = pd[e];
-                                        e++;
+                                        cdm[(size_t)i * n + j] = pd[e2];
+                                        cdm[(size_t)j * n + i] = pd[e2];
+                                        e2++;
                                 }
                         }
                         cluster_root[ci] = upgma(B, cdm.data(), c.samples, node0[ci]);
@@ -568,27 +611,26 @@ int kb_build_tree(kb200_ctx* ctx, KbSeqs& S, int n_threads, std::vector<int>& ab
                         B.nodes[(size_t)B.clusters[ci].placeholder] = B.nodes[(size_t)cluster_root[ci]];
                 }
         }
-        const double tt3 = kb_now();
         abc.clear();
         abc.reserve((size_t)3 * (N - 1));
-        emit_tasks(B, root, N, abc);
+        emit_tasks(B, T.root, N, abc);
         if (kb_trace_on()) {
-                fprintf(stderr, "[kb200 trace] guide tree: anchor distances %.1f ms, bisecting k-means %.1f ms (%d threads), leaf distances + upgma %.1f ms\n",
-                        1e3 * (tt1 - tt0), 1e3 * (tt2 - tt1), n_threads, 1e3 * (tt3 - tt2));
+                fprintf(stderr, "[kb200 trace] guide tree: leaf distances + upgma %.1f ms\n", 1e3 * (kb_now() - tt2));
         }
         if ((int)abc.size() != 3 * (N - 1)) {
                 fprintf(stderr, "[kalign_b200] guide tree: %zu tasks for %d sequences\n", abc.size() / 3, N);
                 return KB200_FAIL;
         }
-        seq_distances.resize((size_t)N);
-        for (int i = 0; i < N; i++) {
-                float sum = 0.0f;
-                for (int j = 0; j < num_anchor; j++) sum += dm[(size_t)i * stride + j];
-                const float mean_dist = sum / (float)num_anchor;
-                const float seq_len = (float)S.h_lens[i];
-                seq_distances[(size_t)i] = (seq_len > 0.0f) ? mean_dist / seq_len : 0.0f;
-        }
         return KB200_OK;
+}
+
+// build_tree_kmeans (bisectingKmeans.c:177-271) in one go
+int kb_build_tree(kb200_ctx* ctx, KbSeqs& S, int n_threads, std::vector<int>& abc, std::vector<float>& seq_distances)
+{
+        KbTreeJob T;
+        KB_RUN(kb_tree_prepare(ctx, S, T, seq_distances));
+        kb_tree_bisect(T, n_threads);
+        return kb_tree_finish(ctx, S, T, n_threads, abc);
 }
 
 
@@ -607,6 +649,11 @@ struct kb200_msa {
         std::vector<uint8_t> codes;
         int64_t total = 0;
         KbSeqs S;
+        // deferred guide tree (kb200_kalign): k-means runs on a host thread beside the anchor batch;
+        // proteins keep their 13-letter tree codes on the device for the leaf-cluster distances
+        KbTreeJob* tree_job = nullptr;
+        std::vector<uint8_t> codes_tree;
+        KbSeqs S_tree;
         std::vector<int> abc;
         std::vector<float> seq_distances;
         std::vector<int> posmaps;
@@ -668,13 +715,15 @@ void kb200_msa_free(kb200_msa* M)
         if (!M) return;
         if (M->ctx) cudaSetDevice(M->ctx->device);
         M->S.release();
+        M->S_tree.release();
+        delete M->tree_job;
         delete M;
 }
 
 // everything of kalign_run_seeded (aln_wrap.c:133-205) that precedes the DP stages
-int kb200_msa_create(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_threads, int type,
-                     float gpo, float gpe, float tgpe, int consistency_anchors, float consistency_weight,
-                     kb200_msa** out)
+static int msa_create_impl(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_threads, int type,
+                           float gpo, float gpe, float tgpe, int consistency_anchors, float consistency_weight,
+                           const bool defer_tree, kb200_msa** out)
 {
         if (!ctx || !seq || !len || !out) {
                 return KB200_FAIL;
@@ -774,16 +823,38 @@ int kb200_msa_create(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_thr
         M->gaps.assign((size_t)total + (size_t)N, 0);
         encode_seqs(M, biotype == 1 ? ALPHA_DNA : ALPHA_RED, n_threads);
         const double tc1 = kb_now();
-        int rc = M->S.upload(ctx, M->codes.data(), M->offs.data(), M->lens.data(), N);
-        const double tc2 = kb_now();
-        if (rc == KB200_OK) rc = kb_build_tree(ctx, M->S, n_threads, M->abc, M->seq_distances);
-        if (kb_trace_on()) {
-                fprintf(stderr, "[kb200 trace] msa_create: detect/sort/encode %.1f ms, upload %.1f ms, guide tree %.1f ms\n",
-                        1e3 * (tc1 - tc0), 1e3 * (tc2 - tc1), 1e3 * (kb_now() - tc2));
-        }
-        if (rc == KB200_OK && biotype == 0) {
-                encode_seqs(M, ALPHA_AMB, n_threads);
+        int rc = KB200_OK;
+        double tc2 = tc1;
+        if (!defer_tree) {
                 rc = M->S.upload(ctx, M->codes.data(), M->offs.data(), M->lens.data(), N);
+                tc2 = kb_now();
+                if (rc == KB200_OK) rc = kb_build_tree(ctx, M->S, n_threads, M->abc, M->seq_distances);
+                if (rc == KB200_OK && biotype == 0) {
+                        encode_seqs(M, ALPHA_AMB, n_threads);
+                        rc = M->S.upload(ctx, M->codes.data(), M->offs.data(), M->lens.data(), N);
+                }
+        } else {
+                // only the first stage of the tree here (distance matrix -> seq_distances -> anchors);
+                // kb200_kalign runs k-means beside the anchor batch and finishes the tree afterwards
+                M->tree_job = new KbTreeJob();
+                if (biotype == 0) {
+                        M->codes_tree = M->codes;                    // 13-letter tree alphabet
+                        rc = M->S_tree.upload(ctx, M->codes_tree.data(), M->offs.data(), M->lens.data(), N);
+                        tc2 = kb_now();
+                        if (rc == KB200_OK) rc = kb_tree_prepare(ctx, M->S_tree, *M->tree_job, M->seq_distances);
+                        if (rc == KB200_OK) {
+                                encode_seqs(M, ALPHA_AMB, n_threads);
+                                rc = M->S.upload(ctx, M->codes.data(), M->offs.data(), M->lens.data(), N);
+                        }
+                } else {
+                        rc = M->S.upload(ctx, M->codes.data(), M->offs.data(), M->lens.data(), N);
+                        tc2 = kb_now();
+                        if (rc == KB200_OK) rc = kb_tree_prepare(ctx, M->S, *M->tree_job, M->seq_distances);
+                }
+        }
+        if (kb_trace_on()) {
+                fprintf(stderr, "[kb200 trace] msa_create: detect/sort/encode %.1f ms, upload %.1f ms, guide tree%s %.1f ms\n",
+                        1e3 * (tc1 - tc0), 1e3 * (tc2 - tc1), defer_tree ? " (first stage)" : "", 1e3 * (kb_now() - tc2));
         }
         if (rc == KB200_OK) {
                 // resolve_pfasum_auto, aln_wrap.c:31-68
@@ -813,22 +884,43 @@ int kb200_msa_create(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_thr
         return KB200_OK;
 }
 
+int kb200_msa_create(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_threads, int type,
+                     float gpo, float gpe, float tgpe, int consistency_anchors, float consistency_weight,
+                     kb200_msa** out)
+{
+        return msa_create_impl(ctx, seq, len, numseq, n_threads, type, gpo, gpe, tgpe, consistency_anchors, consistency_weight,
+                               false, out);
+}
+
 // the DP stages (anchor_consistency_build + create_msa_tree) on device-resident sequences;
 // may be called repeatedly (bench), every call recomputes everything.
+static int msa_align_anchor(kb200_msa* M)
+{
+        if (M->K > 0) {
+                KB_RUN(kb_anchor_posmaps_sharded(M->ctx, &M->prm, M->S, M->anchor_ids.data(), M->K, M->posmaps.data(), kb_bonus_on_host(M->K)));
+        }
+        return KB200_OK;
+}
+
+static int msa_align_tree(kb200_msa* M)
+{
+        KB_RUN(kb_align_tree_dev(M->ctx, &M->prm, M->S, M->abc.data(), M->N - 1, M->seq_distances.data(),
+                                 M->K > 0 ? M->posmaps.data() : nullptr, M->K, M->weight, M->n_threads, M->gaps.data(), 1));
+        M->aligned = true;
+        return KB200_OK;
+}
+
 int kb200_msa_align(kb200_msa* M)
 {
-        if (!M) return KB200_FAIL;
+        if (!M || M->tree_job) return KB200_FAIL;       // a deferred tree is finished by kb200_kalign only
         kb200_ctx* ctx = M->ctx;
         KB_CUDA(cudaSetDevice(ctx->device));
         cudaEvent_t e0, e1;
         KB_CUDA(cudaEventCreate(&e0));
         KB_CUDA(cudaEventCreate(&e1));
         KB_CUDA(cudaEventRecord(e0, ctx->stream));
-        if (M->K > 0) {
-                KB_RUN(kb_anchor_posmaps_sharded(ctx, &M->prm, M->S, M->anchor_ids.data(), M->K, M->posmaps.data(), kb_bonus_on_host(M->K)));
-        }
-        KB_RUN(kb_align_tree_dev(ctx, &M->prm, M->S, M->abc.data(), M->N - 1, M->seq_distances.data(),
-                                 M->K > 0 ? M->posmaps.data() : nullptr, M->K, M->weight, M->n_threads, M->gaps.data(), 1));
+        KB_RUN(msa_align_anchor(M));
+        KB_RUN(msa_align_tree(M));
         KB_CUDA(cudaEventRecord(e1, ctx->stream));
         KB_CUDA(cudaEventSynchronize(e1));
         float ms = 0.0f;
@@ -836,7 +928,6 @@ int kb200_msa_align(kb200_msa* M)
         ctx->stats.align_seconds += 1e-3 * (double)ms;
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
-        M->aligned = true;
         return KB200_OK;
 }
 
@@ -909,16 +1000,34 @@ int kb200_kalign(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_threads
         if (!aligned || !out_aln_len) {
                 return KB200_FAIL;
         }
+        // One-shot call: the host-only stage of the guide tree (bisecting k-means) runs on a host
+        // thread while the GPU works through the anchor batch, which needs only seq_distances.
         kb200_msa* M = nullptr;
-        KB_RUN(kb200_msa_create(ctx, seq, len, numseq, n_threads, type, gpo, gpe, tgpe,
-                                consistency_anchors, consistency_weight, &M));
+        KB_RUN(msa_create_impl(ctx, seq, len, numseq, n_threads, type, gpo, gpe, tgpe,
+                               consistency_anchors, consistency_weight, true, &M));
         const double ta0 = kb_now();
-        int rc = kb200_msa_align(M);
+        int rc = KB200_OK;
+        {
+                KbTreeJob* T = M->tree_job;
+                const int nt = M->n_threads;
+                std::thread kmeans([T, nt]() { kb_tree_bisect(*T, nt); });
+                rc = msa_align_anchor(M);
+                kmeans.join();
+                if (rc == KB200_OK) {
+                        rc = kb_tree_finish(ctx, M->biotype == 0 ? M->S_tree : M->S, *T, nt, M->abc);
+                }
+                delete M->tree_job;
+                M->tree_job = nullptr;
+                M->S_tree.release();
+        }
         const double ta1 = kb_now();
+        if (rc == KB200_OK) rc = msa_align_tree(M);
+        const double ta2 = kb_now();
         if (rc == KB200_OK) rc = kb200_msa_result(M, aligned, out_aln_len);
         kb200_msa_free(M);
         if (kb_trace_on()) {
-                fprintf(stderr, "[kb200 trace] kalign: align %.1f ms, result + free %.1f ms\n", 1e3 * (ta1 - ta0), 1e3 * (kb_now() - ta1));
+                fprintf(stderr, "[kb200 trace] kalign: anchor batch || k-means, tree finish %.1f ms, tree levels %.1f ms, result + free %.1f ms\n",
+                        1e3 * (ta1 - ta0), 1e3 * (ta2 - ta1), 1e3 * (kb_now() - ta2));
         }
         return rc;
 }
