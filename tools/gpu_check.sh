@@ -9,10 +9,10 @@ timeout 900 python -m pytest tests -m gpu -x -q > $O/pytest.log 2>&1; echo "pyte
 tail -3 $O/pytest.log
 timeout 600 python bench.py > $O/bench_c3.json 2> $O/bench_c3.err; echo "bench exit $?"
 cat $O/bench_c3.json
-timeout 300 python bench.py --impl reference --steps 1 --warmup 0 > $O/bench_c3_reference.json 2> $O/bench_c3_reference.err; echo "reference arm exit $?"
+if [ -z "$KB200_CHECK_SKIP_REF" ]; then timeout 300 python bench.py --impl reference --steps 1 --warmup 0 > $O/bench_c3_reference.json 2> $O/bench_c3_reference.err; echo "reference arm exit $?"; fi
 KB200_TRACE=1 timeout 300 python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $O/trace_bench.json 2> $O/trace_c3.log
 python tools/trace_sum.py $O/trace_c3.log > $O/trace_sum.txt; cat $O/trace_sum.txt
-for w in C2 C4; do
+for w in ${KB200_CHECK_SHAPES:-C2 C4}; do
   timeout 400 python bench.py --workload $w --steps 2 --warmup 1 --no-cpu-baseline > $O/bench_$w.json 2> $O/bench_$w.err; echo "bench $w exit $?"
   grep -o '"ms_per_step": [0-9.]*\|"seconds_per_call": [0-9.]*' $O/bench_$w.json | tr '\n' ' '; echo
 done
