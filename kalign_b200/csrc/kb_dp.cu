@@ -341,12 +341,12 @@ __device__ void small_sweep(const KbJob& J, const int bwd, const int r0, const i
                 RowCtx<V, K> rc;
                 const unsigned vmask = load_rows<V, K>(J, bwd, r0, r1, v0, tstride, rc);
                 set_table_addr<V, K>(rc, s_tbl);
-                float sA[K], sGA[K], sGB[K], bon[K];
+                float sA[K], sGA[K], sGB[K];
                 int sp_i[K], sp_c[K];
                 float sp_v[K], sp_wrap[K];
 #pragma unroll
                 for (int k = 0; k < K; k++) {
-                        sA[k] = KB_NEGF; sGA[k] = KB_NEGF; sGB[k] = KB_NEGF; bon[k] = 0.0f;
+                        sA[k] = KB_NEGF; sGA[k] = KB_NEGF; sGB[k] = KB_NEGF;
                         sp_i[k] = 0; sp_c[k] = bwd ? -1 : 0x7fffffff; sp_v[k] = 0.0f; sp_wrap[k] = 0.0f;
                 }
                 if constexpr (BONUS) {
@@ -389,7 +389,7 @@ __device__ void small_sweep(const KbJob& J, const int bwd, const int r0, const i
                         const float4 q = S[0];
                         Trip up = {q.x, q.y, q.z};
                         const Trip got = up;
-                        cells<V, K, true, MODE_FIRST, BONUS, false>(J, rc, vmask, first_term, last_term, cc, bon, sparse, dstep, sp_i, sp_c, sp_v, sp_wrap, nullptr, s_tbl, sA, sGA, sGB, d, up);
+                        cells<V, K, true, MODE_FIRST, BONUS, false>(J, rc, vmask, first_term, last_term, cc, dstep, sp_i, sp_c, sp_v, sp_wrap, nullptr, s_tbl, sA, sGA, sGB, d, up);
                         d = got;
                         S[0] = make_float4(up.a, up.ga, up.gb, 0.0f);
                 }
@@ -398,7 +398,7 @@ __device__ void small_sweep(const KbJob& J, const int bwd, const int r0, const i
                         const float4 q = S[u];
                         Trip up = {q.x, q.y, q.z};
                         const Trip got = up;
-                        cells<V, K, true, MODE_MID, BONUS, false>(J, rc, vmask, first_term, last_term, cc, bon, sparse, dstep, sp_i, sp_c, sp_v, sp_wrap, nullptr, s_tbl, sA, sGA, sGB, d, up);
+                        cells<V, K, true, MODE_MID, BONUS, false>(J, rc, vmask, first_term, last_term, cc, dstep, sp_i, sp_c, sp_v, sp_wrap, nullptr, s_tbl, sA, sGA, sGB, d, up);
                         d = got;
                         S[u] = make_float4(up.a, up.ga, up.gb, 0.0f);
                 }
@@ -406,7 +406,7 @@ __device__ void small_sweep(const KbJob& J, const int bwd, const int r0, const i
                         column(C);
                         const float4 q = S[C];
                         Trip up = {q.x, q.y, q.z};
-                        cells<V, K, true, MODE_LAST, BONUS, false>(J, rc, vmask, first_term, last_term, cc, bon, sparse, dstep, sp_i, sp_c, sp_v, sp_wrap, nullptr, s_tbl, sA, sGA, sGB, d, up);
+                        cells<V, K, true, MODE_LAST, BONUS, false>(J, rc, vmask, first_term, last_term, cc, dstep, sp_i, sp_c, sp_v, sp_wrap, nullptr, s_tbl, sA, sGA, sGB, d, up);
                         S[C] = make_float4(up.a, up.ga, up.gb, 0.0f);
                 }
         }

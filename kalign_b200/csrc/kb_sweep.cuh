@@ -140,8 +140,8 @@ __device__ __forceinline__ float2 add2(const float2 a, const float2 b)
 template <int V, int K, bool TAIL, int MODE, int BONUS, bool BSM>
 __device__ __forceinline__ void cells(const KbJob& J, const RowCtx<V, K>& rc, const unsigned vmask,
                                       const bool first_term, const bool last_term,
-                                      const ColCtx<V>& cc, const float (&bon)[K],
-                                      const bool sparse, const int bdir, int (&sp_i)[K], int (&sp_c)[K], float (&sp_v)[K],
+                                      const ColCtx<V>& cc,
+                                      const int bdir, int (&sp_i)[K], int (&sp_c)[K], float (&sp_v)[K],
                                       const float (&sp_wrap)[K], const int2* __restrict__ s_bon,
                                       const float* __restrict__ s_tbl,
                                       float (&sA)[K], float (&sGA)[K], float (&sGB)[K],
@@ -301,8 +301,8 @@ __device__ __forceinline__ void cells_mid2(const KbJob& J, const RowCtx<V, K>& r
 template <int V, int K, bool TAIL, int MODE, int BONUS, bool BSM>
 __device__ __forceinline__ void cells(const KbJob& J, const RowCtx<V, K>& rc, const unsigned vmask,
                                       const bool first_term, const bool last_term,
-                                      const ColCtx<V>& cc, const float (&bon)[K],
-                                      const bool sparse, const int bdir, int (&sp_i)[K], int (&sp_c)[K], float (&sp_v)[K],
+                                      const ColCtx<V>& cc,
+                                      const int bdir, int (&sp_i)[K], int (&sp_c)[K], float (&sp_v)[K],
                                       const float (&sp_wrap)[K], const int2* __restrict__ s_bon,
                                       const float* __restrict__ s_tbl,
                                       float (&sA)[K], float (&sGA)[K], float (&sGB)[K],
@@ -658,9 +658,6 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
         // column input of the current step (filled one step ahead); lane 0 starts on column 0 at t=0
         float4 curA = make_float4(0.f, 0.f, 0.f, 0.f), curB = curA;
         int cur_cres = 0;
-        float cur_bon[K];
-#pragma unroll
-        for (int k = 0; k < K; k++) cur_bon[k] = 0.0f;
         // sparse consistency bonus: per row the index / column / value of the next entry in sweep
         // direction, and the value the forward sweep picks up at j == len_b (flat index (i+1, 0))
         const bool sparse = (BONUS == BONUS_SPARSE) && (J.bkey != nullptr);
@@ -801,9 +798,9 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                         }
                         const Trip got = up;
                         if constexpr (STEADY) {
-                                cells<V, K, TAIL, MODE_MID, BONUS, true>(J, rc, vmask, first_term, last_term, cc, cur_bon, sparse, bdir, sp_i, sp_c, sp_v, sp_wrap, my_bon, s_tbl, sA, sGA, sGB, d, up);
+                                cells<V, K, TAIL, MODE_MID, BONUS, true>(J, rc, vmask, first_term, last_term, cc, bdir, sp_i, sp_c, sp_v, sp_wrap, my_bon, s_tbl, sA, sGA, sGB, d, up);
                         } else {
-                                cells<V, K, TAIL, MODE_EDGE, BONUS, true>(J, rc, vmask, first_term, last_term, cc, cur_bon, sparse, bdir, sp_i, sp_c, sp_v, sp_wrap, my_bon, s_tbl, sA, sGA, sGB, d, up, u == 0, u == C);
+                                cells<V, K, TAIL, MODE_EDGE, BONUS, true>(J, rc, vmask, first_term, last_term, cc, bdir, sp_i, sp_c, sp_v, sp_wrap, my_bon, s_tbl, sA, sGA, sGB, d, up, u == 0, u == C);
                         }
                         d = got;
                         bot = up;
