@@ -183,6 +183,8 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
+        # rank 0 alone runs the reference arm: it may use every host thread of the node
+        host_threads = max(1, effective_cpus())
         # bounded sample of the same workload, every step re-runs it
         times = []
         seqs = None
