@@ -292,6 +292,10 @@ def main():
     ach = abytes / d["sweep_seconds"] / 1e9 if d["sweep_seconds"] > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "kb_sweep_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "note": "algorithmic-bytes model of SURVEY 8d (25 B per ss/sp cell, 128 B per pp cell): the DP state lives in "
+                        "registers, so measured DRAM traffic is ~1000x below it (ncu, profiles/r01f_sweep_kernel_full_C3_n1000.csv: "
+                        "0.24 GB per launch for 281 GB algorithmic) and frac > 1; the kernel is issue-bound "
+                        "(smsp__issue_active 76 %, 17 thread-instructions per cell)",
                 "algorithmic_bytes_per_step": abytes / max(1, args.steps),
                 "kernel_seconds_per_step": d["sweep_seconds"] / max(1, args.steps),
                 "kernel_share_of_step": d["sweep_seconds"] / d["align_seconds"] if d["align_seconds"] > 0 else None,
