@@ -129,6 +129,18 @@ def algorithmic_bytes(st):
     return 25.0 * (ss + sp) + 128.0 * pp + 4.0 * bonus
 
 
+def golden_sha(workload, n):
+    """SHA-256 of the reference's alignment of this workload (tests/golden/full_<wl>.npz, written by
+    tools/gen_golden_full.py from the unmodified reference), or None when no fixture fits"""
+    p = os.path.join(ROOT, "tests", "golden", "full_%s.npz" % workload)
+    if not os.path.exists(p):
+        return None
+    g = np.load(p, allow_pickle=False)
+    if n is not None and int(g["n"]) != n:
+        return None
+    return str(g["msa_sha256"])
+
+
 def delta(a, b):
     return {k: b[k] - a[k] for k in b}
 
@@ -287,6 +299,7 @@ def main():
                "includes": "encode, H2D, bpm distances, host guide tree, DP stages, D2H, finalise"}
         ok = all(r.replace("-", "") == s for r, s in zip(rows, seqs))
         e2e["residues_preserved"] = bool(ok)
+        e2e["msa_sha256"] = synth.msa_sha256(rows)
     peak, peak_src, _ = peaks()
     abytes = algorithmic_bytes(d)
     ach = abytes / d["sweep_seconds"] / 1e9 if d["sweep_seconds"] > 0 else 0.0
@@ -316,6 +329,25 @@ def main():
             "wall_s_timed_region": w1 - w0, "create_seconds": t_create,
             "collectives_per_step": d["n_collectives"] / max(1, args.steps), "collective_bytes_per_step": d["collective_bytes"] / max(1, args.steps),
             "dp_round_seconds_per_step": d["dp_seconds"] / max(1, args.steps)}
+    # ---- identity with the reference: hash of the alignment the timed steps produced (every rank
+    #      holds the full result) against the golden hash of the unmodified reference's alignment
+    step_rows = m.result()
+    sha = synth.msa_sha256(step_rows)
+    want = golden_sha(args.workload, len(seqs))
+    same_all = True
+    if world > 1:
+        # every rank must hold the same alignment: compare the hashes' first 8 bytes
+        hv = torch.tensor([int(sha[:15], 16)], dtype=torch.int64, device="cuda")
+        hmax = hv.clone(); dist.all_reduce(hmax, op=dist.ReduceOp.MAX)
+        hmin = hv.clone(); dist.all_reduce(hmin, op=dist.ReduceOp.MIN)
+        same_all = bool(int(hmax[0]) == int(hmin[0]))
+    line["msa_sha256"] = sha
+    line["msa_sha256_reference"] = want
+    line["msa_identical_to_reference"] = (None if want is None else bool(sha == want and same_all and
+                                          (e2e is None or e2e.get("msa_sha256") == want)))
+    line["msa_identical_on_all_ranks"] = same_all
+    if want is not None and not line["msa_identical_to_reference"]:
+        sys.stderr.write("bench.py: ALIGNMENT DIFFERS FROM THE REFERENCE (sha %s, want %s)\n" % (sha, want))
     # ---- CPU baseline beside it (rank 0, N=1 only)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:

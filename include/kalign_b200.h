@@ -170,6 +170,10 @@ int  kb200_msa_create(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_th
 int  kb200_msa_align(kb200_msa* m);
 int  kb200_msa_result(kb200_msa* m, char*** aligned, int* out_aln_len);
 int  kb200_msa_info(kb200_msa* m, int* numseq, int* biotype, int* n_anchors);
+/* the guide tree kb200_msa_create built (build_tree_kmeans, lib/src/bisectingKmeans.c:177-271):
+   tasks_abc receives (numseq-1) x 3 ints (a, b, c) in task order (sorted by c), seq_distances
+   numseq floats (msa->seq_distances, :247-256), both in the sorted index space; either may be NULL */
+int  kb200_msa_tree(kb200_msa* m, int* tasks_abc, float* seq_distances);
 void kb200_msa_free(kb200_msa* m);
 
 #ifdef __cplusplus

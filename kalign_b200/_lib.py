@@ -47,7 +47,7 @@ class Stats(C.Structure):
 EXPORTS = ["kb200_device_count", "kb200_ctx_create", "kb200_ctx_destroy", "kb200_get_stats",
            "kb200_version", "kb200_params_init", "kb200_pair_align_batch", "kb200_distances",
            "kb200_anchor_posmaps", "kb200_select_anchors", "kb200_align_tree", "kb200_kalign",
-           "kb200_msa_create", "kb200_msa_align", "kb200_msa_result", "kb200_msa_info", "kb200_msa_free",
+           "kb200_msa_create", "kb200_msa_align", "kb200_msa_result", "kb200_msa_info", "kb200_msa_tree", "kb200_msa_free",
            "kb200_comm_unique_id", "kb200_ctx_comm_init", "kb200_ctx_comm_destroy", "kb200_partition"]
 
 _lib = None
@@ -113,6 +113,8 @@ def load():
     lib.kb200_msa_result.restype = C.c_int
     lib.kb200_msa_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.kb200_msa_info.restype = C.c_int
+    lib.kb200_msa_tree.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.kb200_msa_tree.restype = C.c_int
     lib.kb200_msa_free.argtypes = [C.c_void_p]
     lib.kb200_msa_free.restype = None
     lib.kb200_comm_unique_id.argtypes = [C.c_void_p, C.c_int]
@@ -312,6 +314,16 @@ class Msa:
             libc.free(out[i])
         libc.free(C.cast(out, C.c_void_p))
         return rows
+
+    def tree(self):
+        """(tasks (N-1) x 3 int32, seq_distances float32[N]) in the sorted index space"""
+        n = C.c_int(0)
+        self.lib.kb200_msa_info(self.h, C.byref(n), None, None)
+        abc = np.zeros((n.value - 1, 3), dtype=np.int32)
+        sd = np.zeros(n.value, dtype=np.float32)
+        if self.lib.kb200_msa_tree(self.h, abc.ctypes.data, sd.ctypes.data) != 0:
+            raise RuntimeError("kb200_msa_tree failed")
+        return abc, sd
 
     def close(self):
         if self.h:

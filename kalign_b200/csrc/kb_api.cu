@@ -67,6 +67,12 @@ void kb200_ctx_destroy(kb200_ctx* ctx)
                 b->release();
         }
         ctx->arena.release();
+        ctx->pinned.release();
+        ctx->d_stats.release();
+        for (cudaEvent_t e : ctx->ev_pool) {
+                cudaEventDestroy(e);
+        }
+        ctx->ev_pool.clear();
         for (KbDevBuf& b : ctx->seq_pool) {
                 b.release();
         }
@@ -236,7 +242,7 @@ int kb200_pair_align_batch(kb200_ctx* ctx, const kb200_params* prm, const kb200_
         std::vector<float> hscore((size_t)njobs);
         KB_CUDA(cudaMemcpyAsync(hpath.data(), dpath, npath * sizeof(int), cudaMemcpyDeviceToHost, st));
         KB_CUDA(cudaMemcpyAsync(hscore.data(), dscore, (size_t)njobs * sizeof(float), cudaMemcpyDeviceToHost, st));
-        KB_CUDA(cudaStreamSynchronize(st));
+        KB_RUN(kb_collect(ctx));       // waits for the stream; engine error flags -> KB200_FAIL
         ctx->stats.d2h_bytes += (double)(npath * sizeof(int) + (size_t)njobs * sizeof(float));
         op = 0;
         for (int i = 0; i < njobs; i++) {

@@ -98,6 +98,37 @@ struct KbDevBuf {
         template <typename T> T* as() const { return (T*)p; }
 };
 
+// pinned host staging: descriptors are written here and copied with cudaMemcpyAsync, so that no
+// host-to-device copy has to wait for (or be waited on by) anything; reset() at the points where
+// the stream is known to be idle (one per guide-tree level)
+struct KbPinned {
+        std::vector<void*> blocks;
+        std::vector<size_t> caps;
+        size_t cur = 0, used = 0;
+        void* get(size_t bytes);
+        void reset() { cur = 0; used = 0; }
+        void release();
+};
+
+// per Hirschberg round (depth) of one engine call: everything the kernels of the round exchange
+// lives on the device, so the host enqueues all rounds without reading anything back
+struct KbRound {
+        unsigned cursor;        // sweep kernel: next work unit
+        unsigned nunits;        // plan kernel -> sweep kernel
+        unsigned nboxes;        // boxes of this round (written by the meet-up of the previous one)
+        unsigned thin;          // plan kernel -> sweep kernel: thin (32-row) strips this round
+};
+constexpr int KB_MAX_ROUNDS = 48;
+
+// device-side statistics / error flags, accumulated over engine calls, read back by kb_collect()
+struct KbDevStats {
+        unsigned long long cells[8];     // sweep ss/sp/pp, bonus, small ss/sp/pp
+        unsigned long long nboxes;
+        unsigned flags;                  // KB_FLAG_*
+        unsigned pad;
+};
+enum { KB_FLAG_BOX_OVERFLOW = 1, KB_FLAG_UNIT_OVERFLOW = 2, KB_FLAG_SMALL_OVERFLOW = 4, KB_FLAG_ROUNDS = 8, KB_FLAG_STACK = 16 };
+
 // chunked bump arena for device-resident profiles; chunks are kept across calls (reset())
 struct KbArena {
         std::vector<void*> chunks;
@@ -119,6 +150,15 @@ struct kb200_ctx {
         cudaStream_t stream = nullptr;
         cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
         kb200_stats stats;
+        // timed spans whose events are resolved at the next kb_collect() (no host wait per launch)
+        std::vector<cudaEvent_t> ev_pool;
+        std::vector<int> ev_kind;        // kind of span i (events 2i, 2i+1): KB_SPAN_*
+        size_t ev_used = 0;
+        KbPinned pinned;
+        KbDevBuf d_stats;                // KbDevStats
+        unsigned rows_tag_floor = 0;     // row buffer holds no tag >= this from an earlier owner (0: must be cleared)
+        const void* tbl_src = nullptr;   // score table currently staged in d_tbl (host pointer identity + stride)
+        int tbl_stride = 0;
         // engine scratch
         KbDevBuf d_jobs, d_boxA, d_boxB, d_boxS, d_counters, d_rows, d_tbl, d_units, d_prog, d_pack, d_ppidx;
         // device buffers of released sequence sets, reused by the next upload (cudaMalloc / cudaFree
@@ -134,7 +174,19 @@ struct kb200_ctx {
         KbArena arena;
 };
 
-// DP engine (kb_dp.cu): run all jobs (device-resident descriptors are built from `jobs`, whose
+enum { KB_SPAN_SWEEP = 0, KB_SPAN_DP = 1, KB_SPAN_SMALL = 2 };
+// timed span on the context's stream: begin returns the span id (or -1), end closes it
+int kb_span_begin(kb200_ctx* ctx, int kind);
+void kb_span_end(kb200_ctx* ctx, int span);
+// asynchronous host->device copy through the pinned staging area
+int kb_h2d(kb200_ctx* ctx, void* dst, const void* src, size_t bytes);
+// wait for the stream, fold device statistics and timed spans into ctx->stats, report device-side
+// error flags (work-list overflow ...) as KB200_FAIL
+int kb_collect(kb200_ctx* ctx);
+
+// DP engine (kb_dp.cu): enqueue all jobs; NO host synchronisation -- results, statistics and error
+// flags are valid after the next kb_collect() / stream synchronisation.
+// run all jobs (device-resident descriptors are built from `jobs`, whose
 // pointers are device pointers; rowF/rowB are assigned here).  subm: 23*23 floats (host).
 int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>& jobs);
 

@@ -35,41 +35,63 @@ namespace {
 
 // ---------------------------------------------------------------------------------------------
 // plan: cut every (box, direction) into strips, reserve a contiguous, ordered unit range
-__global__ void kb_plan_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes, const int nboxes,
-                               const int thin, const int batch_bonus, KbUnit* __restrict__ units,
-                               unsigned* __restrict__ nunits)
+__global__ void kb_plan_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes, KbRound* __restrict__ rnd,
+                               const unsigned long long rows_total, const unsigned resident_warps, const int force_thin,
+                               const int batch_bonus, KbUnit* __restrict__ units, const unsigned unit_cap,
+                               KbDevStats* __restrict__ dstats)
 {
+        const unsigned nboxes = rnd->nboxes;
+        if (nboxes == 0u) {
+                return;
+        }
+        // thin strips when thick ones could not occupy the machine: the rows still alive at this
+        // depth are at most rows_total, spread over nboxes boxes (every thread computes the same value)
+        const unsigned long long thick_units = rows_total / 128ull + 2ull * (unsigned long long)nboxes;
+        int thin = (thick_units < 2ull * (unsigned long long)resident_warps) ? 1 : 0;
+        if (force_thin >= 0) thin = force_thin;
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+                rnd->thin = (unsigned)thin;
+                atomicAdd(&dstats->nboxes, (unsigned long long)nboxes);
+        }
         const int lane = threadIdx.x & 31;
-        const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-        int nstr = 0;
-        if (item < 2LL * nboxes) {
-                const KbBox bx = boxes[item >> 1];
-                const int bwd = (int)(item & 1);
-                const int mid = (bx.ea - bx.sa) / 2 + bx.sa;
-                const int R = bwd ? (bx.ea - mid) : (mid - bx.sa);
-                const int rps = rows_per_strip(jobs[bx.job].kind, jobs[bx.job].nalpha, thin, batch_bonus != 0);
-                nstr = (R + rps - 1) / rps;
-                if (nstr < 1) nstr = 1;
-        }
-        // warp-inclusive scan of nstr
-        int incl = nstr;
+        const long long items = 2LL * (long long)nboxes;
+        const long long nth = (long long)gridDim.x * blockDim.x;
+        for (long long base = (long long)blockIdx.x * blockDim.x + (threadIdx.x - lane); base < items; base += nth) {
+                const long long item = base + lane;
+                int nstr = 0;
+                if (item < items) {
+                        const KbBox bx = boxes[item >> 1];
+                        const int bwd = (int)(item & 1);
+                        const int mid = (bx.ea - bx.sa) / 2 + bx.sa;
+                        const int R = bwd ? (bx.ea - mid) : (mid - bx.sa);
+                        const int rps = rows_per_strip(jobs[bx.job].kind, jobs[bx.job].nalpha, thin, batch_bonus != 0);
+                        nstr = (R + rps - 1) / rps;
+                        if (nstr < 1) nstr = 1;
+                }
+                // warp-inclusive scan of nstr
+                int incl = nstr;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o) incl += v;
-        }
-        const int warp_total = __shfl_sync(FULL, incl, 31);
-        unsigned base = 0;
-        if (lane == 31 && warp_total > 0) {
-                base = atomicAdd(nunits, (unsigned)warp_total);
-        }
-        base = __shfl_sync(FULL, base, 31);
-        const unsigned mine = base + (unsigned)(incl - nstr);
-        for (int s = 0; s < nstr; s++) {
-                KbUnit un;
-                un.item = (int)item;
-                un.strip = s;
-                units[mine + s] = un;
+                for (int o = 1; o < 32; o <<= 1) {
+                        const int v = __shfl_up_sync(FULL, incl, o);
+                        if (lane >= o) incl += v;
+                }
+                const int warp_total = __shfl_sync(FULL, incl, 31);
+                unsigned ubase = 0;
+                if (lane == 31 && warp_total > 0) {
+                        ubase = atomicAdd(&rnd->nunits, (unsigned)warp_total);
+                }
+                ubase = __shfl_sync(FULL, ubase, 31);
+                if ((unsigned long long)ubase + (unsigned long long)warp_total > (unsigned long long)unit_cap) {
+                        if (lane == 0) atomicOr(&dstats->flags, (unsigned)KB_FLAG_UNIT_OVERFLOW);
+                        continue;       // the sweep leaves these boxes alone; the call is reported as failed
+                }
+                const unsigned mine = ubase + (unsigned)(incl - nstr);
+                for (int s2 = 0; s2 < nstr; s2++) {
+                        KbUnit un;
+                        un.item = (int)item;
+                        un.strip = s2;
+                        units[mine + s2] = un;
+                }
         }
 }
 
@@ -134,11 +156,16 @@ __device__ __forceinline__ void put_child(KbBox* __restrict__ next, int slot, in
 }
 
 __global__ void __launch_bounds__(128)
-kb_meetup_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes, const int nboxes,
+kb_meetup_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes, const KbRound* __restrict__ rnd,
                  KbBox* __restrict__ next, unsigned int* __restrict__ next_count,
                  KbBox* __restrict__ small, unsigned int* __restrict__ small_count, const int small_rows, const int small_cols,
-                 unsigned long long* __restrict__ cells)
+                 const unsigned box_cap, KbDevStats* __restrict__ dstats)
 {
+        const int nboxes = (int)rnd->nboxes;
+        if (nboxes == 0) {
+                return;
+        }
+        unsigned long long* const cells = dstats->cells;
         const int lane = threadIdx.x & 31;
         const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
         const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -261,6 +288,10 @@ kb_meetup_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes
                                 const int nsml = (smL ? 1 : 0) + (smR ? 1 : 0);
                                 if (nbig) {
                                         unsigned slot = atomicAdd(next_count, (unsigned)nbig);
+                                        if (slot + (unsigned)nbig > box_cap) {
+                                                atomicOr(&dstats->flags, (unsigned)KB_FLAG_BOX_OVERFLOW);
+                                                continue;
+                                        }
                                         if (hasL && !smL) {
                                                 put_child(next, (int)slot, bx.job, bx.depth + 1, lsa, lea, lsb, leb, fin, lb0);
                                                 slot++;
@@ -271,6 +302,10 @@ kb_meetup_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes
                                 }
                                 if (nsml) {
                                         unsigned slot = atomicAdd(small_count, (unsigned)nsml);
+                                        if (slot + (unsigned)nsml > box_cap) {
+                                                atomicOr(&dstats->flags, (unsigned)KB_FLAG_SMALL_OVERFLOW);
+                                                continue;
+                                        }
                                         if (smL) {
                                                 put_child(small, (int)slot, bx.job, bx.depth + 1, lsa, lea, lsb, leb, fin, lb0);
                                                 slot++;
@@ -414,7 +449,7 @@ __device__ void small_sweep(const KbJob& J, const int bwd, const int r0, const i
 
 template <int V, int MAXC, int BONUS>
 __device__ void small_box_run(const KbJob& J, const KbBox& root, const float* __restrict__ s_tbl, const int tstride,
-                              unsigned long long& ncells)
+                              unsigned long long& ncells, unsigned& err)
 {
         // rows per pass (register budget as in the strips: 8 for plain seq-seq, 4, 2 for 23-letter profiles)
         constexpr int KR = (V == V_PP23) ? 2 : ((V == V_SS && BONUS == BONUS_NONE) ? 8 : 4);
@@ -519,41 +554,201 @@ __device__ void small_box_run(const KbJob& J, const KbBox& root, const float* __
                         Rr.sa = mid + 1; Rr.sb = c + 1; Rr.f0 = KA;
                         break;
                 }
-                if (Rr.sa < Rr.ea && Rr.sb < Rr.eb && sp < SMALL_STACK) stack[sp++] = Rr;
-                if (L.sa < L.ea && L.sb < L.eb && sp < SMALL_STACK) stack[sp++] = L;
+                // a full stack is an error of the call (reported through KbDevStats::flags), never a
+                // silently dropped box: the depth is bounded by log2(SMALL_ROWS_MAX) + 2 < SMALL_STACK
+                if (Rr.sa < Rr.ea && Rr.sb < Rr.eb) {
+                        if (sp < SMALL_STACK) stack[sp++] = Rr; else err |= (unsigned)KB_FLAG_STACK;
+                }
+                if (L.sa < L.ea && L.sb < L.eb) {
+                        if (sp < SMALL_STACK) stack[sp++] = L; else err |= (unsigned)KB_FLAG_STACK;
+                }
         }
 }
 
 template <int MAXC, int BONUS>
 __global__ void __launch_bounds__(128, 4)
 kb_small_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes, const unsigned* __restrict__ nsmall_p,
-                unsigned long long* __restrict__ cells, const float* __restrict__ tbl, const int tstride)
+                const unsigned box_cap, KbDevStats* __restrict__ dstats, const float* __restrict__ tbl, const int tstride)
 {
+        unsigned n = *nsmall_p;
+        if (n == 0u) {
+                return;
+        }
+        if (n > box_cap) n = box_cap;        // overflow was flagged by the meet-up
         __shared__ float s_tbl[TBL_MAX];
         for (int i = threadIdx.x; i < TBL_MAX; i += blockDim.x) {
                 s_tbl[i] = tbl[i];
         }
         __syncthreads();
-        const unsigned n = *nsmall_p;
+        unsigned long long* const cells = dstats->cells;
         const unsigned nth = gridDim.x * blockDim.x;
         for (unsigned b = blockIdx.x * blockDim.x + threadIdx.x; b < n; b += nth) {
                 const KbBox bx = boxes[b];
                 const KbJob J = jobs[bx.job];
                 unsigned long long nc = 0;
-                if (J.kind == KB200_KIND_SS) small_box_run<V_SS, MAXC, BONUS>(J, bx, s_tbl, tstride, nc);
-                else if (J.kind == KB200_KIND_SP) small_box_run<V_SP, MAXC, BONUS>(J, bx, s_tbl, tstride, nc);
-                else if (J.nalpha <= 5) small_box_run<V_PP5, MAXC, BONUS>(J, bx, s_tbl, tstride, nc);
-                else small_box_run<V_PP23, MAXC, BONUS>(J, bx, s_tbl, tstride, nc);
+                unsigned err = 0;
+                if (J.kind == KB200_KIND_SS) small_box_run<V_SS, MAXC, BONUS>(J, bx, s_tbl, tstride, nc, err);
+                else if (J.kind == KB200_KIND_SP) small_box_run<V_SP, MAXC, BONUS>(J, bx, s_tbl, tstride, nc, err);
+                else if (J.nalpha <= 5) small_box_run<V_PP5, MAXC, BONUS>(J, bx, s_tbl, tstride, nc, err);
+                else small_box_run<V_PP23, MAXC, BONUS>(J, bx, s_tbl, tstride, nc, err);
                 atomicAdd(cells + 4 + J.kind, nc);
                 if (J.bonus || J.bkey) {
                         atomicAdd(cells + 3, nc);
                 }
+                if (err) {
+                        atomicOr(&dstats->flags, err);
+                }
         }
 }
+
+static_assert(SMALL_STACK >= 7 + 3, "explicit DFS stack: log2(SMALL_ROWS_MAX) + 3 frames");
 
 } // namespace
 
 // ---------------------------------------------------------------------------------------------
+
+// ---- pinned staging, timed spans, deferred statistics ------------------------------------------
+
+void* KbPinned::get(size_t bytes)
+{
+        bytes = (bytes + 255) & ~(size_t)255;
+        while (true) {
+                if (cur < blocks.size()) {
+                        if (used + bytes <= caps[cur]) {
+                                void* r = (char*)blocks[cur] + used;
+                                used += bytes;
+                                return r;
+                        }
+                        cur++;
+                        used = 0;
+                        continue;
+                }
+                const size_t want = std::max<size_t>((size_t)16 << 20, bytes);
+                void* p = nullptr;
+                if (cudaMallocHost(&p, want) != cudaSuccess) {
+                        cudaGetLastError();
+                        fprintf(stderr, "[kalign_b200] cudaMallocHost(%zu) failed\n", want);
+                        return nullptr;
+                }
+                blocks.push_back(p);
+                caps.push_back(want);
+        }
+}
+
+void KbPinned::release()
+{
+        for (void* p : blocks) {
+                cudaFreeHost(p);
+        }
+        blocks.clear();
+        caps.clear();
+        cur = used = 0;
+}
+
+int kb_h2d(kb200_ctx* ctx, void* dst, const void* src, size_t bytes)
+{
+        if (bytes == 0) {
+                return KB200_OK;
+        }
+        void* stage = ctx->pinned.get(bytes);
+        if (!stage) {
+                return KB200_FAIL;
+        }
+        memcpy(stage, src, bytes);
+        KB_CUDA(cudaMemcpyAsync(dst, stage, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        return KB200_OK;
+}
+
+int kb_span_begin(kb200_ctx* ctx, int kind)
+{
+        const size_t id = ctx->ev_used;
+        if (ctx->ev_pool.size() < 2 * (id + 1)) {
+                cudaEvent_t a = nullptr, b = nullptr;
+                if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) {
+                        cudaGetLastError();
+                        return -1;
+                }
+                ctx->ev_pool.push_back(a);
+                ctx->ev_pool.push_back(b);
+                ctx->ev_kind.push_back(kind);
+        }
+        ctx->ev_kind[id] = kind;
+        ctx->ev_used = id + 1;
+        cudaEventRecord(ctx->ev_pool[2 * id], ctx->stream);
+        return (int)id;
+}
+
+void kb_span_end(kb200_ctx* ctx, int span)
+{
+        if (span >= 0) {
+                cudaEventRecord(ctx->ev_pool[2 * (size_t)span + 1], ctx->stream);
+        }
+}
+
+static int ensure_dstats(kb200_ctx* ctx)
+{
+        if (!ctx->d_stats.p) {
+                KB_RUN(ctx->d_stats.ensure(sizeof(KbDevStats)));
+                KB_CUDA(cudaMemsetAsync(ctx->d_stats.p, 0, sizeof(KbDevStats), ctx->stream));
+        }
+        return KB200_OK;
+}
+
+int kb_collect(kb200_ctx* ctx)
+{
+        cudaStream_t st = ctx->stream;
+        KbDevStats hs;
+        memset(&hs, 0, sizeof(hs));
+        if (ctx->d_stats.p) {
+                KB_CUDA(cudaMemcpyAsync(&hs, ctx->d_stats.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
+                KB_CUDA(cudaMemsetAsync(ctx->d_stats.p, 0, sizeof(KbDevStats), st));
+        }
+        KB_CUDA(cudaStreamSynchronize(st));
+        ctx->pinned.reset();     // every staged copy has completed
+        for (int k = 0; k < 3; k++) {
+                ctx->stats.dp_cells += (double)hs.cells[k] + (double)hs.cells[4 + k];
+        }
+        ctx->stats.cells_ss += (double)hs.cells[0] + (double)hs.cells[4];
+        ctx->stats.cells_sp += (double)hs.cells[1] + (double)hs.cells[5];
+        ctx->stats.cells_pp += (double)hs.cells[2] + (double)hs.cells[6];
+        ctx->stats.cells_bonus += (double)hs.cells[3];
+        ctx->stats.small_ss += (double)hs.cells[4];
+        ctx->stats.small_sp += (double)hs.cells[5];
+        ctx->stats.small_pp += (double)hs.cells[6];
+        ctx->stats.n_boxes += (long long)hs.nboxes;
+        for (size_t i = 0; i < ctx->ev_used; i++) {
+                float ms = 0.0f;
+                if (cudaEventElapsedTime(&ms, ctx->ev_pool[2 * i], ctx->ev_pool[2 * i + 1]) != cudaSuccess) {
+                        cudaGetLastError();
+                        continue;
+                }
+                const double sec = 1e-3 * (double)ms;
+                if (ctx->ev_kind[i] == KB_SPAN_SWEEP) ctx->stats.sweep_seconds += sec;
+                else if (ctx->ev_kind[i] == KB_SPAN_DP) ctx->stats.dp_seconds += sec;
+                else ctx->stats.small_seconds += sec;
+        }
+        ctx->ev_used = 0;
+        if (hs.flags) {
+                fprintf(stderr, "[kalign_b200] engine error flags 0x%x:%s%s%s%s%s\n", hs.flags,
+                        (hs.flags & KB_FLAG_BOX_OVERFLOW) ? " box work-list overflow" : "",
+                        (hs.flags & KB_FLAG_UNIT_OVERFLOW) ? " unit list overflow" : "",
+                        (hs.flags & KB_FLAG_SMALL_OVERFLOW) ? " small-box list overflow" : "",
+                        (hs.flags & KB_FLAG_ROUNDS) ? " boxes left after the last round" : "",
+                        (hs.flags & KB_FLAG_STACK) ? " small-box recursion stack overflow" : "");
+                return KB200_FAIL;
+        }
+        return KB200_OK;
+}
+
+namespace {
+// boxes that survive the last enqueued round would be lost: flag them
+__global__ void kb_rounds_check_kernel(const KbRound* __restrict__ last, KbDevStats* __restrict__ dstats)
+{
+        if (last->nboxes != 0u) {
+                atomicOr(&dstats->flags, (unsigned)KB_FLAG_ROUNDS);
+        }
+}
+} // namespace
 
 int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>& jobs)
 {
@@ -562,6 +757,8 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
                 return KB200_OK;
         }
         cudaStream_t st = ctx->stream;
+        KB_RUN(ensure_dstats(ctx));
+        KbDevStats* d_stats = ctx->d_stats.as<KbDevStats>();
         // row buffers, packed column records
         size_t total_cols = 0;
         size_t box_cap = 0;
@@ -570,9 +767,11 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
         std::vector<int> pp_jobs;
         std::vector<long long> pp_prefix;
         long long pp_cols = 0;
+        int max_rows = 1;
         for (int i = 0; i < n; i++) {
                 total_cols += (size_t)(jobs[i].len_a + jobs[i].len_b + 2);
                 box_cap += (size_t)std::max(1, jobs[i].len_a);
+                max_rows = std::max(max_rows, jobs[i].len_a);
                 // every box contributes <= ceil(rows/32) + 2 units, rows of same-depth boxes are disjoint
                 unit_cap += (size_t)jobs[i].len_a / 32 + 2 * (size_t)std::max(1, jobs[i].len_a) + 4;
                 if (jobs[i].kind == KB200_KIND_PP) {
@@ -583,9 +782,29 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
                         pack_floats += (size_t)(jobs[i].len_b + 2) * pw;
                 }
         }
-        KB_RUN(ctx->d_rows.ensure(2 * total_cols * sizeof(float4)));
-        // stale rows (an earlier batch, an earlier context) must never carry a live hand-off tag
-        KB_CUDA(cudaMemsetAsync(ctx->d_rows.p, 0, 2 * total_cols * sizeof(float4), st));
+        if (box_cap > 0x7fffffffull || unit_cap > 0xfffffff0ull) {
+                fprintf(stderr, "[kalign_b200] batch too large for the 32-bit work lists (%zu rows)\n", box_cap);
+                return KB200_FAIL;
+        }
+        {
+                // Row buffers carry the hand-off tags.  Tags only grow within a context, so a buffer
+                // that was cleared when it was allocated never holds a tag a later launch could
+                // mistake for its own; it is cleared again only when it is re-allocated (fresh memory
+                // may hold anything) or when the tag counter is about to wrap.
+                const size_t need = 2 * total_cols * sizeof(float4);
+                const void* before = ctx->d_rows.p;
+                const size_t cap_before = ctx->d_rows.cap;
+                KB_RUN(ctx->d_rows.ensure(need));
+                const unsigned tags_needed = 65536u * (unsigned)(KB_MAX_ROUNDS + 2);
+                const bool wrap = ctx->tag_counter > 0xfff00000u - tags_needed;
+                if (wrap) {
+                        ctx->tag_counter = 65536u;
+                }
+                if (ctx->d_rows.p != before || ctx->d_rows.cap != cap_before || wrap || ctx->rows_tag_floor == 0u) {
+                        KB_CUDA(cudaMemsetAsync(ctx->d_rows.p, 0, ctx->d_rows.cap, st));
+                        ctx->rows_tag_floor = 1u;
+                }
+        }
         KB_RUN(ctx->d_pack.ensure(pack_floats * sizeof(float) + 64));
         {
                 float4* base = ctx->d_rows.as<float4>();
@@ -604,12 +823,12 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
                 }
         }
         KB_RUN(ctx->d_jobs.ensure(sizeof(KbJob) * (size_t)n));
-        KB_CUDA(cudaMemcpyAsync(ctx->d_jobs.p, jobs.data(), sizeof(KbJob) * (size_t)n, cudaMemcpyHostToDevice, st));
+        KB_RUN(kb_h2d(ctx, ctx->d_jobs.p, jobs.data(), sizeof(KbJob) * (size_t)n));
         KB_RUN(ctx->d_boxA.ensure(sizeof(KbBox) * box_cap));
         KB_RUN(ctx->d_boxB.ensure(sizeof(KbBox) * box_cap));
         KB_RUN(ctx->d_boxS.ensure(sizeof(KbBox) * box_cap));
         KB_RUN(ctx->d_units.ensure(sizeof(KbUnit) * unit_cap));
-        KB_RUN(ctx->d_counters.ensure(128));
+        KB_RUN(ctx->d_counters.ensure(sizeof(KbRound) * (KB_MAX_ROUNDS + 2) + 64));
         KB_RUN(ctx->d_tbl.ensure(sizeof(float) * TBL_MAX));
         // shared-memory score table: row stride = alphabet size, so that a 5-letter table (25
         // entries) puts every entry in its own bank -- lanes reading different entries never conflict
@@ -619,57 +838,61 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
         }
         const int tstride = (max_alpha <= 5) ? 5 : 23;
         {
-                std::vector<float> tbl(TBL_MAX, 0.0f);
+                float* tbl = (float*)ctx->pinned.get(sizeof(float) * TBL_MAX);
+                if (!tbl) return KB200_FAIL;
+                memset(tbl, 0, sizeof(float) * TBL_MAX);
                 for (int i = 0; i < tstride; i++) {
                         for (int j = 0; j < tstride; j++) {
                                 tbl[i * tstride + j] = subm_host[i * 23 + j];
                         }
                 }
-                KB_CUDA(cudaMemcpyAsync(ctx->d_tbl.p, tbl.data(), sizeof(float) * tbl.size(), cudaMemcpyHostToDevice, st));
-                KB_CUDA(cudaStreamSynchronize(st));   // tbl is a stack-lifetime vector
+                KB_CUDA(cudaMemcpyAsync(ctx->d_tbl.p, tbl, sizeof(float) * TBL_MAX, cudaMemcpyHostToDevice, st));
         }
         if (!pp_jobs.empty()) {
                 KB_RUN(ctx->d_ppidx.ensure(sizeof(int) * pp_jobs.size() + sizeof(long long) * pp_jobs.size() + 64));
                 long long* d_pref = ctx->d_ppidx.as<long long>();
                 int* d_idx = (int*)(d_pref + pp_jobs.size());
-                KB_CUDA(cudaMemcpyAsync(d_pref, pp_prefix.data(), sizeof(long long) * pp_jobs.size(), cudaMemcpyHostToDevice, st));
-                KB_CUDA(cudaMemcpyAsync(d_idx, pp_jobs.data(), sizeof(int) * pp_jobs.size(), cudaMemcpyHostToDevice, st));
+                KB_RUN(kb_h2d(ctx, d_pref, pp_prefix.data(), sizeof(long long) * pp_jobs.size()));
+                KB_RUN(kb_h2d(ctx, d_idx, pp_jobs.data(), sizeof(int) * pp_jobs.size()));
                 const int grid = (int)std::min<long long>((pp_cols + 255) / 256, (long long)ctx->sm_count * 16);
                 kb_pack_kernel<<<grid, 256, 0, st>>>(ctx->d_jobs.as<KbJob>(), d_idx, (int)pp_jobs.size(), d_pref, pp_cols);
                 KB_CUDA(cudaGetLastError());
-                KB_CUDA(cudaStreamSynchronize(st));
                 ctx->stats.n_launches += 1;
         }
-        std::vector<KbBox> init;
-        init.reserve(n);
         size_t rows_total = 0;
-        for (int i = 0; i < n; i++) {
-                if (jobs[i].len_a <= 0 || jobs[i].len_b <= 0) {
-                        continue;
+        unsigned ninit = 0;
+        {
+                KbBox* init = (KbBox*)ctx->pinned.get(sizeof(KbBox) * (size_t)n);
+                if (!init) return KB200_FAIL;
+                for (int i = 0; i < n; i++) {
+                        if (jobs[i].len_a <= 0 || jobs[i].len_b <= 0) {
+                                continue;
+                        }
+                        KbBox b;
+                        b.job = i; b.sa = 0; b.ea = jobs[i].len_a; b.sb = 0; b.eb = jobs[i].len_b;
+                        b.f0a = 0.0F; b.f0ga = KB_NEGF; b.f0gb = KB_NEGF;
+                        b.b0a = 0.0F; b.b0ga = KB_NEGF; b.b0gb = KB_NEGF;
+                        b.depth = 0;
+                        init[ninit++] = b;
+                        rows_total += (size_t)jobs[i].len_a;
                 }
-                KbBox b;
-                b.job = i; b.sa = 0; b.ea = jobs[i].len_a; b.sb = 0; b.eb = jobs[i].len_b;
-                b.f0a = 0.0F; b.f0ga = KB_NEGF; b.f0gb = KB_NEGF;
-                b.b0a = 0.0F; b.b0ga = KB_NEGF; b.b0gb = KB_NEGF;
-                b.depth = 0;
-                init.push_back(b);
-                rows_total += (size_t)jobs[i].len_a;
+                if (ninit == 0) {
+                        return KB200_OK;
+                }
+                KB_CUDA(cudaMemcpyAsync(ctx->d_boxA.p, init, sizeof(KbBox) * (size_t)ninit, cudaMemcpyHostToDevice, st));
         }
-        if (init.empty()) {
-                return KB200_OK;
+        // per-round control words: [r] = {cursor, nunits, nboxes, thin}; then the small-box count
+        KbRound* d_rounds = ctx->d_counters.as<KbRound>();
+        unsigned* d_nsmall = (unsigned*)(d_rounds + KB_MAX_ROUNDS + 1);
+        KB_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(KbRound) * (KB_MAX_ROUNDS + 2), st));
+        {
+                unsigned* h = (unsigned*)ctx->pinned.get(sizeof(unsigned));
+                if (!h) return KB200_FAIL;
+                *h = ninit;
+                KB_CUDA(cudaMemcpyAsync(&d_rounds[0].nboxes, h, sizeof(unsigned), cudaMemcpyHostToDevice, st));
         }
-        KB_CUDA(cudaMemcpyAsync(ctx->d_boxA.p, init.data(), sizeof(KbBox) * init.size(), cudaMemcpyHostToDevice, st));
-        KB_CUDA(cudaStreamSynchronize(st));
-        // counters: [0] sweep cursor, [1] next box count, [2] unit count, [4..11] cells (u64 x4)
-        KB_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 128, st));
-        unsigned count = (unsigned)init.size();
         KbBox* cur = ctx->d_boxA.as<KbBox>();
         KbBox* nxt = ctx->d_boxB.as<KbBox>();
-        unsigned int* d_cursor = ctx->d_counters.as<unsigned int>();
-        unsigned int* d_next = d_cursor + 1;
-        unsigned int* d_nunits = d_cursor + 2;
-        unsigned long long* d_cells = (unsigned long long*)(d_cursor + 4);   // [ss, sp, pp, bonus]
-        unsigned int* d_nsmall = d_cursor + 3;
         KbBox* d_small = ctx->d_boxS.as<KbBox>();
         const bool use_small = getenv("KB200_NO_SMALL") == nullptr;
         // thread-per-box threshold: with enough jobs to fill the machine the deep rounds (boxes of a
@@ -689,9 +912,7 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
         // KB200_THIN=0|1 forces thick / thin strips (tests run every batch both ways)
         int force_thin = -1;
         if (const char* e = getenv("KB200_THIN")) force_thin = (atoi(e) != 0) ? 1 : 0;
-        float sweep_ms = 0.0f;
         const bool trace = getenv("KB200_TRACE") != nullptr;
-        int round = 0;
         // all-or-nothing: a job without bonus in a bonus batch simply has an empty list / null dense
         bool batch_bonus = false, batch_dense = false;
         for (int i = 0; i < n; i++) {
@@ -704,109 +925,96 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
         }
         // resident warps of the persistent sweep grid
         const int sweep_ctas = ctx->sm_count * 4;
-        const size_t resident_warps = (size_t)sweep_ctas * WARPS_PER_CTA;
-        KB_CUDA(cudaEventRecord(ctx->ev0, st));
-        while (count > 0) {
-                KB_CUDA(cudaMemsetAsync(d_cursor, 0, 12, st));
-                // thin strips when thick ones could not occupy the machine: the rows still alive
-                // at this depth are at most rows_total, spread over `count` boxes
-                const size_t thick_units = rows_total / 128 + 2 * (size_t)count;
-                int thin = (thick_units < 2 * resident_warps) ? 1 : 0;
-                if (force_thin >= 0) thin = force_thin;
-                const unsigned items = 2u * count;
+        const unsigned resident_warps = (unsigned)(sweep_ctas * WARPS_PER_CTA);
+        // Rounds.  A box of R rows has children of at most R/2 + 1 rows and the recursion ends below
+        // two rows, so ceil(log2(rows)) + 2 rounds always suffice.  Every round is enqueued without
+        // looking at the device: a round whose box count turned out to be zero costs three empty
+        // launches.  kb_rounds_check_kernel flags boxes that would be left over.
+        int nrounds = 2;
+        while ((1 << (nrounds - 2)) < max_rows && nrounds < KB_MAX_ROUNDS) nrounds++;
+        nrounds = std::min(nrounds + 1, KB_MAX_ROUNDS);
+        const int span_dp = kb_span_begin(ctx, KB_SPAN_DP);
+        for (int round = 0; round < nrounds; round++) {
+                KbRound* rnd = d_rounds + round;
+                // boxes this round can hold at most: twice the previous round's, never more than the rows
+                const unsigned long long bound = std::min<unsigned long long>((unsigned long long)box_cap,
+                                                                              (unsigned long long)ninit << std::min(round, 40));
                 // tags: unique per launch (8192 strips per sweep at most: 256k rows), never 0
                 ctx->tag_counter += 65536u;
-                if (ctx->tag_counter > 0xfff00000u) ctx->tag_counter = 65536u;
                 const unsigned tag_base = ctx->tag_counter;
-                kb_plan_kernel<<<(items + 127) / 128, 128, 0, st>>>(ctx->d_jobs.as<KbJob>(), cur, (int)count, thin, batch_bonus ? 1 : 0,
-                                                                     ctx->d_units.as<KbUnit>(), d_nunits);
-                KB_CUDA(cudaEventRecord(ctx->ev2, st));
+                const int pgrid = (int)std::min<unsigned long long>((2 * bound + 127) / 128, (unsigned long long)ctx->sm_count * 8);
+                kb_plan_kernel<<<pgrid, 128, 0, st>>>(ctx->d_jobs.as<KbJob>(), cur, rnd, (unsigned long long)rows_total, resident_warps,
+                                                       force_thin, batch_bonus ? 1 : 0, ctx->d_units.as<KbUnit>(), (unsigned)unit_cap, d_stats);
+                KB_CUDA(cudaGetLastError());
+                const int span = kb_span_begin(ctx, KB_SPAN_SWEEP);
                 {
                         const KbJob* dj = ctx->d_jobs.as<KbJob>();
                         const KbUnit* du = ctx->d_units.as<KbUnit>();
                         const float* dt = ctx->d_tbl.as<float>();
                         const int thr = WARPS_PER_CTA * 32;
+                        // no more CTAs than the round can have units (one warp per unit)
+                        const unsigned long long ubound = std::min<unsigned long long>((unsigned long long)unit_cap,
+                                                                                       2 * bound + (unsigned long long)rows_total / 32 + 2);
+                        const int grid = (int)std::max<unsigned long long>(1, std::min<unsigned long long>((unsigned long long)sweep_ctas,
+                                                                                                           (ubound + WARPS_PER_CTA - 1) / WARPS_PER_CTA));
                         if (batch_dense) {
-                                KB_CUDA(kb_sweep_launch_dense(sweep_ctas, thr, st, dj, cur, du, d_nunits, d_cursor, tag_base, dt, thin, tstride));
+                                KB_CUDA(kb_sweep_launch_dense(grid, thr, st, dj, cur, du, rnd, tag_base, dt, tstride));
                         } else if (batch_bonus) {
-                                KB_CUDA(kb_sweep_launch_sparse(sweep_ctas, thr, st, dj, cur, du, d_nunits, d_cursor, tag_base, dt, thin, tstride));
+                                KB_CUDA(kb_sweep_launch_sparse(grid, thr, st, dj, cur, du, rnd, tag_base, dt, tstride));
                         } else {
-                                KB_CUDA(kb_sweep_launch_none(sweep_ctas, thr, st, dj, cur, du, d_nunits, d_cursor, tag_base, dt, thin, tstride));
+                                KB_CUDA(kb_sweep_launch_none(grid, thr, st, dj, cur, du, rnd, tag_base, dt, tstride));
                         }
                 }
-                KB_CUDA(cudaEventRecord(ctx->ev3, st));
-                int mgrid = (int)std::min<unsigned>((count + 3) / 4, (unsigned)(ctx->sm_count * 16));
-                kb_meetup_kernel<<<mgrid, 128, 0, st>>>(ctx->d_jobs.as<KbJob>(), cur, (int)count, nxt, d_next,
-                                                        use_small ? d_small : nullptr, d_nsmall, small_rows, small_cols, d_cells);
+                kb_span_end(ctx, span);
+                const int mgrid = (int)std::max<unsigned long long>(1, std::min<unsigned long long>((bound + 3) / 4, (unsigned long long)ctx->sm_count * 16));
+                kb_meetup_kernel<<<mgrid, 128, 0, st>>>(ctx->d_jobs.as<KbJob>(), cur, rnd, nxt, &d_rounds[round + 1].nboxes,
+                                                        use_small ? d_small : nullptr, d_nsmall, small_rows, small_cols, (unsigned)box_cap, d_stats);
                 KB_CUDA(cudaGetLastError());
-                unsigned host_counts[4] = {0, 0, 0, 0};
-                KB_CUDA(cudaMemcpyAsync(host_counts, d_cursor, sizeof(host_counts), cudaMemcpyDeviceToHost, st));
-                KB_CUDA(cudaStreamSynchronize(st));
-                const unsigned next_count = host_counts[1];
-                float ms = 0.0f;
-                cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3);
-                sweep_ms += ms;
-                if (trace) {
-                        fprintf(stderr, "[kb200 trace] jobs=%d round=%d boxes=%u units=%u thin=%d sweep_ms=%.3f\n", n, round, count,
-                                host_counts[2], thin, ms);
-                }
-                round++;
-                ctx->stats.n_boxes += count;
                 ctx->stats.n_launches += 3;
-                if ((size_t)next_count > box_cap || (size_t)host_counts[2] > unit_cap || (size_t)host_counts[3] > box_cap) {
-                        fprintf(stderr, "[kalign_b200] work-list overflow (boxes %u > %zu or units %u > %zu)\n", next_count, box_cap,
-                                host_counts[2], unit_cap);
-                        return KB200_FAIL;
+                if (trace) {
+                        // debugging aid only: per-round read-back (serialises the rounds)
+                        KbRound hr;
+                        KB_CUDA(cudaMemcpyAsync(&hr, rnd, sizeof(hr), cudaMemcpyDeviceToHost, st));
+                        KB_CUDA(cudaStreamSynchronize(st));
+                        float ms = 0.0f;
+                        cudaEventElapsedTime(&ms, ctx->ev_pool[2 * (size_t)span], ctx->ev_pool[2 * (size_t)span + 1]);
+                        if (hr.nboxes) {
+                                fprintf(stderr, "[kb200 trace] jobs=%d round=%d boxes=%u units=%u thin=%u sweep_ms=%.3f\n", n, round, hr.nboxes,
+                                        hr.nunits, hr.thin, ms);
+                        }
                 }
-                count = next_count;
                 std::swap(cur, nxt);
         }
+        kb_rounds_check_kernel<<<1, 1, 0, st>>>(d_rounds + nrounds, d_stats);
         {
                 // every box that became small during the rounds: finish its recursion in one launch
-                KB_CUDA(cudaEventRecord(ctx->ev2, st));
-                const int sgrid = ctx->sm_count * 4;
+                const int span = kb_span_begin(ctx, KB_SPAN_SMALL);
+                const int sgrid = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->sm_count * 4, (box_cap + 127) / 128));
                 const KbJob* dj = ctx->d_jobs.as<KbJob>();
                 const float* dt = ctx->d_tbl.as<float>();
+                const unsigned bc = (unsigned)box_cap;
                 const int fam = batch_dense ? BONUS_DENSE : (batch_bonus ? BONUS_SPARSE : BONUS_NONE);
                 if (small_cols <= SMALL_COLS) {
-                        if (fam == BONUS_DENSE) kb_small_kernel<SMALL_COLS, BONUS_DENSE><<<sgrid, 128, 0, st>>>(dj, d_small, d_nsmall, d_cells, dt, tstride);
-                        else if (fam == BONUS_SPARSE) kb_small_kernel<SMALL_COLS, BONUS_SPARSE><<<sgrid, 128, 0, st>>>(dj, d_small, d_nsmall, d_cells, dt, tstride);
-                        else kb_small_kernel<SMALL_COLS, BONUS_NONE><<<sgrid, 128, 0, st>>>(dj, d_small, d_nsmall, d_cells, dt, tstride);
+                        if (fam == BONUS_DENSE) kb_small_kernel<SMALL_COLS, BONUS_DENSE><<<sgrid, 128, 0, st>>>(dj, d_small, d_nsmall, bc, d_stats, dt, tstride);
+                        else if (fam == BONUS_SPARSE) kb_small_kernel<SMALL_COLS, BONUS_SPARSE><<<sgrid, 128, 0, st>>>(dj, d_small, d_nsmall, bc, d_stats, dt, tstride);
+                        else kb_small_kernel<SMALL_COLS, BONUS_NONE><<<sgrid, 128, 0, st>>>(dj, d_small, d_nsmall, bc, d_stats, dt, tstride);
                 } else {
-                        if (fam == BONUS_DENSE) kb_small_kernel<SMALL_COLS_MAX, BONUS_DENSE><<<sgrid, 128, 0, st>>>(dj, d_small, d_nsmall, d_cells, dt, tstride);
-                        else if (fam == BONUS_SPARSE) kb_small_kernel<SMALL_COLS_MAX, BONUS_SPARSE><<<sgrid, 128, 0, st>>>(dj, d_small, d_nsmall, d_cells, dt, tstride);
-                        else kb_small_kernel<SMALL_COLS_MAX, BONUS_NONE><<<sgrid, 128, 0, st>>>(dj, d_small, d_nsmall, d_cells, dt, tstride);
+                        if (fam == BONUS_DENSE) kb_small_kernel<SMALL_COLS_MAX, BONUS_DENSE><<<sgrid, 128, 0, st>>>(dj, d_small, d_nsmall, bc, d_stats, dt, tstride);
+                        else if (fam == BONUS_SPARSE) kb_small_kernel<SMALL_COLS_MAX, BONUS_SPARSE><<<sgrid, 128, 0, st>>>(dj, d_small, d_nsmall, bc, d_stats, dt, tstride);
+                        else kb_small_kernel<SMALL_COLS_MAX, BONUS_NONE><<<sgrid, 128, 0, st>>>(dj, d_small, d_nsmall, bc, d_stats, dt, tstride);
                 }
                 KB_CUDA(cudaGetLastError());
-                KB_CUDA(cudaEventRecord(ctx->ev3, st));
-                KB_CUDA(cudaEventSynchronize(ctx->ev3));
-                float sms = 0.0f;
-                cudaEventElapsedTime(&sms, ctx->ev2, ctx->ev3);
-                ctx->stats.small_seconds += 1e-3 * (double)sms;
-                ctx->stats.n_launches += 1;
+                kb_span_end(ctx, span);
+                ctx->stats.n_launches += 2;
                 if (trace) {
                         unsigned ns = 0;
-                        cudaMemcpy(&ns, d_nsmall, sizeof(unsigned), cudaMemcpyDeviceToHost);
+                        KB_CUDA(cudaMemcpyAsync(&ns, d_nsmall, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+                        KB_CUDA(cudaStreamSynchronize(st));
+                        float sms = 0.0f;
+                        cudaEventElapsedTime(&sms, ctx->ev_pool[2 * (size_t)span], ctx->ev_pool[2 * (size_t)span + 1]);
                         fprintf(stderr, "[kb200 trace] jobs=%d small(<=%dx%d) boxes=%u small_ms=%.3f\n", n, small_rows, small_cols, ns, sms);
                 }
         }
-        KB_CUDA(cudaEventRecord(ctx->ev1, st));
-        unsigned long long cells[7] = {0, 0, 0, 0, 0, 0, 0};   // sweep ss/sp/pp, bonus, small ss/sp/pp
-        KB_CUDA(cudaMemcpyAsync(cells, d_cells, sizeof(cells), cudaMemcpyDeviceToHost, st));
-        KB_CUDA(cudaStreamSynchronize(st));
-        float ms = 0.0f;
-        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-        ctx->stats.dp_seconds += 1e-3 * (double)ms;
-        ctx->stats.sweep_seconds += 1e-3 * (double)sweep_ms;
-        for (int k = 0; k < 3; k++) {
-                ctx->stats.dp_cells += (double)cells[k] + (double)cells[4 + k];
-        }
-        ctx->stats.cells_ss += (double)cells[0] + (double)cells[4];
-        ctx->stats.cells_sp += (double)cells[1] + (double)cells[5];
-        ctx->stats.cells_pp += (double)cells[2] + (double)cells[6];
-        ctx->stats.cells_bonus += (double)cells[3];
-        ctx->stats.small_ss += (double)cells[4];
-        ctx->stats.small_sp += (double)cells[5];
-        ctx->stats.small_pp += (double)cells[6];
+        kb_span_end(ctx, span_dp);
         return KB200_OK;
 }

@@ -331,7 +331,7 @@ int kb_anchor_posmaps_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S, co
                 KB_RUN(kb_run_hirschberg(ctx, prm->subm, jobs));
                 t1 = std::chrono::steady_clock::now();
                 KB_RUN(ctx->d_stage4.ensure(sizeof(KbPathJob) * pjobs.size()));
-                KB_CUDA(cudaMemcpyAsync(ctx->d_stage4.p, pjobs.data(), sizeof(KbPathJob) * pjobs.size(), cudaMemcpyHostToDevice, st));
+                KB_RUN(kb_h2d(ctx, ctx->d_stage4.p, pjobs.data(), sizeof(KbPathJob) * pjobs.size()));
                 KB_RUN(kb_code_paths(ctx, ctx->d_stage4.as<KbPathJob>(), (int)pjobs.size()));
         }
         if (getenv("KB200_TRACE")) {
@@ -339,11 +339,11 @@ int kb_anchor_posmaps_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S, co
                 t2 = std::chrono::steady_clock::now();
         }
         if (!posmaps) {
-                KB_CUDA(cudaStreamSynchronize(st));
+                KB_RUN(kb_collect(ctx));
                 return KB200_OK;
         }
         KB_CUDA(cudaMemcpyAsync(posmaps + out_begin, d_out, sizeof(int) * out_n, cudaMemcpyDeviceToHost, st));
-        KB_CUDA(cudaStreamSynchronize(st));
+        KB_RUN(kb_collect(ctx));
         if (getenv("KB200_TRACE")) {
                 const auto t3 = std::chrono::steady_clock::now();
                 auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {

@@ -810,6 +810,14 @@ int kb200_msa_info(kb200_msa* M, int* numseq, int* biotype, int* n_anchors)
         return KB200_OK;
 }
 
+int kb200_msa_tree(kb200_msa* M, int* tasks_abc, float* seq_distances)
+{
+        if (!M || M->tree_job || (int)M->abc.size() != 3 * (M->N - 1)) return KB200_FAIL;
+        if (tasks_abc) memcpy(tasks_abc, M->abc.data(), sizeof(int) * M->abc.size());
+        if (seq_distances) memcpy(seq_distances, M->seq_distances.data(), sizeof(float) * (size_t)M->N);
+        return KB200_OK;
+}
+
 int kb200_kalign(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_threads, int type,
                  float gpo, float gpe, float tgpe, int consistency_anchors, float consistency_weight,
                  char*** aligned, int* out_aln_len)

@@ -927,10 +927,17 @@ __device__ void sweep_unit(const KbJob& J, const KbBox& bx, const int bwd, const
 template <int BONUS>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
 kb_sweep_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes,
-                const KbUnit* __restrict__ units, const unsigned* __restrict__ nunits_p,
-                unsigned int* __restrict__ cursor, const unsigned tag_base,
-                const float* __restrict__ tbl, const int thin, const int tstride)
+                const KbUnit* __restrict__ units, KbRound* __restrict__ rnd, const unsigned tag_base,
+                const float* __restrict__ tbl, const int tstride)
 {
+        // the round's unit count and strip regime were written by kb_plan_kernel (device memory:
+        // the host enqueues every round of a call without reading anything back)
+        const unsigned total = rnd->nunits;
+        if (total == 0u) {
+                return;
+        }
+        const int thin = (int)rnd->thin;
+        unsigned int* const cursor = &rnd->cursor;
         __shared__ float s_tbl[TBL_MAX];
         __shared__ float4 s_ring_all[WARPS_PER_CTA][16];     // hand-off ring (row above), one per warp
         // per warp: 5-letter profile-profile column records (two 64-column rings, 2 KB) or the staged
@@ -947,7 +954,6 @@ kb_sweep_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes,
         float4* s_ring = s_ring_all[threadIdx.x >> 5];
         float4* s_rec = s_rec_all[threadIdx.x >> 5];
         int2* s_bon = (BONUS == BONUS_SPARSE) ? (s_bon_all + (threadIdx.x >> 5) * (BON_SLOTS * BON_KMAX_ROWS * 32)) : s_bon_all;
-        const unsigned total = *nunits_p;
         while (true) {
                 unsigned unit = 0;
                 if (lane == 0) {
@@ -987,8 +993,8 @@ kb_sweep_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes,
 
 // launchers, one per kernel family / translation unit (units: KbUnit array written by kb_plan_kernel)
 cudaError_t kb_sweep_launch_none(int grid, int block, cudaStream_t st, const KbJob* jobs, const KbBox* boxes, const void* units,
-                                 const unsigned* nunits, unsigned* cursor, unsigned tag_base, const float* tbl, int thin, int tstride);
+                                 KbRound* rnd, unsigned tag_base, const float* tbl, int tstride);
 cudaError_t kb_sweep_launch_sparse(int grid, int block, cudaStream_t st, const KbJob* jobs, const KbBox* boxes, const void* units,
-                                   const unsigned* nunits, unsigned* cursor, unsigned tag_base, const float* tbl, int thin, int tstride);
+                                   KbRound* rnd, unsigned tag_base, const float* tbl, int tstride);
 cudaError_t kb_sweep_launch_dense(int grid, int block, cudaStream_t st, const KbJob* jobs, const KbBox* boxes, const void* units,
-                                  const unsigned* nunits, unsigned* cursor, unsigned tag_base, const float* tbl, int thin, int tstride);
+                                  KbRound* rnd, unsigned tag_base, const float* tbl, int tstride);

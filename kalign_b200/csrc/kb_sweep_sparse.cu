@@ -2,7 +2,7 @@
 #include "kb_sweep.cuh"
 
 cudaError_t kb_sweep_launch_sparse(int grid, int block, cudaStream_t st, const KbJob* jobs, const KbBox* boxes, const void* units,
-                                   const unsigned* nunits, unsigned* cursor, unsigned tag_base, const float* tbl, int thin, int tstride)
+                                   KbRound* rnd, unsigned tag_base, const float* tbl, int tstride)
 {
         // 4 resident CTAs per SM
         static bool carveout_set = false;
@@ -10,6 +10,6 @@ cudaError_t kb_sweep_launch_sparse(int grid, int block, cudaStream_t st, const K
                 cudaFuncSetAttribute(kb_sweep_kernel<BONUS_SPARSE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
                 carveout_set = true;
         }
-        kb_sweep_kernel<BONUS_SPARSE><<<grid, block, 0, st>>>(jobs, boxes, static_cast<const KbUnit*>(units), nunits, cursor, tag_base, tbl, thin, tstride);
+        kb_sweep_kernel<BONUS_SPARSE><<<grid, block, 0, st>>>(jobs, boxes, static_cast<const KbUnit*>(units), rnd, tag_base, tbl, tstride);
         return cudaGetLastError();
 }

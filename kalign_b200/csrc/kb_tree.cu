@@ -381,7 +381,7 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
 #define TR(x) do { if ((x) != KB200_OK) { fprintf(stderr, "[kalign_b200] align_tree failure at %s:%d\n", __FILE__, __LINE__); cleanup(); return KB200_FAIL; } } while (0)
 #define TC(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { fprintf(stderr, "[kalign_b200] CUDA error %s at %s:%d\n", cudaGetErrorString(e__), __FILE__, __LINE__); cleanup(); return KB200_FAIL; } } while (0)
         TR(d_subm.ensure(sizeof(float) * 23 * 23));
-        TC(cudaMemcpyAsync(d_subm.p, prm->subm, sizeof(float) * 23 * 23, cudaMemcpyHostToDevice, st));
+        TR(kb_h2d(ctx, d_subm.p, prm->subm, sizeof(float) * 23 * 23));
 
         std::vector<std::vector<std::pair<long long, float>>> bonus_lists;
         std::vector<std::vector<int>> colof((size_t)N);
@@ -403,7 +403,7 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                         const size_t full = (size_t)T.K * (size_t)S.total;
                         if (!posmaps_on_device || ctx->posmaps_tag != (const void*)T.posmaps || ctx->posmaps_n != full) {
                                 TR(ctx->t_posmaps.ensure(sizeof(int) * (full + 8)));
-                                TC(cudaMemcpyAsync(ctx->t_posmaps.p, T.posmaps, sizeof(int) * full, cudaMemcpyHostToDevice, st));
+                                TR(kb_h2d(ctx, ctx->t_posmaps.p, T.posmaps, sizeof(int) * full));
                                 ctx->stats.h2d_bytes += (double)(sizeof(int) * full);
                                 ctx->posmaps_tag = nullptr;      // a caller-owned array may change behind our back
                                 ctx->posmaps_n = 0;
@@ -412,8 +412,7 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                         std::vector<int> aoff((size_t)T.K);
                         for (int k = 0; k < T.K; k++) aoff[(size_t)k] = k * (maxlen + 1);
                         TR(ctx->t_aoff.ensure(sizeof(int) * (size_t)T.K + 16));
-                        TC(cudaMemcpyAsync(ctx->t_aoff.p, aoff.data(), sizeof(int) * (size_t)T.K, cudaMemcpyHostToDevice, st));
-                        TC(cudaStreamSynchronize(st));
+                        TR(kb_h2d(ctx, ctx->t_aoff.p, aoff.data(), sizeof(int) * (size_t)T.K));
                 }
         }
         const size_t inv_per_task = (size_t)T.K * (size_t)(maxlen + 1);
@@ -426,6 +425,8 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                 auto tms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
                         return std::chrono::duration<double, std::milli>(b - a).count();
                 };
+                // KB200_TRACE: phase times need the stream drained at the phase boundaries (debugging aid)
+                auto tsync = [&]() { if (trace) cudaStreamSynchronize(st); };
                 const auto t_level0 = tnow();
                 // ---- per task: scoring offset, operand lengths ----
                 std::vector<float> soff((size_t)nt, 0.0f);
@@ -500,16 +501,15 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                 long long* d_pref_gs = d_pref_leaf + leaves.size();
                 long long* d_pref_mg = d_pref_gs + gsets.size();
                 if (!leaves.empty()) {
-                        TC(cudaMemcpyAsync(d_leaf.p, leaves.data(), sizeof(KbLeafProfile) * leaves.size(), cudaMemcpyHostToDevice, st));
-                        TC(cudaMemcpyAsync(d_pref_leaf, leaf_prefix.data(), sizeof(long long) * leaves.size(), cudaMemcpyHostToDevice, st));
+                        TR(kb_h2d(ctx, d_leaf.p, leaves.data(), sizeof(KbLeafProfile) * leaves.size()));
+                        TR(kb_h2d(ctx, d_pref_leaf, leaf_prefix.data(), sizeof(long long) * leaves.size()));
                         TR(kb_make_profiles(ctx, d_leaf.as<KbLeafProfile>(), (int)leaves.size(), d_pref_leaf, leaf_cols, d_subm.as<float>()));
                 }
                 if (!gsets.empty()) {
-                        TC(cudaMemcpyAsync(d_gapset.p, gsets.data(), sizeof(KbGapSet) * gsets.size(), cudaMemcpyHostToDevice, st));
-                        TC(cudaMemcpyAsync(d_pref_gs, gs_prefix.data(), sizeof(long long) * gsets.size(), cudaMemcpyHostToDevice, st));
+                        TR(kb_h2d(ctx, d_gapset.p, gsets.data(), sizeof(KbGapSet) * gsets.size()));
+                        TR(kb_h2d(ctx, d_pref_gs, gs_prefix.data(), sizeof(long long) * gsets.size()));
                         TR(kb_set_gap_penalties(ctx, d_gapset.as<KbGapSet>(), (int)gsets.size(), d_pref_gs, gs_cols));
                 }
-                TC(cudaStreamSynchronize(st));   // host vectors above go out of scope per level
 
                 // ---- jobs ----
                 std::vector<KbJob> jobs((size_t)nt);
@@ -556,6 +556,7 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                         n_coded += (size_t)la[q] + (size_t)lb[q] + 2;
                         n_scr += (size_t)la[q] + 2;
                 }
+                tsync();
                 const auto t_prep = tnow();
                 // ---- consistency bonus (default mode), dense on device ----
                 if (T.posmaps && dev_state && ntm > 0) {
@@ -640,25 +641,24 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                         long long* d_rwp = (long long*)base; base += sizeof(long long) * row_prefix.size();
                         int* d_sml = (int*)base; base += sizeof(int) * small_list.size();
                         int* d_memb = (int*)base;
-                        TC(cudaMemcpyAsync(d_ops, ops.data(), sizeof(KbBonusOperand) * ops.size(), cudaMemcpyHostToDevice, st));
-                        TC(cudaMemcpyAsync(d_bt, btasks.data(), sizeof(KbBonusTask) * btasks.size(), cudaMemcpyHostToDevice, st));
+                        TR(kb_h2d(ctx, d_ops, ops.data(), sizeof(KbBonusOperand) * ops.size()));
+                        TR(kb_h2d(ctx, d_bt, btasks.data(), sizeof(KbBonusTask) * btasks.size()));
                         if (!small_list.empty()) {
-                                TC(cudaMemcpyAsync(d_smp, small_prefix.data(), sizeof(long long) * small_prefix.size(), cudaMemcpyHostToDevice, st));
-                                TC(cudaMemcpyAsync(d_sml, small_list.data(), sizeof(int) * small_list.size(), cudaMemcpyHostToDevice, st));
+                                TR(kb_h2d(ctx, d_smp, small_prefix.data(), sizeof(long long) * small_prefix.size()));
+                                TR(kb_h2d(ctx, d_sml, small_list.data(), sizeof(int) * small_list.size()));
                         }
                         if (!vops.empty()) {
-                                TC(cudaMemcpyAsync(d_vops, vops.data(), sizeof(KbVoteOp) * vops.size(), cudaMemcpyHostToDevice, st));
+                                TR(kb_h2d(ctx, d_vops, vops.data(), sizeof(KbVoteOp) * vops.size()));
                         }
-                        TC(cudaMemcpyAsync(d_cbp, colb_prefix.data(), sizeof(long long) * colb_prefix.size(), cudaMemcpyHostToDevice, st));
-                        TC(cudaMemcpyAsync(d_rwp, row_prefix.data(), sizeof(long long) * row_prefix.size(), cudaMemcpyHostToDevice, st));
-                        TC(cudaMemcpyAsync(d_memb, memb.data(), sizeof(int) * memb.size(), cudaMemcpyHostToDevice, st));
+                        TR(kb_h2d(ctx, d_cbp, colb_prefix.data(), sizeof(long long) * colb_prefix.size()));
+                        TR(kb_h2d(ctx, d_rwp, row_prefix.data(), sizeof(long long) * row_prefix.size()));
+                        TR(kb_h2d(ctx, d_memb, memb.data(), sizeof(int) * memb.size()));
                         TC(cudaMemsetAsync(ctx->t_binv.p, 0xFF, sizeof(int) * inv_per_task * (size_t)ntm, st));
                         TR(kb_bonus_level(ctx, S, K, T.weight / (float)K, d_ops,
                                           d_sml, d_smp, (int)small_list.size(), small_cols,
                                           d_vops, (int)vops.size(), large_units, large_cols, vote_slots,
                                           d_memb, d_colof, d_posmaps,
                                           d_bt, d_cbp, colb_total, d_rwp, row_total, ntm, ctx->t_aoff.as<int>()));
-                        TC(cudaStreamSynchronize(st));     // host descriptor vectors go out of scope
                 } else if (T.posmaps && !dev_state) {
                         level_bonus(T, q0, q1, rown, rlen, coln, clen, n_threads, colof, bonus_lists);
                         size_t dense = 0, nent = 0;
@@ -683,8 +683,8 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                         }
                         TC(cudaMemsetAsync(d_bonus.p, 0, sizeof(float) * dense, st));
                         if (nent) {
-                                TC(cudaMemcpyAsync(d_bidx.p, hidx.data(), sizeof(long long) * nent, cudaMemcpyHostToDevice, st));
-                                TC(cudaMemcpyAsync(d_bval.p, hval.data(), sizeof(float) * nent, cudaMemcpyHostToDevice, st));
+                                TR(kb_h2d(ctx, d_bidx.p, hidx.data(), sizeof(long long) * nent));
+                                TR(kb_h2d(ctx, d_bval.p, hval.data(), sizeof(float) * nent));
                                 kb_scatter_kernel<<<(unsigned)((nent + 255) / 256), 256, 0, st>>>(d_bonus.as<float>(), d_bidx.as<long long>(), d_bval.as<float>(), (long long)nent);
                                 TC(cudaGetLastError());
                                 ctx->stats.n_launches++;
@@ -692,6 +692,7 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                         TC(cudaStreamSynchronize(st));
                         ctx->stats.h2d_bytes += 12.0 * (double)nent;
                 }
+                tsync();
                 const auto t_bonus = tnow();
                 TR(d_raw.ensure(sizeof(int) * (n_raw + 16)));
                 TR(d_coded.ensure(sizeof(int) * (n_coded + 16)));
@@ -726,10 +727,11 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                         std::vector<KbJob> mine(jobs.begin() + q0, jobs.begin() + q1);
                         TR(kb_run_hirschberg(ctx, prm->subm, mine));
                 }
+                tsync();
                 const auto t_dp = tnow();
                 TR(d_pjobs.ensure(sizeof(KbPathJob) * (size_t)nt + 16));
                 if (ntm > 0) {
-                        TC(cudaMemcpyAsync(d_pjobs.p, pjobs.data() + q0, sizeof(KbPathJob) * (size_t)ntm, cudaMemcpyHostToDevice, st));
+                        TR(kb_h2d(ctx, d_pjobs.p, pjobs.data() + q0, sizeof(KbPathJob) * (size_t)ntm));
                         TR(kb_code_paths(ctx, d_pjobs.as<KbPathJob>(), ntm));
                 }
                 if (ctx->world > 1) {
@@ -766,23 +768,23 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                         TR(ctx->t_wdesc.ensure(sizeof(KbWeaveTask) * wt.size() + sizeof(KbWeaveMember) * wm.size() + 64));
                         KbWeaveTask* d_wt = ctx->t_wdesc.as<KbWeaveTask>();
                         KbWeaveMember* d_wm = (KbWeaveMember*)(d_wt + wt.size());
-                        TC(cudaMemcpyAsync(d_wt, wt.data(), sizeof(KbWeaveTask) * wt.size(), cudaMemcpyHostToDevice, st));
-                        TC(cudaMemcpyAsync(d_wm, wm.data(), sizeof(KbWeaveMember) * wm.size(), cudaMemcpyHostToDevice, st));
+                        TR(kb_h2d(ctx, d_wt, wt.data(), sizeof(KbWeaveTask) * wt.size()));
+                        TR(kb_h2d(ctx, d_wm, wm.data(), sizeof(KbWeaveMember) * wm.size()));
                         TR(kb_weave_level(ctx, S, d_wt, nt, d_wm, (int)wm.size(), d_gaps, d_colof));
-                        TC(cudaStreamSynchronize(st));
                 }
                 // the host only needs every task's alignment length (plen bookkeeping, merged profile
                 // sizes); the coded paths themselves stay on the device (KB200_HOST_BONUS: full copy)
                 std::vector<int> hcoded;
                 std::vector<int> alen((size_t)nt);
                 if (dev_state) {
+                        // THE host synchronisation of the level: alignment lengths + engine statistics / error flags
                         TC(cudaMemcpyAsync(alen.data(), ctx->t_alen.p, sizeof(int) * (size_t)nt, cudaMemcpyDeviceToHost, st));
-                        TC(cudaStreamSynchronize(st));
+                        TR(kb_collect(ctx));
                         ctx->stats.d2h_bytes += (double)(sizeof(int) * (size_t)nt);
                 } else {
                         hcoded.resize(n_coded);
                         TC(cudaMemcpyAsync(hcoded.data(), d_coded.p, sizeof(int) * n_coded, cudaMemcpyDeviceToHost, st));
-                        TC(cudaStreamSynchronize(st));
+                        TR(kb_collect(ctx));
                         ctx->stats.d2h_bytes += (double)(sizeof(int) * n_coded);
                         for (int q = 0; q < nt; q++) alen[(size_t)q] = hcoded[coded_off[(size_t)q]];
                 }
@@ -830,8 +832,8 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                 }
                 if (!mjobs.empty()) {
                         TR(d_mjobs.ensure(sizeof(KbMergeJob) * mjobs.size()));
-                        TC(cudaMemcpyAsync(d_mjobs.p, mjobs.data(), sizeof(KbMergeJob) * mjobs.size(), cudaMemcpyHostToDevice, st));
-                        TC(cudaMemcpyAsync(d_pref_mg, mprefix.data(), sizeof(long long) * mprefix.size(), cudaMemcpyHostToDevice, st));
+                        TR(kb_h2d(ctx, d_mjobs.p, mjobs.data(), sizeof(KbMergeJob) * mjobs.size()));
+                        TR(kb_h2d(ctx, d_pref_mg, mprefix.data(), sizeof(long long) * mprefix.size()));
                         TR(kb_merge_index(ctx, d_mjobs.as<KbMergeJob>(), (int)mjobs.size()));
                         TR(kb_merge_profiles(ctx, d_mjobs.as<KbMergeJob>(), (int)mjobs.size(), d_pref_mg, mcols));
                 }
@@ -841,6 +843,7 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                         for (int r = 0; r <= ctx->world; r++) seg[(size_t)r] = prof_off[(size_t)tb[(size_t)r]] * sizeof(float);
                         TR(kb_allgatherv(ctx, block, seg.data()));
                 }
+                tsync();
                 const auto t_post = tnow();
                 // ---- host bookkeeping while the merge kernels run: gaps, sip, nsip, plen ----
                 if (!dev_state) {
@@ -864,8 +867,8 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                                 std::vector<int>().swap(T.sip[b]);
                         }
                 }
-                TC(cudaStreamSynchronize(st));
                 if (trace) {
+                        TC(cudaStreamSynchronize(st));
                         const auto t_end = tnow();
                         fprintf(stderr, "[kb200 trace] tree level %d: %d tasks prep %.2f bonus %.2f dp %.2f post %.2f weave %.2f ms\n", L, nt,
                                 tms(t_level0, t_prep), tms(t_prep, t_bonus), tms(t_bonus, t_dp), tms(t_dp, t_post), tms(t_post, t_end));
@@ -873,7 +876,7 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
         }
         if (dev_state) {
                 TC(cudaMemcpyAsync(gaps_out, d_gaps, sizeof(int) * ((size_t)S.total + (size_t)N), cudaMemcpyDeviceToHost, st));
-                TC(cudaStreamSynchronize(st));
+                TR(kb_collect(ctx));
                 ctx->stats.d2h_bytes += (double)(sizeof(int) * ((size_t)S.total + (size_t)N));
         } else {
                 for (int i = 0; i < N; i++) {

@@ -62,3 +62,18 @@ def write_fasta(path, seqs):
             f.write(">s%d\n" % i)
             for k in range(0, len(s), 60):
                 f.write(s[k:k + 60] + "\n")
+
+
+def msa_sha256(rows):
+    """SHA-256 of an alignment: the rows in input order joined by a newline.  bench.py prints it in
+    every line and the full-size parity tests compare it with tests/golden/full_*.npz, which
+    tools/gen_golden_full.py wrote from the unmodified reference."""
+    import hashlib
+    h = hashlib.sha256()
+    first = True
+    for r in rows:
+        if not first:
+            h.update(b"\n")
+        first = False
+        h.update(r.encode() if isinstance(r, str) else r)
+    return h.hexdigest()
