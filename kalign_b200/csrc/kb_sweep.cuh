@@ -523,6 +523,115 @@ __device__ __forceinline__ void sparse_init(const KbJob& J, const int bwd, const
         }
 }
 
+// ---- sparse consistency bonus of the warp strips: EVENTS instead of a compare in every cell -----
+// A row carries at most nb (<= 8) bonus entries over thousands of columns.  The strip therefore
+// runs the bonus-free cell routine and keeps, per lane, ONE sorted queue of the (column, row, value)
+// entries of its K rows in shared memory (lane-private slots, conflict-free).  A step costs one
+// integer compare (column of the next event == column of the lane); on a hit -- lane-divergent,
+// rare -- the value is added to the cell's `a` exactly where the reference adds its matrix entry
+// (after the substitution / profile term: aln_seqseq.c:83-85, aln_profileprofile.c:107-109) and the
+// gb chain down the lane's rows of this column is recomputed from the corrected value.  All other
+// cells add the reference's +0.0f, which never changes a value.
+constexpr int BON_QCAP = BON_SLOTS * BON_KMAX_ROWS;          // events per lane
+constexpr int BON_QSLOTS = BON_QCAP + 2 + BON_KMAX_ROWS;     // + two sentinels + the rows' wrap values
+constexpr int BON_DYN_SMEM = WARPS_PER_CTA * BON_QSLOTS * 32 * 8;   // bytes of dynamic shared memory, sparse family
+
+template <int V, int K, bool TAIL, bool EDGE, bool ALLROWS>
+__device__ __forceinline__ void bonus_fix(const KbJob& J, const RowCtx<V, K>& rc, const unsigned vmask, const Trip got,
+                                          const int k0, const float val, const int2* __restrict__ wrapv, const bool e_term,
+                                          float (&sA)[K], float (&sGA)[K], float (&sGB)[K], Trip& u)
+{
+        Trip p = got;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+                float RO, RE, RT;
+                if constexpr (is_ss<V>()) {
+                        RO = J.o; RE = J.e; RT = J.t;
+                } else {
+                        RO = rc.RO[k]; RE = rc.RE[k]; RT = rc.RT[k];
+                }
+                float a = sA[k];
+                if constexpr (ALLROWS) {
+                        a = a + __int_as_float(wrapv[k * 32].x);     // forward sweep, j == len_b: flat index wraps to (i+1, 0)
+                } else {
+                        if (k == k0) a = a + val;
+                }
+                float gb = kmax(p.gb + RE, p.a + RO);
+                if constexpr (EDGE) {
+                        const float gt = kmax(p.gb, p.a) + RT;
+                        gb = e_term ? gt : gb;
+                }
+                float ga = sGA[k];
+                if constexpr (TAIL) {
+                        if (!((vmask >> k) & 1u)) {
+                                a = p.a; ga = p.ga; gb = p.gb;
+                        }
+                }
+                sA[k] = a; sGA[k] = ga; sGB[k] = gb;
+                p.a = a; p.ga = ga; p.gb = gb;
+        }
+        u = p;
+}
+
+// build the lane's event queue: entries of the valid rows whose column the sweep visits, sorted by
+// column.  q[0] / q[n+1] are sentinels that never match a column; returns the index of the first
+// event in sweep direction.  Also stages the rows' wrap values (forward sweep ending at len_b).
+template <int V, int K>
+__device__ __forceinline__ int bonus_queue_init(const KbJob& J, const int bwd, const int sb, const int eb, const RowCtx<V, K>& rc,
+                                                const unsigned vmask, int2* __restrict__ q, bool& wrap_on)
+{
+        static_assert(K <= BON_KMAX_ROWS, "event queue capacity");
+        const int nb = J.nb;
+        // forward cells visit j = sb+1 .. eb, backward cells j = eb-1 .. sb (the first column of a sweep takes no bonus)
+        const int lo = bwd ? sb : sb + 1;
+        const int hi = bwd ? eb - 1 : eb;
+        int n = 0;
+        __syncwarp();
+        q[0] = make_int2((int)0x80000000, 0);
+        wrap_on = false;
+        if (J.bkey != nullptr) {
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                        if ((vmask >> k) & 1u) {
+                                const int* __restrict__ bc = J.bkey + (size_t)rc.irow[k] * (size_t)nb;
+                                const float* __restrict__ bv = J.bval + (size_t)rc.irow[k] * (size_t)nb;
+                                for (int e = 0; e < nb; e++) {
+                                        const int c = __ldg(bc + e);
+                                        if (c >= lo && c <= hi) {
+                                                // insertion from the back: rows are diagonal-correlated, the queue is nearly sorted already
+                                                const int key = (c << 3) | k;
+                                                const int vb = __float_as_int(__ldg(bv + e));
+                                                int y = n;
+                                                while (y >= 1 && q[y * 32].x > key) {
+                                                        q[(y + 1) * 32] = q[y * 32];
+                                                        y--;
+                                                }
+                                                q[(y + 1) * 32] = make_int2(key, vb);
+                                                n++;
+                                        }
+                                }
+                        }
+                }
+                if (!bwd && eb == J.len_b) {
+                        float anyw = 0.0f;
+#pragma unroll
+                        for (int k = 0; k < K; k++) {
+                                float w = 0.0f;
+                                if (((vmask >> k) & 1u) && rc.irow[k] + 1 < J.len_a) {
+                                        const size_t o = (size_t)(rc.irow[k] + 1) * (size_t)nb;
+                                        if (__ldg(J.bkey + o) == 0) w = __ldg(J.bval + o);
+                                }
+                                q[(BON_QCAP + 2 + k) * 32] = make_int2(__float_as_int(w), 0);
+                                anyw = (w != 0.0f) ? 1.0f : anyw;
+                        }
+                        wrap_on = (anyw != 0.0f);
+                }
+        }
+        q[(n + 1) * 32] = make_int2(0x7fffffff, 0);
+        __syncwarp();
+        return bwd ? n : 1;
+}
+
 // One strip of 32*K rows starting at logical row `row0` of the sweep.
 //   in_tag  : tag the row above must carry (0 for strip 0: the init row is generated)
 //   out_tag : tag this strip stamps on the row it emits
@@ -538,7 +647,7 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                             const float* __restrict__ s_tbl, const int tstride, const int lane, float4* s_ring, float4* s_rec,
                             int2* s_bon)
 {
-        static_assert(BONUS != BONUS_SPARSE || K <= BON_KMAX_ROWS, "bonus staging area is sized for K <= 4");
+        static_assert(BONUS != BONUS_SPARSE || K <= BON_KMAX_ROWS, "bonus event queue is sized for K <= 4");
         constexpr int NA = VTraits<V>::NA;
         constexpr int PW4 = (V == V_PP5) ? (PACK5 / 4) : (PACK23 / 4);
         const int C = eb - sb;
@@ -658,21 +767,23 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
         // column input of the current step (filled one step ahead); lane 0 starts on column 0 at t=0
         float4 curA = make_float4(0.f, 0.f, 0.f, 0.f), curB = curA;
         int cur_cres = 0;
-        // sparse consistency bonus: per row the index / column / value of the next entry in sweep
-        // direction, and the value the forward sweep picks up at j == len_b (flat index (i+1, 0))
-        const bool sparse = (BONUS == BONUS_SPARSE) && (J.bkey != nullptr);
-        int2* const my_bon = s_bon + lane;       // lane-private slots [entry][row k][lane]
+        // sparse consistency bonus: the lane's event queue (see bonus_fix / bonus_queue_init above)
+        int2* const my_bon = s_bon + lane;       // lane-private slots [slot][lane]
         const int bdir = bwd ? -1 : 1;
+        int ev_i = 0;                            // queue index of the next event in sweep direction
+        int ev_col = 0x7fffffff;                 // its column (sentinel: never equal to a lane's column)
+        bool wrap_on = false;
+        if constexpr (BONUS == BONUS_SPARSE) {
+                ev_i = bonus_queue_init<V, K>(J, bwd, sb, eb, rc, vmask, my_bon, wrap_on);
+                ev_col = my_bon[ev_i * 32].x >> 3;
+        }
+        // the cell routine runs bonus-free in the sparse family (events) -- dummies for its list arguments
+        constexpr int CB = (BONUS == BONUS_SPARSE) ? BONUS_NONE : BONUS;
         int sp_i[K], sp_c[K];
         float sp_v[K], sp_wrap[K];
 #pragma unroll
         for (int k = 0; k < K; k++) {
-                sp_i[k] = 0; sp_c[k] = bwd ? -1 : 0x7fffffff; sp_v[k] = 0.0f; sp_wrap[k] = 0.0f;
-        }
-        if constexpr (BONUS) {
-                if (sparse) {
-                        sparse_init<V, K, true>(J, bwd, sb, eb, rc, my_bon, sp_i, sp_c, sp_v, sp_wrap);
-                }
+                sp_i[k] = 0; sp_c[k] = 0; sp_v[k] = 0.0f; sp_wrap[k] = 0.0f;
         }
         if constexpr (RECRING) {
                 static_assert(PACK5 == 8, "PP5 record is two float4");
@@ -798,9 +909,28 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                         }
                         const Trip got = up;
                         if constexpr (STEADY) {
-                                cells<V, K, TAIL, MODE_MID, BONUS, true>(J, rc, vmask, first_term, last_term, cc, bdir, sp_i, sp_c, sp_v, sp_wrap, my_bon, s_tbl, sA, sGA, sGB, d, up);
+                                cells<V, K, TAIL, MODE_MID, CB, true>(J, rc, vmask, first_term, last_term, cc, bdir, sp_i, sp_c, sp_v, sp_wrap, my_bon, s_tbl, sA, sGA, sGB, d, up);
                         } else {
-                                cells<V, K, TAIL, MODE_EDGE, BONUS, true>(J, rc, vmask, first_term, last_term, cc, bdir, sp_i, sp_c, sp_v, sp_wrap, my_bon, s_tbl, sA, sGA, sGB, d, up, u == 0, u == C);
+                                cells<V, K, TAIL, MODE_EDGE, CB, true>(J, rc, vmask, first_term, last_term, cc, bdir, sp_i, sp_c, sp_v, sp_wrap, my_bon, s_tbl, sA, sGA, sGB, d, up, u == 0, u == C);
+                        }
+                        if constexpr (BONUS == BONUS_SPARSE) {
+                                if (j == ev_col) {
+                                        // rare, lane-divergent: bonus entries of this lane's rows in this column
+                                        const bool e_term = !STEADY && ((u == 0 && first_term) || (u == C && last_term));
+                                        do {
+                                                const int2 q = my_bon[ev_i * 32];
+                                                bonus_fix<V, K, TAIL, !STEADY, false>(J, rc, vmask, got, q.x & 7, __int_as_float(q.y), my_bon, e_term,
+                                                                                      sA, sGA, sGB, up);
+                                                ev_i += bdir;
+                                                ev_col = my_bon[ev_i * 32].x >> 3;
+                                        } while (j == ev_col);
+                                }
+                                if constexpr (!STEADY) {
+                                        if (wrap_on && u == C) {
+                                                bonus_fix<V, K, TAIL, true, true>(J, rc, vmask, got, 0, 0.0f, my_bon + (BON_QCAP + 2) * 32, last_term,
+                                                                                  sA, sGA, sGB, up);
+                                        }
+                                }
                         }
                         d = got;
                         bot = up;
@@ -836,20 +966,11 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                         boundary(t);
                         // two steps per iteration: the register rotation of the software pipeline
                         // (current <- next column, diagonal <- row above) becomes renaming
-                        // (not in the sparse-bonus family: its list cursors already fill the register file)
-                        if constexpr (BONUS == BONUS_SPARSE) {
 #pragma unroll 1
-                                for (int q = 0; q < HB; q++) {
-                                        step(std::true_type{}, t);
-                                        t++;
-                                }
-                        } else {
-#pragma unroll 1
-                                for (int q = 0; q < HB; q += 2) {
-                                        step(std::true_type{}, t);
-                                        step(std::true_type{}, t + 1);
-                                        t += 2;
-                                }
+                        for (int q = 0; q < HB; q += 2) {
+                                step(std::true_type{}, t);
+                                step(std::true_type{}, t + 1);
+                                t += 2;
                         }
                 }
                 if (t < C) {
@@ -950,10 +1071,11 @@ kb_sweep_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes,
         __syncthreads();
         const int lane = threadIdx.x & 31;
         // sparse bonus lists of the rows of the strip a warp is sweeping (bonus kernel family only)
-        __shared__ int2 s_bon_all[(BONUS == BONUS_SPARSE) ? WARPS_PER_CTA * BON_SLOTS * BON_KMAX_ROWS * 32 : 1];
+        // (dynamic shared memory: with it the CTA exceeds the 48 KB static limit)
+        extern __shared__ int2 s_bon_all[];
         float4* s_ring = s_ring_all[threadIdx.x >> 5];
         float4* s_rec = s_rec_all[threadIdx.x >> 5];
-        int2* s_bon = (BONUS == BONUS_SPARSE) ? (s_bon_all + (threadIdx.x >> 5) * (BON_SLOTS * BON_KMAX_ROWS * 32)) : s_bon_all;
+        int2* s_bon = (BONUS == BONUS_SPARSE) ? (s_bon_all + (threadIdx.x >> 5) * (BON_QSLOTS * 32)) : s_bon_all;
         while (true) {
                 unsigned unit = 0;
                 if (lane == 0) {

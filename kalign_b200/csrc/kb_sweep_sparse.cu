@@ -1,4 +1,4 @@
-// kb_sweep_sparse.cu -- kb_sweep_kernel<BONUS_SPARSE>: sparse per-row bonus lists (tree levels in default mode): + 32 KB of staged lists per CTA, 4 x 47 KB = the whole carve-out.
+// kb_sweep_sparse.cu -- kb_sweep_kernel<BONUS_SPARSE>: sparse per-row bonus lists (tree levels in default mode): per-lane event queues in dynamic shared memory (38 KB per CTA; 4 CTAs x 52 KB per SM).
 #include "kb_sweep.cuh"
 
 cudaError_t kb_sweep_launch_sparse(int grid, int block, cudaStream_t st, const KbJob* jobs, const KbBox* boxes, const void* units,
@@ -8,8 +8,9 @@ cudaError_t kb_sweep_launch_sparse(int grid, int block, cudaStream_t st, const K
         static bool carveout_set = false;
         if (!carveout_set) {
                 cudaFuncSetAttribute(kb_sweep_kernel<BONUS_SPARSE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+                cudaFuncSetAttribute(kb_sweep_kernel<BONUS_SPARSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, BON_DYN_SMEM);
                 carveout_set = true;
         }
-        kb_sweep_kernel<BONUS_SPARSE><<<grid, block, 0, st>>>(jobs, boxes, static_cast<const KbUnit*>(units), rnd, tag_base, tbl, tstride);
+        kb_sweep_kernel<BONUS_SPARSE><<<grid, block, BON_DYN_SMEM, st>>>(jobs, boxes, static_cast<const KbUnit*>(units), rnd, tag_base, tbl, tstride);
         return cudaGetLastError();
 }
