@@ -58,6 +58,10 @@ typedef struct kb200_params {
         float gpo, gpe, tgpe;
         float vsm_amax;           /* variable scoring matrix amax (aln_param.c:96) */
         int   nalpha;             /* 5 (nucleotide codes) or 23 (protein codes) */
+        float dist_scale;         /* aln_param.dist_scale: per-task gap penalty scale (compute_gap_scale,
+                                     lib/src/aln_run.c:126-164); 0 = off (kalign_run_seeded's default) */
+        float use_seq_weights;    /* aln_param.use_seq_weights: pseudo-count of the balanced profile merge
+                                     (update_n, lib/src/aln_setup.c:237-300); 0 = off */
 } kb200_params;
 
 /* one pairwise job for kb200_pair_align_batch (HOST pointers) */
@@ -134,10 +138,25 @@ int kb200_align_tree(kb200_ctx* ctx, const kb200_params* prm,
                      const int* tasks_abc, int ntasks, const float* seq_distances,
                      const int* posmaps, int K, float weight,
                      int* gaps_out);
+/* the same, also returning per task (task order; either may be NULL):
+   task_confidence: task->confidence, the mean meet-up margin margin_sum / margin_count accumulated
+                    in the reference's recursion order (lib/src/aln_seqseq.c:375-385, aln_run.c:390-394);
+   task_plen:       msa->plen[c], the length of the merged profile (aln_run.c:424) */
+int kb200_align_tree_conf(kb200_ctx* ctx, const kb200_params* prm,
+                          const uint8_t* seqs, const int64_t* offs, const int* lens, int nseq,
+                          const int* tasks_abc, int ntasks, const float* seq_distances,
+                          const int* posmaps, int K, float weight,
+                          int* gaps_out, float* task_confidence, int* task_plen);
 
 /* kalign() of lib/include/kalign/kalign.h:45 on the GPU: same arguments, same ownership
    (rows and the array are malloc'd; caller frees).  consistency_anchors = 0 reproduces
-   kalign()/kalign_run(); 5 with weight 2.0 reproduces the CLI default mode. */
+   kalign()/kalign_run(); 5 with weight 2.0 reproduces the CLI default mode.
+   Like kalign()'s array mode (kalign_arr_to_msa, lib/src/msa_op.c:440) the characters are taken as
+   they are: '-' / '.' are NOT stripped (gaps[] start at zero; only file input de-aligns), any
+   character outside the alphabet is coded as residue 0 with a warning (msa_op.c:358-362).
+   Equal-length sequences are ordered by the names "s<i>" (i = input position); the reference leaves
+   the names of an array-mode msa uninitialised, so its own order of equal-length sequences is
+   undefined there -- the FASTA path (names from the file) is the one tests/ and bench.py pin. */
 int kb200_kalign(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_threads, int type,
                  float gpo, float gpe, float tgpe, int consistency_anchors, float consistency_weight,
                  char*** aligned, int* out_aln_len);

@@ -20,9 +20,12 @@
  * There is no CPU fallback: when no CUDA device is usable every seam returns FAIL, and
  * kalign_run()/kalign() fail with it.  Environment: KALIGN_B200_DEVICE selects the GPU (default 0).
  *
- * Not covered (out of scope): --refine all/confident and the inline-refine tree
- * (create_msa_tree_inline_refine stays the reference's CPU code; the two-pass refinement needs
- * msa->sip/nsip/plen of the internal nodes, which this seam does not reconstruct).
+ * Every aln_param field the wrapped functions read is honoured: dist_scale (compute_gap_scale,
+ * aln_run.c:126), use_seq_weights (update_n, aln_setup.c:237), vsm_amax, the consistency table.
+ * create_msa_tree's post-conditions are complete: gaps[], task->confidence (read by --refine
+ * confident, aln_refine.c:70), msa->plen / nsip / sip of the internal nodes (aln_run.c:424-436).
+ * The refinement passes themselves (refine_alignment, create_msa_tree_inline_refine) stay the
+ * reference's CPU code: they rebuild everything from the leaves and only consume task->confidence.
  */
 #include <pthread.h>
 #include <stdint.h>
@@ -122,6 +125,8 @@ static void fill_params(struct msa* msa, struct aln_param* ap, kb200_params* prm
         prm->tgpe = ap->tgpe;
         prm->vsm_amax = ap->vsm_amax;
         prm->nalpha = (msa->biotype == ALN_BIOTYPE_DNA) ? 5 : 23;
+        prm->dist_scale = ap->dist_scale;
+        prm->use_seq_weights = ap->use_seq_weights;
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -311,7 +316,10 @@ int __wrap_create_msa_tree(struct msa* msa, struct aln_param* ap, struct aln_tas
         int* abc = NULL;
         int* gaps = NULL;
         int* posmaps = NULL;
+        float* conf = NULL;
+        int* plen = NULL;
         int own_posmaps = 0;
+        int j, g;
         int K = 0;
         float weight = 0.0F;
         int N = msa->numseq;
@@ -330,7 +338,9 @@ int __wrap_create_msa_tree(struct msa* msa, struct aln_param* ap, struct aln_tas
         }
         abc = malloc(sizeof(int) * 3 * (size_t)(t->n_tasks > 0 ? t->n_tasks : 1));
         gaps = malloc(sizeof(int) * ((size_t)total + (size_t)N));
-        if(!abc || !gaps){
+        conf = malloc(sizeof(float) * (size_t)(t->n_tasks > 0 ? t->n_tasks : 1));
+        plen = malloc(sizeof(int) * (size_t)(t->n_tasks > 0 ? t->n_tasks : 1));
+        if(!abc || !gaps || !conf || !plen){
                 goto ERROR;
         }
         for(i = 0; i < t->n_tasks; i++){
@@ -358,12 +368,31 @@ int __wrap_create_msa_tree(struct msa* msa, struct aln_param* ap, struct aln_tas
                         }
                 }
         }
-        if(kb200_align_tree(ctx, &prm, f.seqs, f.offs, f.lens, N, abc, t->n_tasks, msa->seq_distances,
-                            posmaps, K, weight, gaps) != KB200_OK){
+        if(kb200_align_tree_conf(ctx, &prm, f.seqs, f.offs, f.lens, N, abc, t->n_tasks, msa->seq_distances,
+                                 posmaps, K, weight, gaps, conf, plen) != KB200_OK){
                 goto ERROR;
         }
         for(i = 0; i < N; i++){
                 memcpy(msa->sequences[i]->gaps, gaps + f.offs[i] + i, sizeof(int) * (size_t)(f.lens[i] + 1));
+        }
+        /* the rest of do_align's bookkeeping (aln_run.c:390-436): confidence, plen, nsip, sip */
+        for(i = 0; i < t->n_tasks; i++){
+                const int a = t->list[i]->a;
+                const int b = t->list[i]->b;
+                const int c = t->list[i]->c;
+                t->list[i]->confidence = conf[i];
+                msa->plen[c] = plen[i];
+                msa->nsip[c] = msa->nsip[a] + msa->nsip[b];
+                MREALLOC(msa->sip[c], sizeof(int) * (size_t)(msa->nsip[a] + msa->nsip[b]));
+                g = 0;
+                for(j = msa->nsip[a]; j--;){
+                        msa->sip[c][g] = msa->sip[a][j];
+                        g++;
+                }
+                for(j = msa->nsip[b]; j--;){
+                        msa->sip[c][g] = msa->sip[b][j];
+                        g++;
+                }
         }
         if(own_posmaps){
                 free(posmaps);
@@ -373,6 +402,8 @@ int __wrap_create_msa_tree(struct msa* msa, struct aln_param* ap, struct aln_tas
         g_ct_owner = NULL;
         free(abc);
         free(gaps);
+        free(conf);
+        free(plen);
         flat_free(&f);
         return OK;
 ERROR:
@@ -381,6 +412,8 @@ ERROR:
         }
         free(abc);
         free(gaps);
+        free(conf);
+        free(plen);
         flat_free(&f);
         return FAIL;
 }

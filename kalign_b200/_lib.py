@@ -21,7 +21,8 @@ u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
 class Params(C.Structure):
     _fields_ = [("subm", C.c_float * (23 * 23)),
                 ("gpo", C.c_float), ("gpe", C.c_float), ("tgpe", C.c_float),
-                ("vsm_amax", C.c_float), ("nalpha", C.c_int)]
+                ("vsm_amax", C.c_float), ("nalpha", C.c_int),
+                ("dist_scale", C.c_float), ("use_seq_weights", C.c_float)]
 
 
 class Pair(C.Structure):
@@ -46,7 +47,7 @@ class Stats(C.Structure):
 # every symbol include/kalign_b200.h declares
 EXPORTS = ["kb200_device_count", "kb200_ctx_create", "kb200_ctx_destroy", "kb200_get_stats",
            "kb200_version", "kb200_params_init", "kb200_pair_align_batch", "kb200_distances",
-           "kb200_anchor_posmaps", "kb200_select_anchors", "kb200_align_tree", "kb200_kalign",
+           "kb200_anchor_posmaps", "kb200_select_anchors", "kb200_align_tree", "kb200_align_tree_conf", "kb200_kalign",
            "kb200_msa_create", "kb200_msa_align", "kb200_msa_result", "kb200_msa_info", "kb200_msa_tree", "kb200_msa_free",
            "kb200_comm_unique_id", "kb200_ctx_comm_init", "kb200_ctx_comm_destroy", "kb200_partition"]
 
@@ -100,6 +101,9 @@ def load():
     lib.kb200_align_tree.argtypes = [C.c_void_p, C.POINTER(Params), u8p, i64p, i32p, C.c_int,
                                      i32p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float, i32p]
     lib.kb200_align_tree.restype = C.c_int
+    lib.kb200_align_tree_conf.argtypes = [C.c_void_p, C.POINTER(Params), u8p, i64p, i32p, C.c_int,
+                                          i32p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float, i32p, C.c_void_p, C.c_void_p]
+    lib.kb200_align_tree_conf.restype = C.c_int
     lib.kb200_kalign.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), i32p, C.c_int, C.c_int, C.c_int,
                                  C.c_float, C.c_float, C.c_float, C.c_int, C.c_float,
                                  C.POINTER(C.POINTER(C.c_void_p)), C.POINTER(C.c_int)]
@@ -136,7 +140,7 @@ def make_params(biotype, type_=8, gpo=-1.0, gpe=-1.0, tgpe=-1.0):
     return p
 
 
-def params_from(subm, gpo, gpe, tgpe, nalpha=23, vsm_amax=0.0):
+def params_from(subm, gpo, gpe, tgpe, nalpha=23, vsm_amax=0.0, dist_scale=0.0, use_seq_weights=0.0):
     p = Params()
     flat = np.ascontiguousarray(subm, dtype=np.float32).reshape(-1)
     for i in range(23 * 23):
@@ -144,6 +148,8 @@ def params_from(subm, gpo, gpe, tgpe, nalpha=23, vsm_amax=0.0):
     p.gpo, p.gpe, p.tgpe = float(gpo), float(gpe), float(tgpe)
     p.nalpha = nalpha
     p.vsm_amax = vsm_amax
+    p.dist_scale = dist_scale
+    p.use_seq_weights = use_seq_weights
     return p
 
 
@@ -238,18 +244,21 @@ def posmap_view(posmaps, offs, lens, K, i, k):
     return posmaps[o:o + int(lens[i])]
 
 
-def _align_tree(self, prm, flat, offs, lens, tasks, seq_distances=None, posmaps=None, K=0, weight=2.0):
+def _align_tree(self, prm, flat, offs, lens, tasks, seq_distances=None, posmaps=None, K=0, weight=2.0, confidence=False):
     tasks = np.ascontiguousarray(tasks, dtype=np.int32).reshape(-1)
     n = len(lens)
     gaps = np.zeros(int(lens.sum()) + n, dtype=np.int32)
     sd = None if seq_distances is None else np.ascontiguousarray(seq_distances, dtype=np.float32)
     pm = None if posmaps is None else np.ascontiguousarray(posmaps, dtype=np.int32)
-    rc = self.lib.kb200_align_tree(self.h, C.byref(prm), flat, offs, lens, n, tasks, len(tasks) // 3,
-                                   None if sd is None else sd.ctypes.data,
-                                   None if pm is None else pm.ctypes.data, K, weight, gaps)
+    conf = np.zeros(len(tasks) // 3, dtype=np.float32)
+    rc = self.lib.kb200_align_tree_conf(self.h, C.byref(prm), flat, offs, lens, n, tasks, len(tasks) // 3,
+                                        None if sd is None else sd.ctypes.data,
+                                        None if pm is None else pm.ctypes.data, K, weight, gaps,
+                                        conf.ctypes.data if confidence else None, None)
     if rc != 0:
         raise RuntimeError("kb200_align_tree failed")
-    return [gaps[int(offs[i]) + i: int(offs[i]) + i + int(lens[i]) + 1] for i in range(n)]
+    out = [gaps[int(offs[i]) + i: int(offs[i]) + i + int(lens[i]) + 1] for i in range(n)]
+    return (out, conf) if confidence else out
 
 
 def _kalign(self, seqs, n_threads=1, type_=8, gpo=-1.0, gpe=-1.0, tgpe=-1.0, consistency=0, weight=2.0):

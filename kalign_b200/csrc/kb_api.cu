@@ -62,7 +62,7 @@ void kb200_ctx_destroy(kb200_ctx* ctx)
         }
         KbDevBuf* tbufs[] = {&ctx->t_subm, &ctx->t_leaf, &ctx->t_gapset, &ctx->t_prefix, &ctx->t_raw, &ctx->t_coded, &ctx->t_scr,
                              &ctx->t_pjobs, &ctx->t_mjobs, &ctx->t_src, &ctx->t_bonus, &ctx->t_bidx, &ctx->t_bval, &ctx->t_posmaps,
-                             &ctx->t_gaps, &ctx->t_colof, &ctx->t_aoff, &ctx->t_bpos, &ctx->t_bconf, &ctx->t_binv, &ctx->t_bdesc, &ctx->t_wp, &ctx->t_wdesc, &ctx->t_alen, &ctx->t_bvote};
+                             &ctx->t_gaps, &ctx->t_colof, &ctx->t_aoff, &ctx->t_bpos, &ctx->t_bconf, &ctx->t_binv, &ctx->t_bdesc, &ctx->t_wp, &ctx->t_wdesc, &ctx->t_alen, &ctx->t_bvote, &ctx->t_margin, &ctx->t_conf};
         for (KbDevBuf* b : tbufs) {
                 b->release();
         }
@@ -140,6 +140,8 @@ int kb200_params_init(kb200_params* p, int biotype, int type, float gpo, float g
         p->gpo = t->gpo;
         p->gpe = t->gpe;
         p->tgpe = t->tgpe;
+        p->dist_scale = 0.0f;          // aln_param.c:95,99
+        p->use_seq_weights = 0.0f;
         if (gpo >= 0.0) p->gpo = gpo;
         if (gpe >= 0.0) p->gpe = gpe;
         if (tgpe >= 0.0) p->tgpe = tgpe;

@@ -52,6 +52,12 @@ struct KbJob {
         const float* bval;      // ... and values; nb entries
         int nb;
         float* score;           // optional: top-level meet-up score
+        // optional: per-box meet-up margins (max - max2, aln_seqseq.c:375-385) indexed by the box's
+        // position in the recursion tree (root 1, children 2i / 2i+1); -1 = box without a margin,
+        // all-ones bits = no such box.  Summed in the reference's recursion order by
+        // kb_confidence_kernel (task->confidence, aln_run.c:390-394).
+        float* margins;
+        unsigned margin_cap;
 };
 
 // One Hirschberg box = one (forward sweep, backward sweep, meet-up) triple
@@ -61,7 +67,7 @@ struct __align__(16) KbBox {
         int sa, ea, sb, eb;
         float f0a, f0ga, f0gb;  // injected forward boundary state  (m->f[0])
         float b0a, b0ga, b0gb;  // injected backward boundary state (m->b[0])
-        int depth;
+        unsigned hid;           // position in the job's recursion tree: root 1, children 2*hid (upper-left) / 2*hid+1
 };
 
 // growable device buffer
@@ -127,7 +133,8 @@ struct KbDevStats {
         unsigned flags;                  // KB_FLAG_*
         unsigned pad;
 };
-enum { KB_FLAG_BOX_OVERFLOW = 1, KB_FLAG_UNIT_OVERFLOW = 2, KB_FLAG_SMALL_OVERFLOW = 4, KB_FLAG_ROUNDS = 8, KB_FLAG_STACK = 16 };
+enum { KB_FLAG_BOX_OVERFLOW = 1, KB_FLAG_UNIT_OVERFLOW = 2, KB_FLAG_SMALL_OVERFLOW = 4, KB_FLAG_ROUNDS = 8, KB_FLAG_STACK = 16,
+       KB_FLAG_MARGIN = 32 };
 
 // chunked bump arena for device-resident profiles; chunks are kept across calls (reset())
 struct KbArena {
@@ -168,7 +175,7 @@ struct kb200_ctx {
         KbDevBuf d_stage0, d_stage1, d_stage2, d_stage3, d_stage4, d_stage5;
         // progressive alignment (kb_tree.cu)
         KbDevBuf t_subm, t_leaf, t_gapset, t_prefix, t_raw, t_coded, t_scr, t_pjobs, t_mjobs, t_src, t_bonus, t_bidx, t_bval, t_posmaps,
-                 t_gaps, t_colof, t_aoff, t_bpos, t_bconf, t_binv, t_bdesc, t_wp, t_wdesc, t_alen, t_bvote;
+                 t_gaps, t_colof, t_aoff, t_bpos, t_bconf, t_binv, t_bdesc, t_wp, t_wdesc, t_alen, t_bvote, t_margin, t_conf;
         const void* posmaps_tag = nullptr;   // host array currently mirrored in t_posmaps
         size_t posmaps_n = 0;
         KbArena arena;
@@ -189,6 +196,12 @@ int kb_collect(kb200_ctx* ctx);
 // run all jobs (device-resident descriptors are built from `jobs`, whose
 // pointers are device pointers; rowF/rowB are assigned here).  subm: 23*23 floats (host).
 int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>& jobs);
+
+// task->confidence of every job that carries a margin array: conf_out[j] = margin_sum / margin_count
+// accumulated in the reference's recursion order (0 when no meet-up produced a margin)
+int kb_confidences(kb200_ctx* ctx, int njobs, float* d_conf_out);
+// entries of a job's margin array
+unsigned kb_margin_cap(int len_a);
 
 // bpm (kb_bpm.cu)
 int kb_bpm_pairs(kb200_ctx* ctx, const uint8_t* d_seqs, const int64_t* d_offs, const int* d_lens,

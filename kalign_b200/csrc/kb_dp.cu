@@ -144,14 +144,14 @@ __device__ __forceinline__ void offer(Best& m, const float s, const int key)
         }
 }
 
-__device__ __forceinline__ void put_child(KbBox* __restrict__ next, int slot, int job, int depth,
+__device__ __forceinline__ void put_child(KbBox* __restrict__ next, int slot, int job, unsigned hid,
                                           int sa, int ea, int sb, int eb, Trip f0, Trip b0)
 {
         KbBox c;
         c.job = job; c.sa = sa; c.ea = ea; c.sb = sb; c.eb = eb;
         c.f0a = f0.a; c.f0ga = f0.ga; c.f0gb = f0.gb;
         c.b0a = b0.a; c.b0ga = b0.ga; c.b0gb = b0.gb;
-        c.depth = depth;
+        c.hid = hid;
         next[slot] = c;
 }
 
@@ -234,8 +234,15 @@ kb_meetup_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes
                         if (J.bonus || J.bkey) {
                                 atomicAdd(cells + 3, nc);
                         }
-                        if (bx.depth == 0 && J.score) {
+                        if (bx.hid == 1u && J.score) {
                                 *J.score = m.max;
+                        }
+                        if (J.margins) {
+                                if (bx.hid < J.margin_cap) {
+                                        J.margins[bx.hid] = (m.max2 > KB_NEGF) ? (m.max - m.max2) : -1.0f;
+                                } else {
+                                        atomicOr(&dstats->flags, (unsigned)KB_FLAG_MARGIN);
+                                }
                         }
                         if (m.key != 0x7fffffff && J.path) {
                                 const int c = sb + (m.key >> 3);
@@ -293,11 +300,11 @@ kb_meetup_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes
                                                 continue;
                                         }
                                         if (hasL && !smL) {
-                                                put_child(next, (int)slot, bx.job, bx.depth + 1, lsa, lea, lsb, leb, fin, lb0);
+                                                put_child(next, (int)slot, bx.job, 2u * bx.hid, lsa, lea, lsb, leb, fin, lb0);
                                                 slot++;
                                         }
                                         if (hasR && !smR) {
-                                                put_child(next, (int)slot, bx.job, bx.depth + 1, rsa, rea, rsb, reb, rf0, bin);
+                                                put_child(next, (int)slot, bx.job, 2u * bx.hid + 1u, rsa, rea, rsb, reb, rf0, bin);
                                         }
                                 }
                                 if (nsml) {
@@ -307,11 +314,11 @@ kb_meetup_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes
                                                 continue;
                                         }
                                         if (smL) {
-                                                put_child(small, (int)slot, bx.job, bx.depth + 1, lsa, lea, lsb, leb, fin, lb0);
+                                                put_child(small, (int)slot, bx.job, 2u * bx.hid, lsa, lea, lsb, leb, fin, lb0);
                                                 slot++;
                                         }
                                         if (smR) {
-                                                put_child(small, (int)slot, bx.job, bx.depth + 1, rsa, rea, rsb, reb, rf0, bin);
+                                                put_child(small, (int)slot, bx.job, 2u * bx.hid + 1u, rsa, rea, rsb, reb, rf0, bin);
                                         }
                                 }
                         }
@@ -334,6 +341,7 @@ constexpr int SMALL_STACK = 12;
 struct SBox {
         int sa, ea, sb, eb;
         Trip f0, b0;
+        unsigned hid;
 };
 
 // One sweep of a small box by ONE thread: the rows are taken K at a time through the shared cell
@@ -461,6 +469,7 @@ __device__ void small_box_run(const KbJob& J, const KbBox& root, const float* __
                 b.sa = root.sa; b.ea = root.ea; b.sb = root.sb; b.eb = root.eb;
                 b.f0.a = root.f0a; b.f0.ga = root.f0ga; b.f0.gb = root.f0gb;
                 b.b0.a = root.b0a; b.b0.ga = root.b0ga; b.b0.gb = root.b0gb;
+                b.hid = root.hid;
                 stack[sp++] = b;
         }
         int* __restrict__ path = J.path;
@@ -515,12 +524,21 @@ __device__ void small_box_run(const KbJob& J, const KbBox& root, const float* __
                                 offer(m, f.gb + b.gb + x6last - sub, kb + 6);
                         }
                 }
+                if (J.margins) {
+                        if (bx.hid < J.margin_cap) {
+                                J.margins[bx.hid] = (m.max2 > KB_NEGF) ? (m.max - m.max2) : -1.0f;
+                        } else {
+                                err |= (unsigned)KB_FLAG_MARGIN;
+                        }
+                }
                 if (m.key == 0x7fffffff) {
                         continue;
                 }
                 const int c = sb + (m.key >> 3);
                 const int t = m.key & 7;
                 SBox L, Rr;
+                L.hid = 2u * bx.hid;
+                Rr.hid = 2u * bx.hid + 1u;
                 L.sa = sa; L.sb = sb; L.f0 = bx.f0;
                 Rr.ea = ea; Rr.eb = eb; Rr.b0 = bx.b0;
                 switch (t) {
@@ -729,18 +747,58 @@ int kb_collect(kb200_ctx* ctx)
         }
         ctx->ev_used = 0;
         if (hs.flags) {
-                fprintf(stderr, "[kalign_b200] engine error flags 0x%x:%s%s%s%s%s\n", hs.flags,
+                fprintf(stderr, "[kalign_b200] engine error flags 0x%x:%s%s%s%s%s%s\n", hs.flags,
                         (hs.flags & KB_FLAG_BOX_OVERFLOW) ? " box work-list overflow" : "",
                         (hs.flags & KB_FLAG_UNIT_OVERFLOW) ? " unit list overflow" : "",
                         (hs.flags & KB_FLAG_SMALL_OVERFLOW) ? " small-box list overflow" : "",
                         (hs.flags & KB_FLAG_ROUNDS) ? " boxes left after the last round" : "",
-                        (hs.flags & KB_FLAG_STACK) ? " small-box recursion stack overflow" : "");
+                        (hs.flags & KB_FLAG_STACK) ? " small-box recursion stack overflow" : "",
+                        (hs.flags & KB_FLAG_MARGIN) ? " recursion deeper than the margin array" : "");
                 return KB200_FAIL;
         }
         return KB200_OK;
 }
 
 namespace {
+// task->confidence: the reference adds the margin of every meet-up to margin_sum in the order its
+// recursion visits the boxes -- the box, then everything below its upper-left child, then
+// everything below the lower-right child (aln_runner / aln_continue, aln_controller.c:21,194).
+// A float sum is not associative, so one thread per job replays exactly that order over the
+// job's margin array (explicit stack; the tree is at most ~20 deep).
+__global__ void kb_confidence_kernel(const KbJob* __restrict__ jobs, const int njobs, float* __restrict__ out)
+{
+        const int j = blockIdx.x * blockDim.x + threadIdx.x;
+        if (j >= njobs) {
+                return;
+        }
+        const float* __restrict__ mg = jobs[j].margins;
+        const unsigned cap = jobs[j].margin_cap;
+        if (!mg) {
+                out[j] = 0.0f;
+                return;
+        }
+        unsigned stack[40];
+        int sp = 0;
+        stack[sp++] = 1u;
+        float sum = 0.0f;
+        int count = 0;
+        while (sp > 0) {
+                const unsigned id = stack[--sp];
+                if (id >= cap) continue;
+                const float v = mg[id];
+                if (__float_as_uint(v) == 0xffffffffu) continue;      // no such box
+                if (v >= 0.0f) {
+                        sum = __fadd_rn(sum, v);
+                        count++;
+                }
+                if (sp + 2 <= 40) {
+                        stack[sp++] = 2u * id + 1u;
+                        stack[sp++] = 2u * id;
+                }
+        }
+        out[j] = (count > 0) ? __fdiv_rn(sum, (float)count) : 0.0f;
+}
+
 // boxes that survive the last enqueued round would be lost: flag them
 __global__ void kb_rounds_check_kernel(const KbRound* __restrict__ last, KbDevStats* __restrict__ dstats)
 {
@@ -749,6 +807,22 @@ __global__ void kb_rounds_check_kernel(const KbRound* __restrict__ last, KbDevSt
         }
 }
 } // namespace
+
+unsigned kb_margin_cap(int len_a)
+{
+        unsigned cap = 16;
+        while (cap < 8u * (unsigned)(len_a + 1)) cap <<= 1;
+        return cap;
+}
+
+int kb_confidences(kb200_ctx* ctx, int njobs, float* d_conf_out)
+{
+        if (njobs <= 0) return KB200_OK;
+        kb_confidence_kernel<<<(njobs + 63) / 64, 64, 0, ctx->stream>>>(ctx->d_jobs.as<KbJob>(), njobs, d_conf_out);
+        KB_CUDA(cudaGetLastError());
+        ctx->stats.n_launches++;
+        return KB200_OK;
+}
 
 int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>& jobs)
 {
@@ -872,7 +946,7 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
                         b.job = i; b.sa = 0; b.ea = jobs[i].len_a; b.sb = 0; b.eb = jobs[i].len_b;
                         b.f0a = 0.0F; b.f0ga = KB_NEGF; b.f0gb = KB_NEGF;
                         b.b0a = 0.0F; b.b0ga = KB_NEGF; b.b0gb = KB_NEGF;
-                        b.depth = 0;
+                        b.hid = 1u;
                         init[ninit++] = b;
                         rows_total += (size_t)jobs[i].len_a;
                 }

@@ -34,7 +34,8 @@ int kb_bonus_on_host(int K);
 
 int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                       const int* tasks_abc, int ntasks, const float* seq_distances,
-                      const int* posmaps, int K, float weight, int n_threads, int* gaps_out, int posmaps_on_device);
+                      const int* posmaps, int K, float weight, int n_threads, int* gaps_out, int posmaps_on_device,
+                      float* conf_out = nullptr, int* plen_out = nullptr);
 
 // host threads worth using: min(OpenMP max threads, cgroup CPU quota, 16)
 int kb_default_threads();

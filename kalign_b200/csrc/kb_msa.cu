@@ -732,19 +732,15 @@ int kb200_msa_align(kb200_msa* M)
         if (!M || M->tree_job) return KB200_FAIL;       // a deferred tree is finished by kb200_kalign only
         kb200_ctx* ctx = M->ctx;
         KB_CUDA(cudaSetDevice(ctx->device));
-        cudaEvent_t e0, e1;
-        KB_CUDA(cudaEventCreate(&e0));
-        KB_CUDA(cudaEventCreate(&e1));
-        KB_CUDA(cudaEventRecord(e0, ctx->stream));
+        // timed span of the whole step on the engine's stream (ev2 / ev3 live in the context)
+        KB_CUDA(cudaEventRecord(ctx->ev2, ctx->stream));
         KB_RUN(msa_align_anchor(M));
         KB_RUN(msa_align_tree(M));
-        KB_CUDA(cudaEventRecord(e1, ctx->stream));
-        KB_CUDA(cudaEventSynchronize(e1));
+        KB_CUDA(cudaEventRecord(ctx->ev3, ctx->stream));
+        KB_CUDA(cudaEventSynchronize(ctx->ev3));
         float ms = 0.0f;
-        cudaEventElapsedTime(&ms, e0, e1);
+        cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3);
         ctx->stats.align_seconds += 1e-3 * (double)ms;
-        cudaEventDestroy(e0);
-        cudaEventDestroy(e1);
         return KB200_OK;
 }
 

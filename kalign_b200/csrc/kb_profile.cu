@@ -4,7 +4,7 @@
 // Replaces (behaviour cited, nothing copied):
 //   make_profile_n         lib/src/aln_setup.c:40    leaf profile, (len+2) x 64 floats
 //   set_gap_penalties_n    lib/src/aln_setup.c:101   [27..29] = [55..57] * nsip(other operand)
-//   update_n               lib/src/aln_setup.c:230   merge along the coded path (no seq weights)
+//   update_n               lib/src/aln_setup.c:230   merge along the coded path (incl. the use_seq_weights rebalance)
 //   mirror_path_n          lib/src/aln_setup.c:438
 //   add_gap_info_to_path_n lib/src/aln_setup.c:121
 //   pairwise_align_map     lib/src/anchor_consistency.c:85-111 (coded path -> position map)
@@ -281,8 +281,16 @@ __global__ void kb_merge_kernel(const KbMergeJob* __restrict__ mj, const int njo
                 const int alnlen = M.alnlen;
                 float* np = M.newp + ((size_t)c << 6);
                 float v0, v1;
+                // balanced merge of a match / boundary column: counts [0..22] = a*scaleA + b*scaleB
+                // (two rounded products, one rounded sum), everything else a + b
+                auto balanced0 = [&](const float* a, const float* b) -> float {
+                        if (M.rebalance && lane < 23) {
+                                return __fadd_rn(__fmul_rn(a[lane], M.scaleA), __fmul_rn(b[lane], M.scaleB));
+                        }
+                        return a[lane] + b[lane];
+                };
                 if (c == 0) {
-                        v0 = M.pa[lane] + M.pb[lane];
+                        v0 = balanced0(M.pa, M.pb);
                         v1 = M.pa[lane + 32] + M.pb[lane + 32];
                 } else {
                         const int2 s = M.src[c];
@@ -290,8 +298,19 @@ __global__ void kb_merge_kernel(const KbMergeJob* __restrict__ mj, const int njo
                         const float* b = M.pb + ((size_t)s.y << 6);
                         const int p = (c <= alnlen) ? M.path[c] : 0;
                         if (c > alnlen || !p) {
-                                v0 = a[lane] + b[lane];
+                                v0 = balanced0(a, b);
                                 v1 = a[lane + 32] + b[lane + 32];
+                                if (M.rebalance && c <= alnlen && lane < 23) {
+                                        // newp[32+j] += sum_aa (a[aa]*dA + b[aa]*dB) * subm[aa][j], aa ascending from 0.0f
+                                        const float dA = __fadd_rn(M.scaleA, -1.0f);
+                                        const float dB = __fadd_rn(M.scaleB, -1.0f);
+                                        float delta = 0.0f;
+                                        for (int aa = 0; aa < 23; aa++) {
+                                                const float t = __fadd_rn(__fmul_rn(a[aa], dA), __fmul_rn(b[aa], dB));
+                                                delta = __fadd_rn(delta, __fmul_rn(t, M.subm[aa * 23 + lane]));
+                                        }
+                                        v1 = __fadd_rn(v1, delta);
+                                }
                         } else if (p & 1) {
                                 v0 = gap_adjust_val(b[lane], lane, p, (float)M.sipa, M.gpo, M.gpe, M.tgpe);
                                 v1 = gap_adjust_val(b[lane + 32], lane + 32, p, (float)M.sipa, M.gpo, M.gpe, M.tgpe);

@@ -34,6 +34,11 @@ struct KbMergeJob {
         int alnlen;
         int sipa, sipb;
         float gpo, gpe, tgpe;
+        // balanced merge (use_seq_weights > 0, aln_setup.c:237-300): residue counts of the match columns
+        // are rescaled per side, the summed substitution scores corrected by the matching delta
+        int rebalance;
+        float scaleA, scaleB;
+        const float* subm;      // 23 x 23, device
 };
 
 int kb_make_profiles(kb200_ctx* ctx, const KbLeafProfile* d_leaves, int nleaves,

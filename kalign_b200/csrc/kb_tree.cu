@@ -328,18 +328,26 @@ void level_weave(Tree& T, int nt, const std::vector<int>& tl, const int* tasks_a
 
 } // namespace
 
+// KB200_HOST_BONUS=1 selects the host restatement of the bonus / weave stages -- an explicit A/B
+// switch for debugging, never chosen silently (more anchors than the device kernels handle is an error)
 int kb_bonus_on_host(int K)
 {
-        return (getenv("KB200_HOST_BONUS") != nullptr) || (K > KB_BONUS_KMAX);
+        (void)K;
+        return getenv("KB200_HOST_BONUS") != nullptr;
 }
 
 int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                       const int* tasks_abc, int ntasks, const float* seq_distances,
-                      const int* posmaps, int K, float weight, int n_threads, int* gaps_out, int posmaps_on_device)
+                      const int* posmaps, int K, float weight, int n_threads, int* gaps_out, int posmaps_on_device,
+                      float* conf_out, int* plen_out)
 {
         const int N = S.n;
         if (ntasks != N - 1 || N < 2) {
                 fprintf(stderr, "[kalign_b200] align_tree: need exactly N-1 tasks (N=%d, ntasks=%d)\n", N, ntasks);
+                return KB200_FAIL;
+        }
+        if (K > KB_BONUS_KMAX && posmaps && !kb_bonus_on_host(K)) {
+                fprintf(stderr, "[kalign_b200] align_tree: %d consistency anchors, the device kernels handle at most %d\n", K, KB_BONUS_KMAX);
                 return KB200_FAIL;
         }
         cudaStream_t st = ctx->stream;
@@ -358,6 +366,20 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                 T.gaps[i].assign((size_t)S.h_lens[i] + 1, 0);
         }
         int maxlevel = 0;
+        {
+                // the task list must be sort_tasks' order (lib/src/task.c:114): node c = N + t, both
+                // operands produced earlier and consumed exactly once
+                std::vector<char> used((size_t)NP, 0);
+                for (int t = 0; t < ntasks; t++) {
+                        const int a = tasks_abc[3 * t], b = tasks_abc[3 * t + 1], c = tasks_abc[3 * t + 2];
+                        if (c != N + t || a < 0 || b < 0 || a >= c || b >= c || a == b || used[(size_t)a] || used[(size_t)b]) {
+                                fprintf(stderr, "[kalign_b200] align_tree: task %d (%d, %d -> %d) is not part of a guide tree sorted by node id\n", t, a, b, c);
+                                return KB200_FAIL;
+                        }
+                        used[(size_t)a] = 1;
+                        used[(size_t)b] = 1;
+                }
+        }
         for (int t = 0; t < ntasks; t++) {
                 const int a = tasks_abc[3 * t], b = tasks_abc[3 * t + 1], c = tasks_abc[3 * t + 2];
                 if (a < 0 || b < 0 || c < N || a >= NP || b >= NP || c >= NP) {
@@ -430,12 +452,32 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                 const auto t_level0 = tnow();
                 // ---- per task: scoring offset, operand lengths ----
                 std::vector<float> soff((size_t)nt, 0.0f);
+                // scaled gap penalties of the task (do_align, aln_run.c:227-237: gpo/gpe/tgpe *= gap_scale)
+                std::vector<float> tgpo((size_t)nt, prm->gpo), tgpe_((size_t)nt, prm->gpe), ttgpe((size_t)nt, prm->tgpe);
                 std::vector<int> la((size_t)nt), lb((size_t)nt);
                 for (int q = 0; q < nt; q++) {
                         const int a = tasks_abc[3 * tl[q]], b = tasks_abc[3 * tl[q] + 1];
                         la[q] = (T.nsip[a] == 1) ? S.h_lens[a] : T.plen[a];
                         lb[q] = (T.nsip[b] == 1) ? S.h_lens[b] : T.plen[b];
                         // compute_subm_offset, aln_run.c:166-203
+                        // compute_gap_scale, aln_run.c:126-164
+                        if (prm->dist_scale > 0.0f && seq_distances) {
+                                float sum = 0.0f;
+                                int count = 0;
+                                for (int si : T.sip[a]) { sum += seq_distances[si]; count++; }
+                                for (int si : T.sip[b]) { sum += seq_distances[si]; count++; }
+                                if (count) {
+                                        const float avg_div = sum / (float)count;
+                                        float scale = 1.0f - prm->dist_scale * avg_div;
+                                        if (scale < 0.3f) scale = 0.3f;
+                                        if (scale > 1.0f) scale = 1.0f;
+                                        if (scale < 1.0f) {
+                                                tgpo[q] = prm->gpo * scale;
+                                                tgpe_[q] = prm->gpe * scale;
+                                                ttgpe[q] = prm->tgpe * scale;
+                                        }
+                                }
+                        }
                         const float amax = prm->vsm_amax;
                         if (amax > 0.0f && seq_distances) {
                                 float sum = 0.0f;
@@ -481,7 +523,7 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                                         KbLeafProfile lp;
                                         lp.seq = S.dseq(nd); lp.prof = p; lp.len = len;
                                         lp.nsoff = -soff[q];
-                                        lp.ngpo = -prm->gpo; lp.ngpe = -prm->gpe; lp.ntgpe = -prm->tgpe;
+                                        lp.ngpo = -tgpo[q]; lp.ngpe = -tgpe_[q]; lp.ntgpe = -ttgpe[q];
                                         leaves.push_back(lp);
                                         leaf_prefix.push_back(leaf_cols);
                                         leaf_cols += len + 2;
@@ -528,20 +570,20 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                                 j.kind = KB200_KIND_SS;
                                 if (la[q] < lb[q]) { rown[q] = a; coln[q] = b; } else { rown[q] = b; coln[q] = a; mirror[q] = 1; }
                                 j.seq_r = S.dseq(rown[q]); j.seq_c = S.dseq(coln[q]);
-                                j.o = -prm->gpo; j.e = -prm->gpe; j.t = -prm->tgpe;
+                                j.o = -tgpo[q]; j.e = -tgpe_[q]; j.t = -ttgpe[q];
                                 j.nsoff = -soff[q];
                         } else if (leaf_a) {
                                 j.kind = KB200_KIND_SP;
                                 rown[q] = b; coln[q] = a; mirror[q] = 1;
                                 j.prof_r = T.prof[b]; j.seq_c = S.dseq(a);
                                 const float sipf = (float)T.nsip[b];
-                                j.o = -(prm->gpo * sipf); j.e = -(prm->gpe * sipf); j.t = -(prm->tgpe * sipf);
+                                j.o = -(tgpo[q] * sipf); j.e = -(tgpe_[q] * sipf); j.t = -(ttgpe[q] * sipf);
                         } else if (leaf_b) {
                                 j.kind = KB200_KIND_SP;
                                 rown[q] = a; coln[q] = b;
                                 j.prof_r = T.prof[a]; j.seq_c = S.dseq(b);
                                 const float sipf = (float)T.nsip[a];
-                                j.o = -(prm->gpo * sipf); j.e = -(prm->gpe * sipf); j.t = -(prm->tgpe * sipf);
+                                j.o = -(tgpo[q] * sipf); j.e = -(tgpe_[q] * sipf); j.t = -(ttgpe[q] * sipf);
                         } else {
                                 j.kind = KB200_KIND_PP;
                                 if (la[q] < lb[q]) { rown[q] = a; coln[q] = b; } else { rown[q] = b; coln[q] = a; mirror[q] = 1; }
@@ -723,9 +765,31 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                         }
                 }
                 TC(cudaMemsetAsync(d_raw.p, 0xFF, sizeof(int) * n_raw, st));
+                if (conf_out && ntm > 0) {
+                        // per-box meet-up margins of my tasks (task->confidence, aln_run.c:390-394)
+                        size_t nm = 0;
+                        for (int q = q0; q < q1; q++) nm += kb_margin_cap(rlen[q]);
+                        TR(ctx->t_margin.ensure(sizeof(float) * (nm + 16)));
+                        TC(cudaMemsetAsync(ctx->t_margin.p, 0xFF, sizeof(float) * nm, st));
+                        size_t o = 0;
+                        for (int q = q0; q < q1; q++) {
+                                jobs[(size_t)q].margins = ctx->t_margin.as<float>() + o;
+                                jobs[(size_t)q].margin_cap = kb_margin_cap(rlen[q]);
+                                o += jobs[(size_t)q].margin_cap;
+                        }
+                }
                 {
                         std::vector<KbJob> mine(jobs.begin() + q0, jobs.begin() + q1);
                         TR(kb_run_hirschberg(ctx, prm->subm, mine));
+                }
+                if (conf_out) {
+                        TR(ctx->t_conf.ensure(sizeof(float) * ((size_t)nt + 16)));
+                        if (ntm > 0) TR(kb_confidences(ctx, ntm, ctx->t_conf.as<float>() + q0));
+                        if (ctx->world > 1) {
+                                std::vector<size_t> seg((size_t)ctx->world + 1, 0);
+                                for (int r = 0; r <= ctx->world; r++) seg[(size_t)r] = (size_t)tb[(size_t)r] * sizeof(float);
+                                TR(kb_allgatherv(ctx, ctx->t_conf.p, seg.data()));
+                        }
                 }
                 tsync();
                 const auto t_dp = tnow();
@@ -779,12 +843,28 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                 if (dev_state) {
                         // THE host synchronisation of the level: alignment lengths + engine statistics / error flags
                         TC(cudaMemcpyAsync(alen.data(), ctx->t_alen.p, sizeof(int) * (size_t)nt, cudaMemcpyDeviceToHost, st));
+                        std::vector<float> lconf;
+                        if (conf_out) {
+                                lconf.resize((size_t)nt);
+                                TC(cudaMemcpyAsync(lconf.data(), ctx->t_conf.p, sizeof(float) * (size_t)nt, cudaMemcpyDeviceToHost, st));
+                        }
                         TR(kb_collect(ctx));
+                        if (conf_out) {
+                                for (int q = 0; q < nt; q++) conf_out[tl[(size_t)q]] = lconf[(size_t)q];
+                        }
                         ctx->stats.d2h_bytes += (double)(sizeof(int) * (size_t)nt);
                 } else {
                         hcoded.resize(n_coded);
                         TC(cudaMemcpyAsync(hcoded.data(), d_coded.p, sizeof(int) * n_coded, cudaMemcpyDeviceToHost, st));
+                        std::vector<float> lconf;
+                        if (conf_out) {
+                                lconf.resize((size_t)nt);
+                                TC(cudaMemcpyAsync(lconf.data(), ctx->t_conf.p, sizeof(float) * (size_t)nt, cudaMemcpyDeviceToHost, st));
+                        }
                         TR(kb_collect(ctx));
+                        if (conf_out) {
+                                for (int q = 0; q < nt; q++) conf_out[tl[(size_t)q]] = lconf[(size_t)q];
+                        }
                         ctx->stats.d2h_bytes += (double)(sizeof(int) * n_coded);
                         for (int q = 0; q < nt; q++) alen[(size_t)q] = hcoded[coded_off[(size_t)q]];
                 }
@@ -823,7 +903,17 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                                 m.src = d_src.as<int2>() + osrc;
                                 m.alnlen = alnlen;
                                 m.sipa = T.nsip[a]; m.sipb = T.nsip[b];
-                                m.gpo = prm->gpo; m.gpe = prm->gpe; m.tgpe = prm->tgpe;
+                                m.gpo = prm->gpo; m.gpe = prm->gpe; m.tgpe = prm->tgpe;      // update_n runs with the UNSCALED ap (aln_run.c:407)
+                                m.rebalance = 0; m.scaleA = 1.0f; m.scaleB = 1.0f; m.subm = d_subm.as<float>();
+                                if (prm->use_seq_weights > 0.0f && m.sipa > 0 && m.sipb > 0) {
+                                        // aln_setup.c:252-259
+                                        const float pseudo = prm->use_seq_weights;
+                                        const float total = (float)(m.sipa + m.sipb);
+                                        const float denom = total + 2.0f * pseudo;
+                                        m.scaleA = total * ((float)m.sipa + pseudo) / (denom * (float)m.sipa);
+                                        m.scaleB = total * ((float)m.sipb + pseudo) / (denom * (float)m.sipb);
+                                        m.rebalance = 1;
+                                }
                                 mjobs.push_back(m);
                                 mprefix.push_back(mcols);
                                 mcols += alnlen + 2;
@@ -883,6 +973,9 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                         memcpy(gaps_out + S.h_offs[i] + i, T.gaps[i].data(), sizeof(int) * ((size_t)S.h_lens[i] + 1));
                 }
         }
+        if (plen_out) {
+                for (int t = 0; t < ntasks; t++) plen_out[t] = T.plen[(size_t)tasks_abc[3 * t + 2]];
+        }
         cleanup();
         (void)rc;
         return KB200_OK;
@@ -895,6 +988,14 @@ extern "C" int kb200_align_tree(kb200_ctx* ctx, const kb200_params* prm,
                                 const int* tasks_abc, int ntasks, const float* seq_distances,
                                 const int* posmaps, int K, float weight, int* gaps_out)
 {
+        return kb200_align_tree_conf(ctx, prm, seqs, offs, lens, nseq, tasks_abc, ntasks, seq_distances, posmaps, K, weight, gaps_out, nullptr, nullptr);
+}
+
+extern "C" int kb200_align_tree_conf(kb200_ctx* ctx, const kb200_params* prm,
+                                     const uint8_t* seqs, const int64_t* offs, const int* lens, int nseq,
+                                     const int* tasks_abc, int ntasks, const float* seq_distances,
+                                     const int* posmaps, int K, float weight, int* gaps_out, float* task_confidence, int* task_plen)
+{
         if (!ctx || !prm || !seqs || !offs || !lens || !tasks_abc || !gaps_out || nseq < 2) {
                 return KB200_FAIL;
         }
@@ -903,7 +1004,7 @@ extern "C" int kb200_align_tree(kb200_ctx* ctx, const kb200_params* prm,
         int rc = S.upload(ctx, seqs, offs, lens, nseq);
         if (rc == KB200_OK) {
                 const int nthr = kb_default_threads();
-                rc = kb_align_tree_dev(ctx, prm, S, tasks_abc, ntasks, seq_distances, posmaps, K, weight, nthr, gaps_out, 0);
+                rc = kb_align_tree_dev(ctx, prm, S, tasks_abc, ntasks, seq_distances, posmaps, K, weight, nthr, gaps_out, 0, task_confidence, task_plen);
         }
         S.release();
         return rc;

@@ -227,10 +227,26 @@ static struct msa* seqs_to_msa(char** seqs, int* lens, int n)
 
 /* Run the reference exactly as kalign_run_seeded (aln_wrap.c:133-261) does, refine=NONE,
    default tree (no noise), recording stage wall-clock times.  Returns an opaque handle. */
+void* refh_run_pipeline_ex(char** seqs, int* lens, int n, int n_threads, int type,
+                           float gpo, float gpe, float tgpe,
+                           int consistency_anchors, float consistency_weight,
+                           int stop_after, float dist_scale, float use_seq_weights);
+
 void* refh_run_pipeline(char** seqs, int* lens, int n, int n_threads, int type,
                         float gpo, float gpe, float tgpe,
                         int consistency_anchors, float consistency_weight,
                         int stop_after /* 0 all, 1 after tree, 2 after anchor */)
+{
+        return refh_run_pipeline_ex(seqs, lens, n, n_threads, type, gpo, gpe, tgpe, consistency_anchors, consistency_weight,
+                                    stop_after, 0.0f, 0.0f);
+}
+
+/* dist_scale / use_seq_weights as kalign_run_seeded sets them on the aln_param (aln_wrap.c:193-198);
+   compute_tree_weights (static, aln_wrap.c:70) only fills msa->seq_weights, which the DP path never reads */
+void* refh_run_pipeline_ex(char** seqs, int* lens, int n, int n_threads, int type,
+                           float gpo, float gpe, float tgpe,
+                           int consistency_anchors, float consistency_weight,
+                           int stop_after, float dist_scale, float use_seq_weights)
 {
         struct refh_run* r = calloc(1, sizeof(struct refh_run));
         double t0, t1;
@@ -267,6 +283,8 @@ void* refh_run_pipeline(char** seqs, int* lens, int n, int n_threads, int type,
                 type = KALIGN_TYPE_PROTEIN_PFASUM43; /* harness does not exercise AUTO */
         }
         if(aln_param_init(&r->ap, msa->biotype, n_threads, type, gpo, gpe, tgpe) != OK){ goto ERROR; }
+        if(use_seq_weights >= 0.0f){ r->ap->use_seq_weights = use_seq_weights; }
+        if(dist_scale > 0.0f){ r->ap->dist_scale = dist_scale; }
         if(stop_after == 1){
                 r->t_total = now_s() - tstart;
                 return r;

@@ -98,6 +98,10 @@ def refh():
         lib.refh_run_pipeline.argtypes = [C.POINTER(C.c_char_p), i32p, C.c_int, C.c_int, C.c_int,
                                           C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_int]
         lib.refh_run_pipeline.restype = C.c_void_p
+        lib.refh_run_pipeline_ex.argtypes = [C.POINTER(C.c_char_p), i32p, C.c_int, C.c_int, C.c_int,
+                                             C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_int,
+                                             C.c_float, C.c_float]
+        lib.refh_run_pipeline_ex.restype = C.c_void_p
         for name in ("refh_numseq", "refh_biotype", "refh_alnlen"):
             getattr(lib, name).argtypes = [C.c_void_p]
             getattr(lib, name).restype = C.c_int
@@ -172,13 +176,13 @@ class RefRun:
     """One run of the reference pipeline with access to its intermediate state."""
 
     def __init__(self, seqs, n_threads=1, type_=8, gpo=-1.0, gpe=-1.0, tgpe=-1.0,
-                 consistency=0, weight=2.0, stop_after=0):
+                 consistency=0, weight=2.0, stop_after=0, dist_scale=0.0, use_seq_weights=0.0):
         lib = refh()
         n = len(seqs)
         arr = (C.c_char_p * n)(*[s.encode() if isinstance(s, str) else s for s in seqs])
         lens = np.array([len(s) for s in seqs], dtype=np.int32)
-        self._h = lib.refh_run_pipeline(arr, lens, n, n_threads, type_, gpo, gpe, tgpe,
-                                        consistency, weight, stop_after)
+        self._h = lib.refh_run_pipeline_ex(arr, lens, n, n_threads, type_, gpo, gpe, tgpe,
+                                           consistency, weight, stop_after, dist_scale, use_seq_weights)
         if not self._h:
             raise RuntimeError("reference pipeline failed")
         self.lib = lib

@@ -107,3 +107,78 @@ def test_shuffle_and_thread_invariance(ctx):
     a = ctx.kalign(seqs, n_threads=1, consistency=5)
     b = ctx.kalign(seqs, n_threads=4, consistency=5)
     assert a == b
+
+
+@pytest.mark.parametrize("name,gen,type_", FAMILIES)
+@pytest.mark.parametrize("consistency", [0, 5])
+def test_task_confidence(ctx, name, gen, type_, consistency):
+    """task->confidence (mean meet-up margin, aln_run.c:390-394): the float sum is accumulated in the
+    reference's recursion order, so it is compared for equality, not closeness"""
+    from kalign_b200 import _lib
+    seqs = gen()
+    run = ref_state(seqs, consistency, type_)
+    try:
+        prm = _lib.make_params(run.biotype(), type_)
+        codes = [run.codes(i) for i in range(run.n)]
+        flat, offs, lens = _lib.pack(codes)
+        posmaps, K = None, 0
+        if consistency:
+            anchors = run.anchor_ids()
+            K = len(anchors)
+            posmaps = ctx.anchor_posmaps(prm, flat, offs, lens, anchors)
+        gaps, conf = ctx.align_tree(prm, flat, offs, lens, run.tasks(), run.seq_distances(), posmaps, K, 2.0, confidence=True)
+        want = run.task_confidence()
+        assert np.array_equal(conf, want), np.flatnonzero(conf != want)[:5]
+        for i in range(run.n):
+            assert np.array_equal(gaps[i], run.gaps(i))
+    finally:
+        run.close()
+
+
+@pytest.mark.parametrize("name,gen,type_", FAMILIES)
+@pytest.mark.parametrize("dist_scale,usw", [(0.5, 0.0), (0.0, 2.0), (0.8, 1.0)])
+def test_dist_scale_and_seq_weights(ctx, name, gen, type_, dist_scale, usw):
+    """the non-default aln_param fields kalign_run_seeded / kalign_run_dist_scale pass through the
+    unchanged signature (kalign.h:51-57): per-task gap scaling (compute_gap_scale, aln_run.c:126-164)
+    and the balanced profile merge (update_n with use_seq_weights, aln_setup.c:237-300)"""
+    from kalign_b200 import _lib
+    seqs = gen()
+    run = kbind.RefRun(seqs, n_threads=2, type_=type_, consistency=5, weight=2.0, dist_scale=dist_scale, use_seq_weights=usw)
+    try:
+        subm, gp = run.params()
+        prm = _lib.make_params(run.biotype(), type_)
+        prm.dist_scale = dist_scale
+        prm.use_seq_weights = usw
+        codes = [run.codes(i) for i in range(run.n)]
+        flat, offs, lens = _lib.pack(codes)
+        anchors = run.anchor_ids()
+        K = len(anchors)
+        posmaps = ctx.anchor_posmaps(prm, flat, offs, lens, anchors)
+        gaps, conf = ctx.align_tree(prm, flat, offs, lens, run.tasks(), run.seq_distances(), posmaps, K, 2.0, confidence=True)
+        for i in range(run.n):
+            assert np.array_equal(gaps[i], run.gaps(i)), (name, i)
+        assert np.array_equal(conf, run.task_confidence())
+    finally:
+        run.close()
+
+
+def test_bad_task_list_is_rejected(ctx):
+    """unsorted / duplicated tasks fail loudly instead of dereferencing a missing profile"""
+    from kalign_b200 import _lib
+    seqs = synth.family(8, 40, synth.PROTEIN, seed=5)
+    run = ref_state(seqs, 0, 8)
+    try:
+        prm = _lib.make_params(run.biotype(), 8)
+        codes = [run.codes(i) for i in range(run.n)]
+        flat, offs, lens = _lib.pack(codes)
+        tasks = run.tasks().copy()
+        bad = tasks[::-1].copy()
+        with pytest.raises(RuntimeError):
+            ctx.align_tree(prm, flat, offs, lens, bad, run.seq_distances())
+        dup = tasks.copy()
+        dup[1, 0] = dup[0, 0]
+        with pytest.raises(RuntimeError):
+            ctx.align_tree(prm, flat, offs, lens, dup, run.seq_distances())
+        ctx.align_tree(prm, flat, offs, lens, tasks, run.seq_distances())
+    finally:
+        run.close()
