@@ -36,7 +36,7 @@ namespace {
 // ---------------------------------------------------------------------------------------------
 // plan: cut every (box, direction) into strips, reserve a contiguous, ordered unit range
 __global__ void kb_plan_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes, KbRound* __restrict__ rnd,
-                               const unsigned long long rows_total, const unsigned resident_warps, const int force_thin,
+                               const unsigned long long rows_total, const unsigned resident_warps, const int force_thin, const int thin_k,
                                const int batch_bonus, KbUnit* __restrict__ units, const unsigned unit_cap,
                                KbDevStats* __restrict__ dstats)
 {
@@ -47,8 +47,8 @@ __global__ void kb_plan_kernel(const KbJob* __restrict__ jobs, const KbBox* __re
         // thin strips when thick ones could not occupy the machine: the rows still alive at this
         // depth are at most rows_total, spread over nboxes boxes (every thread computes the same value)
         const unsigned long long thick_units = rows_total / 128ull + 2ull * (unsigned long long)nboxes;
-        int thin = (thick_units < 2ull * (unsigned long long)resident_warps) ? 1 : 0;
-        if (force_thin >= 0) thin = force_thin;
+        int thin = (thick_units < 2ull * (unsigned long long)resident_warps) ? thin_k : 0;
+        if (force_thin >= 0) thin = force_thin ? thin_k : 0;
         if (blockIdx.x == 0 && threadIdx.x == 0) {
                 rnd->thin = (unsigned)thin;
                 atomicAdd(&dstats->nboxes, (unsigned long long)nboxes);
@@ -986,6 +986,13 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
         // KB200_THIN=0|1 forces thick / thin strips (tests run every batch both ways)
         int force_thin = -1;
         if (const char* e = getenv("KB200_THIN")) force_thin = (atoi(e) != 0) ? 1 : 0;
+        // rows per lane of the thin regime.  A lone warp advances one wavefront step in ~320 cycles
+        // whatever its row count (measured, profiles/r02_thin_k.txt), so two rows per lane halve the
+        // number of strips -- and with it the pipeline-fill part of a sweep -- for free; four rows
+        // start to cost per step.  KB200_THIN_K=1|2|4 overrides.
+        int thin_k = 2;
+        if (const char* e = getenv("KB200_THIN_K")) thin_k = std::min(std::max(atoi(e), 1), 4);
+        if (thin_k == 3) thin_k = 2;
         const bool trace = getenv("KB200_TRACE") != nullptr;
         // all-or-nothing: a job without bonus in a bonus batch simply has an empty list / null dense
         bool batch_bonus = false, batch_dense = false;
@@ -1018,7 +1025,7 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
                 const unsigned tag_base = ctx->tag_counter;
                 const int pgrid = (int)std::min<unsigned long long>((2 * bound + 127) / 128, (unsigned long long)ctx->sm_count * 8);
                 kb_plan_kernel<<<pgrid, 128, 0, st>>>(ctx->d_jobs.as<KbJob>(), cur, rnd, (unsigned long long)rows_total, resident_warps,
-                                                       force_thin, batch_bonus ? 1 : 0, ctx->d_units.as<KbUnit>(), (unsigned)unit_cap, d_stats);
+                                                       force_thin, thin_k, batch_bonus ? 1 : 0, ctx->d_units.as<KbUnit>(), (unsigned)unit_cap, d_stats);
                 KB_CUDA(cudaGetLastError());
                 const int span = kb_span_begin(ctx, KB_SPAN_SWEEP);
                 {

@@ -66,7 +66,8 @@ enum { BONUS_NONE = 0, BONUS_SPARSE = 1, BONUS_DENSE = 2 };
 __device__ __host__ __forceinline__ int rows_per_strip(int kind, int nalpha, int thin, bool has_bonus)
 {
         if (thin) {
-                return 32;
+                // thin regime: `thin` rows per lane (1, 2 or 4; 23-letter profile-profile strips have at most 2)
+                return (kind == KB200_KIND_PP && nalpha > 5 && thin > 2) ? 64 : 32 * thin;
         }
         if (kind == KB200_KIND_PP && nalpha > 5) {
                 return 64;
@@ -1015,13 +1016,13 @@ __device__ void sweep_unit(const KbJob& J, const KbBox& bx, const int bwd, const
         (void)nstr;
         const unsigned prev = (strip > 0) ? (tag_base + (unsigned)strip) : 0u;      // tag written by strip-1
         const unsigned mine = tag_base + (unsigned)strip + 1u;
-        const int rem = R - row0;
+        const int rem = (R - row0 < rps) ? (R - row0) : rps;     // rows of THIS strip
         // rows per lane of this strip: the full width of the kind's strips, or -- last strip of a
         // sweep, boxes of the deeper rounds -- the smallest K that covers the remaining rows, so that
         // a 187-row half box runs with 6 rows per lane (97 % of the lanes' rows live) instead of 8
 #define KB_STRIP(KK, TT) sweep_strip<V, KK, TT, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_rec, s_bon)
         const int kneed = (rem + 31) >> 5;
-        if (rps == 32 || kneed <= 1) {
+        if (kneed <= 1) {
                 KB_STRIP(1, true);
         } else if constexpr (V == V_PP23) {
                 if (rem >= 64) KB_STRIP(2, false);
