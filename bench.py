@@ -42,6 +42,7 @@ WORKLOADS = {
     "C2": ("C2", 8, 5, "1000 protein x ~400 aa, default mode (consistency K=5)"),
     "C3": ("C3", 2, 5, "10000 16S-like RNA x ~1500 nt, --type rna, default mode (consistency K=5)"),
     "C4": ("C4", 8, 0, "100000 protein x ~300 aa, --fast"),
+    "C5": ("C5", 0, 5, "1000 SARS-CoV-2-like genomes x ~30 kb, --type dna, default mode (consistency K=5)"),
 }
 
 
@@ -141,6 +142,53 @@ def golden_sha(workload, n):
     return str(g["msa_sha256"])
 
 
+def issue_model():
+    """thread-instructions per DP cell of the sweep kernel families and the DRAM traffic of its
+    dominant launch, from the committed ncu captures of this command (tools/ncu_issue.py)"""
+    p = os.path.join(ROOT, "profiles", "r02_sweep_issue.json")
+    if os.path.exists(p):
+        return json.load(open(p))
+    return {"inst_per_cell": {"none": 17.1, "sparse": 26.0}, "dram_bytes_per_launch": None,
+            "source": "fallback: r01 ncu capture (17.1) / static SASS count (26)"}
+
+
+def bpm_bench(ctx, seqs, type_):
+    """the N x 32 anchor distance matrix of the workload through kb200_distances:
+    pairs/s, word-steps/s (text symbols x 64-bit pattern words) and the fraction of the integer
+    issue ceiling they use (101 SASS instructions per lane and word-step, cuobjdump of
+    kb_bpm_kernel<16>); HBM traffic is n + m + 4 bytes per pair -- negligible, reported as a fraction"""
+    from kalign_b200 import _lib
+    nuc = type_ in (0, 1, 2)
+    tbl = {c: i for i, c in enumerate("ACGTU")} if nuc else {c: i % 13 for i, c in enumerate("ACDEFGHIKLMNPQRSTVWY")}
+    order = sorted(range(len(seqs)), key=lambda i: -len(seqs[i]))
+    lut = np.zeros(256, dtype=np.uint8)
+    for c, v in tbl.items():
+        lut[ord(c)] = min(v, 12) if not nuc else min(v, 3)
+    codes = [lut[np.frombuffer(seqs[i].encode(), dtype=np.uint8)] for i in order]
+    flat, offs, lens = _lib.pack(codes)
+    n = len(codes)
+    rows = np.arange(n, dtype=np.int32)
+    cols = np.arange(0, n, max(1, n // 32), dtype=np.int32)[:32]
+    ctx.distances(flat, offs, lens, rows, cols)           # warm-up
+    s0 = ctx.stats()
+    ctx.distances(flat, offs, lens, rows, cols)
+    s1 = ctx.stats()
+    t = s1["bpm_seconds"] - s0["bpm_seconds"]
+    pairs = s1["bpm_pairs"] - s0["bpm_pairs"]
+    L = lens.astype(np.int64)
+    a, b = np.meshgrid(L, L[cols], indexing="ij")
+    text, pat = np.maximum(a, b), np.minimum(np.minimum(a, b), 1024)
+    words = (pat + 63) // 64
+    wsteps = float(((text + 64 * words - pat) * words).sum())
+    bytes_ = float((text + pat + 4).sum())
+    hbm, _, _ = peaks()
+    return {"pairs_per_sec": pairs / t, "word_steps_per_sec": wsteps / t, "seconds": t, "pairs": pairs,
+            "alu_frac": wsteps * 101.0 / t / (148 * 4 * 32 * 1.965e9),
+            "alu_note": "101 SASS instructions per lane and (symbol, 64-bit word) step (cuobjdump, kb_bpm_kernel<16> inner loop) "
+                        "against 148 SMs x 4 x 32 lanes x 1.965 GHz",
+            "hbm_frac": bytes_ / t / 1e9 / hbm, "kernel": "kb_bpm_kernel"}
+
+
 def delta(a, b):
     return {k: b[k] - a[k] for k in b}
 
@@ -189,7 +237,7 @@ def main():
     cfg, type_, K, label = WORKLOADS[args.workload]
     # the CPU quota is shared by all ranks of the node
     host_threads = max(1, effective_cpus() // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))))
-    default_sample = {"C2": 400, "C3": 160, "C4": 4000}[args.workload]
+    default_sample = {"C2": 400, "C3": 160, "C4": 4000, "C5": 6}[args.workload]
     n_sample = args.ref_sample or default_sample
 
     if args.impl == "reference":
@@ -303,17 +351,38 @@ def main():
     peak, peak_src, _ = peaks()
     abytes = algorithmic_bytes(d)
     ach = abytes / d["sweep_seconds"] / 1e9 if d["sweep_seconds"] > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "kb_sweep_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak, "traffic": None, "peak_source": peak_src,
-                "note": "algorithmic-bytes model of SURVEY 8d (25 B per ss/sp cell, 128 B per pp cell): the DP state lives in "
-                        "registers, so measured DRAM traffic is ~1000x below it (ncu, profiles/r01f_sweep_kernel_full_C3_n1000.csv: "
-                        "0.24 GB per launch for 281 GB algorithmic) and frac > 1; the kernel is issue-bound "
-                        "(smsp__issue_active 76 %, 17 thread-instructions per cell)",
-                "algorithmic_bytes_per_step": abytes / max(1, args.steps),
+    # ---- roofline of the dominant kernel (kb_sweep_kernel).  The DP state of a strip lives in
+    # registers and only one row in 32*K touches memory, so the kernel is bound by ISSUE SLOTS, not by
+    # HBM: ceiling = SMs x 4 schedulers x 32 lanes x SM clock thread-instructions/s; achieved = cells
+    # the kernel processed x thread-instructions per cell (measured with ncu on this command,
+    # profiles/r02_sweep_issue.json: smsp__inst_executed x 32 / cells of the launch, per kernel family)
+    # / the kernel's device time measured live with CUDA events.  The SURVEY 8d algorithmic-bytes
+    # figure against the measured HBM peak is kept beside it (hbm_model): it exceeds 1 because the
+    # model counts state rows that never leave the register file.
+    im = issue_model()
+    in_kernel = d["dp_cells"] - d["small_ss"] - d["small_sp"] - d["small_pp"]
+    tot_cells = d["cells_ss"] + d["cells_sp"] + d["cells_pp"]
+    bonus_in_kernel = d["cells_bonus"] * (in_kernel / tot_cells if tot_cells > 0 else 0.0)
+    tinst = (in_kernel - bonus_in_kernel) * im["inst_per_cell"]["none"] + bonus_in_kernel * im["inst_per_cell"]["sparse"]
+    sm_clock = (clocks.get("sm_mhz") or 1965.0) * 1e6
+    n_sm = 148
+    issue_peak = n_sm * 4 * 32 * sm_clock
+    issue_ach = tinst / d["sweep_seconds"] if d["sweep_seconds"] > 0 else 0.0
+    roofline = {"bound": "issue", "kernel": "kb_sweep_kernel", "achieved": issue_ach / 1e9, "peak": issue_peak / 1e9,
+                "unit": "G thread-instructions/s", "frac": issue_ach / issue_peak,
+                "traffic": im.get("dram_bytes_per_launch"),
+                "traffic_note": im.get("traffic_note"),
+                "peak_source": "%d SMs x 4 schedulers x 32 lanes x %.0f MHz (median SM clock sampled during the timed region)" % (n_sm, sm_clock / 1e6),
+                "inst_per_cell": im["inst_per_cell"], "inst_per_cell_source": im["source"],
+                "cells_per_sec_ceiling": issue_peak / im["inst_per_cell"]["none"],
+                "hbm_model": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                              "peak_source": peak_src, "algorithmic_bytes_per_step": abytes / max(1, args.steps),
+                              "note": "SURVEY 8d contract: 25 B per ss/sp cell, 128 B per pp cell, +4 B per bonus cell; "
+                                      "measured DRAM traffic is ~1000x lower (traffic), so this fraction is not an efficiency"},
                 "kernel_seconds_per_step": d["sweep_seconds"] / max(1, args.steps),
                 "kernel_share_of_step": d["sweep_seconds"] / d["align_seconds"] if d["align_seconds"] > 0 else None,
-                "cells_in_kernel_per_step": (d["dp_cells"] - d["small_ss"] - d["small_sp"] - d["small_pp"]) / max(1, args.steps),
-                "cells_per_sec_in_kernel": (d["dp_cells"] - d["small_ss"] - d["small_sp"] - d["small_pp"]) / d["sweep_seconds"] if d["sweep_seconds"] > 0 else None,
+                "cells_in_kernel_per_step": in_kernel / max(1, args.steps),
+                "cells_per_sec_in_kernel": in_kernel / d["sweep_seconds"] if d["sweep_seconds"] > 0 else None,
                 "small_box_kernel_seconds_per_step": d["small_seconds"] / max(1, args.steps)}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / max(1, args.steps), "higher_is_better": True,
@@ -329,6 +398,11 @@ def main():
             "wall_s_timed_region": w1 - w0, "create_seconds": t_create,
             "collectives_per_step": d["n_collectives"] / max(1, args.steps), "collective_bytes_per_step": d["collective_bytes"] / max(1, args.steps),
             "dp_round_seconds_per_step": d["dp_seconds"] / max(1, args.steps)}
+    try:
+        # single-GPU line only: with a communicator attached kb200_distances is a collective (row shard)
+        line["bpm"] = bpm_bench(ctx, seqs, type_) if world == 1 else None
+    except Exception as e:  # noqa: BLE001
+        line["bpm"] = {"error": repr(e)}
     # ---- identity with the reference: hash of the alignment the timed steps produced (every rank
     #      holds the full result) against the golden hash of the unmodified reference's alignment
     step_rows = m.result()

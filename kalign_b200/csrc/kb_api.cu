@@ -67,6 +67,11 @@ void kb200_ctx_destroy(kb200_ctx* ctx)
                 b->release();
         }
         ctx->arena.release();
+        KbDevBuf* kbufs[] = {&ctx->km_rowsA, &ctx->km_rowsB, &ctx->km_ordA, &ctx->km_ordB, &ctx->km_side, &ctx->km_best, &ctx->km_dmin, &ctx->km_desc};
+        for (KbDevBuf* b : kbufs) {
+                b->release();
+        }
+        if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
         ctx->pinned.release();
         ctx->d_stats.release();
         for (cudaEvent_t e : ctx->ev_pool) {

@@ -179,6 +179,9 @@ struct kb200_ctx {
         const void* posmaps_tag = nullptr;   // host array currently mirrored in t_posmaps
         size_t posmaps_n = 0;
         KbArena arena;
+        // device k-means of the guide tree (kb_kmeans.cu): own stream, scratch kept across calls
+        cudaStream_t stream2 = nullptr;
+        KbDevBuf km_rowsA, km_rowsB, km_ordA, km_ordB, km_side, km_best, km_dmin, km_desc;
 };
 
 enum { KB_SPAN_SWEEP = 0, KB_SPAN_DP = 1, KB_SPAN_SMALL = 2 };

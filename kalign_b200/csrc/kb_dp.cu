@@ -1015,6 +1015,13 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
         while ((1 << (nrounds - 2)) < max_rows && nrounds < KB_MAX_ROUNDS) nrounds++;
         nrounds = std::min(nrounds + 1, KB_MAX_ROUNDS);
         const int span_dp = kb_span_begin(ctx, KB_SPAN_DP);
+        unsigned long long trace_cells = 0;      // KB200_TRACE: cells of the rounds so far (since the last kb_collect)
+        if (trace) {
+                KbDevStats hs;
+                KB_CUDA(cudaMemcpyAsync(&hs, d_stats, sizeof(hs), cudaMemcpyDeviceToHost, st));
+                KB_CUDA(cudaStreamSynchronize(st));
+                trace_cells = hs.cells[0] + hs.cells[1] + hs.cells[2];
+        }
         for (int round = 0; round < nrounds; round++) {
                 KbRound* rnd = d_rounds + round;
                 // boxes this round can hold at most: twice the previous round's, never more than the rows
@@ -1055,14 +1062,18 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
                 if (trace) {
                         // debugging aid only: per-round read-back (serialises the rounds)
                         KbRound hr;
+                        KbDevStats hs;
                         KB_CUDA(cudaMemcpyAsync(&hr, rnd, sizeof(hr), cudaMemcpyDeviceToHost, st));
+                        KB_CUDA(cudaMemcpyAsync(&hs, d_stats, sizeof(hs), cudaMemcpyDeviceToHost, st));
                         KB_CUDA(cudaStreamSynchronize(st));
                         float ms = 0.0f;
                         cudaEventElapsedTime(&ms, ctx->ev_pool[2 * (size_t)span], ctx->ev_pool[2 * (size_t)span + 1]);
+                        const unsigned long long csum = hs.cells[0] + hs.cells[1] + hs.cells[2];
                         if (hr.nboxes) {
-                                fprintf(stderr, "[kb200 trace] jobs=%d round=%d boxes=%u units=%u thin=%u sweep_ms=%.3f\n", n, round, hr.nboxes,
-                                        hr.nunits, hr.thin, ms);
+                                fprintf(stderr, "[kb200 trace] jobs=%d round=%d boxes=%u units=%u thin=%u sweep_ms=%.3f cells=%llu\n", n, round, hr.nboxes,
+                                        hr.nunits, hr.thin, ms, csum - trace_cells);
                         }
+                        trace_cells = csum;
                 }
                 std::swap(cur, nxt);
         }

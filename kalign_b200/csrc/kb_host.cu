@@ -171,8 +171,23 @@ int kb_distances_dev(kb200_ctx* ctx, KbSeqs& S, const int* rows, int nrows, cons
         int* d_cols = d_rows + nrows;
         KB_CUDA(cudaMemcpyAsync(d_rows, rows, sizeof(int) * (size_t)nrows, cudaMemcpyHostToDevice, ctx->stream));
         KB_CUDA(cudaMemcpyAsync(d_cols, cols, sizeof(int) * ncol_items, cudaMemcpyHostToDevice, ctx->stream));
-        KB_RUN(kb_bpm_pairs_words(ctx, words, S.d_seqs.as<uint8_t>(), S.d_offs.as<int64_t>(), S.d_lens.as<int>(),
-                                  d_rows, nrows, d_cols, explicit_pairs ? 0 : ncols, ctx->d_stage5.as<float>()));
+        if (ctx->world > 1 && !explicit_pairs && nrows >= 8 * ctx->world) {
+                // multi-GPU: the rows of the matrix are split contiguously across the ranks
+                // (sequence_distance.c:108 is an `omp parallel for` over the same rows), every rank writes
+                // its rows at their final offsets, one all-gather-v makes the matrix complete everywhere
+                std::vector<size_t> seg((size_t)ctx->world + 1);
+                for (int r = 0; r <= ctx->world; r++) {
+                        seg[(size_t)r] = (size_t)((long long)nrows * r / ctx->world) * (size_t)ncols * sizeof(float);
+                }
+                const int r0 = (int)((long long)nrows * ctx->rank / ctx->world);
+                const int r1 = (int)((long long)nrows * (ctx->rank + 1) / ctx->world);
+                KB_RUN(kb_bpm_pairs_words(ctx, words, S.d_seqs.as<uint8_t>(), S.d_offs.as<int64_t>(), S.d_lens.as<int>(),
+                                          d_rows + r0, r1 - r0, d_cols, ncols, ctx->d_stage5.as<float>() + (size_t)r0 * (size_t)ncols));
+                KB_RUN(kb_allgatherv(ctx, ctx->d_stage5.p, seg.data()));
+        } else {
+                KB_RUN(kb_bpm_pairs_words(ctx, words, S.d_seqs.as<uint8_t>(), S.d_offs.as<int64_t>(), S.d_lens.as<int>(),
+                                          d_rows, nrows, d_cols, explicit_pairs ? 0 : ncols, ctx->d_stage5.as<float>()));
+        }
         KB_CUDA(cudaMemcpyAsync(dm_host, ctx->d_stage5.p, sizeof(float) * npairs, cudaMemcpyDeviceToHost, ctx->stream));
         KB_CUDA(cudaStreamSynchronize(ctx->stream));
         ctx->stats.d2h_bytes += (double)(sizeof(float) * npairs);

@@ -17,6 +17,7 @@
 // calls (d_estimation pair=0 / pair=1) run on the GPU as two batched bpm launches.
 #include "kb_host.cuh"
 #include "kb_kmeans.h"
+#include "kb_kmeans_dev.h"
 
 #include <math.h>
 #include <time.h>
@@ -339,6 +340,38 @@ int kb_tree_prepare(kb200_ctx* ctx, KbSeqs& S, KbTreeJob& T, std::vector<float>&
         return KB200_OK;
 }
 
+// bisecting k-means on the device (kb_kmeans.cu); KB200_HOST_KMEANS=1 keeps the host restatement
+// (kb_kmeans.h) for A/B checks
+void kb_tree_bisect(KbTreeJob& T, int n_threads);
+
+int kb_tree_bisect_any(kb200_ctx* ctx, KbTreeJob& T, int n_threads)
+{
+        if (getenv("KB200_HOST_KMEANS") != nullptr || T.num_anchor != 32 || T.stride != 32) {
+                kb_tree_bisect(T, n_threads);
+                return KB200_OK;
+        }
+        const double tt1 = kb_now();
+        KbKmeansTree K;
+        KB_RUN(kb_kmeans_bisect_dev(ctx, T.dm.data(), T.B.N, K));
+        T.B.nodes.assign(K.left.size(), Node());
+        for (size_t i = 0; i < K.left.size(); i++) {
+                T.B.nodes[i].left = K.left[i];
+                T.B.nodes[i].right = K.right[i];
+        }
+        T.B.clusters.clear();
+        for (size_t l = 0; l < K.leaf_node.size(); l++) {
+                Cluster c;
+                c.samples.assign(K.order.begin() + K.leaf_begin[l], K.order.begin() + K.leaf_end[l]);
+                c.placeholder = K.leaf_node[l];
+                T.B.clusters.push_back(std::move(c));
+        }
+        T.root = K.root;
+        if (kb_trace_on()) {
+                fprintf(stderr, "[kb200 trace] guide tree: bisecting k-means on the device %.1f ms\n", 1e3 * (kb_now() - tt1));
+        }
+        return KB200_OK;
+}
+
 void kb_tree_bisect(KbTreeJob& T, int n_threads)
 {
         const double tt1 = kb_now();
@@ -441,13 +474,52 @@ int kb_tree_finish(kb200_ctx* ctx, KbSeqs& S, KbTreeJob& T, int n_threads, std::
         return KB200_OK;
 }
 
+// multi-GPU: the guide tree is built ONCE, by rank 0 with every host thread of the node (k-means and
+// UPGMA are host code; N ranks each running them with 1/N of the CPU quota only made the public call
+// slower), and the task list is broadcast over NCCL.  Collective: every rank must call it.
+int kb_tree_broadcast(kb200_ctx* ctx, int N, std::vector<int>& abc)
+{
+        if (ctx->world <= 1) {
+                return KB200_OK;
+        }
+        const size_t bytes = sizeof(int) * 3 * (size_t)(N - 1);
+        KB_RUN(ctx->d_stage4.ensure(bytes + 16));
+        if (ctx->rank == 0) {
+                if (abc.size() != (size_t)3 * (size_t)(N - 1)) return KB200_FAIL;
+                KB_CUDA(cudaMemcpyAsync(ctx->d_stage4.p, abc.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        std::vector<size_t> seg((size_t)ctx->world + 1, bytes);       // rank 0 owns the whole buffer
+        seg[0] = 0;
+        KB_RUN(kb_allgatherv(ctx, ctx->d_stage4.p, seg.data()));
+        abc.resize((size_t)3 * (size_t)(N - 1));
+        KB_CUDA(cudaMemcpyAsync(abc.data(), ctx->d_stage4.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        KB_CUDA(cudaStreamSynchronize(ctx->stream));
+        return KB200_OK;
+}
+
+// threads for the host-only tree stages: rank 0 of a multi-GPU run works alone and takes the whole quota
+static int tree_threads(const kb200_ctx* ctx, int n_threads)
+{
+        return (ctx->world > 1) ? kb_default_threads() : n_threads;
+}
+
 // build_tree_kmeans (bisectingKmeans.c:177-271) in one go
 int kb_build_tree(kb200_ctx* ctx, KbSeqs& S, int n_threads, std::vector<int>& abc, std::vector<float>& seq_distances)
 {
         KbTreeJob T;
-        KB_RUN(kb_tree_prepare(ctx, S, T, seq_distances));
-        kb_tree_bisect(T, n_threads);
-        return kb_tree_finish(ctx, S, T, n_threads, abc);
+        KB_RUN(kb_tree_prepare(ctx, S, T, seq_distances));      // N x 32 distances: rows sharded across the ranks
+        int rc = KB200_OK;
+        if (ctx->rank == 0) {
+                rc = kb_tree_bisect_any(ctx, T, tree_threads(ctx, n_threads));
+                if (rc == KB200_OK) rc = kb_tree_finish(ctx, S, T, tree_threads(ctx, n_threads), abc);
+        }
+        if (ctx->world > 1) {
+                // a failure on rank 0 must not leave the other ranks waiting in the collective
+                if (rc != KB200_OK) abc.assign((size_t)3 * (size_t)(S.n - 1), -1);
+                KB_RUN(kb_tree_broadcast(ctx, S.n, abc));
+                if (!abc.empty() && abc[0] < 0) rc = KB200_FAIL;
+        }
+        return rc;
 }
 
 
@@ -830,13 +902,30 @@ int kb200_kalign(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_threads
         int rc = KB200_OK;
         {
                 KbTreeJob* T = M->tree_job;
-                const int nt = M->n_threads;
-                std::thread kmeans([T, nt]() { kb_tree_bisect(*T, nt); });
-                rc = msa_align_anchor(M);
-                kmeans.join();
-                if (rc == KB200_OK) {
-                        rc = kb_tree_finish(ctx, M->biotype == 0 ? M->S_tree : M->S, *T, nt, M->abc);
+                const int nt = tree_threads(ctx, M->n_threads);
+                const bool build = (ctx->rank == 0);          // multi-GPU: rank 0 builds the tree, the others receive it
+                int krc = KB200_OK;
+                // the device k-means runs BEFORE the anchor batch (its CTAs would starve behind the
+                // persistent sweep grid); only the host restatement (KB200_HOST_KMEANS=1) runs beside it
+                const bool host_km = getenv("KB200_HOST_KMEANS") != nullptr;
+                std::thread kmeans;
+                if (build && !host_km) {
+                        krc = kb_tree_bisect_any(ctx, *T, nt);
+                } else if (build) {
+                        kmeans = std::thread([ctx, T, nt, &krc]() { krc = kb_tree_bisect_any(ctx, *T, nt); });
                 }
+                rc = msa_align_anchor(M);
+                if (kmeans.joinable()) kmeans.join();
+                int trc = krc;
+                if (build && trc == KB200_OK) {
+                        trc = kb_tree_finish(ctx, M->biotype == 0 ? M->S_tree : M->S, *T, nt, M->abc);
+                }
+                if (ctx->world > 1) {
+                        if (trc != KB200_OK) M->abc.assign((size_t)3 * (size_t)(M->N - 1), -1);
+                        if (kb_tree_broadcast(ctx, M->N, M->abc) != KB200_OK) rc = KB200_FAIL;
+                        if (!M->abc.empty() && M->abc[0] < 0) trc = KB200_FAIL;
+                }
+                if (rc == KB200_OK) rc = trc;
                 delete M->tree_job;
                 M->tree_job = nullptr;
                 M->S_tree.release();

@@ -646,7 +646,7 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                             const Trip in, float4* __restrict__ rowbuf,
                             const unsigned in_tag, const unsigned out_tag,
                             const float* __restrict__ s_tbl, const int tstride, const int lane, float4* s_ring, float4* s_rec,
-                            int2* s_bon)
+                            int2* s_bon, unsigned long long* s_mbar, unsigned& rec_phase)
 {
         static_assert(BONUS != BONUS_SPARSE || K <= BON_KMAX_ROWS, "bonus event queue is sized for K <= 4");
         constexpr int NA = VTraits<V>::NA;
@@ -712,24 +712,55 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
         // ring as well (cp.async, 16 columns at a time, a block ahead): the per-step record read is
         // an LDS.128 pair instead of an L1-missing global load every fourth column.
         constexpr bool RECRING = (NA > 0 && NA <= 5);
-        float4* const s_recA = s_rec;
-        float4* const s_recB = s_rec + 64;
-        auto rec_issue = [&](const int col0, const int ncols) {
+        // Record ring: 64 columns x 32 B, four blocks of 16 columns.  Ring position of column u is
+        // u + 15 (block 0 holds column 0 only), so that the block a sweep prefetches into never
+        // overlaps the three blocks the 32 lanes are reading.  A block is ONE bulk asynchronous copy
+        // (cp.async.bulk, the TMA engine's linear form) issued by one elected lane: 16 packed column
+        // records are contiguous in the job's cpack array in either sweep direction; completion is
+        // signalled on the block's mbarrier (expect_tx / complete_tx), which the warp waits on
+        // one block ahead of use.  Backward sweeps visit the columns in descending order: the same
+        // contiguous run, read back to front (slot index XOR 15).
+        float4* const s_ring_rec = s_rec;
+        const int rec_flip = bwd ? 15 : 0;
+        auto rec_slot = [&](const int col) -> const float4* {
+                return s_ring_rec + ((((col + 15) & 63) ^ rec_flip) << 1);
+        };
+        auto rec_issue = [&](const int j) {          // block j: columns max(0, 16j-15) .. min(C, 16j)
                 if constexpr (RECRING) {
-                        const int col = col0 + (lane >> 1);
-                        const int half = lane & 1;
-                        if ((lane >> 1) < ncols && col <= C) {
-                                const long long ridx = bwd ? (long long)(eb - col + 1) : (long long)(sb + col);
-                                const float4* src = reinterpret_cast<const float4*>(J.cpack) + ridx * 2 + half;
-                                const unsigned dst = (unsigned)__cvta_generic_to_shared((half ? s_recB : s_recA) + (col & 63));
-                                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                        const int c0 = (j == 0) ? 0 : (16 * j - 15);
+                        const int c1 = (16 * j < C) ? (16 * j) : C;
+                        if (c0 <= c1) {
+                                __syncwarp();        // every lane is done reading the block this copy overwrites
+                                if (lane == 0) {
+                                        const int n = c1 - c0 + 1;
+                                        const long long r0 = bwd ? (long long)(eb - c1 + 1) : (long long)(sb + c0);
+                                        const int s0 = bwd ? (15 - ((c1 + 15) & 15)) : ((c0 + 15) & 15);
+                                        const float* src = J.cpack + r0 * PACK5;
+                                        const unsigned dst = (unsigned)__cvta_generic_to_shared(s_ring_rec + (((j & 3) * 16 + s0) << 1));
+                                        const unsigned bar = (unsigned)__cvta_generic_to_shared(s_mbar + (j & 3));
+                                        const unsigned bytes = (unsigned)n * (unsigned)(PACK5 * sizeof(float));
+                                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+                                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                                     ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+                                }
                         }
                 }
         };
-        auto rec_wait = [&]() {
+        auto rec_wait = [&](const int j) {           // block j has landed (no-op for a block without columns)
                 if constexpr (RECRING) {
-                        asm volatile("cp.async.wait_all;" ::: "memory");
-                        __syncwarp();
+                        const int c0 = (j == 0) ? 0 : (16 * j - 15);
+                        if (c0 <= C) {
+                                const unsigned bar = (unsigned)__cvta_generic_to_shared(s_mbar + (j & 3));
+                                const unsigned parity = (rec_phase >> (j & 3)) & 1u;
+                                unsigned done = 0;
+                                do {
+                                        asm volatile("{\n\t.reg .pred p;\n\t"
+                                                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                                                     "selp.u32 %0, 1, 0, p;\n\t}"
+                                                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+                                } while (!done);
+                                rec_phase ^= 1u << (j & 3);
+                        }
                 }
         };
         // every HB steps (t % HB == 0): commit the hand-off block of columns t .. t+HB-1 and start
@@ -758,8 +789,8 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                 }
                 if constexpr (RECRING) {
                         if ((t & 15) == 0 && t > 0) {
-                                rec_wait();                      // columns t+1 .. t+16 (issued 16 steps ago)
-                                rec_issue(t + 17, 16);           // slots of columns t-47 .. t-32: last read at step t-2
+                                rec_wait((t >> 4) + 1);          // columns t+1 .. t+16 (issued 16 steps ago)
+                                rec_issue((t >> 4) + 2);         // slots of columns t-47 .. t-32: last read at step t-2
                         }
                 }
         };
@@ -788,13 +819,14 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
         }
         if constexpr (RECRING) {
                 static_assert(PACK5 == 8, "PP5 record is two float4");
-                rec_issue(0, 16);
-                rec_issue(16, 16);
-                rec_issue(32, 1);
-                rec_wait();
+                rec_issue(0);
+                rec_issue(1);
+                rec_issue(2);
+                rec_wait(0);
+                rec_wait(1);
                 // lane 0 is on column 0 at step 0; the other lanes read their column 0 one step ahead
-                curA = s_recA[0];
-                curB = s_recB[0];
+                curA = rec_slot(0)[0];
+                curB = rec_slot(0)[1];
         }
         // running pointers instead of per-step index arithmetic: the column visited NEXT (pu = u+1;
         // 1-lane at t=0) and the state column of the current u
@@ -830,8 +862,9 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                 int ncres = 0;
                 if constexpr (RECRING) {
                         // ring slot of column u+1 (lanes outside the box read a slot they never use)
-                        nxtA = s_recA[(u + 1) & 63];
-                        nxtB = s_recB[(u + 1) & 63];
+                        const float4* rp = rec_slot(u + 1);
+                        nxtA = rp[0];
+                        nxtB = rp[1];
                 } else if constexpr (PREF) {
                         const int pu = u + 1;
                         if (STEADY || (pu >= 1 && pu <= C)) {
@@ -987,14 +1020,15 @@ __device__ void sweep_strip(const KbJob& J, const int bwd, const int sb, const i
                         step(std::false_type{}, t);
                 }
         }
-        rec_wait();      // no copy into the record ring may outlive the strip (the area is reused)
+        // every block that was issued has been waited for inside the loop (block j is waited at step
+        // 16(j-1) < C + 32 whenever it has a column), so no copy outlives the strip
         __syncwarp();
 }
 
 template <int V, int BONUS>
 __device__ void sweep_unit(const KbJob& J, const KbBox& bx, const int bwd, const int strip, const int thin,
                            const unsigned tag_base, const float* __restrict__ s_tbl, const int tstride, const int lane,
-                           float4* s_ring, float4* s_rec, int2* s_bon)
+                           float4* s_ring, float4* s_rec, int2* s_bon, unsigned long long* s_mbar, unsigned& rec_phase)
 {
         const int mid = (bx.ea - bx.sa) / 2 + bx.sa;
         const int r0 = bwd ? mid : bx.sa;
@@ -1020,7 +1054,7 @@ __device__ void sweep_unit(const KbJob& J, const KbBox& bx, const int bwd, const
         // rows per lane of this strip: the full width of the kind's strips, or -- last strip of a
         // sweep, boxes of the deeper rounds -- the smallest K that covers the remaining rows, so that
         // a 187-row half box runs with 6 rows per lane (97 % of the lanes' rows live) instead of 8
-#define KB_STRIP(KK, TT) sweep_strip<V, KK, TT, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_rec, s_bon)
+#define KB_STRIP(KK, TT) sweep_strip<V, KK, TT, BONUS>(J, bwd, sb, eb, r0, r1, row0, first_term, last_term, in, rowbuf, prev, mine, s_tbl, tstride, lane, s_ring, s_rec, s_bon, s_mbar, rec_phase)
         const int kneed = (rem + 31) >> 5;
         if (kneed <= 1) {
                 KB_STRIP(1, true);
@@ -1069,7 +1103,19 @@ kb_sweep_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes,
         for (int i = threadIdx.x; i < TBL_MAX; i += blockDim.x) {
                 s_tbl[i] = tbl[i];
         }
+        // one mbarrier per block of a warp's record ring (bulk-copy completion, see sweep_strip)
+        __shared__ unsigned long long s_mbar_all[WARPS_PER_CTA][4];
+        if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                        const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_mbar_all[threadIdx.x >> 5][b]);
+                        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+                }
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
         __syncthreads();
+        unsigned long long* s_mbar = s_mbar_all[threadIdx.x >> 5];
+        unsigned rec_phase = 0;          // phase parity of the warp's four mbarriers
         const int lane = threadIdx.x & 31;
         // sparse bonus lists of the rows of the strip a warp is sweeping (bonus kernel family only)
         // (dynamic shared memory: with it the CTA exceeds the 48 KB static limit)
@@ -1093,20 +1139,20 @@ kb_sweep_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes,
                 const unsigned ps = tag_base;
                 if (J.kind == KB200_KIND_SS) {
                         if (tstride == 5) {
-                                sweep_unit<V_SS5, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
+                                sweep_unit<V_SS5, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane, s_ring, s_rec, s_bon, s_mbar, rec_phase);
                         } else {
-                                sweep_unit<V_SS, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
+                                sweep_unit<V_SS, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane, s_ring, s_rec, s_bon, s_mbar, rec_phase);
                         }
                 } else if (J.kind == KB200_KIND_SP) {
                         if (J.nalpha <= 5) {
-                                sweep_unit<V_SP5, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
+                                sweep_unit<V_SP5, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane, s_ring, s_rec, s_bon, s_mbar, rec_phase);
                         } else {
-                                sweep_unit<V_SP, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
+                                sweep_unit<V_SP, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane, s_ring, s_rec, s_bon, s_mbar, rec_phase);
                         }
                 } else if (J.nalpha <= 5) {
-                        sweep_unit<V_PP5, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
+                        sweep_unit<V_PP5, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane, s_ring, s_rec, s_bon, s_mbar, rec_phase);
                 } else {
-                        sweep_unit<V_PP23, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane, s_ring, s_rec, s_bon);
+                        sweep_unit<V_PP23, BONUS>(J, bx, bwd, un.strip, thin, ps, s_tbl, tstride, lane, s_ring, s_rec, s_bon, s_mbar, rec_phase);
                 }
         }
 }
