@@ -155,8 +155,8 @@ def issue_model():
 def bpm_bench(ctx, seqs, type_):
     """the N x 32 anchor distance matrix of the workload through kb200_distances:
     pairs/s, word-steps/s (text symbols x 64-bit pattern words) and the fraction of the integer
-    issue ceiling they use (101 SASS instructions per lane and word-step, cuobjdump of
-    kb_bpm_kernel<16>); HBM traffic is n + m + 4 bytes per pair -- negligible, reported as a fraction"""
+    issue ceiling they use (53.8 executed thread-instructions per word-step, measured with ncu);
+    HBM traffic is n + m + 4 bytes per pair -- negligible, reported as a fraction"""
     from kalign_b200 import _lib
     nuc = type_ in (0, 1, 2)
     tbl = {c: i for i, c in enumerate("ACGTU")} if nuc else {c: i % 13 for i, c in enumerate("ACDEFGHIKLMNPQRSTVWY")}
@@ -183,10 +183,25 @@ def bpm_bench(ctx, seqs, type_):
     bytes_ = float((text + pat + 4).sum())
     hbm, _, _ = peaks()
     return {"pairs_per_sec": pairs / t, "word_steps_per_sec": wsteps / t, "seconds": t, "pairs": pairs,
-            "alu_frac": wsteps * 101.0 / t / (148 * 4 * 32 * 1.965e9),
-            "alu_note": "101 SASS instructions per lane and (symbol, 64-bit word) step (cuobjdump, kb_bpm_kernel<16> inner loop) "
-                        "against 148 SMs x 4 x 32 lanes x 1.965 GHz",
+            "alu_frac": wsteps * 53.8 / t / (148 * 4 * 32 * 1.965e9),
+            "alu_note": "53.8 executed thread-instructions per (symbol, 64-bit word) step (ncu, profiles/r02_bpm_kernel_full_C3.csv: "
+                        "1.2945e10 warp-instructions x 32 / 7.70e9 word-steps of the C3 N x 32 matrix; the loop body is 101 SASS "
+                        "instructions, part of it predicated) against 148 SMs x 4 x 32 lanes x 1.965 GHz",
             "hbm_frac": bytes_ / t / 1e9 / hbm, "kernel": "kb_bpm_kernel"}
+
+
+def full_reference_record(workload):
+    """the unmodified reference's run of the FULL workload, recorded once in the build container by
+    tools/gen_golden_full.py (tests/golden/full_<wl>.npz: stage times and the hash the GPU result is
+    compared with); not re-run here -- the full C3 takes ~18 minutes on the CPU"""
+    p = os.path.join(ROOT, "tests", "golden", "full_%s.npz" % workload)
+    if not os.path.exists(p):
+        return None
+    g = np.load(p, allow_pickle=False)
+    t = [float(x) for x in g["times"]]
+    return {"n": int(g["n"]), "threads": int(g["threads"]), "dist_tree_s": t[0], "anchor_s": t[1], "tree_aln_s": t[2],
+            "total_s": t[3], "dp_stage_seconds": t[1] + t[2], "msa_sha256": str(g["msa_sha256"]),
+            "where": "build container (8 cores), tools/gen_golden_full.py"}
 
 
 def delta(a, b):
@@ -428,7 +443,12 @@ def main():
             sseqs, t, ref_rows = ref_sample(args.workload, n_sample, host_threads)
             scells, gpu_rows = count_cells_gpu(sseqs, type_, K)
             T = t["anchor"] + t["tree_aln"]
+            full = full_reference_record(args.workload)
+            if full is not None and len(seqs) == full["n"]:
+                full["value"] = (cells / max(1, args.steps)) / full["dp_stage_seconds"]
+                full["unit"] = UNIT
             line["cpu_baseline"] = {"value": scells / T, "unit": UNIT, "cores": host_threads, "kind": "reference",
+                                    "full_config_run": full,
                                     "sample": "first %d sequences of %s; anchor_consistency_build %.2fs (serial in the reference) + create_msa_tree %.2fs on %d threads" % (n_sample, args.workload, t["anchor"], t["tree_aln"], host_threads),
                                     "msa_identical_to_gpu": gpu_rows == ref_rows}
         except Exception as e:  # noqa: BLE001

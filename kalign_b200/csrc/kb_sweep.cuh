@@ -1072,6 +1072,7 @@ __device__ void sweep_unit(const KbJob& J, const KbBox& bx, const int bwd, const
                 if (rem >= 128) KB_STRIP(4, false);
                 else if (kneed == 4) KB_STRIP(4, true);
                 else if (kneed == 3) KB_STRIP(3, true);
+                else if (rem == 64) KB_STRIP(2, false);      // full strips of the thin regime (two rows per lane)
                 else KB_STRIP(2, true);
         }
 #undef KB_STRIP
