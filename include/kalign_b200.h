@@ -117,6 +117,14 @@ int kb200_pair_align_batch(kb200_ctx* ctx, const kb200_params* prm,
 int kb200_distances(kb200_ctx* ctx, const uint8_t* seqs, const int64_t* offs, const int* lens,
                     int nseq, const int* rows, int nrows, const int* cols, int ncols, float* dm);
 
+/* The same on sequences that stay resident on the device between calls (the reference calls
+   d_estimation once per leaf cluster of the guide tree, bisectingKmeans.c:294: thousands of small
+   calls on the same msa).  explicit_pairs != 0: nrows pairs (rows[p], cols[p]) -> dm[p], ncols ignored. */
+typedef struct kb200_seqs kb200_seqs;
+int  kb200_seqs_upload(kb200_ctx* ctx, const uint8_t* seqs, const int64_t* offs, const int* lens, int nseq, kb200_seqs** out);
+int  kb200_distances_on(kb200_seqs* s, const int* rows, int nrows, const int* cols, int ncols, int explicit_pairs, float* dm);
+void kb200_seqs_free(kb200_seqs* s);
+
 /* posmaps: concatenated over i of K maps of len_i ints: map (i,k) starts at
    K*offs[i] + k*lens[i]  (anchor_consistency.c:246-267). Only pairs p in [pair_begin,pair_end)
    of the flattened (i*K+k) list are computed (multi-GPU shard); others are left untouched. */

@@ -17,6 +17,9 @@
  * guide tree, parameter handling, finalise_alignment, the CLI -- is the reference's code, untouched.
  * The result is a libkalign.so.3 + kalign executable that are drop-in for the alignment path.
  *
+ * d_estimation keeps the msa's sequences on the device between its calls (kb200_seqs_upload /
+ * kb200_distances_on) and asks for exactly the pairs the reference's loops leave in the matrix.
+ *
  * There is no CPU fallback: when no CUDA device is usable every seam returns FAIL, and
  * kalign_run()/kalign() fail with it.  Environment: KALIGN_B200_DEVICE selects the GPU (default 0).
  *
@@ -48,9 +51,30 @@
 static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;   /* d_estimation(pair=1) is called from OpenMP tasks */
 static kb200_ctx* g_ctx = NULL;
 
-/* flat copy of the last consistency table (host): handed to kb200_align_tree without re-packing */
+/* flat copy of the last consistency table (host): handed to kb200_align_tree without re-packing;
+   keyed on the table it was made from, touched only under g_lock */
 static struct consistency_table* g_ct_owner = NULL;
 static int* g_posmaps = NULL;
+
+/* sequences resident on the device between the d_estimation calls of one guide tree: bisecting_kmeans
+   calls d_estimation(pair = 1) once per leaf cluster (bisectingKmeans.c:294), thousands of times on the
+   same msa; flattening and uploading the whole msa every time would dominate.  Keyed on (msa, alphabet,
+   numseq); released when create_msa_tree runs (the sequences are re-encoded before it). */
+static struct msa* g_dist_msa = NULL;
+static int g_dist_L = -1;
+static int g_dist_n = 0;
+static kb200_seqs* g_dist_seqs = NULL;
+
+static void dist_cache_drop(void)
+{
+        if(g_dist_seqs){
+                kb200_seqs_free(g_dist_seqs);
+        }
+        g_dist_seqs = NULL;
+        g_dist_msa = NULL;
+        g_dist_L = -1;
+        g_dist_n = 0;
+}
 
 static kb200_ctx* seam_ctx(void)
 {
@@ -139,42 +163,77 @@ float** __wrap_d_estimation(struct msa* msa, int* samples, int num_samples, int 
         float** dm = NULL;
         float* flat = NULL;
         int* rows = NULL;
-        struct flat_msa f = {NULL, NULL, NULL, 0};
+        int* cols = NULL;
         kb200_ctx* ctx = NULL;
         int numseq = msa->numseq;
+        int npairs = 0;
         int i, j;
-        int rc;
+        int rc = KB200_OK;
 
         pthread_mutex_lock(&g_lock);
         ctx = seam_ctx();
-        if(!ctx || flatten(msa, &f) != OK){
+        if(!ctx){
                 pthread_mutex_unlock(&g_lock);
                 goto ERROR;
         }
+        if(!(g_dist_seqs && g_dist_msa == msa && g_dist_L == msa->L && g_dist_n == numseq)){
+                struct flat_msa f = {NULL, NULL, NULL, 0};
+                dist_cache_drop();
+                if(flatten(msa, &f) != OK || kb200_seqs_upload(ctx, f.seqs, f.offs, f.lens, numseq, &g_dist_seqs) != KB200_OK){
+                        flat_free(&f);
+                        g_dist_seqs = NULL;
+                        pthread_mutex_unlock(&g_lock);
+                        goto ERROR;
+                }
+                flat_free(&f);
+                g_dist_msa = msa;
+                g_dist_L = msa->L;
+                g_dist_n = numseq;
+        }
         if(pair){
-                flat = malloc(sizeof(float) * (size_t)num_samples * (size_t)num_samples);
-                rc = flat ? kb200_distances(ctx, f.seqs, f.offs, f.lens, numseq, samples, num_samples, samples, num_samples, flat) : KB200_FAIL;
+                /* the reference's double loop leaves dm[i][j] = dm[j][i] = calc_distance(seq[max(i,j)], seq[min(i,j)]):
+                   one explicit pair per i >= j */
+                npairs = num_samples * (num_samples + 1) / 2;
+                rows = malloc(sizeof(int) * (size_t)(npairs > 0 ? npairs : 1));
+                cols = malloc(sizeof(int) * (size_t)(npairs > 0 ? npairs : 1));
+                flat = malloc(sizeof(float) * (size_t)(npairs > 0 ? npairs : 1));
+                if(rows && cols && flat){
+                        int p = 0;
+                        for(i = 0; i < num_samples; i++){
+                                for(j = 0; j <= i; j++){
+                                        rows[p] = samples[i];
+                                        cols[p] = samples[j];
+                                        p++;
+                                }
+                        }
+                        rc = kb200_distances_on(g_dist_seqs, rows, npairs, cols, 0, 1, flat);
+                }else{
+                        rc = KB200_FAIL;
+                }
         }else{
                 rows = malloc(sizeof(int) * (size_t)numseq);
                 flat = malloc(sizeof(float) * (size_t)numseq * (size_t)num_samples);
-                if(rows){
+                if(rows && flat){
                         for(i = 0; i < numseq; i++){
                                 rows[i] = i;
                         }
+                        rc = kb200_distances_on(g_dist_seqs, rows, numseq, samples, num_samples, 0, flat);
+                }else{
+                        rc = KB200_FAIL;
                 }
-                rc = (rows && flat) ? kb200_distances(ctx, f.seqs, f.offs, f.lens, numseq, rows, numseq, samples, num_samples, flat) : KB200_FAIL;
         }
         pthread_mutex_unlock(&g_lock);
         if(rc != KB200_OK){
                 goto ERROR;
         }
         if(pair){
+                int p = 0;
                 RUN(galloc(&dm, num_samples, num_samples));
                 for(i = 0; i < num_samples; i++){
                         for(j = 0; j <= i; j++){
-                                float v = flat[(size_t)i * (size_t)num_samples + (size_t)j];
-                                dm[i][j] = v;
-                                dm[j][i] = v;
+                                dm[i][j] = flat[p];
+                                dm[j][i] = flat[p];
+                                p++;
                         }
                 }
         }else{
@@ -206,12 +265,12 @@ float** __wrap_d_estimation(struct msa* msa, int* samples, int num_samples, int 
         }
         free(flat);
         free(rows);
-        flat_free(&f);
+        free(cols);
         return dm;
 ERROR:
         free(flat);
         free(rows);
-        flat_free(&f);
+        free(cols);
         return NULL;
 }
 
@@ -290,9 +349,11 @@ int __wrap_anchor_consistency_build(struct msa* msa, struct aln_param* ap, int n
                 }
         }
         /* keep the flat copy for create_msa_tree */
+        pthread_mutex_lock(&g_lock);
         free(g_posmaps);
         g_posmaps = posmaps;
         g_ct_owner = ct;
+        pthread_mutex_unlock(&g_lock);
         flat_free(&f);
         *ct_out = ct;
         return OK;
@@ -326,7 +387,10 @@ int __wrap_create_msa_tree(struct msa* msa, struct aln_param* ap, struct aln_tas
         int i, k;
         int64_t total = 0;
 
+        pthread_mutex_lock(&g_lock);
         ctx = seam_ctx();
+        dist_cache_drop();                               /* the guide tree is built; the sequences were re-encoded */
+        pthread_mutex_unlock(&g_lock);
         if(!ctx){
                 return FAIL;
         }
@@ -351,9 +415,15 @@ int __wrap_create_msa_tree(struct msa* msa, struct aln_param* ap, struct aln_tas
         if(ct){
                 K = ct->n_anchors;
                 weight = ct->weight;
+                pthread_mutex_lock(&g_lock);
                 if(ct == g_ct_owner && g_posmaps){
-                        posmaps = g_posmaps;
-                }else{
+                        posmaps = g_posmaps;             /* ownership moves to this call */
+                        own_posmaps = 1;
+                        g_posmaps = NULL;
+                        g_ct_owner = NULL;
+                }
+                pthread_mutex_unlock(&g_lock);
+                if(!posmaps){
                         /* a table built elsewhere (e.g. by the reference's CPU path): pack it */
                         posmaps = malloc(sizeof(int) * (size_t)total * (size_t)K + sizeof(int));
                         if(!posmaps){
@@ -397,9 +467,6 @@ int __wrap_create_msa_tree(struct msa* msa, struct aln_param* ap, struct aln_tas
         if(own_posmaps){
                 free(posmaps);
         }
-        free(g_posmaps);
-        g_posmaps = NULL;
-        g_ct_owner = NULL;
         free(abc);
         free(gaps);
         free(conf);

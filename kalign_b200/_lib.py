@@ -47,6 +47,7 @@ class Stats(C.Structure):
 # every symbol include/kalign_b200.h declares
 EXPORTS = ["kb200_device_count", "kb200_ctx_create", "kb200_ctx_destroy", "kb200_get_stats",
            "kb200_version", "kb200_params_init", "kb200_pair_align_batch", "kb200_distances",
+           "kb200_seqs_upload", "kb200_distances_on", "kb200_seqs_free",
            "kb200_anchor_posmaps", "kb200_select_anchors", "kb200_align_tree", "kb200_align_tree_conf", "kb200_kalign",
            "kb200_msa_create", "kb200_msa_align", "kb200_msa_result", "kb200_msa_info", "kb200_msa_tree", "kb200_msa_free",
            "kb200_comm_unique_id", "kb200_ctx_comm_init", "kb200_ctx_comm_destroy", "kb200_partition"]
@@ -93,6 +94,12 @@ def load():
     lib.kb200_pair_align_batch.restype = C.c_int
     lib.kb200_distances.argtypes = [C.c_void_p, u8p, i64p, i32p, C.c_int, i32p, C.c_int, i32p, C.c_int, f32p]
     lib.kb200_distances.restype = C.c_int
+    lib.kb200_seqs_upload.argtypes = [C.c_void_p, u8p, i64p, i32p, C.c_int, C.POINTER(C.c_void_p)]
+    lib.kb200_seqs_upload.restype = C.c_int
+    lib.kb200_distances_on.argtypes = [C.c_void_p, i32p, C.c_int, i32p, C.c_int, C.c_int, f32p]
+    lib.kb200_distances_on.restype = C.c_int
+    lib.kb200_seqs_free.argtypes = [C.c_void_p]
+    lib.kb200_seqs_free.restype = None
     lib.kb200_anchor_posmaps.argtypes = [C.c_void_p, C.POINTER(Params), u8p, i64p, i32p, C.c_int,
                                          i32p, C.c_int, C.c_longlong, C.c_longlong, i32p]
     lib.kb200_anchor_posmaps.restype = C.c_int
@@ -224,6 +231,38 @@ def _distances(self, flat, offs, lens, rows, cols):
     if self.lib.kb200_distances(self.h, flat, offs, lens, len(lens), rows, len(rows), cols, len(cols), dm) != 0:
         raise RuntimeError("kb200_distances failed")
     return dm.reshape(len(rows), len(cols))
+
+
+class DeviceSeqs:
+    """sequences resident on the device between distance calls (kb200_seqs_upload / kb200_distances_on)"""
+
+    def __init__(self, ctx, flat, offs, lens):
+        self.lib = ctx.lib
+        h = C.c_void_p()
+        if self.lib.kb200_seqs_upload(ctx.h, flat, offs, lens, len(lens), C.byref(h)) != 0:
+            raise RuntimeError("kb200_seqs_upload failed")
+        self.h = h
+
+    def distances(self, rows, cols):
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        cols = np.ascontiguousarray(cols, dtype=np.int32)
+        dm = np.zeros(len(rows) * len(cols), dtype=np.float32)
+        if self.lib.kb200_distances_on(self.h, rows, len(rows), cols, len(cols), 0, dm) != 0:
+            raise RuntimeError("kb200_distances_on failed")
+        return dm.reshape(len(rows), len(cols))
+
+    def pair_distances(self, a, b):
+        a = np.ascontiguousarray(a, dtype=np.int32)
+        b = np.ascontiguousarray(b, dtype=np.int32)
+        dm = np.zeros(len(a), dtype=np.float32)
+        if self.lib.kb200_distances_on(self.h, a, len(a), b, 0, 1, dm) != 0:
+            raise RuntimeError("kb200_distances_on failed")
+        return dm
+
+    def close(self):
+        if self.h:
+            self.lib.kb200_seqs_free(self.h)
+            self.h = None
 
 
 def _anchor_posmaps(self, prm, flat, offs, lens, anchor_ids, begin=0, end=None, out=None):

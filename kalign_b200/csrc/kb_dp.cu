@@ -976,7 +976,15 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
                 // largest power of two T such that the boxes of T rows (about rows_total / T of them)
                 // still give every resident thread of half the machine a box of its own
                 const size_t want = (size_t)ctx->sm_count * 256;
-                while (small_rows * 2 <= SMALL_ROWS_MAX && rows_total / (size_t)(small_rows * 2) >= want) {
+                // 23-letter profile operands: a thread-per-box sweep re-reads 28-float column records and
+                // keeps 23 residue counts per row, it runs 3-4x slower per cell than the warp strips
+                // (C4 level 2: 0.06 vs 0.21 T cells/s): boxes of more than 64 rows stay with the strips (measured optimum, C4 257 -> 246 ms)
+                int rows_cap = SMALL_ROWS_MAX;
+                for (int i = 0; i < n; i++) {
+                        if (jobs[i].kind != KB200_KIND_SS && jobs[i].nalpha > 5) { rows_cap = 64; break; }
+                }
+                if (const char* e = getenv("KB200_SMALL_ROWS_PROF")) rows_cap = std::min(std::max(atoi(e), SMALL_ROWS), SMALL_ROWS_MAX);
+                while (small_rows * 2 <= rows_cap && rows_total / (size_t)(small_rows * 2) >= want) {
                         small_rows *= 2;
                 }
                 if (small_rows > SMALL_ROWS) small_cols = std::min(2 * small_rows + small_rows / 2, SMALL_COLS_MAX);

@@ -399,6 +399,55 @@ int kb200_distances(kb200_ctx* ctx, const uint8_t* seqs, const int64_t* offs, co
         return rc;
 }
 
+struct kb200_seqs {
+        kb200_ctx* ctx = nullptr;
+        KbSeqs S;
+        std::vector<int64_t> offs;
+        std::vector<int> lens;
+};
+
+int kb200_seqs_upload(kb200_ctx* ctx, const uint8_t* seqs, const int64_t* offs, const int* lens, int nseq, kb200_seqs** out)
+{
+        if (!ctx || !seqs || !offs || !lens || !out || nseq <= 0) {
+                return KB200_FAIL;
+        }
+        *out = nullptr;
+        KB_CUDA(cudaSetDevice(ctx->device));
+        kb200_seqs* h = new kb200_seqs();
+        h->ctx = ctx;
+        h->offs.assign(offs, offs + nseq);
+        h->lens.assign(lens, lens + nseq);
+        if (h->S.upload(ctx, seqs, h->offs.data(), h->lens.data(), nseq) != KB200_OK) {
+                h->S.release();
+                delete h;
+                return KB200_FAIL;
+        }
+        h->S.h_seqs = nullptr;       // the caller's code array is not referenced after the upload
+        *out = h;
+        return KB200_OK;
+}
+
+int kb200_distances_on(kb200_seqs* h, const int* rows, int nrows, const int* cols, int ncols, int explicit_pairs, float* dm)
+{
+        if (!h || !rows || !cols || !dm || nrows < 0) {
+                return KB200_FAIL;
+        }
+        KB_CUDA(cudaSetDevice(h->ctx->device));
+        const int n = h->S.n;
+        const int ncheck = explicit_pairs ? nrows : ncols;
+        for (int i = 0; i < nrows; i++) if (rows[i] < 0 || rows[i] >= n) return KB200_FAIL;
+        for (int i = 0; i < ncheck; i++) if (cols[i] < 0 || cols[i] >= n) return KB200_FAIL;
+        return kb_distances_dev(h->ctx, h->S, rows, nrows, cols, ncols, explicit_pairs ? 1 : 0, dm);
+}
+
+void kb200_seqs_free(kb200_seqs* h)
+{
+        if (!h) return;
+        cudaSetDevice(h->ctx->device);
+        h->S.release();
+        delete h;
+}
+
 int kb200_anchor_posmaps(kb200_ctx* ctx, const kb200_params* prm,
                          const uint8_t* seqs, const int64_t* offs, const int* lens, int nseq,
                          const int* anchor_ids, int K, long long pair_begin, long long pair_end, int* posmaps)

@@ -34,7 +34,7 @@ def test_public_api_and_seams():
         assert f in defined, f
     for w in ("__wrap_d_estimation", "__wrap_anchor_consistency_build", "__wrap_create_msa_tree"):
         assert w in defined, w
-    for f in ("kb200_distances", "kb200_anchor_posmaps", "kb200_select_anchors", "kb200_align_tree_conf", "kb200_ctx_create"):
+    for f in ("kb200_distances_on", "kb200_seqs_upload", "kb200_anchor_posmaps", "kb200_select_anchors", "kb200_align_tree_conf", "kb200_ctx_create"):
         assert f in undefined, f       # resolved by libkalign_b200.so at load time
 
 

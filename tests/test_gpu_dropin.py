@@ -24,6 +24,11 @@ CASES = [
     ("rna_default", lambda: synth.family(80, 300, synth.RNA, seed=23), ["--type", "rna"]),
     ("dna_fast", lambda: synth.family(30, 400, synth.DNA, seed=24, sub=0.05, ins=0.01, dele=0.01), ["--type", "dna", "--fast"]),
     ("two_sequences", lambda: synth.family(2, 90, synth.PROTEIN, seed=25), []),
+    # enough sequences for dozens of bisections: d_estimation(pair = 1) is called once per leaf cluster
+    # on the device-resident sequences, --refine confident reads the task->confidence the seam wrote
+    ("protein_3000_fast", lambda: synth.family(3000, 100, synth.PROTEIN, seed=26), ["--fast"]),
+    ("protein_refine_confident", lambda: synth.family(40, 90, synth.PROTEIN, seed=27), ["--refine", "confident"]),
+    ("rna_refine_all", lambda: synth.family(24, 150, synth.RNA, seed=28), ["--type", "rna", "--refine", "all"]),
 ]
 
 

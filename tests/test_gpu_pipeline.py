@@ -182,3 +182,25 @@ def test_bad_task_list_is_rejected(ctx):
         ctx.align_tree(prm, flat, offs, lens, tasks, run.seq_distances())
     finally:
         run.close()
+
+
+def test_device_resident_distances(ctx):
+    """kb200_seqs_upload / kb200_distances_on (the d_estimation seam keeps the msa on the device between its
+    calls): rectangle and explicit pair list equal the one-shot kb200_distances"""
+    from kalign_b200 import _lib
+    rng = np.random.default_rng(5)
+    codes = [rng.integers(0, 13, size=int(n)).astype(np.uint8) for n in rng.integers(30, 400, size=70)]
+    flat, offs, lens = _lib.pack(codes)
+    rows = np.arange(len(codes), dtype=np.int32)
+    cols = np.array([3, 17, 40, 69, 5], dtype=np.int32)
+    want = ctx.distances(flat, offs, lens, rows, cols)
+    d = _lib.DeviceSeqs(ctx, flat, offs, lens)
+    try:
+        assert np.array_equal(d.distances(rows, cols), want)
+        a = np.array([10, 11, 69, 0, 33], dtype=np.int32)
+        b = np.array([3, 3, 17, 40, 5], dtype=np.int32)
+        got = d.pair_distances(a, b)
+        colidx = {int(c): k for k, c in enumerate(cols)}
+        assert np.array_equal(got, np.array([want[int(x), colidx[int(y)]] for x, y in zip(a, b)], dtype=np.float32))
+    finally:
+        d.close()
