@@ -72,6 +72,10 @@ void kb200_ctx_destroy(kb200_ctx* ctx)
                 b->release();
         }
         if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+        for (kb200_ctx::PinnedBlock& b : ctx->host_pool) {
+                cudaFreeHost(b.p);
+        }
+        ctx->host_pool.clear();
         ctx->pinned.release();
         ctx->d_stats.release();
         for (cudaEvent_t e : ctx->ev_pool) {

@@ -179,6 +179,10 @@ struct kb200_ctx {
         const void* posmaps_tag = nullptr;   // host array currently mirrored in t_posmaps
         size_t posmaps_n = 0;
         KbArena arena;
+        // pinned host blocks handed to msa objects for their gaps[] result (the 60 MB device-to-host copy at
+        // the end of a C3 alignment runs at PCIe speed only into page-locked memory); kept across calls
+        struct PinnedBlock { void* p; size_t cap; bool used; };
+        std::vector<PinnedBlock> host_pool;
         // device k-means of the guide tree (kb_kmeans.cu): own stream, scratch kept across calls
         cudaStream_t stream2 = nullptr;
         KbDevBuf km_rowsA, km_rowsB, km_ordA, km_ordB, km_side, km_best, km_dmin, km_desc;
@@ -205,6 +209,10 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
 int kb_confidences(kb200_ctx* ctx, int njobs, float* d_conf_out);
 // entries of a job's margin array
 unsigned kb_margin_cap(int len_a);
+
+// page-locked host block of at least `bytes` from the context's pool (nullptr on failure) / give it back
+void* kb_host_take(kb200_ctx* ctx, size_t bytes);
+void kb_host_give(kb200_ctx* ctx, void* p);
 
 // bpm (kb_bpm.cu)
 int kb_bpm_pairs(kb200_ctx* ctx, const uint8_t* d_seqs, const int64_t* d_offs, const int* d_lens,

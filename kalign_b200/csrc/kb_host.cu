@@ -99,6 +99,43 @@ int KbSeqs::upload(kb200_ctx* ctx, const uint8_t* seqs, const int64_t* offs, con
         return KB200_OK;
 }
 
+void* kb_host_take(kb200_ctx* ctx, size_t bytes)
+{
+        int best = -1;
+        for (size_t i = 0; i < ctx->host_pool.size(); i++) {
+                const kb200_ctx::PinnedBlock& b = ctx->host_pool[i];
+                if (!b.used && b.cap >= bytes && (best < 0 || b.cap < ctx->host_pool[(size_t)best].cap)) best = (int)i;
+        }
+        if (best >= 0) {
+                ctx->host_pool[(size_t)best].used = true;
+                return ctx->host_pool[(size_t)best].p;
+        }
+        // replace a free block that is too small instead of accumulating them
+        for (size_t i = 0; i < ctx->host_pool.size(); i++) {
+                if (!ctx->host_pool[i].used) {
+                        cudaFreeHost(ctx->host_pool[i].p);
+                        ctx->host_pool.erase(ctx->host_pool.begin() + (long)i);
+                        break;
+                }
+        }
+        void* p = nullptr;
+        const size_t want = bytes + bytes / 8 + 4096;
+        if (cudaMallocHost(&p, want) != cudaSuccess) {
+                cudaGetLastError();
+                fprintf(stderr, "[kalign_b200] cudaMallocHost(%zu) failed\n", want);
+                return nullptr;
+        }
+        ctx->host_pool.push_back({p, want, true});
+        return p;
+}
+
+void kb_host_give(kb200_ctx* ctx, void* p)
+{
+        for (kb200_ctx::PinnedBlock& b : ctx->host_pool) {
+                if (b.p == p) b.used = false;
+        }
+}
+
 float* KbArena::alloc_floats(size_t n)
 {
         const size_t bytes = (n * sizeof(float) + 255) & ~(size_t)255;

@@ -546,7 +546,7 @@ struct kb200_msa {
         std::vector<int> abc;
         std::vector<float> seq_distances;
         std::vector<int> posmaps;
-        std::vector<int> gaps;
+        int* gaps = nullptr;             // total + N ints, page-locked (kb_host_take)
         std::vector<int> anchor_ids;
         kb200_params prm;
         int K = 0;
@@ -605,6 +605,7 @@ void kb200_msa_free(kb200_msa* M)
         if (M->ctx) cudaSetDevice(M->ctx->device);
         M->S.release();
         M->S_tree.release();
+        if (M->gaps && M->ctx) kb_host_give(M->ctx, M->gaps);
         delete M->tree_job;
         delete M;
 }
@@ -709,7 +710,12 @@ static int msa_create_impl(kb200_ctx* ctx, char** seq, int* len, int numseq, int
         }
         M->total = total;
         M->codes.resize((size_t)total + 16);
-        M->gaps.assign((size_t)total + (size_t)N, 0);
+        M->gaps = (int*)kb_host_take(ctx, sizeof(int) * ((size_t)total + (size_t)N));
+        if (!M->gaps) {
+                delete M;
+                return KB200_FAIL;
+        }
+        memset(M->gaps, 0, sizeof(int) * ((size_t)total + (size_t)N));
         encode_seqs(M, biotype == 1 ? ALPHA_DNA : ALPHA_RED, n_threads);
         const double tc1 = kb_now();
         int rc = KB200_OK;
@@ -794,7 +800,7 @@ static int msa_align_anchor(kb200_msa* M)
 static int msa_align_tree(kb200_msa* M)
 {
         KB_RUN(kb_align_tree_dev(M->ctx, &M->prm, M->S, M->abc.data(), M->N - 1, M->seq_distances.data(),
-                                 M->K > 0 ? M->posmaps.data() : nullptr, M->K, M->weight, M->n_threads, M->gaps.data(), 1));
+                                 M->K > 0 ? M->posmaps.data() : nullptr, M->K, M->weight, M->n_threads, M->gaps, 1));
         M->aligned = true;
         return KB200_OK;
 }
@@ -824,7 +830,7 @@ int kb200_msa_result(kb200_msa* M, char*** aligned, int* out_aln_len)
         const int N = M->N;
         int aln_len = M->lens[0];
         {
-                const int* g = M->gaps.data() + M->offs[0] + 0;
+                const int* g = M->gaps + M->offs[0] + 0;
                 for (int j = 0; j <= M->lens[0]; j++) aln_len += g[j];
         }
         std::vector<int> by_rank((size_t)N);
@@ -838,7 +844,7 @@ int kb200_msa_result(kb200_msa* M, char*** aligned, int* out_aln_len)
 #endif
         for (int r = 0; r < N; r++) {
                 const int i = by_rank[(size_t)r];
-                const int* g = M->gaps.data() + M->offs[(size_t)i] + i;
+                const int* g = M->gaps + M->offs[(size_t)i] + i;
                 char* row = (char*)malloc((size_t)aln_len + 1);
                 if (!row) {
                         oom = true;

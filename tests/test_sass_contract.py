@@ -41,3 +41,17 @@ def test_no_packed_fma_anywhere_in_dp():
     for name, body in funcs.items():
         if "kb_dp_cu" in name or "kb_small_kernel" in name:
             assert "FFMA2" not in body, "packed fused multiply-add in " + name
+
+
+def test_profile_column_records_are_staged_by_bulk_async_copies():
+    """north star: "TMA-staged profile columns in shared memory".  The 5-letter profile-profile strips
+    stage their packed column records with cp.async.bulk (the TMA engine's linear form: one elected lane
+    per 16-column block) signalled on an mbarrier -- UBLKCP / SYNCS.ARRIVE.TRANS64 / a phase-checking
+    wait must be in the SASS of every sweep kernel family."""
+    funcs = _functions()
+    sweeps = {n: b for n, b in funcs.items() if "kb_sweep_kernel" in n}
+    assert len(sweeps) == 3
+    for name, body in sweeps.items():
+        assert "UBLKCP" in body, name
+        assert "SYNCS.ARRIVE.TRANS64" in body, name
+        assert "SYNCS.PHASECHK.TRANS64.TRYWAIT" in body, name
