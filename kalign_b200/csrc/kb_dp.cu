@@ -583,8 +583,10 @@ __device__ void small_box_run(const KbJob& J, const KbBox& root, const float* __
         }
 }
 
-template <int MAXC, int BONUS>
-__global__ void __launch_bounds__(128, 4)
+// ONLY_SS: every job of the batch is sequence-sequence (the anchor batch, tree level 1): the kernel
+// carries no profile code
+template <int MAXC, int BONUS, bool ONLY_SS, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 kb_small_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes, const unsigned* __restrict__ nsmall_p,
                 const unsigned box_cap, KbDevStats* __restrict__ dstats, const float* __restrict__ tbl, const int tstride)
 {
@@ -605,10 +607,14 @@ kb_small_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes,
                 const KbJob J = jobs[bx.job];
                 unsigned long long nc = 0;
                 unsigned err = 0;
-                if (J.kind == KB200_KIND_SS) small_box_run<V_SS, MAXC, BONUS>(J, bx, s_tbl, tstride, nc, err);
-                else if (J.kind == KB200_KIND_SP) small_box_run<V_SP, MAXC, BONUS>(J, bx, s_tbl, tstride, nc, err);
-                else if (J.nalpha <= 5) small_box_run<V_PP5, MAXC, BONUS>(J, bx, s_tbl, tstride, nc, err);
-                else small_box_run<V_PP23, MAXC, BONUS>(J, bx, s_tbl, tstride, nc, err);
+                if constexpr (ONLY_SS) {
+                        small_box_run<V_SS, MAXC, BONUS>(J, bx, s_tbl, tstride, nc, err);
+                } else {
+                        if (J.kind == KB200_KIND_SS) small_box_run<V_SS, MAXC, BONUS>(J, bx, s_tbl, tstride, nc, err);
+                        else if (J.kind == KB200_KIND_SP) small_box_run<V_SP, MAXC, BONUS>(J, bx, s_tbl, tstride, nc, err);
+                        else if (J.nalpha <= 5) small_box_run<V_PP5, MAXC, BONUS>(J, bx, s_tbl, tstride, nc, err);
+                        else small_box_run<V_PP23, MAXC, BONUS>(J, bx, s_tbl, tstride, nc, err);
+                }
                 atomicAdd(cells + 4 + J.kind, nc);
                 if (J.bonus || J.bkey) {
                         atomicAdd(cells + 3, nc);
@@ -1089,20 +1095,33 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
         {
                 // every box that became small during the rounds: finish its recursion in one launch
                 const int span = kb_span_begin(ctx, KB_SPAN_SMALL);
+                // 4 CTAs per SM (fewer were measured slower: 50 / 57 / 63 / 85 ms at 4 / 3 / 2 / 1 on C3)
                 const int sgrid = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->sm_count * 4, (box_cap + 127) / 128));
                 const KbJob* dj = ctx->d_jobs.as<KbJob>();
                 const float* dt = ctx->d_tbl.as<float>();
                 const unsigned bc = (unsigned)box_cap;
                 const int fam = batch_dense ? BONUS_DENSE : (batch_bonus ? BONUS_SPARSE : BONUS_NONE);
-                if (small_cols <= SMALL_COLS) {
-                        if (fam == BONUS_DENSE) kb_small_kernel<SMALL_COLS, BONUS_DENSE><<<sgrid, 128, 0, st>>>(dj, d_small, d_nsmall, bc, d_stats, dt, tstride);
-                        else if (fam == BONUS_SPARSE) kb_small_kernel<SMALL_COLS, BONUS_SPARSE><<<sgrid, 128, 0, st>>>(dj, d_small, d_nsmall, bc, d_stats, dt, tstride);
-                        else kb_small_kernel<SMALL_COLS, BONUS_NONE><<<sgrid, 128, 0, st>>>(dj, d_small, d_nsmall, bc, d_stats, dt, tstride);
-                } else {
-                        if (fam == BONUS_DENSE) kb_small_kernel<SMALL_COLS_MAX, BONUS_DENSE><<<sgrid, 128, 0, st>>>(dj, d_small, d_nsmall, bc, d_stats, dt, tstride);
-                        else if (fam == BONUS_SPARSE) kb_small_kernel<SMALL_COLS_MAX, BONUS_SPARSE><<<sgrid, 128, 0, st>>>(dj, d_small, d_nsmall, bc, d_stats, dt, tstride);
-                        else kb_small_kernel<SMALL_COLS_MAX, BONUS_NONE><<<sgrid, 128, 0, st>>>(dj, d_small, d_nsmall, bc, d_stats, dt, tstride);
+                bool only_ss = true;
+                for (int i = 0; i < n; i++) {
+                        if (jobs[i].kind != KB200_KIND_SS) { only_ss = false; break; }
                 }
+                // (6 or 8 CTAs per SM for the all-seq-seq variant were measured: no gain -- the kernel is bound by its
+                //  instruction count and divergence, not by occupancy or DRAM; profiles/r02_small_kernel_full_C3.csv)
+#define KB_SMALL_LAUNCH(MC, FAM) \
+        do { \
+                if (only_ss) kb_small_kernel<MC, FAM, true, 4><<<sgrid, 128, 0, st>>>(dj, d_small, d_nsmall, bc, d_stats, dt, tstride); \
+                else kb_small_kernel<MC, FAM, false, 4><<<sgrid, 128, 0, st>>>(dj, d_small, d_nsmall, bc, d_stats, dt, tstride); \
+        } while (0)
+                if (small_cols <= SMALL_COLS) {
+                        if (fam == BONUS_DENSE) KB_SMALL_LAUNCH(SMALL_COLS, BONUS_DENSE);
+                        else if (fam == BONUS_SPARSE) KB_SMALL_LAUNCH(SMALL_COLS, BONUS_SPARSE);
+                        else KB_SMALL_LAUNCH(SMALL_COLS, BONUS_NONE);
+                } else {
+                        if (fam == BONUS_DENSE) KB_SMALL_LAUNCH(SMALL_COLS_MAX, BONUS_DENSE);
+                        else if (fam == BONUS_SPARSE) KB_SMALL_LAUNCH(SMALL_COLS_MAX, BONUS_SPARSE);
+                        else KB_SMALL_LAUNCH(SMALL_COLS_MAX, BONUS_NONE);
+                }
+#undef KB_SMALL_LAUNCH
                 KB_CUDA(cudaGetLastError());
                 kb_span_end(ctx, span);
                 ctx->stats.n_launches += 2;
