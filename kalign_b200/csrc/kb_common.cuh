@@ -123,6 +123,9 @@ struct KbRound {
         unsigned nunits;        // plan kernel -> sweep kernel
         unsigned nboxes;        // boxes of this round (written by the meet-up of the previous one)
         unsigned thin;          // plan kernel -> sweep kernel: thin (32-row) strips this round
+        unsigned maxrows;       // plan kernel -> sweep kernel: most rows any sweep of this round has
+        unsigned kinds;         // plan kernel -> sweep kernel: bit k set = the round has a box of job kind k
+        unsigned pad0, pad1;
 };
 constexpr int KB_MAX_ROUNDS = 48;
 

@@ -59,6 +59,8 @@ __global__ void kb_plan_kernel(const KbJob* __restrict__ jobs, const KbBox* __re
         for (long long base = (long long)blockIdx.x * blockDim.x + (threadIdx.x - lane); base < items; base += nth) {
                 const long long item = base + lane;
                 int nstr = 0;
+                int myrows = 0;
+                unsigned mykind = 0u;
                 if (item < items) {
                         const KbBox bx = boxes[item >> 1];
                         const int bwd = (int)(item & 1);
@@ -67,6 +69,17 @@ __global__ void kb_plan_kernel(const KbJob* __restrict__ jobs, const KbBox* __re
                         const int rps = rows_per_strip(jobs[bx.job].kind, jobs[bx.job].nalpha, thin, batch_bonus != 0);
                         nstr = (R + rps - 1) / rps;
                         if (nstr < 1) nstr = 1;
+                        myrows = R;
+                        mykind = 1u << jobs[bx.job].kind;
+                }
+                // what the sweep kernel needs to choose sub-warp groups for a round of small boxes
+                {
+                        const unsigned wr = __reduce_max_sync(FULL, (unsigned)myrows);
+                        const unsigned wk = __reduce_or_sync(FULL, mykind);
+                        if (lane == 0) {
+                                atomicMax(&rnd->maxrows, wr);
+                                atomicOr(&rnd->kinds, wk);
+                        }
                 }
                 // warp-inclusive scan of nstr
                 int incl = nstr;
@@ -990,6 +1003,18 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
                         if (jobs[i].kind != KB200_KIND_SS && jobs[i].nalpha > 5) { rows_cap = 64; break; }
                 }
                 if (const char* e = getenv("KB200_SMALL_ROWS_PROF")) rows_cap = std::min(std::max(atoi(e), SMALL_ROWS), SMALL_ROWS_MAX);
+                // all-seq-seq batches without bonus (anchor batch, --fast level 1): rounds of small boxes run as
+                // sub-warp groups (sweep_group), which beat the thread-per-box kernel down to ~64-row boxes
+                {
+                        bool all_ss_plain = true;
+                        for (int i = 0; i < n; i++) {
+                                if (jobs[i].kind != KB200_KIND_SS || jobs[i].bonus || jobs[i].bkey) { all_ss_plain = false; break; }
+                        }
+                        if (all_ss_plain) {
+                                rows_cap = 64;        // measured on C3: 128 -> 390, 64 -> 379, 32 -> 382, 16 -> 391 ms per step
+                                if (const char* e = getenv("KB200_SMALL_ROWS_SS")) rows_cap = std::min(std::max(atoi(e), SMALL_ROWS), SMALL_ROWS_MAX);
+                        }
+                }
                 while (small_rows * 2 <= rows_cap && rows_total / (size_t)(small_rows * 2) >= want) {
                         small_rows *= 2;
                 }

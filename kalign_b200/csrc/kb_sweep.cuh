@@ -1078,6 +1078,156 @@ __device__ void sweep_unit(const KbJob& J, const KbBox& bx, const int bwd, const
 #undef KB_STRIP
 }
 
+// ---- sub-warp groups for rounds of small seq-seq boxes -------------------------------------------
+// A sweep of R <= 128 rows leaves most of a 32-lane strip idle (R = 46: two rows per lane at 72 %
+// lane use, 32 fill/drain steps on ~190 columns).  In such rounds a warp is cut into groups of W = 8
+// or 16 lanes; every group sweeps its OWN (box, direction) as a single strip -- W x K rows, K the
+// smallest of {2,3,4,6,8} that covers the warp's tallest sweep -- with a skew of only W columns.  No
+// hand-off: the init row is generated, the last lane of the group writes the bottom row for the
+// meet-up.  Same cell routine, same operands, same order as the strips.
+template <int V, int K, int W>
+__device__ void sweep_group(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes, const KbUnit* __restrict__ units,
+                            const unsigned unit, const bool valid, const unsigned out_tag,
+                            const float* __restrict__ s_tbl, const int tstride, const int lane, float4* s_rec)
+{
+        static_assert(is_ss<V>(), "groups sweep sequence-sequence boxes");
+        const int glane = lane & (W - 1);
+        // per-lane view of the group's unit (an invalid group mirrors unit 0 of the launch and computes nothing)
+        const KbUnit un = units[valid ? unit : 0u];
+        const KbBox bx = boxes[un.item >> 1];
+        const int bwd = un.item & 1;
+        const KbJob J = jobs[bx.job];
+        const int mid = (bx.ea - bx.sa) / 2 + bx.sa;
+        const int r0 = bwd ? mid : bx.sa;
+        const int r1 = bwd ? bx.ea : mid;
+        const int sb = bx.sb, eb = bx.eb;
+        const int C = eb - sb;
+        const bool first_term = bwd ? (eb == J.len_b) : (sb == 0);
+        const bool last_term = bwd ? (sb == 0) : (eb == J.len_b);
+        float4* __restrict__ rowbuf = (bwd ? J.rowB : J.rowF) + (bx.sa + bx.sb);
+        Trip in;
+        if (bwd) {
+                in.a = bx.b0a; in.ga = bx.b0ga; in.gb = bx.b0gb;
+        } else {
+                in.a = bx.f0a; in.ga = bx.f0ga; in.gb = bx.f0gb;
+        }
+        RowCtx<V, K> rc;
+        const unsigned vmask = load_rows<V, K>(J, bwd, r0, r1, glane * K, tstride, rc);
+        set_table_addr<V, K>(rc, s_tbl);
+        if constexpr (V == V_SS5) {
+                float* sp = reinterpret_cast<float*>(s_rec) + lane;
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+#pragma unroll
+                        for (int c = 0; c < 5; c++) {
+                                sp[(k * 5 + c) * 32] = s_tbl[rc.rbase[k] + c] + J.nsoff;
+                        }
+                }
+                rc.sprow = sp;
+                __syncwarp();
+        }
+        float sA[K], sGA[K], sGB[K];
+        int sp_i[K], sp_c[K];
+        float sp_v[K], sp_wrap[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+                sA[k] = KB_NEGF; sGA[k] = KB_NEGF; sGB[k] = KB_NEGF;
+                sp_i[k] = 0; sp_c[k] = 0; sp_v[k] = 0.0f; sp_wrap[k] = 0.0f;
+        }
+        Trip d = {KB_NEGF, KB_NEGF, KB_NEGF};
+        Trip bot = {KB_NEGF, KB_NEGF, KB_NEGF};
+        float genA = in.a, genGA = in.ga;
+        const int dstep = bwd ? -1 : 1;
+        int jcur = bwd ? (eb + glane) : (sb - glane);
+        const long long pr_first = bwd ? (long long)(eb - (1 - glane)) : (long long)(sb + (1 - glane)) - 1;
+        const uint8_t* seqp = J.seq_c + pr_first;
+        int cur_cres = 0;
+        // the warp runs the steps of its longest group; steps in which every lane of every valid group
+        // sits on an interior column take the cheaper interior-column routine
+        const int cmax = (int)__reduce_max_sync(FULL, (unsigned)(valid ? C : 0));
+        const int cmin = (int)__reduce_min_sync(FULL, (unsigned)(valid ? C : 0x7fffffff));
+        const int steps = cmax + W;
+        ColCtx<V> cc;
+        cc.CO = J.o; cc.CE = J.e; cc.COp = J.o;
+        const float CT = J.t;
+        auto step = [&](auto steady_tag, const int t) {
+                constexpr bool STEADY = decltype(steady_tag)::value;
+                const int u = t - glane;
+                Trip up;
+                up.a = __shfl_up_sync(FULL, bot.a, 1, W);
+                up.ga = __shfl_up_sync(FULL, bot.ga, 1, W);
+                up.gb = __shfl_up_sync(FULL, bot.gb, 1, W);
+                const bool act = valid && (STEADY || ((u >= 0) && (u <= C)));
+                int ncres = 0;
+                {
+                        const int pu = u + 1;
+                        if (valid && (STEADY || (pu >= 1 && pu <= C))) {
+                                ncres = (int)__ldg(seqp);
+                        }
+                }
+                if (act) {
+                        cc.jcol = jcur;
+                        cc.cres = cur_cres;
+                        if (glane == 0) {
+                                // the init row (aln_seqseq.c:43-58), one column per step
+                                if (!STEADY && u == 0) {
+                                        up = in;
+                                } else if (STEADY || u < C) {
+                                        const float nga = first_term ? (kmax(genGA, genA) + CT) : kmax(genGA + cc.CE, genA + cc.CO);
+                                        up.a = KB_NEGF; up.ga = nga; up.gb = KB_NEGF;
+                                        genA = KB_NEGF; genGA = nga;
+                                } else {
+                                        up.a = KB_NEGF; up.ga = KB_NEGF; up.gb = KB_NEGF;
+                                }
+                        }
+                        const Trip got = up;
+                        if constexpr (STEADY) {
+                                cells<V, K, true, MODE_MID, BONUS_NONE, true>(J, rc, vmask, first_term, last_term, cc, dstep, sp_i, sp_c, sp_v, sp_wrap, nullptr, s_tbl, sA, sGA, sGB, d, up);
+                        } else {
+                                cells<V, K, true, MODE_EDGE, BONUS_NONE, true>(J, rc, vmask, first_term, last_term, cc, dstep, sp_i, sp_c, sp_v, sp_wrap, nullptr, s_tbl, sA, sGA, sGB, d, up, u == 0, u == C);
+                        }
+                        d = got;
+                        bot = up;
+                        if (glane == W - 1) {
+                                rowbuf[u] = make_float4(bot.a, bot.ga, bot.gb, __uint_as_float(out_tag));
+                        }
+                }
+                cur_cres = ncres;
+                jcur += dstep;
+                seqp += dstep;
+        };
+        int t = 0;
+        const int t_fill = (steps < W) ? steps : W;
+        for (; t < t_fill; t++) step(std::false_type{}, t);
+        // W <= t <= cmin - 1: every lane of every valid group has 1 <= u <= C - 1
+        for (; t + 2 <= cmin; t += 2) {
+                step(std::true_type{}, t);
+                step(std::true_type{}, t + 1);
+        }
+        for (; t < steps; t++) step(std::false_type{}, t);
+        __syncwarp();
+}
+
+template <int V, int W>
+__device__ __forceinline__ void sweep_group_k(const int kneed, const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes,
+                                              const KbUnit* __restrict__ units, const unsigned unit, const bool valid, const unsigned out_tag,
+                                              const float* __restrict__ s_tbl, const int tstride, const int lane, float4* s_rec)
+{
+#define KB_GROUP(KK) sweep_group<V, KK, W>(jobs, boxes, units, unit, valid, out_tag, s_tbl, tstride, lane, s_rec)
+        if constexpr (W == 16) {
+                // 64 < rows <= 128
+                if (kneed <= 6) KB_GROUP(6); else KB_GROUP(8);
+        } else {
+                if (kneed <= 2) KB_GROUP(2);
+                else if (kneed == 3) KB_GROUP(3);
+                else if (kneed == 4) KB_GROUP(4);
+                else if (kneed <= 6) KB_GROUP(6);
+                else KB_GROUP(8);
+        }
+#undef KB_GROUP
+}
+
 // BONUS is a kernel-level template parameter: a batch either carries consistency bonuses for all
 // of its jobs (tree levels in default mode) or for none (anchor batch, --fast), and the two
 // families get independent register allocation / code size.
@@ -1124,6 +1274,45 @@ kb_sweep_kernel(const KbJob* __restrict__ jobs, const KbBox* __restrict__ boxes,
         float4* s_ring = s_ring_all[threadIdx.x >> 5];
         float4* s_rec = s_rec_all[threadIdx.x >> 5];
         int2* s_bon = (BONUS == BONUS_SPARSE) ? (s_bon_all + (threadIdx.x >> 5) * (BON_QSLOTS * 32)) : s_bon_all;
+        if constexpr (BONUS == BONUS_NONE) {
+                // rounds of small sequence-sequence boxes: sub-warp groups (sweep_group above).  Every box
+                // of such a round is a single strip (maxrows <= 128 < rows per strip), so a unit IS a sweep.
+                const unsigned maxrows = rnd->maxrows;
+                if (!thin && rnd->kinds == (1u << KB200_KIND_SS) && maxrows <= 128u && maxrows >= 1u) {
+                        const int W = (maxrows <= 64u) ? 8 : 16;
+                        const unsigned G = 32u / (unsigned)W;
+                        while (true) {
+                                unsigned base = 0;
+                                if (lane == 0) {
+                                        base = atomicAdd(cursor, G);
+                                }
+                                base = __shfl_sync(FULL, base, 0);
+                                if (base >= total) {
+                                        break;
+                                }
+                                const unsigned unit = base + (unsigned)(lane / W);
+                                const bool valid = unit < total;
+                                // rows of my group's sweep -> rows per lane the warp needs
+                                int R = 0;
+                                if (valid) {
+                                        const KbUnit un = units[unit];
+                                        const KbBox bx = boxes[un.item >> 1];
+                                        const int mid = (bx.ea - bx.sa) / 2 + bx.sa;
+                                        R = (un.item & 1) ? (bx.ea - mid) : (mid - bx.sa);
+                                }
+                                const int kneed = (int)__reduce_max_sync(FULL, (unsigned)((R + W - 1) / W));
+                                const unsigned tag = tag_base + 1u;
+                                if (W == 8) {
+                                        if (tstride == 5) sweep_group_k<V_SS5, 8>(kneed, jobs, boxes, units, unit, valid, tag, s_tbl, tstride, lane, s_rec);
+                                        else sweep_group_k<V_SS, 8>(kneed, jobs, boxes, units, unit, valid, tag, s_tbl, tstride, lane, s_rec);
+                                } else {
+                                        if (tstride == 5) sweep_group_k<V_SS5, 16>(kneed, jobs, boxes, units, unit, valid, tag, s_tbl, tstride, lane, s_rec);
+                                        else sweep_group_k<V_SS, 16>(kneed, jobs, boxes, units, unit, valid, tag, s_tbl, tstride, lane, s_rec);
+                                }
+                        }
+                        return;
+                }
+        }
         while (true) {
                 unsigned unit = 0;
                 if (lane == 0) {
