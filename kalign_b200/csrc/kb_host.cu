@@ -225,9 +225,12 @@ int kb_distances_dev(kb200_ctx* ctx, KbSeqs& S, const int* rows, int nrows, cons
                 KB_RUN(kb_bpm_pairs_words(ctx, words, S.d_seqs.as<uint8_t>(), S.d_offs.as<int64_t>(), S.d_lens.as<int>(),
                                           d_rows, nrows, d_cols, explicit_pairs ? 0 : ncols, ctx->d_stage5.as<float>()));
         }
-        KB_CUDA(cudaMemcpyAsync(dm_host, ctx->d_stage5.p, sizeof(float) * npairs, cudaMemcpyDeviceToHost, ctx->stream));
+        if (dm_host) {
+                KB_CUDA(cudaMemcpyAsync(dm_host, ctx->d_stage5.p, sizeof(float) * npairs, cudaMemcpyDeviceToHost, ctx->stream));
+                ctx->stats.d2h_bytes += (double)(sizeof(float) * npairs);
+        }
+        // dm_host == nullptr: the distances stay in ctx->d_stage5 for a consumer on the device (UPGMA)
         KB_CUDA(cudaStreamSynchronize(ctx->stream));
-        ctx->stats.d2h_bytes += (double)(sizeof(float) * npairs);
         return KB200_OK;
 }
 

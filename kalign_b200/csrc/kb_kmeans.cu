@@ -304,6 +304,70 @@ kb_kmeans_partition_kernel(const KmPart* __restrict__ parts, const unsigned char
         }
 }
 
+// UPGMA of the leaf clusters (upgma, bisectingKmeans.c:974-1053), one warp per cluster (n < 50):
+// the n x n matrix lives in shared memory; every step finds the first minimum of the active upper
+// triangle in row-major scan order (strict <, so ties go to the smallest i*n+j), records the merge and
+// averages row / column node_a exactly as the reference does ((x + y) * 0.5F + 0.001F, two roundings).
+// pd: distances of the cluster's pairs (i < j, row-major), as the batched bpm launch wrote them.
+constexpr int UPGMA_MAXN = 50;
+__global__ void __launch_bounds__(32)
+kb_upgma_kernel(const float* __restrict__ pd, const long long* __restrict__ pair0, const int* __restrict__ csize,
+                const long long* __restrict__ merge0, const int ncl, int2* __restrict__ merges)
+{
+        __shared__ float dm[UPGMA_MAXN * UPGMA_MAXN];
+        const int c = blockIdx.x;
+        if (c >= ncl) return;
+        const int lane = threadIdx.x;
+        const int n = csize[c];
+        const float* __restrict__ src = pd + pair0[c];
+        for (int x = lane; x < n * n; x += 32) {
+                const int i = x / n, j = x % n;
+                float v = 0.0f;
+                if (i != j) {
+                        const int a = (i < j) ? i : j, b = (i < j) ? j : i;
+                        v = src[(long long)a * n - (long long)a * (a + 1) / 2 + (b - a - 1)];
+                }
+                dm[x] = v;
+        }
+        __syncwarp();
+        unsigned long long active = (n >= 64) ? ~0ull : ((1ull << n) - 1ull);
+        int2* __restrict__ out = merges + merge0[c];
+        for (int step = 0; step < n - 1; step++) {
+                float best = FLT_MAX;
+                int bidx = 0x7fffffff;
+                for (int x = lane; x < n * n; x += 32) {
+                        const int i = x / n, j = x % n;
+                        if (i < j && ((active >> i) & 1ull) && ((active >> j) & 1ull)) {
+                                const float v = dm[x];
+                                if (v < best) { best = v; bidx = x; }       // ascending x per lane: first minimum kept
+                        }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+                        if (ov < best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+                }
+                // the reference keeps node_a / node_b of the previous step when nothing is below FLT_MAX; with
+                // finite distances there always is a minimum
+                const int na = bidx / n, nb = bidx % n;
+                if (lane == 0) out[step] = make_int2(na, nb);
+                for (int j = lane; j < n; j += 32) {
+                        if (j != nb) {
+                                dm[na * n + j] = __fadd_rn(__fmul_rn(__fadd_rn(dm[na * n + j], dm[nb * n + j]), 0.5F), 0.001F);
+                        }
+                }
+                __syncwarp();
+                if (lane == 0) dm[na * n + na] = 0.0F;
+                __syncwarp();
+                for (int j = lane; j < n; j += 32) {
+                        dm[j * n + na] = dm[na * n + j];
+                }
+                __syncwarp();
+                active &= ~(1ull << nb);
+        }
+}
+
 struct HCluster {
         int begin, end;
         int node;              // index in the builder's node vector
@@ -316,6 +380,39 @@ struct HCluster {
 };
 
 } // namespace
+
+// UPGMA of all leaf clusters in one launch.  d_pd: the pair distances on the device (cluster after
+// cluster, i < j row-major); csize / pair0 / merge0 per cluster (host); merges_out: sum (n-1) int2.
+int kb_upgma_dev(kb200_ctx* ctx, const float* d_pd, const std::vector<int>& csize, const std::vector<long long>& pair0,
+                 const std::vector<long long>& merge0, long long nmerges, int* merges_out)
+{
+        const int ncl = (int)csize.size();
+        if (ncl == 0 || nmerges == 0) return KB200_OK;
+        for (int n : csize) {
+                if (n >= UPGMA_MAXN) {
+                        fprintf(stderr, "[kalign_b200] UPGMA: cluster of %d sequences (max %d)\n", n, UPGMA_MAXN - 1);
+                        return KB200_FAIL;
+                }
+        }
+        cudaStream_t st = ctx->stream;
+        const size_t bytes = sizeof(int) * (size_t)ncl + sizeof(long long) * 2 * (size_t)ncl + 64;
+        KB_RUN(ctx->km_desc.ensure(bytes + sizeof(int2) * (size_t)nmerges + 64));
+        char* base = ctx->km_desc.as<char>();
+        long long* d_pair0 = (long long*)base;
+        long long* d_merge0 = d_pair0 + ncl;
+        int* d_csize = (int*)(d_merge0 + ncl);
+        int2* d_merges = (int2*)(base + ((bytes + 15) & ~(size_t)15));
+        KB_RUN(kb_h2d(ctx, d_pair0, pair0.data(), sizeof(long long) * (size_t)ncl));
+        KB_RUN(kb_h2d(ctx, d_merge0, merge0.data(), sizeof(long long) * (size_t)ncl));
+        KB_RUN(kb_h2d(ctx, d_csize, csize.data(), sizeof(int) * (size_t)ncl));
+        kb_upgma_kernel<<<ncl, 32, 0, st>>>(d_pd, d_pair0, d_csize, d_merge0, ncl, d_merges);
+        KB_CUDA(cudaGetLastError());
+        ctx->stats.n_launches++;
+        KB_CUDA(cudaMemcpyAsync(merges_out, d_merges, sizeof(int2) * (size_t)nmerges, cudaMemcpyDeviceToHost, st));
+        KB_CUDA(cudaStreamSynchronize(st));
+        ctx->pinned.reset();
+        return KB200_OK;
+}
 
 // Device version of kb_tree_bisect (kb_msa.cu): the k-means tree as plain arrays (KbKmeansTree).
 // dm_host: N x 32 floats.  Uses its own stream, so that it can run beside the anchor batch of the

@@ -14,3 +14,7 @@ struct KbKmeansTree {
 };
 
 int kb_kmeans_bisect_dev(kb200_ctx* ctx, const float* dm_host, int N, KbKmeansTree& out);
+
+// UPGMA of every leaf cluster on the device (kb_upgma_kernel); d_pd = pair distances on the device
+int kb_upgma_dev(kb200_ctx* ctx, const float* d_pd, const std::vector<int>& csize, const std::vector<long long>& pair0,
+                 const std::vector<long long>& merge0, long long nmerges, int* merges_out);

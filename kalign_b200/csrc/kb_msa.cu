@@ -416,9 +416,10 @@ int kb_tree_finish(kb200_ctx* ctx, KbSeqs& S, KbTreeJob& T, int n_threads, std::
                                 }
                         }
                 }
-                std::vector<float> pd(npairs);
+                const bool host_upgma = getenv("KB200_HOST_KMEANS") != nullptr;
+                std::vector<float> pd(host_upgma ? npairs : 0);
                 if (npairs) {
-                        KB_RUN(kb_distances_dev(ctx, S, pa.data(), (int)npairs, pb.data(), 0, 1, pd.data()));
+                        KB_RUN(kb_distances_dev(ctx, S, pa.data(), (int)npairs, pb.data(), 0, 1, host_upgma ? pd.data() : nullptr));
                 }
                 // clusters were recorded in completion order; the result is order independent.
                 // Every cluster gets its node range and its slice of the pair list up front.
@@ -438,6 +439,47 @@ int kb_tree_finish(kb200_ctx* ctx, KbSeqs& S, KbTreeJob& T, int n_threads, std::
                         }
                         B.nodes.resize((size_t)nb);
                 }
+                if (!host_upgma) {
+                        // UPGMA on the device: one warp per cluster, the pair distances never leave the GPU
+                        // (they are still in the distance launch's output buffer); only the merge lists
+                        // (2 ints per internal node) come back, the node bookkeeping of upgma() is replayed here
+                        std::vector<int> csize(ncl);
+                        std::vector<long long> p0(ncl), m0(ncl);
+                        long long nm = 0;
+                        for (size_t ci = 0; ci < ncl; ci++) {
+                                csize[ci] = (int)B.clusters[ci].samples.size();
+                                p0[ci] = (long long)pair0[ci];
+                                m0[ci] = nm;
+                                nm += std::max(0, csize[ci] - 1);
+                        }
+                        std::vector<int> merges((size_t)2 * (size_t)std::max<long long>(nm, 1));
+                        KB_RUN(kb_upgma_dev(ctx, ctx->d_stage5.as<float>(), csize, p0, m0, nm, merges.data()));
+                        for (size_t ci = 0; ci < ncl; ci++) {
+                                const Cluster& c = B.clusters[ci];
+                                const int n = csize[ci];
+                                int next_node = node0[ci];
+                                std::vector<int> tree((size_t)n);
+                                for (int i = 0; i < n; i++) {
+                                        Node nd;
+                                        nd.id = c.samples[(size_t)i];
+                                        tree[(size_t)i] = next_node;
+                                        B.nodes[(size_t)next_node++] = nd;
+                                }
+                                int last_a = 0;
+                                for (int sidx = 0; sidx < n - 1; sidx++) {
+                                        const int a = merges[(size_t)2 * (size_t)(m0[ci] + sidx)];
+                                        const int b = merges[(size_t)2 * (size_t)(m0[ci] + sidx) + 1];
+                                        Node nd;
+                                        nd.left = tree[(size_t)a];
+                                        nd.right = tree[(size_t)b];
+                                        tree[(size_t)a] = next_node;
+                                        B.nodes[(size_t)next_node++] = nd;
+                                        tree[(size_t)b] = -1;
+                                        last_a = a;
+                                }
+                                cluster_root[ci] = tree[(size_t)last_a];
+                        }
+                } else {
 #ifdef _OPENMP
 #pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads > 0 ? n_threads : 1)
 #endif
@@ -455,6 +497,7 @@ int kb_tree_finish(kb200_ctx* ctx, KbSeqs& S, KbTreeJob& T, int n_threads, std::
                                 }
                         }
                         cluster_root[ci] = upgma(B, cdm.data(), c.samples, node0[ci]);
+                }
                 }
                 // splice the UPGMA sub-trees in place of the placeholders
                 for (size_t ci = 0; ci < B.clusters.size(); ci++) {

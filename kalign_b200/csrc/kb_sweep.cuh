@@ -491,6 +491,41 @@ __device__ __forceinline__ void sparse_init(const KbJob& J, const int bwd, const
                 }
                 __syncwarp();
         }
+        if constexpr (!BSM) {
+                // thread-per-box kernel: the lists are read from global memory.  All keys of the K rows are
+                // loaded independently (one latency, not one per probed entry): the lists are sorted, so
+                // the first entry in sweep direction is a count of keys below / up to the bound.
+                int e0[K];
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                        const int* __restrict__ bc = J.bkey + (size_t)rc.irow[k] * (size_t)KS;
+                        int cnt = 0;
+#pragma unroll
+                        for (int x = 0; x < KB_BONUS_KMAX; x++) {
+                                if (x < KS) {
+                                        const int key = __ldg(bc + x);
+                                        cnt += bwd ? ((key <= eb - 1) ? 1 : 0) : ((key < sb + 1) ? 1 : 0);
+                                }
+                        }
+                        e0[k] = bwd ? (cnt - 1) : cnt;
+                }
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                        const int e = e0[k];
+                        if (e >= 0 && e < KS) {
+                                const size_t o = (size_t)rc.irow[k] * (size_t)KS + (size_t)e;
+                                sp_c[k] = __ldg(J.bkey + o);
+                                sp_v[k] = __ldg(J.bval + o);
+                        }
+                        sp_i[k] = e;
+                        if (!bwd && eb == J.len_b && rc.irow[k] + 1 < J.len_a) {
+                                // flat index (i, len_b) of the reference's dense matrix is (i+1, 0)
+                                const size_t o = (size_t)(rc.irow[k] + 1) * (size_t)KS;
+                                if (__ldg(J.bkey + o) == 0) sp_wrap[k] = __ldg(J.bval + o);
+                        }
+                }
+                return;
+        }
 #pragma unroll
         for (int k = 0; k < K; k++) {
                 int e;
