@@ -1020,6 +1020,12 @@ int kb_run_hirschberg(kb200_ctx* ctx, const float* subm_host, std::vector<KbJob>
                 }
                 if (small_rows > SMALL_ROWS) small_cols = std::min(2 * small_rows + small_rows / 2, SMALL_COLS_MAX);
         }
+        // few boxes (top of the guide tree: a handful of big profile pairs per GPU): a single thread finishing
+        // a 16 x 48 box is a 0.3 ms serial tail of the level; hand over only boxes of <= 8 rows there
+        if (small_rows == SMALL_ROWS && rows_total / (size_t)SMALL_ROWS < (size_t)ctx->sm_count * 32 && getenv("KB200_THIN_SMALL_OFF") == nullptr) {
+                small_rows = 8;
+                small_cols = 24;
+        }
         if (const char* e = getenv("KB200_SMALL_ROWS")) small_rows = std::min(std::max(atoi(e), 1), SMALL_ROWS_MAX);
         if (const char* e = getenv("KB200_SMALL_COLS")) small_cols = std::min(std::max(atoi(e), 4), SMALL_COLS_MAX);
         // KB200_THIN=0|1 forces thick / thin strips (tests run every batch both ways)
