@@ -1,5 +1,7 @@
 #!/bin/bash
+# round-2 final check: full GPU parity suite, smoke(), per-workload trace + bench line
 O=gpurun_out/r2l; mkdir -p $O
+python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke exit $?"; tail -1 $O/smoke.log
 timeout 1500 python -m pytest tests -m gpu -x -q > $O/pytest.log 2>&1; echo "pytest exit $?"; tail -5 $O/pytest.log
 for w in C3 C4 C2; do
   KB200_TRACE=1 timeout 600 python bench.py --workload $w --steps 1 --warmup 1 --no-cpu-baseline > $O/trace_$w.json 2> $O/trace_$w.err
