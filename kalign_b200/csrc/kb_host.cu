@@ -36,42 +36,75 @@ int kb_default_threads()
         return std::max(1, std::min(n, 16));
 }
 
-// smallest pooled buffer that is large enough, else the largest one (ensure() regrows it)
-static void take_pooled(kb200_ctx* ctx, KbDevBuf& b, size_t bytes)
+// smallest pooled buffer that is large enough -- and not absurdly larger, so that a 4 KB request does not
+// walk away with the 60 MB buffer the next request needs.  When nothing fits the pool is left alone and
+// the caller's ensure() allocates: after the first call or two every size a workload uses is in the
+// pool, and no later call pays for cudaMalloc / cudaFree (both synchronise the device; measured stalls of
+// 50-400 ms per call when buffers were re-allocated every time).
+void kb_take_pooled(kb200_ctx* ctx, KbDevBuf& b, size_t bytes)
 {
         if (b.p || ctx->seq_pool.empty()) {
                 return;
         }
-        size_t best = 0;
-        bool fits = false;
+        int best = -1;
         for (size_t i = 0; i < ctx->seq_pool.size(); i++) {
                 const size_t c = ctx->seq_pool[i].cap;
-                const size_t cb = ctx->seq_pool[best].cap;
-                if (c >= bytes) {
-                        if (!fits || c < cb) {
-                                best = i;
-                        }
-                        fits = true;
-                } else if (!fits && c > cb) {
-                        best = i;
+                if (c >= bytes && c <= 4 * bytes + ((size_t)1 << 20) && (best < 0 || c < ctx->seq_pool[(size_t)best].cap)) {
+                        best = (int)i;
                 }
         }
-        b = ctx->seq_pool[best];
+        if (best < 0) {
+                return;
+        }
+        b = ctx->seq_pool[(size_t)best];
         ctx->seq_pool.erase(ctx->seq_pool.begin() + (long)best);
+}
+
+// hand a device buffer back to the context's pool
+void kb_give_pooled(kb200_ctx* ctx, KbDevBuf& b)
+{
+        if (!b.p) {
+                return;
+        }
+        if (ctx && ctx->seq_pool.size() < 64) {
+                ctx->seq_pool.push_back(b);
+                b.p = nullptr;
+                b.cap = 0;
+        } else {
+                b.release();
+        }
 }
 
 void KbSeqs::release()
 {
         KbDevBuf* bufs[3] = {&d_seqs, &d_offs, &d_lens};
         for (KbDevBuf* b : bufs) {
-                if (b->p && owner && owner->seq_pool.size() < 24) {
-                        owner->seq_pool.push_back(*b);
-                        b->p = nullptr;
-                        b->cap = 0;
-                } else {
-                        b->release();
-                }
+                kb_give_pooled(owner, *b);
         }
+}
+
+int KbSeqs::alloc(kb200_ctx* ctx, const int64_t* offs, const int* lens, int nseq)
+{
+        h_seqs = nullptr;
+        h_offs = offs;
+        h_lens = lens;
+        n = nseq;
+        total = 0;
+        for (int i = 0; i < nseq; i++) {
+                total = std::max<int64_t>(total, offs[i] + lens[i]);
+        }
+        owner = ctx;
+        kb_take_pooled(ctx, d_seqs, (size_t)total + 16);
+        kb_take_pooled(ctx, d_offs, sizeof(int64_t) * (size_t)nseq);
+        kb_take_pooled(ctx, d_lens, sizeof(int) * (size_t)nseq);
+        KB_RUN(d_seqs.ensure((size_t)total + 16));
+        KB_RUN(d_offs.ensure(sizeof(int64_t) * (size_t)nseq));
+        KB_RUN(d_lens.ensure(sizeof(int) * (size_t)nseq));
+        KB_CUDA(cudaMemcpyAsync(d_offs.p, offs, sizeof(int64_t) * (size_t)nseq, cudaMemcpyHostToDevice, ctx->stream));
+        KB_CUDA(cudaMemcpyAsync(d_lens.p, lens, sizeof(int) * (size_t)nseq, cudaMemcpyHostToDevice, ctx->stream));
+        KB_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->stats.h2d_bytes += 12.0 * nseq;
+        return KB200_OK;
 }
 
 int KbSeqs::upload(kb200_ctx* ctx, const uint8_t* seqs, const int64_t* offs, const int* lens, int nseq)
@@ -85,9 +118,9 @@ int KbSeqs::upload(kb200_ctx* ctx, const uint8_t* seqs, const int64_t* offs, con
                 total = std::max<int64_t>(total, offs[i] + lens[i]);
         }
         owner = ctx;
-        take_pooled(ctx, d_seqs, (size_t)total + 16);
-        take_pooled(ctx, d_offs, sizeof(int64_t) * (size_t)nseq);
-        take_pooled(ctx, d_lens, sizeof(int) * (size_t)nseq);
+        kb_take_pooled(ctx, d_seqs, (size_t)total + 16);
+        kb_take_pooled(ctx, d_offs, sizeof(int64_t) * (size_t)nseq);
+        kb_take_pooled(ctx, d_lens, sizeof(int) * (size_t)nseq);
         KB_RUN(d_seqs.ensure((size_t)total + 16));
         KB_RUN(d_offs.ensure(sizeof(int64_t) * (size_t)nseq));
         KB_RUN(d_lens.ensure(sizeof(int) * (size_t)nseq));
@@ -110,12 +143,15 @@ void* kb_host_take(kb200_ctx* ctx, size_t bytes)
                 ctx->host_pool[(size_t)best].used = true;
                 return ctx->host_pool[(size_t)best].p;
         }
-        // replace a free block that is too small instead of accumulating them
-        for (size_t i = 0; i < ctx->host_pool.size(); i++) {
-                if (!ctx->host_pool[i].used) {
-                        cudaFreeHost(ctx->host_pool[i].p);
-                        ctx->host_pool.erase(ctx->host_pool.begin() + (long)i);
-                        break;
+        // nothing fits: allocate (cudaFreeHost / cudaMallocHost synchronise the device, so free blocks are only
+        // recycled when the pool has grown unreasonably)
+        if (ctx->host_pool.size() >= 32) {
+                for (size_t i = 0; i < ctx->host_pool.size(); i++) {
+                        if (!ctx->host_pool[i].used) {
+                                cudaFreeHost(ctx->host_pool[i].p);
+                                ctx->host_pool.erase(ctx->host_pool.begin() + (long)i);
+                                break;
+                        }
                 }
         }
         void* p = nullptr;

@@ -15,9 +15,15 @@ struct KbSeqs {
         KbDevBuf d_seqs, d_offs, d_lens;
         kb200_ctx* owner = nullptr;      // buffers go back to owner->seq_pool on release
         int upload(kb200_ctx* ctx, const uint8_t* seqs, const int64_t* offs, const int* lens, int nseq);
+        // device buffers + offsets / lengths only: the codes are written by a kernel (seqs may be nullptr)
+        int alloc(kb200_ctx* ctx, const int64_t* offs, const int* lens, int nseq);
         void release();
         const uint8_t* dseq(int i) const { return d_seqs.as<uint8_t>() + h_offs[i]; }
 };
+
+// smallest pooled device buffer of the context that fits (none: the caller's ensure() allocates) / hand one back
+void kb_take_pooled(kb200_ctx* ctx, KbDevBuf& b, size_t bytes);
+void kb_give_pooled(kb200_ctx* ctx, KbDevBuf& b);
 
 // d_estimation replacement on device-resident sequences.
 // explicit == 0: rows x cols rectangle; explicit == 1: nrows pairs (rows[p], cols[p]).

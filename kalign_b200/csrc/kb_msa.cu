@@ -567,6 +567,58 @@ int kb_build_tree(kb200_ctx* ctx, KbSeqs& S, int n_threads, std::vector<int>& ab
 
 
 // ---------------------------------------------------------------------------------------------
+// encode / finalise on the device: the raw characters are uploaded ONCE (sorted order,
+// concatenated); convert_msa_to_internal (lib/src/msa_op.c:344-375) is a table look-up kernel -- run twice
+// for proteins (13-letter tree alphabet, then the 23-letter alignment alphabet) without touching the host --
+// and finalise_alignment (lib/src/msa_op.c:546-598) a scatter: residue p of a sequence lands in column
+// colof[p] = p + sum_{q<=p} gaps[q] of its row, everything else is '-'.
+namespace {
+
+struct KbLut { int8_t t[128]; };
+
+__global__ void kb_encode_kernel(const uint8_t* __restrict__ raw, const long long total, const KbLut lut,
+                                 uint8_t* __restrict__ codes, unsigned* __restrict__ unknown)
+{
+        const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        const long long nth = (long long)gridDim.x * blockDim.x;
+        unsigned bad = 0;
+        for (long long i = gid; i < total; i += nth) {
+                const unsigned ch = raw[i];
+                const int t = (ch < 128u) ? (int)lut.t[ch] : -1;
+                if (t < 0) bad = ch ? ch : 1u;
+                codes[i] = (uint8_t)((t < 0) ? 0 : t);     // unknown characters are coded as 0 (msa_op.c:358-362)
+        }
+        if (bad) atomicMax(unknown, bad);
+}
+
+__global__ void kb_finalise_kernel(const uint8_t* __restrict__ raw, const int64_t* __restrict__ offs, const int* __restrict__ lens,
+                                   const int* __restrict__ rank, const int nseq, const int* __restrict__ colof,
+                                   const long long stride, char* __restrict__ rows)
+{
+        // one warp per sequence; the rows were filled with '-' (and NUL terminators) before
+        const int lane = threadIdx.x & 31;
+        const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        if (i >= nseq) return;
+        const long long off = offs[i];
+        char* __restrict__ row = rows + (long long)rank[i] * stride;
+        for (int p = lane; p < lens[i]; p += 32) {
+                row[colof[off + p]] = (char)raw[off + p];
+        }
+}
+
+__global__ void kb_fill_rows_kernel(char* __restrict__ rows, const long long stride, const int nseq)
+{
+        const long long n = stride * (long long)nseq;
+        const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        const long long nth = (long long)gridDim.x * blockDim.x;
+        for (long long x = gid; x < n; x += nth) {
+                rows[x] = ((x % stride) == stride - 1) ? (char)0 : '-';
+        }
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------
 // staged pipeline object: create (encode, sort, upload, distances, guide tree) -> align (the DP
 // stages on device-resident sequences: anchor batch + progressive alignment) -> result.
 struct kb200_msa {
@@ -578,13 +630,15 @@ struct kb200_msa {
         std::vector<Seq*> order;
         std::vector<int64_t> offs;
         std::vector<int> lens;
-        std::vector<uint8_t> codes;
+        uint8_t* raw = nullptr;          // the input characters, sorted order, concatenated (page-locked)
+        KbDevBuf d_raw, d_rank, d_rows, d_colof;
+        int aln_len = 0;                 // msa->alnlen of the last kb200_msa_align (= plen of the root task)
+        bool gaps_on_host = false;
         int64_t total = 0;
         KbSeqs S;
         // deferred guide tree (kb200_kalign): k-means runs on a host thread beside the anchor batch;
         // proteins keep their 13-letter tree codes on the device for the leaf-cluster distances
         KbTreeJob* tree_job = nullptr;
-        std::vector<uint8_t> codes_tree;
         KbSeqs S_tree;
         std::vector<int> abc;
         std::vector<float> seq_distances;
@@ -598,30 +652,30 @@ struct kb200_msa {
         double t_create = 0, t_tree = 0;
 };
 
-static void encode_seqs(kb200_msa* M, int alpha, int n_threads)
+// convert_msa_to_internal on the device: S gets the codes of alphabet `alpha`
+static int encode_seqs_dev(kb200_msa* M, KbSeqs& S, int alpha)
 {
+        kb200_ctx* ctx = M->ctx;
         const Alphabet a = make_alphabet(alpha);
-        bool warned = false;
-#ifdef _OPENMP
-#pragma omp parallel for schedule(static) num_threads(n_threads) firstprivate(warned)
-#endif
-        for (int i = 0; i < M->N; i++) {
-                const char* s = M->order[(size_t)i]->seq;
-                uint8_t* d = M->codes.data() + M->offs[(size_t)i];
-                for (int j = 0; j < M->lens[(size_t)i]; j++) {
-                        const int ch = (int)(unsigned char)s[j];
-                        const int8_t t = (ch < 128) ? a.to_internal[ch] : (int8_t)-1;
-                        if (t == -1) {
-                                if (!warned) {
-                                        fprintf(stderr, "[kalign_b200] warning: character '%c' does not match the alphabet (coded as 0)\n", s[j]);
-                                        warned = true;
-                                }
-                                d[j] = 0;
-                        } else {
-                                d[j] = (uint8_t)t;
-                        }
-                }
+        KbLut lut;
+        for (int i = 0; i < 128; i++) lut.t[i] = a.to_internal[i];
+        if (!S.d_seqs.p) {
+                KB_RUN(S.alloc(ctx, M->offs.data(), M->lens.data(), M->N));
         }
+        KB_RUN(ctx->d_counters.ensure(sizeof(KbRound) * (KB_MAX_ROUNDS + 2) + 64));
+        unsigned* d_flag = ctx->d_counters.as<unsigned>();
+        KB_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(unsigned), ctx->stream));
+        const int grid = (int)std::min<long long>((M->total + 255) / 256 + 1, (long long)ctx->sm_count * 16);
+        kb_encode_kernel<<<grid, 256, 0, ctx->stream>>>(M->d_raw.as<uint8_t>(), (long long)M->total, lut, S.d_seqs.as<uint8_t>(), d_flag);
+        KB_CUDA(cudaGetLastError());
+        ctx->stats.n_launches++;
+        unsigned bad = 0;
+        KB_CUDA(cudaMemcpyAsync(&bad, d_flag, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+        KB_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (bad) {
+                fprintf(stderr, "[kalign_b200] warning: character '%c' does not match the alphabet (coded as 0)\n", (int)bad < 128 ? (char)bad : '?');
+        }
+        return KB200_OK;
 }
 
 extern "C" {
@@ -649,6 +703,14 @@ void kb200_msa_free(kb200_msa* M)
         M->S.release();
         M->S_tree.release();
         if (M->gaps && M->ctx) kb_host_give(M->ctx, M->gaps);
+        if (M->raw && M->ctx) kb_host_give(M->ctx, M->raw);
+        if (M->ctx) {
+                // device buffers go back to the context's pool like the sequence buffers
+                KbDevBuf* bufs[4] = {&M->d_raw, &M->d_rank, &M->d_rows, &M->d_colof};
+                for (KbDevBuf* b : bufs) {
+                        kb_give_pooled(M->ctx, *b);
+                }
+        }
         delete M->tree_job;
         delete M;
 }
@@ -752,40 +814,61 @@ static int msa_create_impl(kb200_ctx* ctx, char** seq, int* len, int numseq, int
                 total += M->order[(size_t)i]->len;
         }
         M->total = total;
-        M->codes.resize((size_t)total + 16);
-        M->gaps = (int*)kb_host_take(ctx, sizeof(int) * ((size_t)total + (size_t)N));
-        if (!M->gaps) {
-                delete M;
+        M->raw = (uint8_t*)kb_host_take(ctx, (size_t)total + 16);
+        if (!M->raw) {
+                kb200_msa_free(M);
                 return KB200_FAIL;
         }
-        memset(M->gaps, 0, sizeof(int) * ((size_t)total + (size_t)N));
-        encode_seqs(M, biotype == 1 ? ALPHA_DNA : ALPHA_RED, n_threads);
+        // the input characters in sorted order, one contiguous page-locked block: uploaded once, encoded
+        // (and later expanded into the aligned rows) on the device
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(n_threads)
+#endif
+        for (int i = 0; i < N; i++) {
+                memcpy(M->raw + M->offs[(size_t)i], M->order[(size_t)i]->seq, (size_t)M->lens[(size_t)i]);
+        }
         const double tc1 = kb_now();
         int rc = KB200_OK;
         double tc2 = tc1;
-        if (!defer_tree) {
-                rc = M->S.upload(ctx, M->codes.data(), M->offs.data(), M->lens.data(), N);
+        {
+                // pooled device buffer for the raw characters and the rank table
+                kb_take_pooled(ctx, M->d_raw, (size_t)total + 16);
+                kb_take_pooled(ctx, M->d_rank, sizeof(int) * (size_t)N + 16);
+                rc = M->d_raw.ensure((size_t)total + 16);
+                if (rc == KB200_OK) rc = M->d_rank.ensure(sizeof(int) * (size_t)N + 16);
+                // output row of sorted sequence i: its position among the kept sequences in input order
+                // (msa_sort_rank + kalign_msa_to_arr; empty input sequences were dropped)
+                std::vector<int> by_rank((size_t)N), rank((size_t)N);
+                for (int i = 0; i < N; i++) by_rank[(size_t)i] = i;
+                std::sort(by_rank.begin(), by_rank.end(), [&](int x, int y) { return M->order[(size_t)x]->rank < M->order[(size_t)y]->rank; });
+                for (int r = 0; r < N; r++) rank[(size_t)by_rank[(size_t)r]] = r;
+                if (rc == KB200_OK) {
+                        if (cudaMemcpyAsync(M->d_raw.p, M->raw, (size_t)total, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+                            cudaMemcpyAsync(M->d_rank.p, rank.data(), sizeof(int) * (size_t)N, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+                            cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+                                rc = KB200_FAIL;
+                        }
+                        ctx->stats.h2d_bytes += (double)total + 4.0 * N;
+                }
+        }
+        if (rc == KB200_OK && !defer_tree) {
+                rc = encode_seqs_dev(M, M->S, biotype == 1 ? ALPHA_DNA : ALPHA_RED);
                 tc2 = kb_now();
                 if (rc == KB200_OK) rc = kb_build_tree(ctx, M->S, n_threads, M->abc, M->seq_distances);
                 if (rc == KB200_OK && biotype == 0) {
-                        encode_seqs(M, ALPHA_AMB, n_threads);
-                        rc = M->S.upload(ctx, M->codes.data(), M->offs.data(), M->lens.data(), N);
+                        rc = encode_seqs_dev(M, M->S, ALPHA_AMB);
                 }
-        } else {
+        } else if (rc == KB200_OK) {
                 // only the first stage of the tree here (distance matrix -> seq_distances -> anchors);
-                // kb200_kalign runs k-means beside the anchor batch and finishes the tree afterwards
+                // kb200_kalign finishes the tree around the anchor batch
                 M->tree_job = new KbTreeJob();
                 if (biotype == 0) {
-                        M->codes_tree = M->codes;                    // 13-letter tree alphabet
-                        rc = M->S_tree.upload(ctx, M->codes_tree.data(), M->offs.data(), M->lens.data(), N);
+                        rc = encode_seqs_dev(M, M->S_tree, ALPHA_RED);        // 13-letter tree alphabet
                         tc2 = kb_now();
                         if (rc == KB200_OK) rc = kb_tree_prepare(ctx, M->S_tree, *M->tree_job, M->seq_distances);
-                        if (rc == KB200_OK) {
-                                encode_seqs(M, ALPHA_AMB, n_threads);
-                                rc = M->S.upload(ctx, M->codes.data(), M->offs.data(), M->lens.data(), N);
-                        }
+                        if (rc == KB200_OK) rc = encode_seqs_dev(M, M->S, ALPHA_AMB);
                 } else {
-                        rc = M->S.upload(ctx, M->codes.data(), M->offs.data(), M->lens.data(), N);
+                        rc = encode_seqs_dev(M, M->S, ALPHA_DNA);
                         tc2 = kb_now();
                         if (rc == KB200_OK) rc = kb_tree_prepare(ctx, M->S, *M->tree_job, M->seq_distances);
                 }
@@ -842,8 +925,28 @@ static int msa_align_anchor(kb200_msa* M)
 
 static int msa_align_tree(kb200_msa* M)
 {
+        // the gaps stay on the device (kb200_msa_result expands the rows there); only the host restatement
+        // of the weave (KB200_HOST_BONUS) hands them back
+        kb200_ctx* ctx = M->ctx;
+        const bool host_state = kb_bonus_on_host(M->K) != 0;
+        if (host_state && !M->gaps) {
+                M->gaps = (int*)kb_host_take(ctx, sizeof(int) * ((size_t)M->total + (size_t)M->N));
+                if (!M->gaps) return KB200_FAIL;
+                memset(M->gaps, 0, sizeof(int) * ((size_t)M->total + (size_t)M->N));
+        }
+        std::vector<int> plens((size_t)std::max(1, M->N - 1));
+        int* plen = plens.data();
         KB_RUN(kb_align_tree_dev(M->ctx, &M->prm, M->S, M->abc.data(), M->N - 1, M->seq_distances.data(),
-                                 M->K > 0 ? M->posmaps.data() : nullptr, M->K, M->weight, M->n_threads, M->gaps, 1));
+                                 M->K > 0 ? M->posmaps.data() : nullptr, M->K, M->weight, M->n_threads,
+                                 host_state ? M->gaps : nullptr, 1, nullptr, plen));
+        M->aln_len = plens[(size_t)(M->N - 2)];          // msa->alnlen = plen of the root task
+        M->gaps_on_host = host_state;
+        if (!host_state) {
+                // the context's column maps belong to whichever alignment ran last: keep this one's
+                kb_take_pooled(ctx, M->d_colof, sizeof(int) * ((size_t)M->total + 8));
+                KB_RUN(M->d_colof.ensure(sizeof(int) * ((size_t)M->total + 8)));
+                KB_CUDA(cudaMemcpyAsync(M->d_colof.p, ctx->t_colof.p, sizeof(int) * (size_t)M->total, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
         M->aligned = true;
         return KB200_OK;
 }
@@ -871,7 +974,46 @@ int kb200_msa_result(kb200_msa* M, char*** aligned, int* out_aln_len)
         if (!M || !M->aligned || !aligned || !out_aln_len) return KB200_FAIL;
         const double tr0 = kb_now();
         const int N = M->N;
-        int aln_len = M->lens[0];
+        kb200_ctx* ctx = M->ctx;
+        char** out = (char**)calloc((size_t)N, sizeof(char*));
+        if (!out) return KB200_FAIL;
+        bool oom = false;
+        int aln_len = 0;
+        if (!M->gaps_on_host) {
+                // finalise_alignment on the device: rows of '-' with the residues scattered to their columns
+                // (colof, maintained by the weave kernels), one block copied back, cut into the caller's rows
+                KB_CUDA(cudaSetDevice(ctx->device));
+                aln_len = M->aln_len;
+                const long long stride = (long long)aln_len + 1;
+                const size_t bytes = (size_t)stride * (size_t)N;
+                kb_take_pooled(ctx, M->d_rows, bytes + 16);
+                KB_RUN(M->d_rows.ensure(bytes + 16));
+                char* hrows = (char*)kb_host_take(ctx, bytes + 16);
+                if (!hrows) { free(out); return KB200_FAIL; }
+                const int fgrid = (int)std::min<long long>((long long)(bytes / 256) + 1, (long long)ctx->sm_count * 32);
+                kb_fill_rows_kernel<<<fgrid, 256, 0, ctx->stream>>>(M->d_rows.as<char>(), stride, N);
+                kb_finalise_kernel<<<(N * 32 + 127) / 128, 128, 0, ctx->stream>>>(M->d_raw.as<uint8_t>(), M->S.d_offs.as<int64_t>(), M->S.d_lens.as<int>(),
+                                                                              M->d_rank.as<int>(), N, M->d_colof.as<int>(), stride, M->d_rows.as<char>());
+                KB_CUDA(cudaGetLastError());
+                ctx->stats.n_launches += 2;
+                KB_CUDA(cudaMemcpyAsync(hrows, M->d_rows.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+                KB_CUDA(cudaStreamSynchronize(ctx->stream));
+                ctx->stats.d2h_bytes += (double)bytes;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(kb_default_threads())
+#endif
+                for (int r = 0; r < N; r++) {
+                        char* row = (char*)malloc((size_t)stride);
+                        if (!row) {
+                                oom = true;
+                                continue;
+                        }
+                        memcpy(row, hrows + (size_t)r * (size_t)stride, (size_t)stride);
+                        out[r] = row;
+                }
+                kb_host_give(ctx, hrows);
+        } else {
+        aln_len = M->lens[0];
         {
                 const int* g = M->gaps + M->offs[0] + 0;
                 for (int j = 0; j <= M->lens[0]; j++) aln_len += g[j];
@@ -879,9 +1021,6 @@ int kb200_msa_result(kb200_msa* M, char*** aligned, int* out_aln_len)
         std::vector<int> by_rank((size_t)N);
         for (int i = 0; i < N; i++) by_rank[(size_t)i] = i;
         std::sort(by_rank.begin(), by_rank.end(), [&](int x, int y) { return M->order[(size_t)x]->rank < M->order[(size_t)y]->rank; });
-        char** out = (char**)calloc((size_t)N, sizeof(char*));
-        if (!out) return KB200_FAIL;
-        bool oom = false;
 #ifdef _OPENMP
 #pragma omp parallel for schedule(static) num_threads(kb_default_threads())
 #endif
@@ -904,6 +1043,7 @@ int kb200_msa_result(kb200_msa* M, char*** aligned, int* out_aln_len)
                 while (f < aln_len) row[f++] = '-';
                 row[aln_len] = 0;
                 out[r] = row;
+        }
         }
         if (oom) {
                 for (int r = 0; r < N; r++) free(out[r]);

@@ -965,10 +965,13 @@ int kb_align_tree_dev(kb200_ctx* ctx, const kb200_params* prm, KbSeqs& S,
                 }
         }
         if (dev_state) {
-                TC(cudaMemcpyAsync(gaps_out, d_gaps, sizeof(int) * ((size_t)S.total + (size_t)N), cudaMemcpyDeviceToHost, st));
+                // gaps_out == nullptr: the caller keeps working on the device copy (ctx->t_gaps / t_colof)
+                if (gaps_out) {
+                        TC(cudaMemcpyAsync(gaps_out, d_gaps, sizeof(int) * ((size_t)S.total + (size_t)N), cudaMemcpyDeviceToHost, st));
+                        ctx->stats.d2h_bytes += (double)(sizeof(int) * ((size_t)S.total + (size_t)N));
+                }
                 TR(kb_collect(ctx));
-                ctx->stats.d2h_bytes += (double)(sizeof(int) * ((size_t)S.total + (size_t)N));
-        } else {
+        } else if (gaps_out) {
                 for (int i = 0; i < N; i++) {
                         memcpy(gaps_out + S.h_offs[i] + i, T.gaps[i].data(), sizeof(int) * ((size_t)S.h_lens[i] + 1));
                 }
