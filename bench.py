@@ -190,6 +190,46 @@ def bpm_bench(ctx, seqs, type_):
             "hbm_frac": bytes_ / t / 1e9 / hbm, "kernel": "kb_bpm_kernel"}
 
 
+def apair_bench(ctx, rows, with_cpu):
+    """the N x N identity distances of the realign loop (compute_aln_pairwise_dist,
+    lib/src/aln_apair_dist.c:9) on the alignment the timed steps produced, through kb200_aln_pairwise_dist:
+    column-pairs/s in the kernels (CUDA events) and for the whole host-pointer call (upload of the rows,
+    download of the n x n floats into the caller's row allocations); the unmodified reference's serial loop
+    on a bounded sample of the same rows beside it"""
+    n = len(rows)
+    if n > 20000:
+        return {"skipped": "n = %d: the n x n float matrix (%.0f GB) is not benchmarked from python" % (n, 4e-9 * n * n)}
+    alnlen = len(rows[0])
+    ctx.aln_pairwise_dist(rows[:256])                 # warm-up (module load, pinned pool)
+    s0 = ctx.stats()
+    t0 = time.perf_counter()
+    dm = ctx.aln_pairwise_dist(rows)
+    t1 = time.perf_counter()
+    s1 = ctx.stats()
+    tk = s1["apair_seconds"] - s0["apair_seconds"]
+    colpairs = s1["apair_col_pairs"] - s0["apair_col_pairs"]
+    out = {"n": n, "alnlen": alnlen, "kernel_seconds": tk, "call_seconds": t1 - t0,
+           "col_pairs_per_sec_in_kernel": colpairs / tk if tk > 0 else None,
+           "col_pairs_per_sec_call": colpairs / (t1 - t0),
+           "issue_frac": (colpairs * 110.0 / 64.0 / tk / (148 * 4 * 32 * 1.965e9)) if tk > 0 else None,
+           "issue_note": "about 110 SASS instructions per staged word of a 4 x 4 pair block (64 column-pairs; static count of the "
+                         "inner loop, not an ncu measurement) against 148 SMs x 4 x 32 lanes x 1.965 GHz",
+           "h2d_bytes": float(n) * ((alnlen + 3) // 4 * 4), "d2h_bytes": 4.0 * n * n, "kernel": "kb_apair_tile_kernel"}
+    if with_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import kbind
+        ns = min(n, max(64, int((2.0e9 / max(1, alnlen)) ** 0.5)))      # ~1e9 byte compares: a few seconds
+        sample = rows[:ns]
+        c0 = time.perf_counter()
+        want = kbind.ref_aln_pairwise_dist(sample) if kbind.have_ref() else kbind.oracle_aln_pairwise_dist(sample)
+        c1 = time.perf_counter()
+        out["cpu_reference"] = {"col_pairs_per_sec": 0.5 * ns * (ns - 1) * alnlen / (c1 - c0), "cores": 1,
+                                "kind": "reference" if kbind.have_ref() else "port",
+                                "sample": "first %d rows of the same alignment (the reference's loop is serial)" % ns,
+                                "identical_to_gpu": bool(np.array_equal(want, dm[:ns, :ns]))}
+    return out
+
+
 def full_reference_record(workload):
     """the unmodified reference's run of the FULL workload, recorded once in the build container by
     tools/gen_golden_full.py (tests/golden/full_<wl>.npz: stage times and the hash the GPU result is
@@ -421,6 +461,10 @@ def main():
     # ---- identity with the reference: hash of the alignment the timed steps produced (every rank
     #      holds the full result) against the golden hash of the unmodified reference's alignment
     step_rows = m.result()
+    try:
+        line["apair"] = apair_bench(ctx, step_rows, rank == 0 and not args.no_cpu_baseline) if world == 1 else None
+    except Exception as e:  # noqa: BLE001
+        line["apair"] = {"error": repr(e)}
     sha = synth.msa_sha256(step_rows)
     want = golden_sha(args.workload, len(seqs))
     same_all = True

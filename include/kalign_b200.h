@@ -96,6 +96,8 @@ typedef struct kb200_stats {
         double small_seconds;     /* device time of the small-box kernel */
         double small_ss, small_sp, small_pp;   /* cells handled by the small-box kernel (subset of cells_*) */
         double n_collectives, collective_bytes; /* NCCL all-gathers issued / bytes gathered (multi-GPU) */
+        double apair_seconds;     /* device time of the kb200_aln_pairwise_dist kernels */
+        double apair_col_pairs;   /* (row pairs) x (alignment columns) they compared */
 } kb200_stats;
 
 int  kb200_device_count(void);
@@ -124,6 +126,14 @@ typedef struct kb200_seqs kb200_seqs;
 int  kb200_seqs_upload(kb200_ctx* ctx, const uint8_t* seqs, const int64_t* offs, const int* lens, int nseq, kb200_seqs** out);
 int  kb200_distances_on(kb200_seqs* s, const int* rows, int nrows, const int* cols, int ncols, int explicit_pairs, float* dm);
 void kb200_seqs_free(kb200_seqs* s);
+
+/* compute_aln_pairwise_dist (lib/src/aln_apair_dist.c:9), the N x N matrix of the realign loop
+   (kalign_run_realign, lib/src/aln_wrap.c:455-490): rows[i] = alnlen characters of a finished alignment
+   ('-' = gap, as written by finalise_alignment); dm_rows[i][j] = dm_rows[j][i] = 1 - matches / aligned over
+   the columns where both rows hold a residue, 1 when there is none, 0 on the diagonal
+   (pairwise_identity_dist, aln_apair_dist.c:62-82).  dm_rows[i] are the caller's n row allocations of n
+   floats each, the reference's float** layout. */
+int kb200_aln_pairwise_dist(kb200_ctx* ctx, const char* const* rows, int n, int alnlen, float* const* dm_rows);
 
 /* posmaps: concatenated over i of K maps of len_i ints: map (i,k) starts at
    K*offs[i] + k*lens[i]  (anchor_consistency.c:246-267). Only pairs p in [pair_begin,pair_end)

@@ -5,12 +5,18 @@
  * reference's own, unmodified lib/src/*.c (in place, see integration/Makefile) and linked with
  *
  *     -Wl,--wrap=d_estimation -Wl,--wrap=anchor_consistency_build -Wl,--wrap=create_msa_tree
+ *     -Wl,--wrap=compute_aln_pairwise_dist
  *
  * so that the three calls kalign_run_seeded() makes into its hot path
  *
  *     d_estimation()              lib/src/sequence_distance.c:37   (from bisectingKmeans.c:205,294)
  *     anchor_consistency_build()  lib/src/anchor_consistency.c:200 (from aln_wrap.c:211)
  *     create_msa_tree()           lib/src/aln_run.c:43             (from aln_wrap.c:225)
+ *
+ * and the N x N identity distances of the callers that loop over that path (kalign_run_realign,
+ * kalign_post_realign; the ensemble runs reach the same seams through kalign_run_seeded / _realign)
+ *
+ *     compute_aln_pairwise_dist() lib/src/aln_apair_dist.c:9       (from aln_wrap.c:458,604)
  *
  * resolve to the functions below, which flatten struct msa into plain arrays and call the C ABI of
  * libkalign_b200.so (include/kalign_b200.h).  Everything else -- kalign.h, struct msa, I/O, the
@@ -482,5 +488,61 @@ ERROR:
         free(conf);
         free(plen);
         flat_free(&f);
+        return FAIL;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * compute_aln_pairwise_dist (aln_apair_dist.c:9): same float** layout (n rows of n floats, each its
+ * own allocation, released by free_aln_dm); the N^2/2 row comparisons run on the GPU. */
+int __wrap_compute_aln_pairwise_dist(struct msa* msa, float*** dm_ptr)
+{
+        float** dm = NULL;
+        const char** rows = NULL;
+        kb200_ctx* ctx = NULL;
+        int n = 0;
+        int i;
+        int rc;
+
+        ASSERT(msa != NULL, "No MSA");
+        ASSERT(msa->aligned == ALN_STATUS_FINAL, "MSA must be finalized");
+        n = msa->numseq;
+        pthread_mutex_lock(&g_lock);
+        ctx = seam_ctx();
+        pthread_mutex_unlock(&g_lock);
+        if(!ctx){
+                return FAIL;
+        }
+        MMALLOC(dm, sizeof(float*) * n);
+        for(i = 0; i < n; i++){
+                dm[i] = NULL;
+        }
+        for(i = 0; i < n; i++){
+                MMALLOC(dm[i], sizeof(float) * n);
+        }
+        rows = malloc(sizeof(char*) * (size_t)(n > 0 ? n : 1));
+        if(!rows){
+                goto ERROR;
+        }
+        for(i = 0; i < n; i++){
+                rows[i] = msa->sequences[i]->seq;
+        }
+        rc = kb200_aln_pairwise_dist(ctx, rows, n, msa->alnlen, dm);
+        free(rows);
+        rows = NULL;
+        if(rc != KB200_OK){
+                goto ERROR;
+        }
+        *dm_ptr = dm;
+        return OK;
+ERROR:
+        free(rows);
+        if(dm){
+                for(i = 0; i < n; i++){
+                        if(dm[i]){
+                                MFREE(dm[i]);
+                        }
+                }
+                MFREE(dm);
+        }
         return FAIL;
 }

@@ -41,13 +41,14 @@ class Stats(C.Structure):
                 ("cells_ss", C.c_double), ("cells_sp", C.c_double), ("cells_pp", C.c_double),
                 ("cells_bonus", C.c_double), ("align_seconds", C.c_double), ("small_seconds", C.c_double),
                 ("small_ss", C.c_double), ("small_sp", C.c_double), ("small_pp", C.c_double),
-                ("n_collectives", C.c_double), ("collective_bytes", C.c_double)]
+                ("n_collectives", C.c_double), ("collective_bytes", C.c_double),
+                ("apair_seconds", C.c_double), ("apair_col_pairs", C.c_double)]
 
 
 # every symbol include/kalign_b200.h declares
 EXPORTS = ["kb200_device_count", "kb200_ctx_create", "kb200_ctx_destroy", "kb200_get_stats",
            "kb200_version", "kb200_params_init", "kb200_pair_align_batch", "kb200_distances",
-           "kb200_seqs_upload", "kb200_distances_on", "kb200_seqs_free",
+           "kb200_seqs_upload", "kb200_distances_on", "kb200_seqs_free", "kb200_aln_pairwise_dist",
            "kb200_anchor_posmaps", "kb200_select_anchors", "kb200_align_tree", "kb200_align_tree_conf", "kb200_kalign",
            "kb200_msa_create", "kb200_msa_align", "kb200_msa_result", "kb200_msa_info", "kb200_msa_tree", "kb200_msa_free",
            "kb200_comm_unique_id", "kb200_ctx_comm_init", "kb200_ctx_comm_destroy", "kb200_partition"]
@@ -100,6 +101,8 @@ def load():
     lib.kb200_distances_on.restype = C.c_int
     lib.kb200_seqs_free.argtypes = [C.c_void_p]
     lib.kb200_seqs_free.restype = None
+    lib.kb200_aln_pairwise_dist.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    lib.kb200_aln_pairwise_dist.restype = C.c_int
     lib.kb200_anchor_posmaps.argtypes = [C.c_void_p, C.POINTER(Params), u8p, i64p, i32p, C.c_int,
                                          i32p, C.c_int, C.c_longlong, C.c_longlong, i32p]
     lib.kb200_anchor_posmaps.restype = C.c_int
@@ -233,6 +236,21 @@ def _distances(self, flat, offs, lens, rows, cols):
     return dm.reshape(len(rows), len(cols))
 
 
+def _aln_pairwise_dist(self, rows):
+    """kb200_aln_pairwise_dist: rows = equally long aligned strings ('-' = gap) -> (n, n) float32"""
+    n = len(rows)
+    alnlen = len(rows[0]) if n else 0
+    if any(len(r) != alnlen for r in rows):
+        raise ValueError("aligned rows must have one length")
+    enc = [r.encode("ascii") if isinstance(r, str) else bytes(r) for r in rows]
+    arr = (C.c_char_p * n)(*enc)
+    dm = np.full((n, n), np.nan, dtype=np.float32)
+    ptrs = (C.c_void_p * n)(*[dm.ctypes.data + i * n * 4 for i in range(n)])
+    if self.lib.kb200_aln_pairwise_dist(self.h, arr, n, alnlen, ptrs) != 0:
+        raise RuntimeError("kb200_aln_pairwise_dist failed")
+    return dm
+
+
 class DeviceSeqs:
     """sequences resident on the device between distance calls (kb200_seqs_upload / kb200_distances_on)"""
 
@@ -324,6 +342,7 @@ def _kalign(self, seqs, n_threads=1, type_=8, gpo=-1.0, gpe=-1.0, tgpe=-1.0, con
 
 Context.distances = _distances
 Context.anchor_posmaps = _anchor_posmaps
+Context.aln_pairwise_dist = _aln_pairwise_dist
 Context.align_tree = _align_tree
 Context.kalign = _kalign
 

@@ -15,6 +15,7 @@
  *   update_n              lib/src/aln_setup.c:230
  *   mirror_path_n         lib/src/aln_setup.c:438
  *   kalign_run_seeded     lib/src/aln_wrap.c:133  (re-stated call sequence with dumps)
+ *   compute_aln_pairwise_dist lib/src/aln_apair_dist.c:9
  *
  * All functions return 0 on success.
  */
@@ -52,6 +53,7 @@
 #include "aln_run.h"
 #include "anchor_consistency.h"
 #include "bpm.h"
+#include "aln_apair_dist.h"
 #include "kalign/kalign.h"
 
 static double now_s(void)
@@ -483,4 +485,34 @@ double refh_time_public_api(char** seqs, int* lens, int n, int n_threads, int ty
         double t1 = now_s();
         kalign_free_msa(msa);
         return rc == OK ? (t1 - t0) : -1.0;
+}
+
+/* compute_aln_pairwise_dist (aln_apair_dist.c:9) on plain aligned rows: dm_out = n x n floats */
+int refh_aln_pairwise_dist(char** rows, int n, int alnlen, float* dm_out)
+{
+        struct msa m;
+        struct msa_seq* seqs = calloc((size_t)n, sizeof(struct msa_seq));
+        struct msa_seq** ptr = malloc(sizeof(struct msa_seq*) * (size_t)n);
+        float** dm = NULL;
+        int rc = 1;
+        if(!seqs || !ptr){ free(seqs); free(ptr); return 1; }
+        memset(&m, 0, sizeof(m));
+        for(int i = 0; i < n; i++){
+                seqs[i].seq = rows[i];
+                ptr[i] = &seqs[i];
+        }
+        m.sequences = ptr;
+        m.numseq = n;
+        m.alnlen = alnlen;
+        m.aligned = ALN_STATUS_FINAL;
+        if(compute_aln_pairwise_dist(&m, &dm) == OK){
+                for(int i = 0; i < n; i++){
+                        memcpy(dm_out + (size_t)i * (size_t)n, dm[i], sizeof(float) * (size_t)n);
+                }
+                free_aln_dm(dm, n);
+                rc = 0;
+        }
+        free(seqs);
+        free(ptr);
+        return rc;
 }

@@ -131,6 +131,8 @@ def refh():
         lib.refh_distance_matrix.restype = C.c_int
         lib.refh_free.argtypes = [C.c_void_p]
         lib.refh_free.restype = None
+        lib.refh_aln_pairwise_dist.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_int, f32p]
+        lib.refh_aln_pairwise_dist.restype = C.c_int
         lib.refh_time_public_api.argtypes = [C.POINTER(C.c_char_p), i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]
         lib.refh_time_public_api.restype = C.c_double
         _refh = lib
@@ -270,3 +272,34 @@ def ref_distance_matrix(seqs):
     nout = C.c_int(0)
     assert lib.refh_distance_matrix(arr, lens, n, dm, anchors, C.byref(nout)) == 0
     return dm.reshape(n, na), anchors
+
+
+def ref_aln_pairwise_dist(rows):
+    """the reference's compute_aln_pairwise_dist (lib/src/aln_apair_dist.c:9) on aligned strings"""
+    lib = refh()
+    n = len(rows)
+    keep = [r.encode() for r in rows]
+    arr = (C.c_char_p * n)(*keep)
+    dm = np.zeros(n * n, dtype=np.float32)
+    assert lib.refh_aln_pairwise_dist(arr, n, len(rows[0]), dm) == 0
+    return dm.reshape(n, n)
+
+
+def oracle_aln_pairwise_dist(rows):
+    """numpy restatement of pairwise_identity_dist (lib/src/aln_apair_dist.c:62-82): columns where both
+    rows hold a residue are counted, equal characters among them are matches, d = 1 - m / a in float32
+    (1 when a == 0), 0 on the diagonal (aln_apair_dist.c:25).  TEST INFRASTRUCTURE ONLY."""
+    a = np.frombuffer("".join(rows).encode(), dtype=np.uint8).reshape(len(rows), -1)
+    res = a != ord("-")
+    n = len(rows)
+    dm = np.zeros((n, n), dtype=np.float32)
+    for i in range(n):
+        both = res[i][None, :] & res
+        al = both.sum(axis=1).astype(np.int64)
+        m = (both & (a == a[i][None, :])).sum(axis=1).astype(np.int64)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            d = np.float32(1.0) - m.astype(np.float32) / al.astype(np.float32)
+        d = np.where(al == 0, np.float32(1.0), d).astype(np.float32)
+        d[i] = 0.0
+        dm[i] = d
+    return dm

@@ -29,6 +29,14 @@ CASES = [
     ("protein_3000_fast", lambda: synth.family(3000, 100, synth.PROTEIN, seed=26), ["--fast"]),
     ("protein_refine_confident", lambda: synth.family(40, 90, synth.PROTEIN, seed=27), ["--refine", "confident"]),
     ("rna_refine_all", lambda: synth.family(24, 150, synth.RNA, seed=28), ["--type", "rna", "--refine", "all"]),
+    # callers that loop over the path: the ensemble runs (kalign_ensemble, ensemble.c:286-340: per-run
+    # gap penalties + noisy guide trees through the same seams) and the realign loop (kalign_run_realign,
+    # aln_wrap.c:455-490: create_msa_tree -> compute_aln_pairwise_dist on the GPU -> new tree -> create_msa_tree)
+    ("protein_ensemble3", lambda: synth.family(30, 100, synth.PROTEIN, seed=41), ["--ensemble", "3"]),
+    ("rna_ensemble4_refine", lambda: synth.family(24, 160, synth.RNA, seed=42), ["--type", "rna", "--ensemble", "4", "--refine", "confident"]),
+    ("protein_realign2", lambda: synth.family(40, 110, synth.PROTEIN, seed=43), ["--realign", "2"]),
+    ("dna_realign1", lambda: synth.family(70, 260, synth.DNA, seed=44, sub=0.06, ins=0.01, dele=0.01), ["--type", "dna", "--realign", "1"]),
+    ("protein_precise", lambda: synth.family(30, 100, synth.PROTEIN, seed=45), ["--precise"]),
 ]
 
 
