@@ -179,6 +179,30 @@ int kb200_kalign(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_threads
                  float gpo, float gpe, float tgpe, int consistency_anchors, float consistency_weight,
                  char*** aligned, int* out_aln_len);
 
+/* FASTA in / out, host code: the file is mapped and parsed by n_threads threads at once
+   (n_threads <= 0: all the process may use) with the semantics of read_file_stdin + read_fasta
+   (lib/src/msa_io.c:348,412): a line's content ends at its first control character; '>' at the start of a
+   line opens a record whose name is the rest of the line; on the other lines letters are residues,
+   punctuation counts as gap characters in front of the next residue (gaps[len]++), everything else is
+   dropped; letter_freq[128] counts every character of the sequence lines (what detect_alphabet reads).
+   Views returned by kb200_fasta_get / _arrays / _letter_freq stay valid until kb200_fasta_free. */
+typedef struct kb200_fasta kb200_fasta;
+int  kb200_fasta_read(const char* path, int n_threads, kb200_fasta** out);
+int  kb200_fasta_numseq(const kb200_fasta* f);
+/* record i: name, residues (NUL-terminated), length, len + 1 gap counts; any out pointer may be NULL */
+int  kb200_fasta_get(const kb200_fasta* f, int i, const char** name, const char** seq, int* len, const int** gaps);
+const int* kb200_fasta_letter_freq(const kb200_fasta* f);
+/* the (seq, len) arrays kb200_kalign / kalign() take */
+int  kb200_fasta_arrays(const kb200_fasta* f, const char* const** seqs, const int** lens);
+void kb200_fasta_free(kb200_fasta* f);
+/* write_msa_fasta (lib/src/msa_io.c:668): ">name", the row in lines of 60 characters; one buffer, one write */
+int  kb200_fasta_write(const char* path, const char* const* names, const char* const* rows, int n, int alnlen, int n_threads);
+/* the CLI's main path for one FASTA file (src/run_kalign.c: kalign_read_input -> kalign_run_seeded ->
+   kalign_write_msa with the default output format): record names break the ties of the (length, name)
+   sort, empty records are dropped, rows are written in input order */
+int  kb200_kalign_file(kb200_ctx* ctx, const char* infile, const char* outfile, int n_threads, int type,
+                       float gpo, float gpe, float tgpe, int consistency_anchors, float consistency_weight);
+
 /* Multi-GPU (one process per GPU of one node, NCCL over NVLink): rank 0 creates a unique id,
    the caller distributes it (e.g. torch.distributed broadcast), every rank attaches its context.
    With a communicator attached, kb200_msa_align shards the N x K anchor pairs and the tasks of every

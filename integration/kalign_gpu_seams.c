@@ -18,6 +18,15 @@
  *
  *     compute_aln_pairwise_dist() lib/src/aln_apair_dist.c:9       (from aln_wrap.c:458,604)
  *
+ * and, on the two sides of the path, the FASTA reader and writer of the public API (kalign.h:36-37): the
+ * reference's lib sources are compiled with -Dkalign_read_input=kalign_read_input_ref
+ * -Dkalign_write_msa=kalign_write_msa_ref (its own functions stay available under those names, used for
+ * every other format and for standard input / output) and this file defines the public names on top of
+ * kb200_fasta_read / kb200_fasta_write (mapped file, all host threads, one write)
+ *
+ *     kalign_read_input()         lib/src/msa_io.c:80   (read_file_stdin :348, read_fasta :412)
+ *     kalign_write_msa()          lib/src/msa_io.c:193  (write_msa_fasta :668)
+ *
  * resolve to the functions below, which flatten struct msa into plain arrays and call the C ABI of
  * libkalign_b200.so (include/kalign_b200.h).  Everything else -- kalign.h, struct msa, I/O, the
  * guide tree, parameter handling, finalise_alignment, the CLI -- is the reference's code, untouched.
@@ -51,6 +60,8 @@
 #include "task.h"
 #include "aln_param.h"
 #include "anchor_consistency.h"
+#include "msa_alloc.h"
+#include "msa_op.h"
 
 #include "kalign_b200.h"
 
@@ -545,4 +556,173 @@ ERROR:
                 MFREE(dm);
         }
         return FAIL;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * kalign_read_input (msa_io.c:80) for FASTA files.  The format is decided as detect_alignment_format
+ * does (msa_io.c:248-346: the first 100 lines; any Clustal / MSF marker wins over '>'); everything that
+ * is not an unambiguous FASTA file -- standard input, MSF, Clustal, a second input file merged into an
+ * existing msa, a file whose first line has one character (the reference calls that "no input") --
+ * goes to the reference's own reader. */
+int kalign_read_input_ref(char* infile, struct msa** msa, int quiet);
+int kalign_write_msa_ref(struct msa* msa, char* outfile, char* format);
+
+static int fasta_fast_path(const char* infile)
+{
+        static const char* markers[6] = {"multiple sequence alignment", "CLUSTAL W", "CLUSTAL O",
+                                         "!!AA_MULTIPLE_ALIGNMENT", "!!NA_MULTIPLE_ALIGNMENT", "MSF:"};
+        enum { HEAD = 1 << 20 };
+        FILE* f = fopen(infile, "r");
+        char* buf = NULL;
+        size_t n, pos = 0;
+        int lines = 0;
+        int fasta = 0;
+        int ok = 1;
+        if(!f){
+                return 0;
+        }
+        buf = malloc(HEAD + 1);
+        if(!buf){
+                fclose(f);
+                return 0;
+        }
+        n = fread(buf, 1, HEAD, f);
+        while(ok && lines < 100 && pos < n){
+                char* nl = memchr(buf + pos, 10, n - pos);
+                size_t end = nl ? (size_t)(nl - buf) : n;
+                size_t cut = pos;
+                int m;
+                if(!nl && n == HEAD){
+                        ok = 0;                  /* 100 lines do not fit in the head of the file: let the reference decide */
+                        break;
+                }
+                while(cut < end && !((unsigned char)buf[cut] < 32 || buf[cut] == 127)){
+                        cut++;
+                }
+                {
+                        char keep = buf[cut];
+                        buf[cut] = 0;            /* the line's content, as read_file_stdin cuts it (msa_io.c:381-386) */
+                        if(lines == 0 && cut - pos == 1){
+                                ok = 0;
+                        }
+                        if(buf[pos] == 62){
+                                fasta = 1;
+                        }
+                        for(m = 0; m < 6; m++){
+                                if(strstr(buf + pos, markers[m])){
+                                        ok = 0;
+                                }
+                        }
+                        buf[cut] = keep;
+                }
+                pos = end + 1;
+                lines++;
+        }
+        free(buf);
+        fclose(f);
+        return ok && fasta;
+}
+
+int kalign_read_input(char* infile, struct msa** msa, int quiet)
+{
+        struct msa* m = NULL;
+        kb200_fasta* f = NULL;
+        const int* freq = NULL;
+        int n, i, alloc;
+
+        if(!infile || !msa || *msa != NULL || !fasta_fast_path(infile)){
+                return kalign_read_input_ref(infile, msa, quiet);
+        }
+        if(kb200_fasta_read(infile, 0, &f) != KB200_OK){
+                return kalign_read_input_ref(infile, msa, quiet);       /* the reference reports what is wrong with the file */
+        }
+        n = kb200_fasta_numseq(f);
+        alloc = 512 * ((n + 511) / 512 > 0 ? (n + 511) / 512 : 1);     /* alloc_msa(512) + resize_msa steps (msa_io.c:423-431) */
+        RUN(alloc_msa(&m, alloc));
+        for(i = 0; i < n; i++){
+                struct msa_seq* s = m->sequences[i];
+                const char* name = NULL;
+                const char* seq = NULL;
+                const int* gaps = NULL;
+                int len = 0;
+                int a, j;
+                kb200_fasta_get(f, i, &name, &seq, &len, &gaps);
+                MFREE(s->name);
+                MMALLOC(s->name, strlen(name) + 1);
+                strcpy(s->name, name);
+                a = 512 * (len / 512 + 1);                              /* resize_msa_seq steps (msa_alloc.c:141) */
+                if(a != s->alloc_len){
+                        s->alloc_len = a;
+                        MREALLOC(s->seq, sizeof(char) * a);
+                        MREALLOC(s->s, sizeof(uint8_t) * a);
+                        MREALLOC(s->gaps, sizeof(int) * (a + 1));
+                }
+                memcpy(s->seq, seq, (size_t)len);
+                s->seq[len] = 0;
+                memcpy(s->gaps, gaps, sizeof(int) * (size_t)(len + 1));
+                for(j = len + 1; j < a + 1; j++){
+                        s->gaps[j] = 0;
+                }
+                s->len = len;
+        }
+        m->numseq = n;
+        freq = kb200_fasta_letter_freq(f);
+        for(i = 0; i < 128; i++){
+                m->letter_freq[i] = freq[i];
+        }
+        kb200_fasta_free(f);
+        f = NULL;
+        m->quiet = quiet;
+        RUN(detect_alphabet(m));
+        RUN(detect_aligned(m));
+        RUN(set_sip_nsip(m));
+        if(!quiet){
+                LOG_MSG("Read %d sequences from %s.", m->numseq, infile);
+        }
+        *msa = m;
+        m = NULL;
+        /* check_for_sequences (msa_io.c:176-191) */
+        if((*msa)->numseq == 0){
+                ERROR_MSG("No sequences were found in the input files or standard input.");
+        }else if((*msa)->numseq == 1){
+                ERROR_MSG("Only 1 sequence was found in the input files or standard input");
+        }
+        return OK;
+ERROR:
+        if(f){
+                kb200_fasta_free(f);
+        }
+        if(m){
+                kalign_free_msa(m);
+        }
+        return FAIL;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * kalign_write_msa (msa_io.c:193) for FASTA output to a file; other formats and standard output stay
+ * with the reference's writers (parse_format_argument, msa_io.c:223-246: "msf" and "clu" win). */
+int kalign_write_msa(struct msa* msa, char* outfile, char* format)
+{
+        const char** names = NULL;
+        const char** rows = NULL;
+        int i, rc;
+        if(!msa || !outfile || msa->aligned != ALN_STATUS_FINAL ||
+           (format && (strstr(format, "msf") || strstr(format, "clu") || !strstr(format, "fa")))){
+                return kalign_write_msa_ref(msa, outfile, format);
+        }
+        names = malloc(sizeof(char*) * (size_t)(msa->numseq > 0 ? msa->numseq : 1));
+        rows = malloc(sizeof(char*) * (size_t)(msa->numseq > 0 ? msa->numseq : 1));
+        if(!names || !rows){
+                free(names);
+                free(rows);
+                return FAIL;
+        }
+        for(i = 0; i < msa->numseq; i++){
+                names[i] = msa->sequences[i]->name;
+                rows[i] = msa->sequences[i]->seq;
+        }
+        rc = kb200_fasta_write(outfile, names, rows, msa->numseq, msa->alnlen, 0);
+        free(names);
+        free(rows);
+        return rc == KB200_OK ? OK : FAIL;
 }

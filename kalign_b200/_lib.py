@@ -51,6 +51,8 @@ EXPORTS = ["kb200_device_count", "kb200_ctx_create", "kb200_ctx_destroy", "kb200
            "kb200_seqs_upload", "kb200_distances_on", "kb200_seqs_free", "kb200_aln_pairwise_dist",
            "kb200_anchor_posmaps", "kb200_select_anchors", "kb200_align_tree", "kb200_align_tree_conf", "kb200_kalign",
            "kb200_msa_create", "kb200_msa_align", "kb200_msa_result", "kb200_msa_info", "kb200_msa_tree", "kb200_msa_free",
+           "kb200_fasta_read", "kb200_fasta_numseq", "kb200_fasta_get", "kb200_fasta_letter_freq", "kb200_fasta_arrays",
+           "kb200_fasta_free", "kb200_fasta_write", "kb200_kalign_file",
            "kb200_comm_unique_id", "kb200_ctx_comm_init", "kb200_ctx_comm_destroy", "kb200_partition"]
 
 _lib = None
@@ -103,6 +105,24 @@ def load():
     lib.kb200_seqs_free.restype = None
     lib.kb200_aln_pairwise_dist.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     lib.kb200_aln_pairwise_dist.restype = C.c_int
+    lib.kb200_fasta_read.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+    lib.kb200_fasta_read.restype = C.c_int
+    lib.kb200_fasta_numseq.argtypes = [C.c_void_p]
+    lib.kb200_fasta_numseq.restype = C.c_int
+    lib.kb200_fasta_get.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int),
+                                    C.POINTER(C.c_void_p)]
+    lib.kb200_fasta_get.restype = C.c_int
+    lib.kb200_fasta_letter_freq.argtypes = [C.c_void_p]
+    lib.kb200_fasta_letter_freq.restype = C.POINTER(C.c_int)
+    lib.kb200_fasta_arrays.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    lib.kb200_fasta_arrays.restype = C.c_int
+    lib.kb200_fasta_free.argtypes = [C.c_void_p]
+    lib.kb200_fasta_free.restype = None
+    lib.kb200_fasta_write.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int]
+    lib.kb200_fasta_write.restype = C.c_int
+    lib.kb200_kalign_file.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
+                                      C.c_int, C.c_float]
+    lib.kb200_kalign_file.restype = C.c_int
     lib.kb200_anchor_posmaps.argtypes = [C.c_void_p, C.POINTER(Params), u8p, i64p, i32p, C.c_int,
                                          i32p, C.c_int, C.c_longlong, C.c_longlong, i32p]
     lib.kb200_anchor_posmaps.restype = C.c_int
@@ -251,6 +271,59 @@ def _aln_pairwise_dist(self, rows):
     return dm
 
 
+class Fasta:
+    """kb200_fasta_read: records of a FASTA file parsed with the semantics of the reference's read_fasta
+    (lib/src/msa_io.c:412).  Host code -- needs no GPU."""
+
+    def __init__(self, path, n_threads=0):
+        self.lib = load()
+        h = C.c_void_p()
+        if self.lib.kb200_fasta_read(os.fsencode(path), n_threads, C.byref(h)) != 0:
+            raise RuntimeError("kb200_fasta_read failed: %s" % path)
+        self.h = h
+        self.n = self.lib.kb200_fasta_numseq(h)
+
+    def record(self, i):
+        """(name bytes, residues bytes, gaps int32[len + 1])"""
+        name = C.c_char_p()
+        seq = C.c_void_p()
+        ln = C.c_int()
+        gaps = C.c_void_p()
+        if self.lib.kb200_fasta_get(self.h, i, C.byref(name), C.byref(seq), C.byref(ln), C.byref(gaps)) != 0:
+            raise IndexError(i)
+        s = C.string_at(seq.value, ln.value)
+        g = np.ctypeslib.as_array(C.cast(gaps.value, C.POINTER(C.c_int)), shape=(ln.value + 1,)).copy()
+        return name.value, s, g
+
+    def records(self):
+        return [self.record(i) for i in range(self.n)]
+
+    def letter_freq(self):
+        return np.ctypeslib.as_array(self.lib.kb200_fasta_letter_freq(self.h), shape=(128,)).copy()
+
+    def close(self):
+        if self.h:
+            self.lib.kb200_fasta_free(self.h)
+            self.h = None
+
+
+def fasta_write(path, names, rows, n_threads=0):
+    """kb200_fasta_write: what write_msa_fasta (lib/src/msa_io.c:668) writes for these names and rows"""
+    lib = load()
+    n = len(rows)
+    alnlen = len(rows[0]) if n else 0
+    nm = (C.c_char_p * n)(*[x if isinstance(x, bytes) else x.encode() for x in names])
+    rw = (C.c_char_p * n)(*[x if isinstance(x, bytes) else x.encode() for x in rows])
+    if lib.kb200_fasta_write(os.fsencode(path), nm, rw, n, alnlen, n_threads) != 0:
+        raise RuntimeError("kb200_fasta_write failed: %s" % path)
+
+
+def _kalign_file(self, infile, outfile, n_threads=1, type_=8, gpo=-1.0, gpe=-1.0, tgpe=-1.0, consistency=0, weight=2.0):
+    if self.lib.kb200_kalign_file(self.h, os.fsencode(infile), os.fsencode(outfile), n_threads, type_, gpo, gpe, tgpe,
+                                  consistency, weight) != 0:
+        raise RuntimeError("kb200_kalign_file failed")
+
+
 class DeviceSeqs:
     """sequences resident on the device between distance calls (kb200_seqs_upload / kb200_distances_on)"""
 
@@ -343,6 +416,7 @@ def _kalign(self, seqs, n_threads=1, type_=8, gpo=-1.0, gpe=-1.0, tgpe=-1.0, con
 Context.distances = _distances
 Context.anchor_posmaps = _anchor_posmaps
 Context.aln_pairwise_dist = _aln_pairwise_dist
+Context.kalign_file = _kalign_file
 Context.align_tree = _align_tree
 Context.kalign = _kalign
 

@@ -716,9 +716,13 @@ void kb200_msa_free(kb200_msa* M)
 }
 
 // everything of kalign_run_seeded (aln_wrap.c:133-205) that precedes the DP stages
+// names / file_letter_freq: only for file input (kb200_kalign_file): the record names break ties of the
+// (length, name) sort as in the reference's FASTA path, and detect_alphabet sees the letter frequencies
+// read_fasta counted on the sequence lines (msa_io.c:457; gap characters and digits included)
 static int msa_create_impl(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_threads, int type,
                            float gpo, float gpe, float tgpe, int consistency_anchors, float consistency_weight,
-                           const bool defer_tree, kb200_msa** out)
+                           const bool defer_tree, kb200_msa** out, const char* const* names = nullptr,
+                           const int* file_letter_freq = nullptr)
 {
         if (!ctx || !seq || !len || !out) {
                 return KB200_FAIL;
@@ -731,6 +735,9 @@ static int msa_create_impl(kb200_ctx* ctx, char** seq, int* len, int numseq, int
         // ---- kalign_arr_to_msa: letter frequencies, alphabet detection (msa_op.c:440-520,142-215)
         int letter_freq[128];
         memset(letter_freq, 0, sizeof(letter_freq));
+        if (file_letter_freq) {
+                memcpy(letter_freq, file_letter_freq, sizeof(letter_freq));
+        } else
 #ifdef _OPENMP
 #pragma omp parallel num_threads(n_threads)
 #endif
@@ -793,7 +800,7 @@ static int msa_create_impl(kb200_ctx* ctx, char** seq, int* len, int numseq, int
                 s.seq = seq[i];
                 s.len = len[i];
                 s.rank = i;
-                s.name = "s" + std::to_string(i);
+                s.name = names ? std::string(names[i]) : "s" + std::to_string(i);
                 if (len[i] > 0) M->order.push_back(&s);
         }
         const int N = (int)M->order.size();
@@ -1075,9 +1082,9 @@ int kb200_msa_tree(kb200_msa* M, int* tasks_abc, float* seq_distances)
         return KB200_OK;
 }
 
-int kb200_kalign(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_threads, int type,
-                 float gpo, float gpe, float tgpe, int consistency_anchors, float consistency_weight,
-                 char*** aligned, int* out_aln_len)
+static int kalign_named(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_threads, int type,
+                        float gpo, float gpe, float tgpe, int consistency_anchors, float consistency_weight,
+                        char*** aligned, int* out_aln_len, const char* const* names, const int* file_letter_freq)
 {
         if (!aligned || !out_aln_len) {
                 return KB200_FAIL;
@@ -1086,7 +1093,7 @@ int kb200_kalign(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_threads
         // thread while the GPU works through the anchor batch, which needs only seq_distances.
         kb200_msa* M = nullptr;
         KB_RUN(msa_create_impl(ctx, seq, len, numseq, n_threads, type, gpo, gpe, tgpe,
-                               consistency_anchors, consistency_weight, true, &M));
+                               consistency_anchors, consistency_weight, true, &M, names, file_letter_freq));
         const double ta0 = kb_now();
         int rc = KB200_OK;
         {
@@ -1128,6 +1135,56 @@ int kb200_kalign(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_threads
                 fprintf(stderr, "[kb200 trace] kalign: anchor batch || k-means, tree finish %.1f ms, tree levels %.1f ms, result + free %.1f ms\n",
                         1e3 * (ta1 - ta0), 1e3 * (ta2 - ta1), 1e3 * (kb_now() - ta2));
         }
+        return rc;
+}
+
+int kb200_kalign(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_threads, int type,
+                 float gpo, float gpe, float tgpe, int consistency_anchors, float consistency_weight,
+                 char*** aligned, int* out_aln_len)
+{
+        return kalign_named(ctx, seq, len, numseq, n_threads, type, gpo, gpe, tgpe, consistency_anchors, consistency_weight,
+                            aligned, out_aln_len, nullptr, nullptr);
+}
+
+// the CLI's main path for one FASTA file (src/run_kalign.c:395-470: kalign_read_input -> kalign_run_seeded ->
+// kalign_write_msa, default output format), file to file
+int kb200_kalign_file(kb200_ctx* ctx, const char* infile, const char* outfile, int n_threads, int type,
+                      float gpo, float gpe, float tgpe, int consistency_anchors, float consistency_weight)
+{
+        if (!ctx || !infile || !outfile) {
+                return KB200_FAIL;
+        }
+        kb200_fasta* f = nullptr;
+        KB_RUN(kb200_fasta_read(infile, n_threads, &f));
+        const int n = kb200_fasta_numseq(f);
+        if (n < 2) {
+                // check_for_sequences, msa_io.c:176-191
+                fprintf(stderr, "[kalign_b200] %s\n", n == 1 ? "Only 1 sequence was found in the input files or standard input"
+                                                             : "No sequences were found in the input files or standard input.");
+                kb200_fasta_free(f);
+                return KB200_FAIL;
+        }
+        std::vector<char*> seqs((size_t)n);
+        std::vector<int> lens((size_t)n);
+        std::vector<const char*> names((size_t)n), kept;
+        for (int i = 0; i < n; i++) {
+                const char* sq = nullptr;
+                kb200_fasta_get(f, i, &names[(size_t)i], &sq, &lens[(size_t)i], nullptr);
+                seqs[(size_t)i] = (char*)sq;
+                if (lens[(size_t)i] > 0) kept.push_back(names[(size_t)i]);      // empty records are dropped (msa_check.c:66-139)
+        }
+        char** rows = nullptr;
+        int alnlen = 0;
+        int rc = kalign_named(ctx, seqs.data(), lens.data(), n, n_threads, type, gpo, gpe, tgpe, consistency_anchors,
+                              consistency_weight, &rows, &alnlen, names.data(), kb200_fasta_letter_freq(f));
+        if (rc == KB200_OK) {
+                rc = kb200_fasta_write(outfile, kept.data(), rows, (int)kept.size(), alnlen, n_threads);
+        }
+        if (rows) {
+                for (size_t i = 0; i < kept.size(); i++) free(rows[i]);
+                free(rows);
+        }
+        kb200_fasta_free(f);
         return rc;
 }
 

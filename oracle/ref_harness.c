@@ -16,6 +16,7 @@
  *   mirror_path_n         lib/src/aln_setup.c:438
  *   kalign_run_seeded     lib/src/aln_wrap.c:133  (re-stated call sequence with dumps)
  *   compute_aln_pairwise_dist lib/src/aln_apair_dist.c:9
+ *   kalign_read_input     lib/src/msa_io.c:80   (record dumps for the FASTA parser's parity tests)
  *
  * All functions return 0 on success.
  */
@@ -512,6 +513,65 @@ int refh_aln_pairwise_dist(char** rows, int n, int alnlen, float* dm_out)
                 free_aln_dm(dm, n);
                 rc = 0;
         }
+        free(seqs);
+        free(ptr);
+        return rc;
+}
+
+/* kalign_read_input (msa_io.c:80) on a file; the msa is returned as an opaque handle (NULL on failure) */
+void* refh_read_input(const char* path)
+{
+        struct msa* msa = NULL;
+        if(kalign_read_input((char*)path, &msa, 1) != OK){
+                return NULL;
+        }
+        return msa;
+}
+
+int refh_msa_numseq(void* h){ return ((struct msa*)h)->numseq; }
+int refh_msa_biotype(void* h){ return ((struct msa*)h)->biotype; }
+int refh_msa_aligned(void* h){ return ((struct msa*)h)->aligned; }
+int refh_msa_seq_len(void* h, int i){ return ((struct msa*)h)->sequences[i]->len; }
+int refh_msa_name_len(void* h, int i){ return (int)strlen(((struct msa*)h)->sequences[i]->name); }
+
+void refh_msa_record(void* h, int i, char* name_out, char* seq_out, int* gaps_out)
+{
+        struct msa_seq* s = ((struct msa*)h)->sequences[i];
+        strcpy(name_out, s->name);
+        memcpy(seq_out, s->seq, (size_t)s->len);
+        memcpy(gaps_out, s->gaps, sizeof(int) * (size_t)(s->len + 1));
+}
+
+void refh_msa_letter_freq(void* h, int* out128)
+{
+        memcpy(out128, ((struct msa*)h)->letter_freq, sizeof(int) * 128);
+}
+
+void refh_msa_free(void* h)
+{
+        kalign_free_msa((struct msa*)h);
+}
+
+/* kalign_write_msa (msa_io.c:193) on plain names and finished rows */
+int refh_write_rows(char** names, char** rows, int n, int alnlen, const char* path, const char* format)
+{
+        struct msa m;
+        struct msa_seq* seqs = calloc((size_t)(n > 0 ? n : 1), sizeof(struct msa_seq));
+        struct msa_seq** ptr = malloc(sizeof(struct msa_seq*) * (size_t)(n > 0 ? n : 1));
+        int rc;
+        if(!seqs || !ptr){ free(seqs); free(ptr); return 1; }
+        memset(&m, 0, sizeof(m));
+        for(int i = 0; i < n; i++){
+                seqs[i].name = names[i];
+                seqs[i].seq = rows[i];
+                seqs[i].len = alnlen;
+                ptr[i] = &seqs[i];
+        }
+        m.sequences = ptr;
+        m.numseq = n;
+        m.alnlen = alnlen;
+        m.aligned = ALN_STATUS_FINAL;
+        rc = kalign_write_msa(&m, (char*)path, (char*)format) == OK ? 0 : 1;
         free(seqs);
         free(ptr);
         return rc;

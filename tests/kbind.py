@@ -133,6 +133,22 @@ def refh():
         lib.refh_free.restype = None
         lib.refh_aln_pairwise_dist.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_int, f32p]
         lib.refh_aln_pairwise_dist.restype = C.c_int
+        lib.refh_read_input.argtypes = [C.c_char_p]
+        lib.refh_read_input.restype = C.c_void_p
+        for f in ("refh_msa_numseq", "refh_msa_biotype", "refh_msa_aligned"):
+            getattr(lib, f).argtypes = [C.c_void_p]
+            getattr(lib, f).restype = C.c_int
+        for f in ("refh_msa_seq_len", "refh_msa_name_len"):
+            getattr(lib, f).argtypes = [C.c_void_p, C.c_int]
+            getattr(lib, f).restype = C.c_int
+        lib.refh_msa_record.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, i32p]
+        lib.refh_msa_record.restype = None
+        lib.refh_msa_letter_freq.argtypes = [C.c_void_p, i32p]
+        lib.refh_msa_letter_freq.restype = None
+        lib.refh_msa_free.argtypes = [C.c_void_p]
+        lib.refh_msa_free.restype = None
+        lib.refh_write_rows.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_char_p, C.c_char_p]
+        lib.refh_write_rows.restype = C.c_int
         lib.refh_time_public_api.argtypes = [C.POINTER(C.c_char_p), i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]
         lib.refh_time_public_api.restype = C.c_double
         _refh = lib
@@ -303,3 +319,89 @@ def oracle_aln_pairwise_dist(rows):
         d[i] = 0.0
         dm[i] = d
     return dm
+
+
+def ref_read_fasta(path):
+    """the reference's kalign_read_input (lib/src/msa_io.c:80) on a file:
+    (records [(name bytes, residues bytes, gaps int32[len + 1])], letter_freq int32[128]) or None when it fails"""
+    lib = refh()
+    h = lib.refh_read_input(os.fsencode(path))
+    if not h:
+        return None
+    try:
+        recs = []
+        for i in range(lib.refh_msa_numseq(h)):
+            ln = lib.refh_msa_seq_len(h, i)
+            name = C.create_string_buffer(lib.refh_msa_name_len(h, i) + 1)
+            seq = C.create_string_buffer(ln + 1)
+            gaps = np.zeros(ln + 1, dtype=np.int32)
+            lib.refh_msa_record(h, i, name, seq, gaps)
+            recs.append((name.value, seq.raw[:ln], gaps))
+        freq = np.zeros(128, dtype=np.int32)
+        lib.refh_msa_letter_freq(h, freq)
+        return recs, freq
+    finally:
+        lib.refh_msa_free(h)
+
+
+def ref_write_fasta(path, names, rows):
+    """the reference's kalign_write_msa(..., "fasta") (lib/src/msa_io.c:193,668) on names and finished rows"""
+    lib = refh()
+    n = len(rows)
+    nm = (C.c_char_p * max(1, n))(*[x if isinstance(x, bytes) else x.encode() for x in names])
+    rw = (C.c_char_p * max(1, n))(*[x if isinstance(x, bytes) else x.encode() for x in rows])
+    assert lib.refh_write_rows(nm, rw, n, len(rows[0]) if n else 0, os.fsencode(path), b"fasta") == 0
+
+
+_ALPHA = set(range(ord("A"), ord("Z") + 1)) | set(range(ord("a"), ord("z") + 1))
+_PUNCT = set(range(33, 48)) | set(range(58, 65)) | set(range(91, 97)) | set(range(123, 127))
+
+
+def oracle_read_fasta(data):
+    """pure-python restatement of read_file_stdin + read_fasta (lib/src/msa_io.c:348-482) on the bytes of a
+    file: lines split at newline, a line's content ends at its first control character (< 32 or 127), '>' as the
+    first character opens a record, letters are residues, punctuation is counted in gaps[len], all characters
+    of sequence lines are counted in letter_freq.  Returns (records, letter_freq) or None where the
+    reference fails (sequence data before the first header).  TEST INFRASTRUCTURE ONLY."""
+    recs = []
+    freq = np.zeros(128, dtype=np.int32)
+    lines = data.split(b"\n")
+    if lines and lines[-1] == b"":
+        lines.pop()                      # getline yields no line after a final newline
+    cur = None
+    for raw in lines:
+        cut = len(raw)
+        for i, ch in enumerate(raw):
+            if ch < 32 or ch == 127:
+                cut = i
+                break
+        line = raw[:cut]
+        if line[:1] == b">":
+            cur = [bytes(line[1:]), bytearray(), [0]]
+            recs.append(cur)
+            continue
+        for ch in line:
+            if ch < 128:
+                freq[ch] += 1
+            if ch in _ALPHA:
+                if cur is None:
+                    return None
+                cur[1].append(ch)
+                cur[2].append(0)
+            elif ch in _PUNCT:
+                if cur is None:
+                    return None
+                cur[2][-1] += 1
+    return [(r[0], bytes(r[1]), np.array(r[2], dtype=np.int32)) for r in recs], freq
+
+
+def oracle_write_fasta(names, rows):
+    """restatement of write_msa_fasta (lib/src/msa_io.c:668-717): the bytes of the output file"""
+    out = bytearray()
+    for nm, r in zip(names, rows):
+        nm = nm if isinstance(nm, bytes) else nm.encode()
+        r = r if isinstance(r, bytes) else r.encode()
+        out += b">" + nm + b"\n"
+        for j in range(0, len(r), 60):
+            out += r[j:j + 60] + b"\n"
+    return bytes(out)

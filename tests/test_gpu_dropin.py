@@ -93,3 +93,34 @@ def test_kalign_entry_point_identical(tmp_path):
         rows[tag] = json.load(open(outp))
     assert rows["gpu"] == rows["ref"]
     assert all(r.replace("-", "") == s for r, s in zip(rows["gpu"], seqs))
+
+
+@pytest.mark.parametrize("kind,flags,kw", [("protein", [], dict(type_=8, consistency=5)), ("rna", ["--type", "rna", "--fast"], dict(type_=2, consistency=0))])
+def test_kalign_file_identical_to_reference_cli(tmp_path, kind, flags, kw):
+    """kb200_kalign_file (FASTA file in, FASTA file out through the product's own reader / writer) against the
+    reference CLI on a file whose record names decide the order of equal-length sequences, with gap characters,
+    lower case, an empty record and CRLF line ends in the input"""
+    from kalign_b200 import _lib
+    seqs = synth.family(60, 90, synth.PROTEIN if kind == "protein" else synth.RNA, seed=51)
+    seqs = [s[:80] if i % 3 == 0 else s for i, s in enumerate(seqs)]          # many equal lengths
+    fa = str(tmp_path / "in.fa")
+    with open(fa, "wb") as f:
+        for i, s in enumerate(seqs):
+            f.write(b">%c%d some text\r\n" % (b"zyxw"[i % 4], 1000 - i))
+            body = s if i % 5 else s.lower()
+            if i == 7:
+                body = body[:30] + "--" + body[30:]
+            for j in range(0, len(body), 50):
+                f.write(body[j:j + 50].encode() + b"\r\n")
+            if i == 11:
+                f.write(b">empty record\r\n")
+    ref_out = str(tmp_path / "ref.afa")
+    p = subprocess.run([REF_CLI, "-i", fa, "-o", ref_out, "-n", "4"] + flags, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert p.returncode == 0, p.stdout[-2000:]
+    ctx = _lib.Context(0)
+    try:
+        out = str(tmp_path / "gpu.afa")
+        ctx.kalign_file(fa, out, n_threads=4, weight=2.0, **kw)
+    finally:
+        ctx.close()
+    assert open(out, "rb").read() == open(ref_out, "rb").read()
