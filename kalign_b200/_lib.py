@@ -391,15 +391,21 @@ def _align_tree(self, prm, flat, offs, lens, tasks, seq_distances=None, posmaps=
     return (out, conf) if confidence else out
 
 
-def _kalign(self, seqs, n_threads=1, type_=8, gpo=-1.0, gpe=-1.0, tgpe=-1.0, consistency=0, weight=2.0):
+def _kalign(self, seqs, n_threads=1, type_=8, gpo=-1.0, gpe=-1.0, tgpe=-1.0, consistency=0, weight=2.0, timing=None):
+    """kb200_kalign on python strings.  timing: optional list; the wall-clock seconds of the C call alone (host
+    char** in, malloc'd host rows out -- what a C caller of kalign() sees) are appended to it."""
+    import time
     n = len(seqs)
     keep = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
     arr = (C.c_char_p * n)(*keep)
     lens = np.array([len(s) for s in keep], dtype=np.int32)
     out = C.POINTER(C.c_void_p)()
     alen = C.c_int(0)
+    t0 = time.perf_counter()
     rc = self.lib.kb200_kalign(self.h, arr, lens, n, n_threads, type_, gpo, gpe, tgpe, consistency, weight,
                                C.byref(out), C.byref(alen))
+    if timing is not None:
+        timing.append(time.perf_counter() - t0)
     if rc != 0:
         raise RuntimeError("kb200_kalign failed")
     libc = C.CDLL(None)

@@ -199,6 +199,11 @@ int kb200_aln_pairwise_dist(kb200_ctx* ctx, const char* const* rows, int n, int 
                         kb_host_give(ctx, stage);
                         return KB200_FAIL;
                 }
+        }
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(kb_default_threads())
+#endif
+        for (int i = 0; i < n; i++) {
                 memcpy(stage + (size_t)i * row_bytes, rows[i], (size_t)alnlen);
                 memset(stage + (size_t)i * row_bytes + (size_t)alnlen, '-', row_bytes - (size_t)alnlen);
         }
@@ -271,8 +276,12 @@ int kb200_aln_pairwise_dist(kb200_ctx* ctx, const char* const* rows, int n, int 
                 if (e == cudaSuccess) {
                         const size_t r0 = b * band_rows;
                         const size_t nr = std::min(band_rows, (size_t)n - r0);
-                        for (size_t r = 0; r < nr; r++) {
-                                memcpy(dm_rows[r0 + r], pin[b & 1] + r * (size_t)n, (size_t)n * sizeof(float));
+                        const float* src = pin[b & 1];
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(kb_default_threads())
+#endif
+                        for (long long r = 0; r < (long long)nr; r++) {
+                                memcpy(dm_rows[r0 + (size_t)r], src + (size_t)r * (size_t)n, (size_t)n * sizeof(float));
                         }
                 }
         }
