@@ -211,9 +211,10 @@ def apair_bench(ctx, rows, with_cpu):
     out = {"n": n, "alnlen": alnlen, "kernel_seconds": tk, "call_seconds": t1 - t0,
            "col_pairs_per_sec_in_kernel": colpairs / tk if tk > 0 else None,
            "col_pairs_per_sec_call": colpairs / (t1 - t0),
-           "issue_frac": (colpairs * 110.0 / 64.0 / tk / (148 * 4 * 32 * 1.965e9)) if tk > 0 else None,
-           "issue_note": "about 110 SASS instructions per staged word of a 4 x 4 pair block (64 column-pairs; static count of the "
-                         "inner loop, not an ncu measurement) against 148 SMs x 4 x 32 lanes x 1.965 GHz",
+           "issue_frac": (colpairs * 2.108 / tk / (148 * 4 * 32 * 1.965e9)) if tk > 0 else None,
+           "issue_note": "2.108 executed thread-instructions per column-pair (ncu, profiles/r02_apair_kernel_full.csv: 2.838e9 "
+                         "warp-instructions x 32 / 4.307e10 column-pairs of a 4096 x 5136 alignment; smsp__issue_active 71 %) "
+                         "against 148 SMs x 4 x 32 lanes x 1.965 GHz",
            "h2d_bytes": float(n) * ((alnlen + 3) // 4 * 4), "d2h_bytes": 4.0 * n * n, "kernel": "kb_apair_tile_kernel"}
     if with_cpu:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
