@@ -179,6 +179,36 @@ int kb200_kalign(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_threads
                  float gpo, float gpe, float tgpe, int consistency_anchors, float consistency_weight,
                  char*** aligned, int* out_aln_len);
 
+/* kalign_run_seeded (lib/include/kalign/kalign.h:51, lib/src/aln_wrap.c:133) on plain arrays, refine = none:
+   kb200_kalign plus
+     tree_seed, tree_noise : tree_seed != 0 && tree_noise > 0 builds the guide tree from anchor distances
+                             multiplied by max(0.1, gaussian(1, tree_noise)) drawn from the reference's generator
+                             (build_tree_kmeans_noisy, lib/src/bisectingKmeans.c:76-176; lib/src/tlrng.c)
+     dist_scale            : ap->dist_scale (compute_gap_scale, lib/src/aln_run.c:126)
+     vsm_amax, use_seq_weights : >= 0 override the defaults of aln_param_init (aln_wrap.c:193-199) */
+int kb200_kalign_seeded(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_threads, int type,
+                        float gpo, float gpe, float tgpe, unsigned long long tree_seed, float tree_noise,
+                        float dist_scale, float vsm_amax, float use_seq_weights,
+                        int consistency_anchors, float consistency_weight, char*** aligned, int* out_aln_len);
+/* the n noise factors of build_tree_kmeans_noisy for (seed, sigma), in the order they are applied
+   (row by row over the N x 32 anchor distances).  Host code. */
+int kb200_tree_noise(unsigned long long seed, float sigma, long long n, float* out);
+
+/* Ensemble (kalign_ensemble, lib/src/ensemble.c:221-340): n_runs independent alignments of the
+   same sequences -- run 0 with the base penalties, run k > 0 with penalties scaled by entry k % 12 of the
+   reference's table and a noisy guide tree seeded seed + k (resolve_run_params, ensemble.c:55-76).
+   kb200_ensemble_run_params resolves run k's parameters, kb200_ensemble_run computes run k (gpo / gpe / tgpe
+   < 0: the defaults of the detected alphabet; use_seq_weights < 0 means 0 here, ensemble.c:248).  The runs
+   share nothing, so they shard over GPUs with no collective: rank r of `world` processes (one per GPU)
+   computes the runs k with k % world == r.  POAR consensus / scoring of the collected runs is host code and
+   stays the reference's. */
+int kb200_ensemble_run_params(float base_gpo, float base_gpe, float base_tgpe, int run, unsigned long long seed,
+                              float* gpo, float* gpe, float* tgpe, unsigned long long* tree_seed, float* tree_noise);
+int kb200_ensemble_run(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_threads, int type,
+                       float gpo, float gpe, float tgpe, int run, unsigned long long seed,
+                       float dist_scale, float vsm_amax, float use_seq_weights,
+                       int consistency_anchors, float consistency_weight, char*** aligned, int* out_aln_len);
+
 /* FASTA in / out, host code: the file is mapped and parsed by n_threads threads at once
    (n_threads <= 0: all the process may use) with the semantics of read_file_stdin + read_fasta
    (lib/src/msa_io.c:348,412): a line's content ends at its first control character; '>' at the start of a

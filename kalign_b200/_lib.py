@@ -51,6 +51,7 @@ EXPORTS = ["kb200_device_count", "kb200_ctx_create", "kb200_ctx_destroy", "kb200
            "kb200_seqs_upload", "kb200_distances_on", "kb200_seqs_free", "kb200_aln_pairwise_dist",
            "kb200_anchor_posmaps", "kb200_select_anchors", "kb200_align_tree", "kb200_align_tree_conf", "kb200_kalign",
            "kb200_msa_create", "kb200_msa_align", "kb200_msa_result", "kb200_msa_info", "kb200_msa_tree", "kb200_msa_free",
+           "kb200_kalign_seeded", "kb200_tree_noise", "kb200_ensemble_run_params", "kb200_ensemble_run",
            "kb200_fasta_read", "kb200_fasta_numseq", "kb200_fasta_get", "kb200_fasta_letter_freq", "kb200_fasta_arrays",
            "kb200_fasta_free", "kb200_fasta_write", "kb200_kalign_file",
            "kb200_comm_unique_id", "kb200_ctx_comm_init", "kb200_ctx_comm_destroy", "kb200_partition"]
@@ -105,6 +106,19 @@ def load():
     lib.kb200_seqs_free.restype = None
     lib.kb200_aln_pairwise_dist.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     lib.kb200_aln_pairwise_dist.restype = C.c_int
+    lib.kb200_kalign_seeded.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), i32p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
+                                        C.c_ulonglong, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float,
+                                        C.POINTER(C.POINTER(C.c_void_p)), C.POINTER(C.c_int)]
+    lib.kb200_kalign_seeded.restype = C.c_int
+    lib.kb200_tree_noise.argtypes = [C.c_ulonglong, C.c_float, C.c_longlong, f32p]
+    lib.kb200_tree_noise.restype = C.c_int
+    lib.kb200_ensemble_run_params.argtypes = [C.c_float, C.c_float, C.c_float, C.c_int, C.c_ulonglong, C.POINTER(C.c_float),
+                                              C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_ulonglong), C.POINTER(C.c_float)]
+    lib.kb200_ensemble_run_params.restype = C.c_int
+    lib.kb200_ensemble_run.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), i32p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
+                                       C.c_int, C.c_ulonglong, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float,
+                                       C.POINTER(C.POINTER(C.c_void_p)), C.POINTER(C.c_int)]
+    lib.kb200_ensemble_run.restype = C.c_int
     lib.kb200_fasta_read.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
     lib.kb200_fasta_read.restype = C.c_int
     lib.kb200_fasta_numseq.argtypes = [C.c_void_p]
@@ -271,6 +285,67 @@ def _aln_pairwise_dist(self, rows):
     return dm
 
 
+def tree_noise(seed, sigma, n):
+    """kb200_tree_noise: the factors build_tree_kmeans_noisy multiplies the anchor distances with (host code)"""
+    out = np.zeros(n, dtype=np.float32)
+    if load().kb200_tree_noise(seed, sigma, n, out) != 0:
+        raise RuntimeError("kb200_tree_noise failed")
+    return out
+
+
+def ensemble_run_params(base_gpo, base_gpe, base_tgpe, run, seed):
+    """kb200_ensemble_run_params -> (gpo, gpe, tgpe, tree_seed, tree_noise) of run `run`"""
+    g, e, t, n = C.c_float(), C.c_float(), C.c_float(), C.c_float()
+    ts = C.c_ulonglong()
+    if load().kb200_ensemble_run_params(base_gpo, base_gpe, base_tgpe, run, seed, C.byref(g), C.byref(e), C.byref(t), C.byref(ts), C.byref(n)) != 0:
+        raise RuntimeError("kb200_ensemble_run_params failed")
+    return g.value, e.value, t.value, ts.value, n.value
+
+
+def _rows_out(lib_, out, alen, nrows):
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    rows = []
+    for i in range(nrows):
+        rows.append(C.string_at(out[i], alen.value).decode())
+        libc.free(out[i])
+    libc.free(C.cast(out, C.c_void_p))
+    return rows
+
+
+def _kalign_seeded(self, seqs, n_threads=1, type_=8, gpo=-1.0, gpe=-1.0, tgpe=-1.0, tree_seed=0, tree_noise=0.0,
+                   dist_scale=0.0, vsm_amax=-1.0, use_seq_weights=-1.0, consistency=0, weight=2.0):
+    """kb200_kalign_seeded: kalign_run_seeded on python strings"""
+    n = len(seqs)
+    keep = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
+    arr = (C.c_char_p * n)(*keep)
+    lens = np.array([len(s) for s in keep], dtype=np.int32)
+    out = C.POINTER(C.c_void_p)()
+    alen = C.c_int(0)
+    if self.lib.kb200_kalign_seeded(self.h, arr, lens, n, n_threads, type_, gpo, gpe, tgpe, tree_seed, tree_noise, dist_scale,
+                                    vsm_amax, use_seq_weights, consistency, weight, C.byref(out), C.byref(alen)) != 0:
+        raise RuntimeError("kb200_kalign_seeded failed")
+    return _rows_out(self.lib, out, alen, int((lens > 0).sum()))
+
+
+def _ensemble_runs(self, seqs, n_runs, seed=42, rank=0, world=1, n_threads=1, type_=8, gpo=-1.0, gpe=-1.0, tgpe=-1.0,
+                   dist_scale=0.0, vsm_amax=-1.0, use_seq_weights=-1.0, consistency=0, weight=2.0):
+    """the runs k of a kalign_ensemble with k % world == rank (one process per GPU, no collective): {k: rows}"""
+    n = len(seqs)
+    keep = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
+    arr = (C.c_char_p * n)(*keep)
+    lens = np.array([len(s) for s in keep], dtype=np.int32)
+    res = {}
+    for k in range(rank, n_runs, world):
+        out = C.POINTER(C.c_void_p)()
+        alen = C.c_int(0)
+        if self.lib.kb200_ensemble_run(self.h, arr, lens, n, n_threads, type_, gpo, gpe, tgpe, k, seed, dist_scale, vsm_amax,
+                                       use_seq_weights, consistency, weight, C.byref(out), C.byref(alen)) != 0:
+            raise RuntimeError("kb200_ensemble_run %d failed" % k)
+        res[k] = _rows_out(self.lib, out, alen, int((lens > 0).sum()))
+    return res
+
+
 class Fasta:
     """kb200_fasta_read: records of a FASTA file parsed with the semantics of the reference's read_fasta
     (lib/src/msa_io.c:412).  Host code -- needs no GPU."""
@@ -423,6 +498,8 @@ Context.distances = _distances
 Context.anchor_posmaps = _anchor_posmaps
 Context.aln_pairwise_dist = _aln_pairwise_dist
 Context.kalign_file = _kalign_file
+Context.kalign_seeded = _kalign_seeded
+Context.ensemble_runs = _ensemble_runs
 Context.align_tree = _align_tree
 Context.kalign = _kalign
 

@@ -284,6 +284,75 @@ struct KbTreeJob {
         int num_anchor = 0;
         int stride = 0;
         int root = -1;
+        uint64_t tree_seed = 0;          // build_tree_kmeans_noisy (bisectingKmeans.c:76): seed != 0 && noise > 0
+        float tree_noise = 0.0f;
+};
+
+// The multiplicative noise build_tree_kmeans_noisy puts on the N x 32 anchor distances
+// (bisectingKmeans.c:104-116): factor = max(0.1, gaussian(1, sigma)) drawn row by row from the reference's
+// generator (lib/src/tlrng.c): xoshiro256** (public domain, Blackman & Vigna) seeded by four splitmix64
+// steps (init_rng :218-271), uniform = next / 2^64 redrawn while 0 (tl_random_double :87), Box-Muller with
+// the second variate kept for the next call (tl_random_gaussian :105-124).  Same libm, same operation
+// order: the factors are bit-identical, and so is everything that follows.
+struct KbNoise {
+        uint64_t s[4];
+        bool gen = false;
+        double z1 = 0.0;
+        static uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+        explicit KbNoise(uint64_t seed)
+        {
+                bool ok = false;
+                while (!ok) {
+                        for (int i = 0; i < 4; i++) {
+                                uint64_t z = (seed += 0x9e3779b97f4a7c15ULL);
+                                z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+                                z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+                                s[i] = z ^ (z >> 31);
+                                if (s[i]) ok = true;
+                        }
+                }
+        }
+        uint64_t next()
+        {
+                const uint64_t r = rotl(s[1] * 5, 7) * 9;
+                const uint64_t t = s[1] << 17;
+                s[2] ^= s[0];
+                s[3] ^= s[1];
+                s[1] ^= s[2];
+                s[0] ^= s[3];
+                s[2] ^= t;
+                s[3] = rotl(s[3], 45);
+                return r;
+        }
+        double uniform()
+        {
+                double y;
+                do {
+                        y = (double)next() / 18446744073709551616.0;
+                } while (y == 0.0);
+                return y;
+        }
+        double gaussian(double mu, double sigma)
+        {
+                gen = !gen;
+                if (!gen) {
+                        return z1 * sigma + mu;
+                }
+                double u1, u2;
+                do {
+                        u1 = uniform();
+                        u2 = uniform();
+                } while (u1 <= DBL_EPSILON);
+                const double z0 = sqrt(-2.0 * log(u1)) * cos(2.0 * M_PI * u2);
+                z1 = sqrt(-2.0 * log(u1)) * sin(2.0 * M_PI * u2);
+                return z0 * sigma + mu;
+        }
+        float factor(float sigma)
+        {
+                double n = gaussian(1.0, (double)sigma);
+                if (n < 0.1) n = 0.1;
+                return (float)n;
+        }
 };
 
 int kb_tree_prepare(kb200_ctx* ctx, KbSeqs& S, KbTreeJob& T, std::vector<float>& seq_distances)
@@ -317,6 +386,14 @@ int kb_tree_prepare(kb200_ctx* ctx, KbSeqs& S, KbTreeJob& T, std::vector<float>&
                 KB_RUN(kb_distances_dev(ctx, S, rows.data(), N, anchors.data(), num_anchor, 0, tmp.data()));
                 for (int i = 0; i < N; i++) {
                         memcpy(T.dm.data() + (size_t)i * stride, tmp.data() + (size_t)i * num_anchor, sizeof(float) * (size_t)num_anchor);
+                }
+        }
+        if (T.tree_seed != 0 && T.tree_noise > 0.0f) {
+                KbNoise rng(T.tree_seed);
+                for (int i = 0; i < N; i++) {
+                        for (int j = 0; j < num_anchor; j++) {
+                                T.dm[(size_t)i * stride + j] *= rng.factor(T.tree_noise);
+                        }
                 }
         }
         T.num_anchor = num_anchor;
@@ -547,9 +624,12 @@ static int tree_threads(const kb200_ctx* ctx, int n_threads)
 }
 
 // build_tree_kmeans (bisectingKmeans.c:177-271) in one go
-int kb_build_tree(kb200_ctx* ctx, KbSeqs& S, int n_threads, std::vector<int>& abc, std::vector<float>& seq_distances)
+int kb_build_tree(kb200_ctx* ctx, KbSeqs& S, int n_threads, std::vector<int>& abc, std::vector<float>& seq_distances,
+                  uint64_t tree_seed = 0, float tree_noise = 0.0f)
 {
         KbTreeJob T;
+        T.tree_seed = tree_seed;
+        T.tree_noise = tree_noise;
         KB_RUN(kb_tree_prepare(ctx, S, T, seq_distances));      // N x 32 distances: rows sharded across the ranks
         int rc = KB200_OK;
         if (ctx->rank == 0) {
@@ -716,14 +796,52 @@ void kb200_msa_free(kb200_msa* M)
 }
 
 // everything of kalign_run_seeded (aln_wrap.c:133-205) that precedes the DP stages
-// names / file_letter_freq: only for file input (kb200_kalign_file): the record names break ties of the
-// (length, name) sort as in the reference's FASTA path, and detect_alphabet sees the letter frequencies
-// read_fasta counted on the sequence lines (msa_io.c:457; gap characters and digits included)
+// detect_alphabet (msa_op.c:142-215): 0 protein, 1 nucleotide, 2 undecided
+static int kb_detect_biotype(const int* letter_freq)
+{
+        int biotype = 2;
+        double DNA[128], protein[128];
+        const char* DNA_letters = "acgtunACGTUN";
+        const char* protein_letters = "acdefghiklmnpqrstvwyACDEFGHIKLMNPQRSTVWY";
+        for (int i = 0; i < 128; i++) {
+                DNA[i] = log(0.0001 * 1.0 / 116.0);
+                protein[i] = log(0.0001 * 1.0 / 88.0);
+        }
+        for (int i = 0; i < 12; i++) DNA[(int)DNA_letters[i]] = log(0.9999 * 1.0 / 12.0);
+        for (int i = 0; i < 40; i++) protein[(int)protein_letters[i]] = log(0.9999 * 1.0 / 40.0);
+        double dna_prob = 0.0, prot_prob = 0.0;
+        for (int i = 0; i < 128; i++) {
+                if (letter_freq[i]) {
+                        dna_prob += DNA[i] * (double)letter_freq[i];
+                        prot_prob += protein[i] * (double)letter_freq[i];
+                }
+        }
+        if (dna_prob > prot_prob) biotype = 1;
+        else if (prot_prob > dna_prob) biotype = 0;
+        return biotype;
+}
+
+// what kalign_run_seeded takes beyond kalign() (aln_wrap.c:133-139, 169-199), plus the two things only file input has
+struct KbRunOpts {
+        // names / file_letter_freq: only for file input (kb200_kalign_file): the record names break ties of the
+        // (length, name) sort as in the reference's FASTA path, and detect_alphabet sees the letter frequencies
+        // read_fasta counted on the sequence lines (msa_io.c:457; gap characters and digits included)
+        const char* const* names = nullptr;
+        const int* file_letter_freq = nullptr;
+        uint64_t tree_seed = 0;          // != 0 with tree_noise > 0: build_tree_kmeans_noisy
+        float tree_noise = 0.0f;
+        float dist_scale = 0.0f;         // ap->dist_scale (always assigned)
+        float vsm_amax = -1.0f;          // >= 0 overrides the default
+        float use_seq_weights = -1.0f;   // >= 0 overrides the default
+};
+static const KbRunOpts kb_default_opts;
+
 static int msa_create_impl(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_threads, int type,
                            float gpo, float gpe, float tgpe, int consistency_anchors, float consistency_weight,
-                           const bool defer_tree, kb200_msa** out, const char* const* names = nullptr,
-                           const int* file_letter_freq = nullptr)
+                           const bool defer_tree, kb200_msa** out, const KbRunOpts& opts = kb_default_opts)
 {
+        const char* const* names = opts.names;
+        const int* file_letter_freq = opts.file_letter_freq;
         if (!ctx || !seq || !len || !out) {
                 return KB200_FAIL;
         }
@@ -758,27 +876,7 @@ static int msa_create_impl(kb200_ctx* ctx, char** seq, int* len, int numseq, int
 #endif
                 for (int c = 0; c < 128; c++) letter_freq[c] += local[c];
         }
-        int biotype = 2;
-        {
-                double DNA[128], protein[128];
-                const char* DNA_letters = "acgtunACGTUN";
-                const char* protein_letters = "acdefghiklmnpqrstvwyACDEFGHIKLMNPQRSTVWY";
-                for (int i = 0; i < 128; i++) {
-                        DNA[i] = log(0.0001 * 1.0 / 116.0);
-                        protein[i] = log(0.0001 * 1.0 / 88.0);
-                }
-                for (int i = 0; i < 12; i++) DNA[(int)DNA_letters[i]] = log(0.9999 * 1.0 / 12.0);
-                for (int i = 0; i < 40; i++) protein[(int)protein_letters[i]] = log(0.9999 * 1.0 / 40.0);
-                double dna_prob = 0.0, prot_prob = 0.0;
-                for (int i = 0; i < 128; i++) {
-                        if (letter_freq[i]) {
-                                dna_prob += DNA[i] * (double)letter_freq[i];
-                                prot_prob += protein[i] * (double)letter_freq[i];
-                        }
-                }
-                if (dna_prob > prot_prob) biotype = 1;
-                else if (prot_prob > dna_prob) biotype = 0;
-        }
+        const int biotype = kb_detect_biotype(letter_freq);
         if (biotype == 2) {
                 fprintf(stderr, "[kalign_b200] Unable to determine what alphabet to use.\n");
                 return KB200_FAIL;
@@ -861,7 +959,7 @@ static int msa_create_impl(kb200_ctx* ctx, char** seq, int* len, int numseq, int
         if (rc == KB200_OK && !defer_tree) {
                 rc = encode_seqs_dev(M, M->S, biotype == 1 ? ALPHA_DNA : ALPHA_RED);
                 tc2 = kb_now();
-                if (rc == KB200_OK) rc = kb_build_tree(ctx, M->S, n_threads, M->abc, M->seq_distances);
+                if (rc == KB200_OK) rc = kb_build_tree(ctx, M->S, n_threads, M->abc, M->seq_distances, opts.tree_seed, opts.tree_noise);
                 if (rc == KB200_OK && biotype == 0) {
                         rc = encode_seqs_dev(M, M->S, ALPHA_AMB);
                 }
@@ -869,6 +967,8 @@ static int msa_create_impl(kb200_ctx* ctx, char** seq, int* len, int numseq, int
                 // only the first stage of the tree here (distance matrix -> seq_distances -> anchors);
                 // kb200_kalign finishes the tree around the anchor batch
                 M->tree_job = new KbTreeJob();
+                M->tree_job->tree_seed = opts.tree_seed;
+                M->tree_job->tree_noise = opts.tree_noise;
                 if (biotype == 0) {
                         rc = encode_seqs_dev(M, M->S_tree, ALPHA_RED);        // 13-letter tree alphabet
                         tc2 = kb_now();
@@ -897,6 +997,10 @@ static int msa_create_impl(kb200_ctx* ctx, char** seq, int* len, int numseq, int
                         }
                 }
                 rc = kb200_params_init(&M->prm, biotype, type, gpo, gpe, tgpe);
+                // aln_wrap.c:193-199
+                M->prm.dist_scale = opts.dist_scale;
+                if (opts.vsm_amax >= 0.0f) M->prm.vsm_amax = opts.vsm_amax;
+                if (opts.use_seq_weights >= 0.0f) M->prm.use_seq_weights = opts.use_seq_weights;
         }
         if (rc == KB200_OK && consistency_anchors > 0 && N >= 3) {
                 M->K = std::min(consistency_anchors, N);
@@ -1084,7 +1188,7 @@ int kb200_msa_tree(kb200_msa* M, int* tasks_abc, float* seq_distances)
 
 static int kalign_named(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_threads, int type,
                         float gpo, float gpe, float tgpe, int consistency_anchors, float consistency_weight,
-                        char*** aligned, int* out_aln_len, const char* const* names, const int* file_letter_freq)
+                        char*** aligned, int* out_aln_len, const KbRunOpts& opts)
 {
         if (!aligned || !out_aln_len) {
                 return KB200_FAIL;
@@ -1093,7 +1197,7 @@ static int kalign_named(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_
         // thread while the GPU works through the anchor batch, which needs only seq_distances.
         kb200_msa* M = nullptr;
         KB_RUN(msa_create_impl(ctx, seq, len, numseq, n_threads, type, gpo, gpe, tgpe,
-                               consistency_anchors, consistency_weight, true, &M, names, file_letter_freq));
+                               consistency_anchors, consistency_weight, true, &M, opts));
         const double ta0 = kb_now();
         int rc = KB200_OK;
         {
@@ -1143,7 +1247,101 @@ int kb200_kalign(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_threads
                  char*** aligned, int* out_aln_len)
 {
         return kalign_named(ctx, seq, len, numseq, n_threads, type, gpo, gpe, tgpe, consistency_anchors, consistency_weight,
-                            aligned, out_aln_len, nullptr, nullptr);
+                            aligned, out_aln_len, kb_default_opts);
+}
+
+// kalign_run_seeded (lib/include/kalign/kalign.h:51, aln_wrap.c:133) on plain arrays; refine = none
+int kb200_kalign_seeded(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_threads, int type,
+                        float gpo, float gpe, float tgpe, unsigned long long tree_seed, float tree_noise,
+                        float dist_scale, float vsm_amax, float use_seq_weights,
+                        int consistency_anchors, float consistency_weight, char*** aligned, int* out_aln_len)
+{
+        KbRunOpts o;
+        o.tree_seed = (uint64_t)tree_seed;
+        o.tree_noise = tree_noise;
+        o.dist_scale = dist_scale;
+        o.vsm_amax = vsm_amax;
+        o.use_seq_weights = use_seq_weights;
+        return kalign_named(ctx, seq, len, numseq, n_threads, type, gpo, gpe, tgpe, consistency_anchors, consistency_weight,
+                            aligned, out_aln_len, o);
+}
+
+// multiplicative factors of build_tree_kmeans_noisy, in the order they are applied (row by row)
+int kb200_tree_noise(unsigned long long seed, float sigma, long long n, float* out)
+{
+        if (!out || n < 0 || seed == 0) {
+                return KB200_FAIL;
+        }
+        KbNoise rng((uint64_t)seed);
+        for (long long i = 0; i < n; i++) {
+                out[i] = rng.factor(sigma);
+        }
+        return KB200_OK;
+}
+
+// resolve_run_params (ensemble.c:55-76): run 0 = the base penalties, no noise; run k > 0 = base penalties scaled by
+// entry k % 12 of the reference's table (ensemble.c:33-46) and a noisy guide tree seeded seed + k
+int kb200_ensemble_run_params(float base_gpo, float base_gpe, float base_tgpe, int run, unsigned long long seed,
+                              float* gpo, float* gpe, float* tgpe, unsigned long long* tree_seed, float* tree_noise)
+{
+        static const float tbl[12][4] = {
+                {1.0f, 1.0f, 1.0f, 0.0f},  {0.5f, 1.5f, 0.8f, 0.20f}, {1.5f, 0.5f, 1.2f, 0.20f}, {0.7f, 0.7f, 0.5f, 0.25f},
+                {1.4f, 1.4f, 1.5f, 0.25f}, {0.8f, 1.2f, 1.0f, 0.30f}, {1.3f, 0.8f, 0.7f, 0.30f}, {0.6f, 1.0f, 1.3f, 0.15f},
+                {1.0f, 0.6f, 0.6f, 0.15f}, {1.8f, 1.0f, 1.0f, 0.35f}, {1.0f, 1.8f, 1.8f, 0.35f}, {0.4f, 0.4f, 0.3f, 0.20f}};
+        if (run < 0 || !gpo || !gpe || !tgpe || !tree_seed || !tree_noise) {
+                return KB200_FAIL;
+        }
+        if (run == 0) {
+                *gpo = base_gpo;
+                *gpe = base_gpe;
+                *tgpe = base_tgpe;
+                *tree_seed = 0;
+                *tree_noise = 0.0f;
+        } else {
+                const float* e = tbl[run % 12];
+                *gpo = base_gpo * e[0];
+                *gpe = base_gpe * e[1];
+                *tgpe = base_tgpe * e[2];
+                *tree_seed = seed + (unsigned long long)run;
+                *tree_noise = e[3];
+        }
+        return KB200_OK;
+}
+
+// one of the independent alignment runs of kalign_ensemble (ensemble.c:286-340).  The runs share nothing:
+// a caller with several GPUs (one process per GPU) gives run k to rank k % world -- no collective on the data
+// path -- and collects the rows for the reference's POAR consensus / scoring, which stays host code.
+int kb200_ensemble_run(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_threads, int type,
+                       float gpo, float gpe, float tgpe, int run, unsigned long long seed,
+                       float dist_scale, float vsm_amax, float use_seq_weights,
+                       int consistency_anchors, float consistency_weight, char*** aligned, int* out_aln_len)
+{
+        if (!ctx || !seq || !len || numseq < 2 || run < 0) {
+                return KB200_FAIL;
+        }
+        // base penalties: aln_param_init's defaults for the detected alphabet where the caller passes < 0
+        // (ensemble.c:268-273).  The alphabet is detected from the letters as kb200_kalign does.
+        int freq[128];
+        memset(freq, 0, sizeof(freq));
+        for (int i = 0; i < numseq; i++) {
+                for (int j = 0; j < len[i]; j++) {
+                        const int ch = (int)(unsigned char)seq[i][j];
+                        if (ch < 128) freq[ch]++;
+                }
+        }
+        const int biotype = kb_detect_biotype(freq);
+        if (biotype == 2) {
+                fprintf(stderr, "[kalign_b200] Unable to determine what alphabet to use.\n");
+                return KB200_FAIL;
+        }
+        kb200_params base;
+        KB_RUN(kb200_params_init(&base, biotype, type == KB200_TYPE_PROTEIN_PFASUM_AUTO ? KB200_TYPE_PROTEIN_PFASUM43 : type, gpo, gpe, tgpe));
+        float rg, re, rt, noise;
+        unsigned long long ts;
+        KB_RUN(kb200_ensemble_run_params(base.gpo, base.gpe, base.tgpe, run, seed, &rg, &re, &rt, &ts, &noise));
+        if (use_seq_weights < 0.0f) use_seq_weights = 0.0f;      // ensemble.c:248-250
+        return kb200_kalign_seeded(ctx, seq, len, numseq, n_threads, type, rg, re, rt, ts, noise, dist_scale, vsm_amax, use_seq_weights,
+                                   consistency_anchors, consistency_weight, aligned, out_aln_len);
 }
 
 // the CLI's main path for one FASTA file (src/run_kalign.c:395-470: kalign_read_input -> kalign_run_seeded ->
@@ -1175,8 +1373,11 @@ int kb200_kalign_file(kb200_ctx* ctx, const char* infile, const char* outfile, i
         }
         char** rows = nullptr;
         int alnlen = 0;
+        KbRunOpts fo;
+        fo.names = names.data();
+        fo.file_letter_freq = kb200_fasta_letter_freq(f);
         int rc = kalign_named(ctx, seqs.data(), lens.data(), n, n_threads, type, gpo, gpe, tgpe, consistency_anchors,
-                              consistency_weight, &rows, &alnlen, names.data(), kb200_fasta_letter_freq(f));
+                              consistency_weight, &rows, &alnlen, fo);
         if (rc == KB200_OK) {
                 rc = kb200_fasta_write(outfile, kept.data(), rows, (int)kept.size(), alnlen, n_threads);
         }

@@ -55,6 +55,7 @@
 #include "anchor_consistency.h"
 #include "bpm.h"
 #include "aln_apair_dist.h"
+#include "tlrng.h"
 #include "kalign/kalign.h"
 
 static double now_s(void)
@@ -575,4 +576,40 @@ int refh_write_rows(char** names, char** rows, int n, int alnlen, const char* pa
         free(seqs);
         free(ptr);
         return rc;
+}
+
+/* the noise factors of build_tree_kmeans_noisy (bisectingKmeans.c:104-116), from the reference's own generator */
+int refh_tree_noise(uint64_t seed, float sigma, long long n, float* out)
+{
+        struct rng_state* rng = init_rng(seed);
+        if(!rng){ return 1; }
+        for(long long i = 0; i < n; i++){
+                double noise = tl_random_gaussian(rng, 1.0, (double)sigma);
+                if(noise < 0.1) noise = 0.1;
+                out[i] = (float)noise;
+        }
+        free_rng(rng);
+        return 0;
+}
+
+/* kalign_run_seeded (aln_wrap.c:133) end to end on plain arrays; rows in input order, concatenated with NULs.
+   out must hold n * (cap + 1) bytes; returns the alignment length or -1 */
+int refh_run_seeded(char** seqs, int* lens, int n, int n_threads, int type, float gpo, float gpe, float tgpe,
+                    uint64_t tree_seed, float tree_noise, float dist_scale, float vsm_amax, float use_seq_weights,
+                    int consistency_anchors, float consistency_weight, char* out, int cap)
+{
+        struct msa* msa = seqs_to_msa(seqs, lens, n);
+        int L = -1;
+        if(!msa){ return -1; }
+        if(kalign_run_seeded(msa, n_threads, type, gpo, gpe, tgpe, KALIGN_REFINE_NONE, 0, tree_seed, tree_noise,
+                             dist_scale, vsm_amax, use_seq_weights, consistency_anchors, consistency_weight) == OK
+           && msa->alnlen <= cap){
+                L = msa->alnlen;
+                for(int i = 0; i < msa->numseq; i++){
+                        memcpy(out + (size_t)i * (size_t)(L + 1), msa->sequences[i]->seq, (size_t)L);
+                        out[(size_t)i * (size_t)(L + 1) + (size_t)L] = 0;
+                }
+        }
+        kalign_free_msa(msa);
+        return L;
 }

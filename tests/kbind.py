@@ -149,6 +149,11 @@ def refh():
         lib.refh_msa_free.restype = None
         lib.refh_write_rows.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_char_p, C.c_char_p]
         lib.refh_write_rows.restype = C.c_int
+        lib.refh_tree_noise.argtypes = [C.c_uint64, C.c_float, C.c_longlong, f32p]
+        lib.refh_tree_noise.restype = C.c_int
+        lib.refh_run_seeded.argtypes = [C.POINTER(C.c_char_p), i32p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
+                                        C.c_uint64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_char_p, C.c_int]
+        lib.refh_run_seeded.restype = C.c_int
         lib.refh_time_public_api.argtypes = [C.POINTER(C.c_char_p), i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]
         lib.refh_time_public_api.restype = C.c_double
         _refh = lib
@@ -405,3 +410,43 @@ def oracle_write_fasta(names, rows):
         for j in range(0, len(r), 60):
             out += r[j:j + 60] + b"\n"
     return bytes(out)
+
+
+def ref_tree_noise(seed, sigma, n):
+    """noise factors of build_tree_kmeans_noisy from the reference's generator (lib/src/tlrng.c)"""
+    out = np.zeros(n, dtype=np.float32)
+    assert refh().refh_tree_noise(seed, sigma, n, out) == 0
+    return out
+
+
+def ref_run_seeded(seqs, n_threads=2, type_=8, gpo=-1.0, gpe=-1.0, tgpe=-1.0, tree_seed=0, tree_noise=0.0, dist_scale=0.0,
+                   vsm_amax=-1.0, use_seq_weights=-1.0, consistency=0, weight=2.0):
+    """the reference's kalign_run_seeded (lib/src/aln_wrap.c:133) on strings named s0..; aligned rows in input order"""
+    lib = refh()
+    n = len(seqs)
+    keep = [s.encode() for s in seqs]
+    arr = (C.c_char_p * n)(*keep)
+    lens = np.array([len(s) for s in keep], dtype=np.int32)
+    cap = 8 * max(len(s) for s in seqs) + 64
+    buf = C.create_string_buffer(n * (cap + 1))
+    L = lib.refh_run_seeded(arr, lens, n, n_threads, type_, gpo, gpe, tgpe, tree_seed, tree_noise, dist_scale, vsm_amax,
+                            use_seq_weights, consistency, weight, buf, cap)
+    assert L >= 0
+    raw = buf.raw
+    return [raw[i * (L + 1):i * (L + 1) + L].decode() for i in range(n)]
+
+
+_refens = None
+
+
+def ref_resolve_run_params(base_gpo, base_gpe, base_tgpe, k, seed):
+    """the reference's static resolve_run_params (lib/src/ensemble.c:55), through oracle/ref_ensemble_params.c"""
+    global _refens
+    if _refens is None:
+        _refens = C.CDLL(os.path.join(os.path.dirname(REF_SO), "libref_ensemble.so"))
+        _refens.refh_resolve_run_params.argtypes = [C.c_float, C.c_float, C.c_float, C.c_int, C.c_uint64, C.POINTER(C.c_float),
+                                                    C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_uint64), C.POINTER(C.c_float)]
+    g, e, t, nz = C.c_float(), C.c_float(), C.c_float(), C.c_float()
+    rs = C.c_uint64()
+    _refens.refh_resolve_run_params(base_gpo, base_gpe, base_tgpe, k, seed, C.byref(g), C.byref(e), C.byref(t), C.byref(rs), C.byref(nz))
+    return g.value, e.value, t.value, rs.value, nz.value
