@@ -190,6 +190,15 @@ int kb200_kalign_seeded(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_
                         float gpo, float gpe, float tgpe, unsigned long long tree_seed, float tree_noise,
                         float dist_scale, float vsm_amax, float use_seq_weights,
                         int consistency_anchors, float consistency_weight, char*** aligned, int* out_aln_len);
+/* build_tree_kmeans / build_tree_kmeans_noisy (lib/src/bisectingKmeans.c:177,76) on plain arrays: anchor distances,
+   bisecting k-means and the UPGMA of the leaf clusters on the GPU.  seqs: codes of the TREE alphabet (13-letter
+   reduced protein / nucleotide, what msa->sequences[i]->s holds when the reference calls it), sorted order.
+   tasks_abc: (nseq - 1) x 3 ints (a, b, c) in the order create_tasks (:1084) fills struct aln_tasks -- a node, its left
+   subtree, its right subtree; seq_distances (may be NULL): msa->seq_distances (:247-256). */
+int kb200_guide_tree(kb200_ctx* ctx, const uint8_t* seqs, const int64_t* offs, const int* lens, int nseq, int n_threads,
+                     unsigned long long tree_seed, float tree_noise, int* tasks_abc, float* seq_distances);
+/* creation order of a task list sorted by c (node ids nseq + index), host code */
+int kb200_tasks_creation_order(const int* tasks_sorted, int ntasks, int nseq, int* tasks_out);
 /* the n noise factors of build_tree_kmeans_noisy for (seed, sigma), in the order they are applied
    (row by row over the N x 32 anchor distances).  Host code. */
 int kb200_tree_noise(unsigned long long seed, float sigma, long long n, float* out);

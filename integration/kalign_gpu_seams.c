@@ -5,7 +5,7 @@
  * reference's own, unmodified lib/src/*.c (in place, see integration/Makefile) and linked with
  *
  *     -Wl,--wrap=d_estimation -Wl,--wrap=anchor_consistency_build -Wl,--wrap=create_msa_tree
- *     -Wl,--wrap=compute_aln_pairwise_dist
+ *     -Wl,--wrap=compute_aln_pairwise_dist -Wl,--wrap=build_tree_kmeans -Wl,--wrap=build_tree_kmeans_noisy
  *
  * so that the three calls kalign_run_seeded() makes into its hot path
  *
@@ -26,6 +26,10 @@
  *
  *     kalign_read_input()         lib/src/msa_io.c:80   (read_file_stdin :348, read_fasta :412)
  *     kalign_write_msa()          lib/src/msa_io.c:193  (write_msa_fasta :668)
+ *
+ * The guide tree as a whole (build_tree_kmeans / build_tree_kmeans_noisy, lib/src/bisectingKmeans.c:177,76, from
+ * aln_wrap.c:171,173,298,396) goes to kb200_guide_tree: anchor distances, bisecting k-means and the UPGMA of the leaf
+ * clusters run on the GPU, so d_estimation is only reached by callers outside the run wrappers.
  *
  * resolve to the functions below, which flatten struct msa into plain arrays and call the C ABI of
  * libkalign_b200.so (include/kalign_b200.h).  Everything else -- kalign.h, struct msa, I/O, the
@@ -64,6 +68,10 @@
 #include "msa_op.h"
 
 #include "kalign_b200.h"
+
+#ifdef HAVE_OPENMP
+#include <omp.h>
+#endif
 
 static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;   /* d_estimation(pair=1) is called from OpenMP tasks */
 static kb200_ctx* g_ctx = NULL;
@@ -725,4 +733,74 @@ int kalign_write_msa(struct msa* msa, char* outfile, char* format)
         free(names);
         free(rows);
         return rc == KB200_OK ? OK : FAIL;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * build_tree_kmeans / build_tree_kmeans_noisy (bisectingKmeans.c:177,76): same post-conditions -- the task
+ * list in create_tasks' order (a node, its left subtree, its right subtree) and msa->seq_distances. */
+static int guide_tree_on_gpu(struct msa* msa, struct aln_tasks** tasks, uint64_t seed, float noise_sigma)
+{
+        struct aln_tasks* t = NULL;
+        struct flat_msa f = {NULL, NULL, NULL, 0};
+        kb200_ctx* ctx = NULL;
+        int* abc = NULL;
+        int numseq;
+        int n_threads = 1;
+        int i;
+
+        ASSERT(msa != NULL, "No alignment.");
+        t = *tasks;
+        if(!t){
+                RUN(alloc_tasks(&t, msa->numseq));
+                *tasks = t;
+        }
+        numseq = msa->numseq;
+        pthread_mutex_lock(&g_lock);
+        ctx = seam_ctx();
+        pthread_mutex_unlock(&g_lock);
+        if(!ctx){
+                return FAIL;
+        }
+#ifdef HAVE_OPENMP
+        n_threads = omp_get_max_threads();
+#endif
+        if(!msa->quiet){
+                LOG_MSG("Calculating pairwise distances and building the guide tree (GPU)");
+        }
+        if(msa->seq_distances == NULL){
+                MMALLOC(msa->seq_distances, sizeof(float) * numseq);
+        }
+        RUN(flatten(msa, &f));
+        abc = malloc(sizeof(int) * 3 * (size_t)(numseq > 1 ? numseq - 1 : 1));
+        if(!abc){
+                goto ERROR;
+        }
+        if(kb200_guide_tree(ctx, f.seqs, f.offs, f.lens, numseq, n_threads, (unsigned long long)seed, noise_sigma, abc,
+                            msa->seq_distances) != KB200_OK){
+                goto ERROR;
+        }
+        for(i = 0; i < numseq - 1; i++){
+                struct task* task = t->list[t->n_tasks];
+                task->a = abc[3 * i];
+                task->b = abc[3 * i + 1];
+                task->c = abc[3 * i + 2];
+                t->n_tasks++;
+        }
+        free(abc);
+        flat_free(&f);
+        return OK;
+ERROR:
+        free(abc);
+        flat_free(&f);
+        return FAIL;
+}
+
+int __wrap_build_tree_kmeans(struct msa* msa, struct aln_tasks** tasks)
+{
+        return guide_tree_on_gpu(msa, tasks, 0, 0.0f);
+}
+
+int __wrap_build_tree_kmeans_noisy(struct msa* msa, struct aln_tasks** tasks, uint64_t seed, float noise_sigma)
+{
+        return guide_tree_on_gpu(msa, tasks, seed, noise_sigma);
 }

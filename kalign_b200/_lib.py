@@ -51,7 +51,7 @@ EXPORTS = ["kb200_device_count", "kb200_ctx_create", "kb200_ctx_destroy", "kb200
            "kb200_seqs_upload", "kb200_distances_on", "kb200_seqs_free", "kb200_aln_pairwise_dist",
            "kb200_anchor_posmaps", "kb200_select_anchors", "kb200_align_tree", "kb200_align_tree_conf", "kb200_kalign",
            "kb200_msa_create", "kb200_msa_align", "kb200_msa_result", "kb200_msa_info", "kb200_msa_tree", "kb200_msa_free",
-           "kb200_kalign_seeded", "kb200_tree_noise", "kb200_ensemble_run_params", "kb200_ensemble_run",
+           "kb200_guide_tree", "kb200_tasks_creation_order", "kb200_kalign_seeded", "kb200_tree_noise", "kb200_ensemble_run_params", "kb200_ensemble_run",
            "kb200_fasta_read", "kb200_fasta_numseq", "kb200_fasta_get", "kb200_fasta_letter_freq", "kb200_fasta_arrays",
            "kb200_fasta_free", "kb200_fasta_write", "kb200_kalign_file",
            "kb200_comm_unique_id", "kb200_ctx_comm_init", "kb200_ctx_comm_destroy", "kb200_partition"]
@@ -110,6 +110,10 @@ def load():
                                         C.c_ulonglong, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float,
                                         C.POINTER(C.POINTER(C.c_void_p)), C.POINTER(C.c_int)]
     lib.kb200_kalign_seeded.restype = C.c_int
+    lib.kb200_guide_tree.argtypes = [C.c_void_p, u8p, i64p, i32p, C.c_int, C.c_int, C.c_ulonglong, C.c_float, i32p, f32p]
+    lib.kb200_guide_tree.restype = C.c_int
+    lib.kb200_tasks_creation_order.argtypes = [i32p, C.c_int, C.c_int, i32p]
+    lib.kb200_tasks_creation_order.restype = C.c_int
     lib.kb200_tree_noise.argtypes = [C.c_ulonglong, C.c_float, C.c_longlong, f32p]
     lib.kb200_tree_noise.restype = C.c_int
     lib.kb200_ensemble_run_params.argtypes = [C.c_float, C.c_float, C.c_float, C.c_int, C.c_ulonglong, C.POINTER(C.c_float),
@@ -283,6 +287,25 @@ def _aln_pairwise_dist(self, rows):
     if self.lib.kb200_aln_pairwise_dist(self.h, arr, n, alnlen, ptrs) != 0:
         raise RuntimeError("kb200_aln_pairwise_dist failed")
     return dm
+
+
+def tasks_creation_order(tasks_sorted, nseq):
+    """kb200_tasks_creation_order: a task list sorted by c -> the order create_tasks filled it in"""
+    t = np.ascontiguousarray(tasks_sorted, dtype=np.int32).reshape(-1, 3)
+    out = np.zeros_like(t)
+    if load().kb200_tasks_creation_order(t.reshape(-1), len(t), nseq, out.reshape(-1)) != 0:
+        raise RuntimeError("kb200_tasks_creation_order failed")
+    return out
+
+
+def _guide_tree(self, flat, offs, lens, n_threads=2, tree_seed=0, tree_noise=0.0):
+    """kb200_guide_tree on tree-alphabet codes -> (tasks (n-1) x 3 in creation order, seq_distances)"""
+    n = len(lens)
+    abc = np.zeros(3 * (n - 1), dtype=np.int32)
+    sd = np.zeros(n, dtype=np.float32)
+    if self.lib.kb200_guide_tree(self.h, flat, offs, lens, n, n_threads, tree_seed, tree_noise, abc, sd) != 0:
+        raise RuntimeError("kb200_guide_tree failed")
+    return abc.reshape(-1, 3), sd
 
 
 def tree_noise(seed, sigma, n):
@@ -499,6 +522,7 @@ Context.anchor_posmaps = _anchor_posmaps
 Context.aln_pairwise_dist = _aln_pairwise_dist
 Context.kalign_file = _kalign_file
 Context.kalign_seeded = _kalign_seeded
+Context.guide_tree = _guide_tree
 Context.ensemble_runs = _ensemble_runs
 Context.align_tree = _align_tree
 Context.kalign = _kalign

@@ -1266,6 +1266,73 @@ int kb200_kalign_seeded(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_
                             aligned, out_aln_len, o);
 }
 
+// create_tasks (bisectingKmeans.c:1084-1114) fills the task list in pre-order -- a node, its left subtree, its
+// right subtree -- and only create_msa_tree sorts it by c (sort_tasks, task.c:114).  Host code.
+int kb200_tasks_creation_order(const int* tasks_sorted, int ntasks, int nseq, int* tasks_out)
+{
+        if (!tasks_sorted || !tasks_out || ntasks < 0 || nseq < 1) {
+                return KB200_FAIL;
+        }
+        for (int t = 0; t < ntasks; t++) {
+                if (tasks_sorted[3 * t + 2] != nseq + t) {
+                        return KB200_FAIL;       // node ids are nseq + task index in the sorted list
+                }
+        }
+        if (ntasks == 0) {
+                return KB200_OK;
+        }
+        std::vector<int> stack;
+        stack.push_back(nseq + ntasks - 1);
+        int k = 0;
+        while (!stack.empty()) {
+                const int node = stack.back();
+                stack.pop_back();
+                if (node < nseq) {
+                        continue;
+                }
+                const int t = node - nseq;
+                if (t < 0 || t >= ntasks || k >= ntasks) {
+                        return KB200_FAIL;
+                }
+                tasks_out[3 * k] = tasks_sorted[3 * t];
+                tasks_out[3 * k + 1] = tasks_sorted[3 * t + 1];
+                tasks_out[3 * k + 2] = node;
+                k++;
+                stack.push_back(tasks_sorted[3 * t + 1]);     // right is visited after the whole left subtree
+                stack.push_back(tasks_sorted[3 * t]);
+        }
+        return k == ntasks ? KB200_OK : KB200_FAIL;
+}
+
+// build_tree_kmeans / build_tree_kmeans_noisy (bisectingKmeans.c:177,76) on plain arrays: the whole guide tree on
+// the GPU -- anchor distances (bpm), bisecting k-means, UPGMA of the leaf clusters -- for callers that hold the
+// sequences in the tree alphabet (the drop-in's seam).  tasks_abc: (nseq - 1) x 3 in the reference's creation order.
+int kb200_guide_tree(kb200_ctx* ctx, const uint8_t* seqs, const int64_t* offs, const int* lens, int nseq, int n_threads,
+                     unsigned long long tree_seed, float tree_noise, int* tasks_abc, float* seq_distances)
+{
+        if (!ctx || !seqs || !offs || !lens || nseq < 2 || !tasks_abc) {
+                return KB200_FAIL;
+        }
+        KB_CUDA(cudaSetDevice(ctx->device));
+        if (n_threads < 1) n_threads = 1;
+        n_threads = std::min(n_threads, kb_default_threads());
+        KbSeqs S;
+        int rc = S.upload(ctx, seqs, offs, lens, nseq);
+        std::vector<int> abc;
+        std::vector<float> sd;
+        if (rc == KB200_OK) {
+                rc = kb_build_tree(ctx, S, n_threads, abc, sd, (uint64_t)tree_seed, tree_noise);
+        }
+        S.release();
+        if (rc != KB200_OK || (int)abc.size() != 3 * (nseq - 1)) {
+                return KB200_FAIL;
+        }
+        if (seq_distances) {
+                memcpy(seq_distances, sd.data(), sizeof(float) * (size_t)nseq);
+        }
+        return kb200_tasks_creation_order(abc.data(), nseq - 1, nseq, tasks_abc);
+}
+
 // multiplicative factors of build_tree_kmeans_noisy, in the order they are applied (row by row)
 int kb200_tree_noise(unsigned long long seed, float sigma, long long n, float* out)
 {

@@ -32,9 +32,10 @@ def test_public_api_and_seams():
     defined, undefined = _nm()
     for f in KALIGN_H_API:
         assert f in defined, f
-    for w in ("__wrap_d_estimation", "__wrap_anchor_consistency_build", "__wrap_create_msa_tree", "__wrap_compute_aln_pairwise_dist"):
+    for w in ("__wrap_d_estimation", "__wrap_anchor_consistency_build", "__wrap_create_msa_tree", "__wrap_compute_aln_pairwise_dist",
+              "__wrap_build_tree_kmeans", "__wrap_build_tree_kmeans_noisy"):
         assert w in defined, w
-    for f in ("kb200_aln_pairwise_dist", "kb200_distances_on", "kb200_seqs_upload", "kb200_anchor_posmaps", "kb200_select_anchors", "kb200_align_tree_conf", "kb200_ctx_create"):
+    for f in ("kb200_guide_tree", "kb200_fasta_read", "kb200_fasta_write", "kb200_aln_pairwise_dist", "kb200_distances_on", "kb200_seqs_upload", "kb200_anchor_posmaps", "kb200_select_anchors", "kb200_align_tree_conf", "kb200_ctx_create"):
         assert f in undefined, f       # resolved by libkalign_b200.so at load time
 
 
@@ -44,6 +45,8 @@ def test_run_seeded_calls_the_seams():
     dis = subprocess.run(["objdump", "-d", "--no-show-raw-insn", LIB], stdout=subprocess.PIPE, text=True, check=True).stdout
     body = dis.split("<kalign_run_seeded>:")[1].split("\n\n")[0]
     assert "__wrap_create_msa_tree" in body and "__wrap_anchor_consistency_build" in body
+    assert "__wrap_build_tree_kmeans" in body and "__wrap_build_tree_kmeans_noisy" in body
+    assert "<build_tree_kmeans@plt>" not in body
     assert "<create_msa_tree@plt>" not in body and "<anchor_consistency_build@plt>" not in body
     assert "call" in dis and "<d_estimation@plt>" not in dis
     # the realign loop reaches the GPU for its N x N identity distances as well

@@ -92,3 +92,39 @@ def test_ensemble_runs_equal_reference(ctx, fk):
     for k in range(n_runs):
         assert got[k] == [str(x) for x in Z["ens_%s_%d" % (fk, k)]], k
     assert any(got[k] != got[0] for k in range(1, n_runs))
+
+
+def test_creation_order_equals_reference_golden():
+    """create_tasks (lib/src/bisectingKmeans.c:1084) fills the list in pre-order; tests/golden/full_T3.npz holds the
+    reference's list of the C3 tree (N = 10 000) before any sort: sorting it by c and restoring the creation order
+    with kb200_tasks_creation_order must give it back"""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "full_T3.npz"))
+    t, n = g["tasks"], int(g["n"])
+    srt = t[np.argsort(t[:, 2], kind="stable")]
+    assert not np.array_equal(srt, t)
+    assert np.array_equal(_lib.tasks_creation_order(srt, n), t)
+    assert t[0, 2] == 2 * n - 2                       # the root comes first
+    bad = srt.copy()
+    bad[5, 2] += 1
+    with pytest.raises(RuntimeError):
+        _lib.tasks_creation_order(bad, n)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["rna_default", "dna_default"])
+def test_guide_tree_entry_point(ctx, tag):
+    """kb200_guide_tree on the tree-alphabet codes of a committed reference run: the reference's task list and
+    msa->seq_distances (for nucleotides the tree alphabet is the alignment alphabet the fixture stores)"""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "msa_%s.npz" % tag))
+    n = len(z["seqs"])
+    flat, offs, lens = _lib.pack([np.ascontiguousarray(z["codes%d" % i]) for i in range(n)])
+    abc, sd = ctx.guide_tree(flat, offs, lens)
+    assert np.array_equal(sd, z["seq_distances"])
+    want = z["tasks"]
+    want = want[np.argsort(want[:, 2], kind="stable")]
+    assert np.array_equal(abc[np.argsort(abc[:, 2], kind="stable")], want)
+    assert np.array_equal(abc, _lib.tasks_creation_order(want, n))
+    # a noisy tree of the same sequences is another tree, deterministically
+    a1, _ = ctx.guide_tree(flat, offs, lens, tree_seed=11, tree_noise=0.4)
+    a2, _ = ctx.guide_tree(flat, offs, lens, tree_seed=11, tree_noise=0.4)
+    assert np.array_equal(a1, a2)
