@@ -16,8 +16,14 @@
  *                              (recursive_aln / do_align / aln_runner, the aln_task scheduler)
  *
  * kb200_pair_align_batch exposes the batched Hirschberg engine itself (aln_runner,
- * lib/src/aln_controller.c:21) and kb200_kalign / kb200_msa_run mirror the public
- * kalign() / kalign_run_seeded() of lib/include/kalign/kalign.h:45,51 on plain arrays.
+ * lib/src/aln_controller.c:21); kb200_kalign / kb200_kalign_seeded mirror the public
+ * kalign() / kalign_run_seeded() of lib/include/kalign/kalign.h:45,51 on plain arrays
+ * (kb200_msa_* is the same call sequence in stages).  On either side of the path:
+ *
+ *   kb200_guide_tree        <->  build_tree_kmeans[_noisy]()   lib/src/bisectingKmeans.c:177,76
+ *   kb200_aln_pairwise_dist <->  compute_aln_pairwise_dist()   lib/src/aln_apair_dist.c:9   (realign loop)
+ *   kb200_ensemble_run      <->  one run of kalign_ensemble()  lib/src/ensemble.c:286-340
+ *   kb200_fasta_read/_write <->  read_fasta / write_msa_fasta  lib/src/msa_io.c:412,668     (host code)
  *
  * Index space: like the reference after msa_sort_len_name (lib/src/msa_sort.c:14) all per-sequence
  * arrays below are in the caller's order; "seqs" is the concatenation of the internal residue
