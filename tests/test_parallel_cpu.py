@@ -81,3 +81,41 @@ def test_two_rank_gloo():
     for rank, same, covered, share, got in res:
         assert same and covered and got
         assert 0.35 < share < 0.65
+
+
+def _ensemble_worker(rank, world, port, q):
+    """the host side of an ensemble sharded over `world` processes: every rank resolves the parameters of ITS runs
+    (kb200_ensemble_run_params, host code) and the ranks gather them with gloo, as a caller would gather the rows"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_runs, seed = 9, 42
+    mine = torch.full((n_runs, 6), -1.0, dtype=torch.float64)
+    for k in range(rank, n_runs, world):
+        g, e, t, ts, nz = _lib.ensemble_run_params(5.5, 2.0, 1.0, k, seed)
+        mine[k] = torch.tensor([k, g, e, t, float(ts), nz], dtype=torch.float64)
+    parts = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    q.put((rank, torch.stack(parts).numpy()))
+    dist.destroy_process_group()
+
+
+def test_ensemble_runs_two_rank_gloo():
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ensemble_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert np.array_equal(res[0], res[1])                       # every rank ends with the same table
+    parts = res[0]
+    for k in range(9):
+        owner = k % world
+        assert parts[owner][k][0] == k and parts[1 - owner][k][0] == -1     # each run resolved by exactly one rank
+        g, e, t, ts, nz = _lib.ensemble_run_params(5.5, 2.0, 1.0, k, 42)
+        assert np.array_equal(parts[owner][k], np.array([k, g, e, t, float(ts), nz]))
