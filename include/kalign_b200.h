@@ -203,6 +203,11 @@ int kb200_kalign_seeded(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_
    subtree, its right subtree; seq_distances (may be NULL): msa->seq_distances (:247-256). */
 int kb200_guide_tree(kb200_ctx* ctx, const uint8_t* seqs, const int64_t* offs, const int* lens, int nseq, int n_threads,
                      unsigned long long tree_seed, float tree_noise, int* tasks_abc, float* seq_distances);
+/* the code tables convert_msa_to_internal uses (create_alphabet, lib/src/alphabet.c:140-302): letters = 5 (nucleotide:
+   A C G T/U and N for every IUPAC ambiguity code), 13 (reduced protein alphabet of the guide tree), 23 (protein
+   alphabet of the alignment, ARNDCQEGHILKMFPSTWYVBZX, U as X); to_internal[128] maps a character to its code, -1 when it
+   is not in the alphabet (such characters are coded 0 with a warning, msa_op.c:358-362); *L = number of codes.  Host code. */
+int kb200_alphabet(int letters, signed char* to_internal, int* L);
 /* creation order of a task list sorted by c (node ids nseq + index), host code */
 int kb200_tasks_creation_order(const int* tasks_sorted, int ntasks, int nseq, int* tasks_out);
 /* the n noise factors of build_tree_kmeans_noisy for (seed, sigma), in the order they are applied

@@ -51,7 +51,7 @@ EXPORTS = ["kb200_device_count", "kb200_ctx_create", "kb200_ctx_destroy", "kb200
            "kb200_seqs_upload", "kb200_distances_on", "kb200_seqs_free", "kb200_aln_pairwise_dist",
            "kb200_anchor_posmaps", "kb200_select_anchors", "kb200_align_tree", "kb200_align_tree_conf", "kb200_kalign",
            "kb200_msa_create", "kb200_msa_align", "kb200_msa_result", "kb200_msa_info", "kb200_msa_tree", "kb200_msa_free",
-           "kb200_guide_tree", "kb200_tasks_creation_order", "kb200_kalign_seeded", "kb200_tree_noise", "kb200_ensemble_run_params", "kb200_ensemble_run",
+           "kb200_alphabet", "kb200_guide_tree", "kb200_tasks_creation_order", "kb200_kalign_seeded", "kb200_tree_noise", "kb200_ensemble_run_params", "kb200_ensemble_run",
            "kb200_fasta_read", "kb200_fasta_numseq", "kb200_fasta_get", "kb200_fasta_letter_freq", "kb200_fasta_arrays",
            "kb200_fasta_free", "kb200_fasta_write", "kb200_kalign_file",
            "kb200_comm_unique_id", "kb200_ctx_comm_init", "kb200_ctx_comm_destroy", "kb200_partition"]
@@ -110,6 +110,8 @@ def load():
                                         C.c_ulonglong, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float,
                                         C.POINTER(C.POINTER(C.c_void_p)), C.POINTER(C.c_int)]
     lib.kb200_kalign_seeded.restype = C.c_int
+    lib.kb200_alphabet.argtypes = [C.c_int, np.ctypeslib.ndpointer(dtype=np.int8, flags="C_CONTIGUOUS"), C.POINTER(C.c_int)]
+    lib.kb200_alphabet.restype = C.c_int
     lib.kb200_guide_tree.argtypes = [C.c_void_p, u8p, i64p, i32p, C.c_int, C.c_int, C.c_ulonglong, C.c_float, i32p, f32p]
     lib.kb200_guide_tree.restype = C.c_int
     lib.kb200_tasks_creation_order.argtypes = [i32p, C.c_int, C.c_int, i32p]
@@ -287,6 +289,15 @@ def _aln_pairwise_dist(self, rows):
     if self.lib.kb200_aln_pairwise_dist(self.h, arr, n, alnlen, ptrs) != 0:
         raise RuntimeError("kb200_aln_pairwise_dist failed")
     return dm
+
+
+def alphabet(letters):
+    """kb200_alphabet -> (to_internal int8[128], L)"""
+    t = np.zeros(128, dtype=np.int8)
+    L = C.c_int(0)
+    if load().kb200_alphabet(letters, t, C.byref(L)) != 0:
+        raise RuntimeError("kb200_alphabet failed")
+    return t, L.value
 
 
 def tasks_creation_order(tasks_sorted, nseq):

@@ -1266,6 +1266,19 @@ int kb200_kalign_seeded(kb200_ctx* ctx, char** seq, int* len, int numseq, int n_
                             aligned, out_aln_len, o);
 }
 
+// the code tables of convert_msa_to_internal (create_alphabet, lib/src/alphabet.c:140-302): letters = 5
+// (nucleotide), 13 (reduced protein, guide tree), 23 (protein, alignment); -1 = not in the alphabet.  Host code.
+int kb200_alphabet(int letters, signed char* to_internal, int* L)
+{
+        if (!to_internal || (letters != ALPHA_DNA && letters != ALPHA_RED && letters != ALPHA_AMB)) {
+                return KB200_FAIL;
+        }
+        const Alphabet a = make_alphabet(letters);
+        for (int i = 0; i < 128; i++) to_internal[i] = (signed char)a.to_internal[i];
+        if (L) *L = a.L;
+        return KB200_OK;
+}
+
 // create_tasks (bisectingKmeans.c:1084-1114) fills the task list in pre-order -- a node, its left subtree, its
 // right subtree -- and only create_msa_tree sorts it by c (sort_tasks, task.c:114).  Host code.
 int kb200_tasks_creation_order(const int* tasks_sorted, int ntasks, int nseq, int* tasks_out)
