@@ -2,7 +2,7 @@
  * kalign_gpu_seams.c -- the reference-side binding of INTEGRATION.md, built for real.
  *
  * This file is the ONE host-side C file a kalign maintainer adds.  It is compiled together with the
- * reference's own, unmodified lib/src/*.c (in place, see integration/Makefile) and linked with
+ * reference's own, unmodified C files of lib/src (in place, see integration/Makefile) and linked with
  *
  *     -Wl,--wrap=d_estimation -Wl,--wrap=anchor_consistency_build -Wl,--wrap=create_msa_tree
  *     -Wl,--wrap=compute_aln_pairwise_dist -Wl,--wrap=build_tree_kmeans -Wl,--wrap=build_tree_kmeans_noisy
